@@ -1,0 +1,141 @@
+/*
+ * rfinv_b200.h -- C-ABI of the B200-native forward-model + likelihood path of RF_INV.
+ *
+ * This is the drop-in boundary.  Every entry point is `extern "C"`, takes
+ * plain pointers, int32_t and double, and returns an int status (0 = ok, non-zero = error, text via
+ * rfinv_last_error()).  The library never calls exit(); NaN log-likelihoods are values, not errors.
+ * A Fortran host binds these with `interface ... bind(C)` blocks (see include/rfinv_b200_capi.f90
+ * and INTEGRATION.md).
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   rfinv_create            <- module globals set up by get_params/read_obs (src/params.f90:101-476),
+ *                              read_ref_model (src/model.f90:109-171), init_filter (src/forward.f90:95-119),
+ *                              init_fftw (src/fftw.f90:41-48), init_r_inv (src/likelihood.f90:168-241)
+ *   rfinv_eval_batch        <- calc_likelihood (src/likelihood.f90:56-101), batched over chains; the
+ *                              call sites are src/pt_mcmc.f90:178-180 and src/likelihood.f90:156-160
+ *   rfinv_format_model_batch<- format_model (src/model.f90:175-290)
+ *   rfinv_pt_*              <- init_model (src/model.f90:43-107), init_sig/init_rft
+ *                              (src/likelihood.f90:107-163), init_pt_mcmc (src/pt_mcmc.f90:296-464),
+ *                              mcmc (src/pt_mcmc.f90:54-290), pt_control (src/pt_mcmc.f90:468-576)
+ *   rfinv_write_outputs     <- output_results (src/mcmc_out.f90:35-322)
+ *   rfinv_params_*          <- get_params / read_obs / read_ref_model (file formats are a contract)
+ *
+ * Array layouts follow the reference's Fortran arrays with the chain as the slowest index, i.e. what a
+ * Fortran caller already holds: z(k_max-1, C), dvp(k_max, C), dvs(k_max, C), sig(ntrc, C),
+ * rft(nfft, ntrc, C).  On device the library re-lays them out chain-fastest (structure of arrays).
+ */
+#ifndef RFINV_B200_H
+#define RFINV_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RFINV_ABI_VERSION 1
+
+/* status codes */
+#define RFINV_OK 0
+#define RFINV_ERR_ARG 1      /* bad argument / unsupported configuration */
+#define RFINV_ERR_CUDA 2     /* CUDA runtime failure (no device, launch failure, out of memory) */
+#define RFINV_ERR_IO 3       /* file could not be read / written / parsed */
+#define RFINV_ERR_STATE 4    /* call out of order (e.g. pt_step before pt_init) */
+
+/* Immutable configuration: the reference's module globals (src/params.f90:50-96, src/model.f90:35-36). */
+typedef struct rfinv_config {
+  /* observation and RF synthesis */
+  int32_t ntrc;         /* N_TRC */
+  int32_t nfft;         /* N_FFT; must be a power of two, 32 <= nfft <= 4096 */
+  int32_t nsmp;         /* samples in [T_START, T_END] (src/params.f90:446-448); nsmp <= nfft */
+  int32_t deconv_mode;  /* 0: normalise by vertical, 1: water-level deconvolution */
+  double delta;         /* sampling interval as read from the SAC header (float32 promoted) */
+  double t_start;       /* T_START */
+  double sdep;          /* SEA_DEP (km); > 0 prepends a water layer */
+  const double* rayps;  /* [ntrc] ray parameters (s/km) */
+  const double* a_gus;  /* [ntrc] Gaussian filter parameters */
+  const int32_t* ipha;  /* [ntrc] 1 = P receiver function, -1 = S receiver function */
+  const double* obs;    /* [ntrc][nsmp] observed traces = Fortran obs(1:nsmp, itrc) */
+  const double* r_inv;  /* [ntrc][nsmp][nsmp] inverse data covariance (src/likelihood.f90:222), or NULL:
+                           the library then builds it itself from a_gus/delta (symmetric eigen-solver) */
+  /* reference velocity model */
+  int32_t nref;
+  int32_t pad0_;
+  double z_ref_min;
+  double dz_ref;
+  const double* vp_ref; /* [nref] */
+  const double* vs_ref; /* [nref] */
+  /* prior and model validity */
+  int32_t vp_mode;      /* 0: dVp fixed at 0, 1: solved */
+  int32_t k_min;
+  int32_t k_max;        /* 2 <= k_max <= 64 (fixed device layout) */
+  int32_t prior_mode;   /* 1: Laplace, 2: Gaussian */
+  double z_min, z_max, h_min;
+  double dvs_prior, dvp_prior;
+  const double* sig_min; /* [ntrc] */
+  const double* sig_max; /* [ntrc] */
+  double vp_min, vp_max, vs_min, vs_max, vpvs_min, vpvs_max;
+  /* proposal widths */
+  double dev_z, dev_dvs, dev_dvp, dev_sig;
+  /* parallel tempering */
+  int32_t nburn, niter, ncorr;
+  int32_t nchains;      /* chains per (virtual) rank = per mt19937 stream */
+  int32_t ncool;        /* non-tempered chains per rank */
+  int32_t iseed;        /* I_SEED; rank r is seeded iseed + r*r*10000 + 23*r (src/rf_inv.f90:75) */
+  double t_high;
+  /* posterior histograms (src/pt_mcmc.f90:396-433) */
+  int32_t nbin_z, nbin_vs, nbin_vp, nbin_vpvs, nbin_sig, nbin_amp;
+  double amp_min, amp_max;
+} rfinv_config;
+
+typedef struct rfinv_handle rfinv_handle;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int32_t rfinv_abi_version(void);
+/* Thread-local text of the last error returned to this thread. */
+const char* rfinv_last_error(void);
+/* Number of CUDA devices visible; negative status on CUDA failure. */
+int32_t rfinv_device_count(void);
+
+/* ---- evaluator ------------------------------------------------------------------------------ */
+/* Uploads the configuration (filters, twiddles, observed data, R^-1, reference model) to `device`
+ * and creates one stream.  The handle is single-owner: one call at a time per handle.           */
+int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out);
+void rfinv_destroy(rfinv_handle* h);
+/* Use an externally owned cudaStream_t (passed as an integer) for all work of this handle. */
+int32_t rfinv_set_stream(rfinv_handle* h, uint64_t cuda_stream);
+
+/* calc_likelihood(fwd_flag=.true.) for C models at once.  HOST pointers in and out.
+ *   k[C], z[C][k_max-1], dvp[C][k_max], dvs[C][k_max], sig[C][ntrc]
+ *   logl[C]               out
+ *   rft[C][ntrc][nfft]    out, may be NULL
+ *   is_valid[C]           out, may be NULL (format_model's flag; logl is computed regardless, like the reference) */
+int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                         const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid);
+
+/* Same evaluation with DEVICE pointers in the library's chain-fastest layout:
+ *   k[C], z[k_max-1][C], dvp[k_max][C], dvs[k_max][C], sig[ntrc][C], logl[C],
+ *   rft_smp[ntrc][C][nsmp] (first nsmp samples only; may be 0), is_valid[C] (may be 0).
+ * Asynchronous on the handle's stream.                                                          */
+int32_t rfinv_eval_batch_device(rfinv_handle* h, int32_t C, uint64_t d_k, uint64_t d_z, uint64_t d_dvp,
+                                uint64_t d_dvs, uint64_t d_sig, uint64_t d_logl, uint64_t d_rft_smp,
+                                uint64_t d_is_valid);
+
+/* format_model for C models (HOST pointers): nlay[C], alpha/beta/rho/h [C][k_max+1] (k_max+1 is the
+ * largest nlay: k_max-1 interfaces + half space + optional sea layer), is_valid[C].             */
+int32_t rfinv_format_model_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z,
+                                 const double* dvp, const double* dvs, int32_t* nlay, double* alpha,
+                                 double* beta, double* rho, double* hthick, uint8_t* is_valid);
+
+/* Copies the R^-1 actually in use back to the host ([ntrc][nsmp][nsmp]). */
+int32_t rfinv_get_r_inv(rfinv_handle* h, double* r_inv);
+/* Waits for all work queued on the handle's stream. */
+int32_t rfinv_synchronize(rfinv_handle* h);
+
+/* Timing / accounting of the last rfinv_eval_batch* call: number of kernels launched by it. */
+int32_t rfinv_last_launch_count(rfinv_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RFINV_B200_H */
