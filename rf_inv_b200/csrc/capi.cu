@@ -1,0 +1,451 @@
+// C-ABI of the evaluator (include/rfinv_b200.h): handle life cycle, configuration upload, batched
+// calc_likelihood with host or device buffers.  No torch types, no CPU compute fallback: every entry
+// point that evaluates models launches the CUDA kernels or fails with RFINV_ERR_CUDA.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include "rfinv_handle.h"
+
+static thread_local char g_err[1024] = "";
+
+void rfinv_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// ---- host-side init services ------------------------------------------------------------------
+// init_filter, src/forward.f90:95-119 (same operation order)
+void build_filter(const rfinv_config& c, std::vector<double>& flt) {
+  const int nh = c.nfft / 2 + 1;
+  flt.resize((size_t)c.ntrc * nh);
+  const double df = 1.0 / (c.delta * c.nfft);
+  for (int t = 0; t < c.ntrc; ++t) {
+    const double fac_norm = c.nfft * c.a_gus[t] * c.delta / std::sqrt(RFINV_PI);
+    for (int i = 0; i < nh; ++i) {
+      const double omega = i * 2.0 * RFINV_PI * df;
+      const double q = omega / (2.0 * c.a_gus[t]);
+      flt[(size_t)t * nh + i] = std::exp(-(q * q)) / fac_norm;
+    }
+  }
+}
+
+// exp(+2 pi i m / n), exact symmetries of the octants
+void build_twiddles(int n, std::vector<double2>& tw) {
+  tw.resize(n);
+  for (int m = 0; m < n; ++m) {
+    const double ang = 2.0 * RFINV_PI * (double)m / (double)n;
+    tw[m] = make_double2(std::cos(ang), std::sin(ang));
+  }
+  tw[0] = make_double2(1.0, 0.0);
+  if (n % 4 == 0) { tw[n / 4] = make_double2(0.0, 1.0); tw[n / 2] = make_double2(-1.0, 0.0); tw[3 * n / 4] = make_double2(0.0, -1.0); }
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric matrix (row-major n x n): A = V diag(w) V^T.
+// Used for init_r_inv when the caller passes no R^-1.  R = r^((i-j)^2) is symmetric positive
+// semi-definite, so its SVD (what the reference asks LAPACK dgesvd for, src/likelihood.f90:197-205) is
+// its eigen-decomposition.
+void jacobi_eigh(std::vector<double>& a, int n, std::vector<double>& w, std::vector<double>& v) {
+  v.assign((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < n; ++i) {
+      diag += a[(size_t)i * n + i] * a[(size_t)i * n + i];
+      for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j];
+    }
+    if (off <= 1e-30 * diag) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = a[(size_t)p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
+        const double theta = (aqq - app) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < n; ++k) {  // columns p,q
+          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
+          a[(size_t)k * n + p] = cs * akp - sn * akq;
+          a[(size_t)k * n + q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < n; ++k) {  // rows p,q
+          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
+          a[(size_t)p * n + k] = cs * apk - sn * aqk;
+          a[(size_t)q * n + k] = sn * apk + cs * aqk;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
+          v[(size_t)k * n + p] = cs * vkp - sn * vkq;
+          v[(size_t)k * n + q] = sn * vkp + cs * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
+}
+
+// init_r_inv, src/likelihood.f90:168-241: R^-1 = sum_{s_i > 1e-3} v_i v_i^T / s_i
+void build_r_inv(const rfinv_config& c, std::vector<double>& rinv) {
+  const int S = c.nsmp;
+  rinv.assign((size_t)c.ntrc * S * S, 0.0);
+  std::vector<double> a, w, v;
+  for (int t = 0; t < c.ntrc; ++t) {
+    bool same = false;  // traces with the same Gaussian width share R^-1
+    for (int u = 0; u < t; ++u)
+      if (c.a_gus[u] == c.a_gus[t]) {
+        std::memcpy(&rinv[(size_t)t * S * S], &rinv[(size_t)u * S * S], sizeof(double) * (size_t)S * S);
+        same = true;
+        break;
+      }
+    if (same) continue;
+    const double r = std::exp(-(c.a_gus[t] * c.a_gus[t]) * (c.delta * c.delta));
+    a.resize((size_t)S * S);
+    for (int i = 0; i < S; ++i)
+      for (int j = 0; j < S; ++j) a[(size_t)i * S + j] = std::pow(r, (double)((i - j) * (i - j)));
+    jacobi_eigh(a, S, w, v);
+    double* out = &rinv[(size_t)t * S * S];
+    for (int e = 0; e < S; ++e) {
+      if (!(w[e] > 1.0e-3)) continue;
+      const double inv = 1.0 / w[e];
+      for (int i = 0; i < S; ++i) {
+        const double vi = v[(size_t)i * S + e] * inv;
+        for (int j = 0; j < S; ++j) out[(size_t)i * S + j] += vi * v[(size_t)j * S + e];
+      }
+    }
+  }
+}
+
+template <typename T>
+int upload(const std::vector<T>& h, T** d) {
+  RFINV_CUDA_CHECK(cudaMalloc((void**)d, sizeof(T) * std::max<size_t>(h.size(), 1)));
+  if (!h.empty()) RFINV_CUDA_CHECK(cudaMemcpy(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice));
+  return RFINV_OK;
+}
+
+int check_config(const rfinv_config* c) {
+  if (!c) { rfinv_set_error("config is NULL"); return RFINV_ERR_ARG; }
+  if (c->ntrc < 1 || c->ntrc > RFINV_MAX_TRC) { rfinv_set_error("ntrc must be in [1,%d]", RFINV_MAX_TRC); return RFINV_ERR_ARG; }
+  if (c->nfft < 64 || c->nfft > 4096 || (c->nfft & (c->nfft - 1))) {
+    rfinv_set_error("nfft=%d unsupported: the shared-memory FFT needs a power of two in [64,4096]", c->nfft);
+    return RFINV_ERR_ARG;
+  }
+  if (c->nsmp < 1 || c->nsmp > c->nfft) { rfinv_set_error("nsmp must be in [1,nfft]"); return RFINV_ERR_ARG; }
+  if (c->deconv_mode != 0 && c->deconv_mode != 1) { rfinv_set_error("deconv_mode must be either 0 or 1"); return RFINV_ERR_ARG; }
+  if (c->vp_mode != 0 && c->vp_mode != 1) { rfinv_set_error("vp_mode should be 0 or 1"); return RFINV_ERR_ARG; }
+  if (c->k_max < 2 || c->k_max > RFINV_MAX_K || c->k_min < 1 || c->k_min >= c->k_max) {
+    rfinv_set_error("need 1 <= k_min < k_max <= %d", RFINV_MAX_K);
+    return RFINV_ERR_ARG;
+  }
+  if (!c->rayps || !c->a_gus || !c->ipha || !c->obs || !c->vp_ref || !c->vs_ref || !c->sig_min || !c->sig_max || c->nref < 1) {
+    rfinv_set_error("rayps/a_gus/ipha/obs/vp_ref/vs_ref/sig_min/sig_max must be set");
+    return RFINV_ERR_ARG;
+  }
+  for (int t = 0; t < c->ntrc; ++t)
+    if (c->ipha[t] != 1 && c->ipha[t] != -1) { rfinv_set_error("ipha must be 1 or -1"); return RFINV_ERR_ARG; }
+  if (!(c->delta > 0.0) || !(c->dz_ref > 0.0)) { rfinv_set_error("delta and dz_ref must be positive"); return RFINV_ERR_ARG; }
+  return RFINV_OK;
+}
+
+// chain-major host layout -> chain-fastest device layout: out[i*C + c] = in[c*len + i]
+__global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int C, int len) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * len) return;
+  const int c = (int)(idx % C), i = (int)(idx / C);
+  out[idx] = in[(size_t)c * len + i];
+}
+
+}  // namespace
+
+int rfinv_handle::ensure_capacity(int C) {
+  if (C <= cap) return RFINV_OK;
+  free_workspace();
+  const int km = cfg.k_max, T = cfg.ntrc;
+  const size_t Cz = (size_t)C;
+  RFINV_CUDA_CHECK(cudaSetDevice(device));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_k, sizeof(int) * Cz));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_z, sizeof(double) * Cz * (km - 1)));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvp, sizeof(double) * Cz * km));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_misfit, sizeof(double) * Cz * T * dc.nsmp_pad));
+  RFINV_CUDA_CHECK(cudaMemset(d_misfit, 0, sizeof(double) * Cz * T * dc.nsmp_pad));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_phi, sizeof(double) * Cz * T));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_logl, sizeof(double) * Cz));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_valid, Cz));
+  cap = C;
+  return RFINV_OK;
+}
+
+void rfinv_handle::free_workspace() {
+  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage);
+  cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full);
+  d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = nullptr;
+  d_valid = nullptr;
+  cap = 0; cap_rft_full = 0;
+}
+
+int rfinv_handle::eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs,
+                              const double* sig, double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid,
+                              const int* active, int n_active) {
+  // misfit scratch is sized by capacity; its [t][c] stride uses the C of this call
+  ModelBatch mb;
+  mb.C = C; mb.k = k; mb.z = z; mb.dvp = dvp; mb.dvs = dvs; mb.sig = sig; mb.active = active; mb.n_active = n_active;
+  EvalOutputs out;
+  out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_full = rft_full; out.is_valid = is_valid;
+  int st;
+  launches = 0;
+  if ((st = rfinv_launch_forward(dc, mb, out, stream)) != RFINV_OK) return st;
+  ++launches;
+  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, stream)) != RFINV_OK) return st;
+  ++launches;
+  if (logl) {
+    if ((st = rfinv_launch_loglik(dc, C, d_phi, sig, logl, stream)) != RFINV_OK) return st;
+    ++launches;
+  }
+  return RFINV_OK;
+}
+
+extern "C" {
+
+int32_t rfinv_abi_version(void) { return RFINV_ABI_VERSION; }
+const char* rfinv_last_error(void) { return g_err; }
+
+int32_t rfinv_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    rfinv_set_error("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return -RFINV_ERR_CUDA;
+  }
+  return n;
+}
+
+int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out) {
+  if (!out) { rfinv_set_error("out is NULL"); return RFINV_ERR_ARG; }
+  *out = nullptr;
+  int st = check_config(cfg);
+  if (st != RFINV_OK) return st;
+  int ndev = 0;
+  RFINV_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) {
+    rfinv_set_error("device %d not available (%d CUDA devices visible); this library has no CPU path", device, ndev);
+    return RFINV_ERR_CUDA;
+  }
+  RFINV_CUDA_CHECK(cudaSetDevice(device));
+  rfinv_handle* h = new rfinv_handle();
+  h->device = device;
+  // deep copy of the configuration
+  h->cfg = *cfg;
+  const int T = cfg->ntrc, S = cfg->nsmp;
+  h->h_rayps.assign(cfg->rayps, cfg->rayps + T);
+  h->h_a_gus.assign(cfg->a_gus, cfg->a_gus + T);
+  h->h_ipha.assign(cfg->ipha, cfg->ipha + T);
+  h->h_obs.assign(cfg->obs, cfg->obs + (size_t)T * S);
+  h->h_vp_ref.assign(cfg->vp_ref, cfg->vp_ref + cfg->nref);
+  h->h_vs_ref.assign(cfg->vs_ref, cfg->vs_ref + cfg->nref);
+  h->h_sig_min.assign(cfg->sig_min, cfg->sig_min + T);
+  h->h_sig_max.assign(cfg->sig_max, cfg->sig_max + T);
+  if (cfg->r_inv) h->h_r_inv.assign(cfg->r_inv, cfg->r_inv + (size_t)T * S * S);
+  else build_r_inv(*cfg, h->h_r_inv);
+  h->cfg.rayps = h->h_rayps.data(); h->cfg.a_gus = h->h_a_gus.data(); h->cfg.ipha = h->h_ipha.data();
+  h->cfg.obs = h->h_obs.data(); h->cfg.vp_ref = h->h_vp_ref.data(); h->cfg.vs_ref = h->h_vs_ref.data();
+  h->cfg.sig_min = h->h_sig_min.data(); h->cfg.sig_max = h->h_sig_max.data(); h->cfg.r_inv = h->h_r_inv.data();
+
+  DevConfig& d = h->dc;
+  std::memset(&d, 0, sizeof(d));
+  d.ntrc = T; d.nfft = cfg->nfft; d.nh = cfg->nfft / 2 + 1; d.nsmp = S;
+  d.log2n = 0; while ((1 << d.log2n) < cfg->nfft) ++d.log2n;
+  d.deconv_mode = cfg->deconv_mode; d.vp_mode = cfg->vp_mode; d.k_min = cfg->k_min; d.k_max = cfg->k_max;
+  d.prior_mode = cfg->prior_mode; d.nref = cfg->nref;
+  d.ray_common = 1;  // check_ray, src/forward.f90:59-76
+  for (int t = 1; t < T; ++t)
+    if (cfg->rayps[t] != cfg->rayps[0] || cfg->ipha[t] != cfg->ipha[0]) d.ray_common = 0;
+  d.nsmp_pad = ((S + 63) / 64) * 64;
+  d.delta = cfg->delta; d.t_start = cfg->t_start; d.sdep = cfg->sdep; d.z_ref_min = cfg->z_ref_min; d.dz_ref = cfg->dz_ref;
+  d.z_min = cfg->z_min; d.z_max = cfg->z_max; d.h_min = cfg->h_min;
+  d.vp_min = cfg->vp_min; d.vp_max = cfg->vp_max; d.vs_min = cfg->vs_min; d.vs_max = cfg->vs_max;
+  d.vpvs_min = cfg->vpvs_min; d.vpvs_max = cfg->vpvs_max;
+  d.domg = 2.0 * RFINV_PI / (cfg->nfft * cfg->delta);  // src/forward.f90:241
+  for (int t = 0; t < T; ++t) { d.rayp[t] = cfg->rayps[t]; d.ipha[t] = cfg->ipha[t]; }
+
+  std::vector<double> flt;
+  build_filter(*cfg, flt);
+  std::vector<double2> tw;
+  build_twiddles(cfg->nfft, tw);
+  // R^-1: symmetrised (the quadratic form only sees the symmetric part) and zero padded to the tile
+  const int Sp = d.nsmp_pad;
+  std::vector<double> rpad((size_t)T * Sp * Sp, 0.0);
+  for (int t = 0; t < T; ++t)
+    for (int i = 0; i < S; ++i)
+      for (int j = 0; j < S; ++j)
+        rpad[((size_t)t * Sp + i) * Sp + j] =
+            0.5 * (h->h_r_inv[((size_t)t * S + i) * S + j] + h->h_r_inv[((size_t)t * S + j) * S + i]);
+#define RFINV_TRY(x) do { st = (x); if (st != RFINV_OK) { rfinv_destroy(h); return st; } } while (0)
+  RFINV_TRY(upload(flt, &h->d_flt));
+  RFINV_TRY(upload(tw, &h->d_tw));
+  RFINV_TRY(upload(h->h_obs, &h->d_obs));
+  RFINV_TRY(upload(h->h_vp_ref, &h->d_vp_ref));
+  RFINV_TRY(upload(h->h_vs_ref, &h->d_vs_ref));
+  RFINV_TRY(upload(rpad, &h->d_r_inv));
+#undef RFINV_TRY
+  d.flt = h->d_flt; d.tw = h->d_tw; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { rfinv_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); rfinv_destroy(h); return RFINV_ERR_CUDA; }
+  h->own_stream = true;
+  *out = h;
+  return RFINV_OK;
+}
+
+void rfinv_destroy(rfinv_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  h->free_workspace();
+  h->free_pt();
+  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int32_t rfinv_set_stream(rfinv_handle* h, uint64_t cuda_stream) {
+  if (!h) { rfinv_set_error("handle is NULL"); return RFINV_ERR_ARG; }
+  if (h->own_stream && h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+  h->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  h->own_stream = false;
+  return RFINV_OK;
+}
+
+int32_t rfinv_synchronize(rfinv_handle* h) {
+  if (!h) { rfinv_set_error("handle is NULL"); return RFINV_ERR_ARG; }
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return RFINV_OK;
+}
+
+int32_t rfinv_last_launch_count(rfinv_handle* h) { return h ? h->launches : 0; }
+
+int32_t rfinv_get_r_inv(rfinv_handle* h, double* r_inv) {
+  if (!h || !r_inv) { rfinv_set_error("NULL argument"); return RFINV_ERR_ARG; }
+  std::memcpy(r_inv, h->h_r_inv.data(), sizeof(double) * h->h_r_inv.size());
+  return RFINV_OK;
+}
+
+static int upload_models(rfinv_handle* h, int C, const int32_t* k, const double* z, const double* dvp, const double* dvs,
+                         const double* sig) {
+  const int km = h->cfg.k_max, T = h->cfg.ntrc;
+  cudaStream_t s = h->stream;
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k, k, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, s));
+  struct Item { const double* src; double* dst; int len; } items[4] = {
+      {z, h->d_z, km - 1}, {dvp, h->d_dvp, km}, {dvs, h->d_dvs, km}, {sig, h->d_sig, T}};
+  for (const Item& it : items) {
+    const size_t nel = (size_t)C * it.len;
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, it.src, sizeof(double) * nel, cudaMemcpyHostToDevice, s));
+    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(h->d_stage, it.dst, C, it.len);
+    RFINV_CUDA_CHECK(cudaGetLastError());
+  }
+  return RFINV_OK;
+}
+
+int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                         const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid) {
+  if (!h || C < 0 || (C > 0 && (!k || !z || !dvp || !dvs || !sig || !logl))) {
+    rfinv_set_error("rfinv_eval_batch: NULL argument");
+    return RFINV_ERR_ARG;
+  }
+  if (C == 0) return RFINV_OK;
+  for (int c = 0; c < C; ++c)
+    if (k[c] < 1 || k[c] > h->cfg.k_max - 1) {
+      rfinv_set_error("rfinv_eval_batch: k[%d]=%d outside [1,k_max-1]", c, k[c]);
+      return RFINV_ERR_ARG;
+    }
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  int st = h->ensure_capacity(C);
+  if (st != RFINV_OK) return st;
+  if (rft) {
+    const size_t need = (size_t)C * h->cfg.ntrc * h->cfg.nfft;
+    if (need > h->cap_rft_full) {
+      cudaFree(h->d_rft_full);
+      h->d_rft_full = nullptr; h->cap_rft_full = 0;
+      RFINV_CUDA_CHECK(cudaMalloc((void**)&h->d_rft_full, sizeof(double) * need));
+      h->cap_rft_full = need;
+    }
+  }
+  if ((st = upload_models(h, C, k, z, dvp, dvs, sig)) != RFINV_OK) return st;
+  st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
+                      is_valid ? h->d_valid : nullptr, nullptr, 0);
+  if (st != RFINV_OK) return st;
+  h->launches += 4;  // the four layout kernels of upload_models
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+  if (rft)
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(rft, h->d_rft_full, sizeof(double) * (size_t)C * h->cfg.ntrc * h->cfg.nfft,
+                                     cudaMemcpyDeviceToHost, h->stream));
+  if (is_valid) RFINV_CUDA_CHECK(cudaMemcpyAsync(is_valid, h->d_valid, (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return RFINV_OK;
+}
+
+int32_t rfinv_eval_batch_device(rfinv_handle* h, int32_t C, uint64_t d_k, uint64_t d_z, uint64_t d_dvp, uint64_t d_dvs,
+                                uint64_t d_sig, uint64_t d_logl, uint64_t d_rft_smp, uint64_t d_is_valid) {
+  if (!h || C < 0 || (C > 0 && (!d_k || !d_z || !d_dvp || !d_dvs || !d_sig || !d_logl))) {
+    rfinv_set_error("rfinv_eval_batch_device: NULL argument");
+    return RFINV_ERR_ARG;
+  }
+  if (C == 0) return RFINV_OK;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  int st = h->ensure_capacity(C);
+  if (st != RFINV_OK) return st;
+  return h->eval_device(C, reinterpret_cast<const int*>(d_k), reinterpret_cast<const double*>(d_z),
+                        reinterpret_cast<const double*>(d_dvp), reinterpret_cast<const double*>(d_dvs),
+                        reinterpret_cast<const double*>(d_sig), reinterpret_cast<double*>(d_logl),
+                        reinterpret_cast<double*>(d_rft_smp), nullptr, reinterpret_cast<uint8_t*>(d_is_valid), nullptr, 0);
+}
+
+int32_t rfinv_format_model_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                                 const double* dvs, int32_t* nlay, double* alpha, double* beta, double* rho,
+                                 double* hthick, uint8_t* is_valid) {
+  if (!h || C < 0 || (C > 0 && (!k || !z || !dvp || !dvs || !nlay || !alpha || !beta || !rho || !hthick || !is_valid))) {
+    rfinv_set_error("rfinv_format_model_batch: NULL argument");
+    return RFINV_ERR_ARG;
+  }
+  if (C == 0) return RFINV_OK;
+  for (int c = 0; c < C; ++c)
+    if (k[c] < 1 || k[c] > h->cfg.k_max - 1) {
+      rfinv_set_error("rfinv_format_model_batch: k[%d]=%d outside [1,k_max-1]", c, k[c]);
+      return RFINV_ERR_ARG;
+    }
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  int st = h->ensure_capacity(C);
+  if (st != RFINV_OK) return st;
+  std::vector<double> sig((size_t)C * h->cfg.ntrc, 1.0);
+  if ((st = upload_models(h, C, k, z, dvp, dvs, sig.data())) != RFINV_OK) return st;
+  const int stride = h->cfg.k_max + 1;
+  int* d_nlay = nullptr;
+  double* d_out = nullptr;
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_nlay, sizeof(int) * (size_t)C));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_out, sizeof(double) * (size_t)C * stride * 4));
+  RFINV_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)C * stride * 4, h->stream));
+  ModelBatch mb;
+  mb.C = C; mb.k = h->d_k; mb.z = h->d_z; mb.dvp = h->d_dvp; mb.dvs = h->d_dvs; mb.sig = h->d_sig; mb.active = nullptr; mb.n_active = 0;
+  const size_t blk = (size_t)C * stride;
+  st = rfinv_launch_format_model(h->dc, mb, d_nlay, d_out, d_out + blk, d_out + 2 * blk, d_out + 3 * blk, h->d_valid, h->stream);
+  if (st == RFINV_OK) {
+    cudaMemcpyAsync(nlay, d_nlay, sizeof(int) * (size_t)C, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(alpha, d_out, sizeof(double) * blk, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(beta, d_out + blk, sizeof(double) * blk, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(rho, d_out + 2 * blk, sizeof(double) * blk, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(hthick, d_out + 3 * blk, sizeof(double) * blk, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(is_valid, h->d_valid, (size_t)C, cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { rfinv_set_error("format_model: %s", cudaGetErrorString(e)); st = RFINV_ERR_CUDA; }
+  }
+  cudaFree(d_nlay); cudaFree(d_out);
+  return st;
+}
+
+}  // extern "C"

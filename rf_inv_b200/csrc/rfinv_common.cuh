@@ -1,0 +1,101 @@
+// Shared device-side definitions of the B200 forward+likelihood path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "../../include/rfinv_b200.h"
+
+#define RFINV_MAX_TRC 16     // traces per model (kernel parameter arrays)
+#define RFINV_MAX_K 64       // k_max upper bound: fixed per-chain layer storage
+#define RFINV_MAX_LAY (RFINV_MAX_K + 2)
+
+#define RFINV_PI 3.1415926535897931  // src/forward.f90:33
+
+// Immutable per-handle constants, passed to kernels by value (the reference's module globals).
+struct DevConfig {
+  int ntrc, nfft, nh, nsmp, log2n;
+  int deconv_mode, vp_mode, k_min, k_max, prior_mode, nref, ray_common;
+  int nsmp_pad;                 // nsmp rounded up to the likelihood tile (64)
+  double delta, t_start, sdep, z_ref_min, dz_ref, z_min, z_max, h_min;
+  double vp_min, vp_max, vs_min, vs_max, vpvs_min, vpvs_max;
+  double domg;                  // 2 pi / (nfft * delta), src/forward.f90:241
+  double rayp[RFINV_MAX_TRC];
+  int ipha[RFINV_MAX_TRC];
+  const double* flt;            // [ntrc][nh]   Gaussian filter, src/forward.f90:95-119
+  const double2* tw;            // [nfft]       exp(+2 pi i m / nfft)
+  const double* obs;            // [ntrc][nsmp]
+  const double* vp_ref;         // [nref]
+  const double* vs_ref;         // [nref]
+  const double* r_inv;          // [ntrc][nsmp_pad][nsmp_pad] zero padded, symmetric
+};
+
+// Chain-fastest (structure-of-arrays) model batch in HBM.
+struct ModelBatch {
+  int C;                        // number of models
+  const int* k;                 // [C]
+  const double* z;              // [k_max-1][C]
+  const double* dvp;            // [k_max][C]
+  const double* dvs;            // [k_max][C]
+  const double* sig;            // [ntrc][C]
+  const int* active;            // optional list of model indices to evaluate (nullptr = all)
+  int n_active;
+};
+
+// Fortran NINT (round half away from zero)
+__host__ __device__ __forceinline__ int f_nint(double x) {
+  return x >= 0.0 ? (int)floor(x + 0.5) : -(int)floor(-x + 0.5);
+}
+
+// src/model.f90:298-314 -- Brocher (2005) with the reference's float32 coefficients.  Written with
+// explicit round-to-nearest mul/add so no FMA contraction changes the bits (the top-layer validity test
+// and the densities in mcmc_out depend on it).
+__device__ __forceinline__ double vp_to_rho(double a1) {
+  double a2 = __dmul_rn(a1, a1), a3 = __dmul_rn(a2, a1), a4 = __dmul_rn(a3, a1), a5 = __dmul_rn(a4, a1);
+  double p = __dmul_rn((double)1.6612f, a1);
+  p = __dsub_rn(p, __dmul_rn((double)0.4721f, a2));
+  p = __dadd_rn(p, __dmul_rn((double)0.0671f, a3));
+  p = __dsub_rn(p, __dmul_rn((double)0.0043f, a4));
+  p = __dadd_rn(p, __dmul_rn((double)0.000106f, a5));
+  return p;
+}
+
+// One layer of format_model (src/model.f90:209-283): reference velocity lookup at the layer's mid depth.
+// Returns false when the layer violates the velocity bounds (src/model.f90:219-224).
+__device__ __forceinline__ bool layer_velocity(const DevConfig& cfg, double zc, double d_vs, double d_vp, double& alpha,
+                                               double& beta) {
+  int iz = f_nint(__ddiv_rn(__dsub_rn(zc, cfg.z_ref_min), cfg.dz_ref)) + 1;
+  iz = iz < 1 ? 1 : (iz > cfg.nref ? cfg.nref : iz);  // the reference would index out of bounds
+  beta = __dadd_rn(cfg.vs_ref[iz - 1], d_vs);
+  alpha = cfg.vp_mode == 1 ? __dadd_rn(cfg.vp_ref[iz - 1], d_vp) : cfg.vp_ref[iz - 1];
+  double ratio = __ddiv_rn(alpha, beta);
+  return !(alpha < cfg.vp_min || alpha > cfg.vp_max || beta < cfg.vs_min || beta > cfg.vs_max ||
+           ratio < cfg.vpvs_min || ratio > cfg.vpvs_max);
+}
+
+#define RFINV_CUDA_CHECK(expr)                                                        \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      rfinv_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+      return RFINV_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+void rfinv_set_error(const char* fmt, ...);
+
+// kernel launchers (forward.cu, likelihood.cu); all asynchronous on `stream`
+struct EvalOutputs {
+  double* misfit;     // [ntrc][C][nsmp_pad]  rft(1:nsmp) - obs, zero padded          (required)
+  double* rft_smp;    // [ntrc][C][nsmp]      first nsmp samples of the RF (optional)
+  double* rft_full;   // [C][ntrc][nfft]      complete RF, the reference's prop_rft (optional)
+  uint8_t* is_valid;  // [C]                  format_model's flag (optional)
+};
+int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, cudaStream_t stream);
+// phi[ntrc][C] = m^T R^-1 m per trace and model
+int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
+                          int n_active, cudaStream_t stream);
+// logl[c] = sum_t -0.5 phi/sig^2 - nsmp log(sig)   (src/likelihood.f90:94-96)
+int rfinv_launch_loglik(const DevConfig& cfg, int C, const double* phi, const double* sig, double* logl,
+                        cudaStream_t stream);
+int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,
+                              double* rho, double* h, uint8_t* is_valid, cudaStream_t stream);
