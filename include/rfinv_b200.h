@@ -46,7 +46,7 @@ extern "C" {
 typedef struct rfinv_config {
   /* observation and RF synthesis */
   int32_t ntrc;         /* N_TRC */
-  int32_t nfft;         /* N_FFT; must be a power of two, 32 <= nfft <= 4096 */
+  int32_t nfft;         /* N_FFT; must be a power of two, 64 <= nfft <= 4096 */
   int32_t nsmp;         /* samples in [T_START, T_END] (src/params.f90:446-448); nsmp <= nfft */
   int32_t deconv_mode;  /* 0: normalise by vertical, 1: water-level deconvolution */
   double delta;         /* sampling interval as read from the SAC header (float32 promoted) */
@@ -134,6 +134,14 @@ int32_t rfinv_synchronize(rfinv_handle* h);
 
 /* Timing / accounting of the last rfinv_eval_batch* call: number of kernels launched by it. */
 int32_t rfinv_last_launch_count(rfinv_handle* h);
+/* enable != 0: bracket every kernel of the evaluation with CUDA events on the handle's stream. */
+int32_t rfinv_set_timing(rfinv_handle* h, int32_t enable);
+/* Device time (ms) of the kernels of the last evaluation: ms[0] forward, ms[1] quadratic form, ms[2] logL.
+ * Synchronises the stream.  Requires rfinv_set_timing(h, 1).                                      */
+int32_t rfinv_get_timing(rfinv_handle* h, double* ms);
+/* FP64 roofline denominators measured on `device` right now: dense DFMA and DMMA (mma.sync m8n8k4)
+ * loops on all SMs, best of a few repetitions; TFLOP/s.                                           */
+int32_t rfinv_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,9 @@ SIGNATURES = {
     "rfinv_get_r_inv": (C.c_int32, [C.c_void_p, dp]),
     "rfinv_synchronize": (C.c_int32, [C.c_void_p]),
     "rfinv_last_launch_count": (C.c_int32, [C.c_void_p]),
+    "rfinv_set_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rfinv_get_timing": (C.c_int32, [C.c_void_p, dp]),
+    "rfinv_measure_fp64_peak": (C.c_int32, [C.c_int32, dp, dp]),
 }
 
 _lib = None

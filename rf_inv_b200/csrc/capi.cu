@@ -201,14 +201,18 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_full = rft_full; out.is_valid = is_valid;
   int st;
   launches = 0;
+  if (timing) cudaEventRecord(ev[0], stream);
   if ((st = rfinv_launch_forward(dc, mb, out, stream)) != RFINV_OK) return st;
   ++launches;
+  if (timing) cudaEventRecord(ev[1], stream);
   if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, stream)) != RFINV_OK) return st;
   ++launches;
+  if (timing) cudaEventRecord(ev[2], stream);
   if (logl) {
     if ((st = rfinv_launch_loglik(dc, C, d_phi, sig, logl, stream)) != RFINV_OK) return st;
     ++launches;
   }
+  if (timing) cudaEventRecord(ev[3], stream);
   return RFINV_OK;
 }
 
@@ -311,6 +315,8 @@ void rfinv_destroy(rfinv_handle* h) {
   h->free_pt();
   cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  for (int i = 0; i < 4; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
@@ -329,6 +335,27 @@ int32_t rfinv_synchronize(rfinv_handle* h) {
 }
 
 int32_t rfinv_last_launch_count(rfinv_handle* h) { return h ? h->launches : 0; }
+
+int32_t rfinv_set_timing(rfinv_handle* h, int32_t enable) {
+  if (!h) { rfinv_set_error("handle is NULL"); return RFINV_ERR_ARG; }
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if (enable && !h->ev[0])
+    for (int i = 0; i < 4; ++i) RFINV_CUDA_CHECK(cudaEventCreate(&h->ev[i]));
+  h->timing = enable != 0;
+  return RFINV_OK;
+}
+
+int32_t rfinv_get_timing(rfinv_handle* h, double* ms) {
+  if (!h || !ms) { rfinv_set_error("NULL argument"); return RFINV_ERR_ARG; }
+  if (!h->timing) { rfinv_set_error("rfinv_get_timing: call rfinv_set_timing(h, 1) first"); return RFINV_ERR_STATE; }
+  RFINV_CUDA_CHECK(cudaEventSynchronize(h->ev[3]));
+  for (int i = 0; i < 3; ++i) {
+    float f = 0.f;
+    RFINV_CUDA_CHECK(cudaEventElapsedTime(&f, h->ev[i], h->ev[i + 1]));
+    ms[i] = f;
+  }
+  return RFINV_OK;
+}
 
 int32_t rfinv_get_r_inv(rfinv_handle* h, double* r_inv) {
   if (!h || !r_inv) { rfinv_set_error("NULL argument"); return RFINV_ERR_ARG; }

@@ -28,6 +28,8 @@ struct rfinv_handle {
   uint8_t* d_valid = nullptr;
   size_t cap_rft_full = 0;
   int launches = 0;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // parallel-tempering state (pt.cu)
   PtState* pt = nullptr;
 

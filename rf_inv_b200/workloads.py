@@ -144,3 +144,25 @@ def flops_per_eval(cfg: RFConfig, k_mean: float, rank_r: Tuple[float, ...] = Non
     fft = T * 5.0 * n * np.log2(n)
     quad = T * (1.0 * S * S + 3.0 * S)
     return dict(propagator=prop, fft=fft, quadform=quad, total=prop + fft + quad)
+
+
+def lapack_r_inv(cfg: RFConfig) -> np.ndarray:
+    """init_r_inv the way the reference does it (src/likelihood.f90:168-241): LAPACK dgesvd of
+    R_ij = r^((i-j)^2), truncated at s > 1e-3 -- here through scipy's gesvd driver.  Returns the array in
+    the memory order of the Fortran r_inv(i,j,t): [ntrc][nsmp][nsmp] with element [t][j][i]."""
+    import scipy.linalg
+
+    S = cfg.nsmp
+    out = np.empty((cfg.ntrc, S, S))
+    idx = np.arange(S)
+    d2 = ((idx[:, None] - idx[None, :]) ** 2).astype(np.float64)
+    cache = {}
+    for t in range(cfg.ntrc):
+        a = float(cfg.a_gus[t])
+        if a not in cache:
+            r = np.exp(-a ** 2 * cfg.delta ** 2)
+            u, s, vt = scipy.linalg.svd(np.power(r, d2), full_matrices=True, lapack_driver="gesvd")
+            dinv = np.where(s > 1.0e-3, 1.0 / s, 0.0)
+            cache[a] = np.ascontiguousarray(((vt.T * dinv[None, :]) @ u.T).T)
+        out[t] = cache[a]
+    return out

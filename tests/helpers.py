@@ -72,3 +72,10 @@ def rel_err_rft(a: np.ndarray, b: np.ndarray) -> float:
     """max |a-b| relative to max |b| per (model, trace) -- the bar of SURVEY.md 8d."""
     scale = np.max(np.abs(b), axis=-1, keepdims=True)
     return float(np.nanmax(np.abs(a - b) / scale))
+
+
+def logl_err(cfg: RFConfig, a: np.ndarray, b: np.ndarray, sig: np.ndarray) -> float:
+    """|a-b| relative to the magnitude of the terms logL is summed from (src/likelihood.f90:94-96):
+    logL = sum_t -phi/(2 sig^2) - nsmp log(sig) can cancel to ~0, so |logL| alone is not a fair scale."""
+    scale = np.abs(b) + cfg.nsmp * np.sum(np.abs(np.log(sig)), axis=1)
+    return float(np.nanmax(np.abs(a - b) / scale))

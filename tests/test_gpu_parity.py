@@ -1,0 +1,199 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI, against the oracle on the same inputs.
+
+Tolerances (BASELINE.json north_star): synthetic RFs and log-likelihoods within 1e-9 relative in fp64.
+  * rft:  max |gpu - oracle| <= 1e-9 * max|rft| per (model, trace)
+  * logL: |gpu - oracle| <= 1e-9 * (|logL| + nsmp * sum_t |log sig_t|)   (the terms logL is summed from)
+format_model outputs (layer stack, validity flag) are bit-exact.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle_c
+from rf_inv_b200 import capi, workloads
+from rf_inv_b200.evaluator import Evaluator
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+V = np.load(os.path.join(helpers.GOLDEN, "oracle_vectors.npz"))
+G = np.load(os.path.join(helpers.GOLDEN, "sample_syn.npz"))
+
+VARIANTS = {
+    "land_P": dict(), "sea_P": dict(sdep=2.0), "land_S": dict(ipha=[-1, -1], rayps=[0.10, 0.12]),
+    "sea_S_deconv": dict(sdep=1.0, ipha=[-1, -1], deconv_mode=1), "P_deconv": dict(deconv_mode=1),
+    "common": dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), "vp1_tstart": dict(vp_mode=1, t_start=-3.0),
+    "three_traces_mixed": dict(ntrc=3, rayps=[0.05, 0.06, 0.11], a_gus=[2.0, 4.0, 8.0], ipha=[1, 1, -1],
+                               sig_min=[0.01, 0.02, 0.03], sig_max=[0.01, 0.02, 0.03], sdep=1.5),
+    "n64": dict(nfft=64, nsmp=40), "n128": dict(nfft=128, nsmp=64), "n512": dict(nfft=512, nsmp=200),
+    "n1024_k20": dict(nfft=1024, nsmp=512, k_max=20, z_max=40.0),
+    "n2048_k30": dict(nfft=2048, nsmp=1000, k_max=30, z_max=40.0),
+    "n4096": dict(nfft=4096, nsmp=300, k_max=12),
+    "nsmp_eq_nfft": dict(nfft=128, nsmp=128),
+}
+
+
+def gpu_vs_oracle(cfg, models):
+    ll_o, rft_o, val_o = oracle_c.eval_batch(cfg, models["k"], models["z"], models["dvp"], models["dvs"], models["sig"])
+    with Evaluator(cfg) as ev:
+        ll_g, rft_g, val_g = ev.calc_likelihood(models["k"], models["z"], models["dvp"], models["dvs"], models["sig"],
+                                                want_rft=True, want_valid=True)
+        assert ev.last_launch_count >= 3
+    return (ll_g, rft_g, val_g), (ll_o, rft_o, val_o)
+
+
+@pytest.mark.parametrize("name", sorted(VARIANTS))
+def test_eval_batch_matches_oracle(name):
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(**VARIANTS[name]), noise=0.01)
+    m = workloads.draw_models(cfg, 96, seed=3, dvs_scale=0.3)
+    (ll_g, rft_g, val_g), (ll_o, rft_o, val_o) = gpu_vs_oracle(cfg, m)
+    assert np.array_equal(val_g, val_o)
+    assert helpers.rel_err_rft(rft_g, rft_o) < RTOL
+    assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < RTOL
+
+
+def test_golden_traces_from_reference_fixture():
+    """The reference's own fixture: true.velmod -> sample_{1,2}.trc (float32); the CUDA path reproduces every sample
+    bit-exactly after rounding to float32, like the oracle does."""
+    cfg = helpers.small_config(delta=float(G["delta"]))
+    cfg.obs = np.stack([G["trc1"], G["trc2"]]).astype(np.float64)
+    cfg.r_inv = helpers.scipy_r_inv(cfg)
+    tm = workloads.true_model(cfg)
+    with Evaluator(cfg) as ev:
+        ll, rft, valid = ev.calc_likelihood(tm["k"], tm["z"], tm["dvp"], tm["dvs"], tm["sig"], want_rft=True, want_valid=True)
+        nlay, alpha, beta, rho, h, ok = ev.format_model(tm["k"], tm["z"], tm["dvp"], tm["dvs"])
+    assert valid[0] and ok[0] and nlay[0] == 3
+    vm = G["true_velmod"]
+    assert np.allclose(alpha[0, :3], vm[:, 0], rtol=0, atol=0) and np.allclose(beta[0, :3], vm[:, 1], rtol=0, atol=1e-15)
+    assert rho[0, 0] == 2.5347508187769563                      # float32 Brocher coefficients
+    assert np.array_equal(rft[0, 0, :101].astype(np.float32), G["trc1"])
+    assert np.array_equal(rft[0, 1, :101].astype(np.float32), G["trc2"])
+    # observed == synthetic up to float32 storage: phi ~ 0, logL ~ -sum nsmp log(sig)
+    assert abs(ll[0] - (-2 * 101 * np.log(0.01))) < 1e-3 * abs(2 * 101 * np.log(0.01))
+
+
+@pytest.mark.parametrize("name", ["land_P", "sea_P", "land_S", "sea_S_deconv", "P_deconv", "common", "vp1_tstart"])
+def test_committed_numpy_oracle_vectors(name):
+    cfg = helpers.small_config(**VARIANTS[name])
+    cfg.obs = V[name + "/obs"]
+    cfg.r_inv = helpers.scipy_r_inv(cfg)
+    m = {k: V[f"{name}/{k}"] for k in ("k", "z", "dvp", "dvs", "sig")}
+    with Evaluator(cfg) as ev:
+        ll, rft, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+    assert helpers.rel_err_rft(rft, V[name + "/rft"]) < RTOL
+    assert helpers.logl_err(cfg, ll, V[name + "/logl"], m["sig"]) < RTOL
+
+
+def test_format_model_bit_exact_incl_invalid_models():
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(sdep=2.0, vp_mode=1))
+    m = workloads.draw_models(cfg, 200, seed=5)
+    m["z"][:60] *= 0.08                      # interfaces above the sea floor / too thin layers
+    m["dvs"][60:90] -= 3.5                   # velocities out of bounds
+    with Evaluator(cfg) as ev:
+        nlay, alpha, beta, rho, h, ok = ev.format_model(m["k"], m["z"], m["dvp"], m["dvs"])
+    n_bad = 0
+    for i in range(200):
+        o = oracle_c.format_model(cfg, int(m["k"][i]), m["z"][i], m["dvp"][i], m["dvs"][i])
+        assert o[0] == nlay[i] and o[5] == ok[i]
+        n = o[0]
+        assert np.array_equal(o[1], alpha[i, :n]) and np.array_equal(o[2], beta[i, :n])
+        assert np.array_equal(o[3], rho[i, :n]) and np.array_equal(o[4], h[i, :n])
+        n_bad += not o[5]
+    assert 20 < n_bad < 200
+
+
+def test_edge_cases_k1_kmax_minus_1_single_model_and_empty():
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(k_max=6))
+    km = cfg.k_max
+    k = np.array([1, km - 1, 1], dtype=np.int32)
+    z = np.zeros((3, km - 1)); dvp = np.zeros((3, km)); dvs = np.zeros((3, km))
+    z[0, 0] = 5.0
+    z[1, :km - 1] = [12.0, 3.0, 9.0, 6.0, 15.0]       # unsorted on purpose
+    dvs[1, :km - 1] = [0.3, -0.2, 0.1, 0.4, 0.0]
+    z[2, 0] = 19.999                                  # interface just above z_max
+    sig = np.full((3, 2), 0.01)
+    m = dict(k=k, z=z, dvp=dvp, dvs=dvs, sig=sig)
+    (ll_g, rft_g, val_g), (ll_o, rft_o, val_o) = gpu_vs_oracle(cfg, m)
+    assert np.array_equal(val_g, val_o) and helpers.rel_err_rft(rft_g, rft_o) < RTOL
+    assert helpers.logl_err(cfg, ll_g, ll_o, sig) < RTOL
+    with Evaluator(cfg) as ev:
+        ll, _, _ = ev.calc_likelihood(k[:0], z[:0], dvp[:0], dvs[:0], sig[:0])       # empty batch
+        assert ll.shape == (0,)
+        ll1, _, _ = ev.calc_likelihood(k[:1], z[:1], dvp[:1], dvs[:1], sig[:1])      # ragged: batch of one
+        assert abs(ll1[0] - ll_g[0]) == 0.0
+        with pytest.raises(capi.RfinvError):                                         # k outside [1, k_max-1]
+            ev.calc_likelihood(np.array([km], dtype=np.int32), z[:1], dvp[:1], dvs[:1], sig[:1])
+
+
+def test_post_critical_ray_gives_nan_like_the_reference():
+    # 1/alpha^2 < p^2 -> sqrt of a negative number -> NaN logL (SURVEY.md 7 "post-critical rays"): a value, not an error
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(rayps=[0.06, 0.21]))
+    m = workloads.draw_models(cfg, 4, seed=1, dvs_scale=0.1)
+    (ll_g, _, _), (ll_o, _, _) = gpu_vs_oracle(cfg, m)
+    assert np.isnan(ll_o).all() and np.isnan(ll_g).all()
+
+
+def test_internal_r_inv_matches_lapack_route():
+    # r_inv = NULL: the library builds R^-1 itself (Jacobi eigen-solver) instead of LAPACK dgesvd
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(a_gus=[4.0, 2.5]), noise=0.01)
+    ref = cfg.r_inv.copy()
+    m = workloads.draw_models(cfg, 16, seed=8, dvs_scale=0.3)
+    ll_o, _, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    cfg.r_inv = None
+    with Evaluator(cfg) as ev:
+        own = ev.r_inv()
+        ll_g, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    assert np.max(np.abs(own - ref)) / np.max(np.abs(ref)) < 1e-9
+    assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < 1e-8
+
+
+def test_device_resident_entry_and_determinism():
+    import torch
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(nfft=512, nsmp=200), noise=0.01)
+    m = workloads.draw_models(cfg, 300, seed=12, dvs_scale=0.3)
+    soa = workloads.to_soa(m)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
+    logl = torch.empty(300, dtype=torch.float64, device=dev)
+    rft = torch.empty((cfg.ntrc, 300, cfg.nsmp), dtype=torch.float64, device=dev)
+    valid = torch.empty(300, dtype=torch.uint8, device=dev)
+    with Evaluator(cfg) as ev:
+        ev.set_stream(torch.cuda.current_stream().cuda_stream)
+        runs = []
+        for _ in range(2):
+            ev.calc_likelihood_device(300, d["k"].data_ptr(), d["z"].data_ptr(), d["dvp"].data_ptr(), d["dvs"].data_ptr(),
+                                      d["sig"].data_ptr(), logl.data_ptr(), rft.data_ptr(), valid.data_ptr())
+            torch.cuda.synchronize()
+            runs.append((logl.cpu().numpy().copy(), rft.cpu().numpy().copy()))
+        ll_h, rft_h, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])   # no atomics: bit-stable
+    assert np.array_equal(runs[0][0], ll_h)
+    assert np.array_equal(np.transpose(runs[0][1], (1, 0, 2)), rft_h[:, :, :cfg.nsmp])
+    assert valid.cpu().numpy().all()
+
+
+@pytest.mark.parametrize("workload,n_models", [("c2", 4096), ("target", 2048), ("c5", 512)])
+def test_full_size_properties(workload, n_models):
+    """BASELINE.json sizes: the oracle checks a seeded subsample; size-independent properties cover the rest:
+    permutation equivariance, sigma scaling of logL (phi is sigma independent), time-shift property of t_start."""
+    cfg = workloads.make_config(workload)
+    cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
+    m = workloads.draw_models(cfg, n_models, seed=21, dvs_scale=0.5)
+    with Evaluator(cfg) as ev:
+        ll, _, valid = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_valid=True)
+        perm = np.random.default_rng(0).permutation(n_models)
+        ll_p, _, _ = ev.calc_likelihood(m["k"][perm], m["z"][perm], m["dvp"][perm], m["dvs"][perm], m["sig"][perm])
+        sig2 = m["sig"] * 2.0
+        ll_2, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], sig2)
+    assert valid.all() and np.isfinite(ll).all()
+    assert np.array_equal(ll[perm], ll_p)
+    # logL(2 sig) = -phi/(8 sig^2) - S sum log(2 sig)  ==>  recover phi-term from both and compare
+    S = cfg.nsmp
+    q1 = ll + S * np.sum(np.log(m["sig"]), axis=1)          # = -0.5 sum phi/sig^2
+    q2 = ll_2 + S * np.sum(np.log(sig2), axis=1)            # = q1 / 4
+    assert np.max(np.abs(q2 * 4.0 - q1) / (np.abs(q1) + S)) < 1e-9
+    sub = np.arange(0, n_models, max(1, n_models // 48))
+    ll_o, _, _ = oracle_c.eval_batch(cfg, m["k"][sub], m["z"][sub], m["dvp"][sub], m["dvs"][sub], m["sig"][sub], want_rft=False)
+    assert helpers.logl_err(cfg, ll[sub], ll_o, m["sig"][sub]) < RTOL
