@@ -179,14 +179,15 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_phi, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_logl, sizeof(double) * Cz));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_valid, Cz));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_scratch, sizeof(double) * rfinv_forward_scratch_doubles(dc, C)));
   cap = C;
   return RFINV_OK;
 }
 
 void rfinv_handle::free_workspace() {
   cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage);
-  cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full);
-  d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = nullptr;
+  cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch);
+  d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = d_scratch = nullptr;
   d_valid = nullptr;
   cap = 0; cap_rft_full = 0;
 }
@@ -202,8 +203,8 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   int st;
   launches = 0;
   if (timing) cudaEventRecord(ev[0], stream);
-  if ((st = rfinv_launch_forward(dc, mb, out, stream)) != RFINV_OK) return st;
-  ++launches;
+  if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream)) != RFINV_OK) return st;
+  launches += 2;
   if (timing) cudaEventRecord(ev[1], stream);
   if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, stream)) != RFINV_OK) return st;
   ++launches;

@@ -22,23 +22,29 @@
 
 namespace {
 
+// Per (model, ray, solid layer) constants of the real propagator B_l, written by prep_kernel.
 struct LayerConst {
   double thx, the;            // domg*xi*h, domg*eta*h : phase advance per frequency bin
-  double cbx, sbx, cbe, sbe;  // rotation by B*thx, B*the (B = blockDim.x = frequency stride of a thread)
+  double cbx, sbx, cbe, sbe;  // rotation by B*thx, B*the (B = threads per CTA = frequency stride of a thread)
   double g, bp;               // 2 beta^2 p^2, 1 - 2 beta^2 p^2
   double c12a, c12b, c21a, c21b, c13a, c13b, c24a, c24b, c31a, c31b, c42a, c42b;
   double c14, c41;
-  double dcx, dsx, dce, dse;  // cos/sin at the DC pseudo-frequency 1.0e-5 (src/forward.f90:246-248)
 };
+constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 22
 
 struct HalfSpace {
   double e11, e12, e13, e14, e21, e22, e23, e24;  // E^-1 rows 3,4 with the 1/w factors removed
 };
 
-struct Water {
-  double thw, cbw, sbw, rw, dcw, dsw;  // phase per bin, stride rotation, rho_w/xi_w, DC cos/sin
-  int present;
+// Per (model, ray) constants written by prep_kernel.
+struct RayConst {
+  HalfSpace hs;
+  double thw, cbw, sbw, rw;   // water layer: phase per bin, stride rotation, rho_w/xi_w
+  double tp;                  // direct-arrival delay (src/forward.f90:474-491)
+  double2 edge[4];            // fr, fv at the DC pseudo-frequency and at Nyquist
+  int k, valid;
 };
+constexpr int RC_DOUBLES = sizeof(RayConst) / sizeof(double);
 
 __device__ __forceinline__ void rot(double& c, double& s, double cb, double sb) {
   double c2 = c * cb - s * sb;
@@ -108,6 +114,119 @@ __device__ __forceinline__ void surface_response(const HalfSpace& H, const doubl
   fv = make_double2(-uz.x, uz.y);
 }
 
+// ------------------------------------------------------------------------------------------------
+// prep_kernel: one thread per (model, ray).  format_model (src/model.f90:175-290), the per-layer
+// constants of the real propagator for this ray, half-space / water-layer constants, the direct-arrival
+// delay, and the two bins that do not fit the regular frequency grid of forward_kernel: the DC
+// pseudo-frequency omega = 1.0e-5 (src/forward.f90:246-248) and the Nyquist bin.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
+                                                   double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
+                                                   int n_items, int ntr_eff, int nthr_fwd) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
+  const int c = mb.active ? mb.active[ci] : ci;
+  const int km = cfg.k_max, C = mb.C;
+  int k = mb.k[c];
+  k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
+  const double p = cfg.rayp[t0];
+  const int ipha = cfg.ipha[t0];
+  double z[RFINV_MAX_K], dp[RFINV_MAX_K], ds[RFINV_MAX_K];
+  for (int i = 0; i < k; ++i) {
+    z[i] = mb.z[(size_t)i * C + c]; dp[i] = mb.dvp[(size_t)i * C + c]; ds[i] = mb.dvs[(size_t)i * C + c];
+  }
+  for (int i = 1; i < k; ++i) {  // src/sort.f90:34-68 (any correct sort; keys are distinct)
+    const double a = z[i], b = dp[i], d = ds[i];
+    int m = i - 1;
+    while (m >= 0 && z[m] > a) { z[m + 1] = z[m]; dp[m + 1] = dp[m]; ds[m + 1] = ds[m]; --m; }
+    z[m + 1] = a; dp[m + 1] = b; ds[m + 1] = d;
+  }
+  RayConst R;
+  // water layer (src/model.f90:201-207, src/forward.f90:424-442) and start vectors of the two edge bins
+  double ya0[4] = {1.0, 0.0, 0.0, 0.0}, yb0[4], ya1[4] = {1.0, 0.0, 0.0, 0.0}, yb1[4], cw0 = 1.0, cw1 = 1.0;
+  const double nyq = (double)(cfg.nfft / 2);
+  if (cfg.sdep > 0.0) {
+    const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
+    const double xiw = sqrt(1.0 / (aw * aw) - p * p);
+    R.thw = cfg.domg * xiw * hw;
+    sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
+    R.rw = rhow / xiw;
+    double sw;
+    sincos((double)1.0e-5f * xiw * hw, &sw, &cw0);
+    yb0[0] = 0.0; yb0[1] = cw0; yb0[2] = 0.0; yb0[3] = -R.rw * sw;
+    sincos(nyq * R.thw, &sw, &cw1);
+    yb1[0] = 0.0; yb1[1] = cw1; yb1[2] = 0.0; yb1[3] = -R.rw * sw;
+  } else {
+    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0; R.rw = 0.0;
+    yb0[0] = 0.0; yb0[1] = 1.0; yb0[2] = 0.0; yb0[3] = 0.0;
+    yb1[0] = 0.0; yb1[1] = 1.0; yb1[2] = 0.0; yb1[3] = 0.0;
+  }
+  bool valid = true;
+  double tp = 0.0;
+  LayerConst* lc = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km;
+  const double p2 = __dmul_rn(p, p);
+  for (int l = 0; l <= k; ++l) {
+    double zc, h, dvs_l, dvp_l;
+    if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, z[0])); h = __dsub_rn(z[0], cfg.sdep); dvs_l = ds[0]; dvp_l = dp[0]; }
+    else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(z[l], z[l - 1])); h = __dsub_rn(z[l], z[l - 1]); dvs_l = ds[l]; dvp_l = dp[l]; }
+    else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, z[k - 1])); h = 999.0;
+           dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; }
+    double a, b;
+    bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
+    if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
+    else if (l < k) ok = ok && !(h < cfg.h_min);           // src/model.f90:257
+    valid = valid && ok;
+    const double rho = vp_to_rho(a);
+    const double beta2 = __dmul_rn(b, b);
+    const double bp = 1.0 - 2.0 * beta2 * p2;
+    const double eta = sqrt(__dsub_rn(__ddiv_rn(1.0, beta2), p2));              // src/forward.f90:395
+    const double xi = sqrt(__dsub_rn(__ddiv_rn(1.0, __dmul_rn(a, a)), p2));    // src/forward.f90:396
+    if (l < k) {
+      if (cfg.deconv_mode == 0) tp = __dadd_rn(tp, __dmul_rn(h, ipha == 1 ? xi : eta));  // src/forward.f90:489-491
+      LayerConst L;
+      L.thx = cfg.domg * xi * h;
+      L.the = cfg.domg * eta * h;
+      sincos((double)nthr_fwd * L.thx, &L.sbx, &L.cbx);
+      sincos((double)nthr_fwd * L.the, &L.sbe, &L.cbe);
+      L.g = 2.0 * beta2 * p2;
+      L.bp = bp;
+      L.c12a = -p * bp / xi;            L.c12b = 2.0 * p * beta2 * eta;
+      L.c21a = 2.0 * p * beta2 * xi;    L.c21b = -p * bp / eta;
+      L.c13a = p2 / (xi * rho);         L.c13b = eta / rho;
+      L.c24a = xi / rho;                L.c24b = p2 / (eta * rho);
+      L.c31a = -4.0 * rho * beta2 * beta2 * p2 * xi;   L.c31b = -rho * bp * bp / eta;
+      L.c42a = -rho * bp * bp / xi;                    L.c42b = -4.0 * rho * beta2 * beta2 * p2 * eta;
+      L.c14 = p / rho;
+      L.c41 = 2.0 * beta2 * rho * p * bp;
+      lc[l] = L;
+      double c1, s1, c2, s2;
+      sincos((double)1.0e-5f * xi * h, &s1, &c1);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
+      sincos((double)1.0e-5f * eta * h, &s2, &c2);
+      layer_step(L, c1, s1, c2, s2, ya0, yb0);
+      sincos(nyq * L.thx, &s1, &c1);
+      sincos(nyq * L.the, &s2, &c2);
+      layer_step(L, c1, s1, c2, s2, ya1, yb1);
+    } else {  // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors
+      R.hs.e11 = beta2 * p / a;
+      R.hs.e12 = bp / (2.0 * a * xi);
+      R.hs.e13 = p / (2.0 * rho * a * xi);
+      R.hs.e14 = 1.0 / (2.0 * rho * a);
+      R.hs.e21 = bp / (2.0 * b * eta);
+      R.hs.e22 = b * p;
+      R.hs.e23 = 1.0 / (2.0 * rho * b);
+      R.hs.e24 = p / (2.0 * rho * b * eta);
+    }
+  }
+  surface_response(R.hs, ya0, yb0, cw0, ipha, R.edge[0], R.edge[1]);
+  surface_response(R.hs, ya1, yb1, cw1, ipha, R.edge[2], R.edge[3]);
+  R.tp = tp;
+  R.k = k;
+  R.valid = valid;
+  reinterpret_cast<RayConst*>(rc_out)[item] = R;
+  if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
+}
+
 // In-place-pair Stockham inverse FFT (sign +, unnormalised) of n complex points in shared memory.
 // Returns the buffer holding the result.
 __device__ double2* fft_inverse(double2* x, double2* y, int n, int log2n, const double2* __restrict__ tw, int tid,
@@ -162,8 +281,16 @@ __device__ __forceinline__ double block_max(double v, double* scratch, int tid, 
   return r;
 }
 
-template <int J, int BMAX>
-__global__ void __launch_bounds__(BMAX) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out) {
+// ------------------------------------------------------------------------------------------------
+// forward_kernel: one CTA per (model, ray); thread `tid` owns frequency bins j = tid + m*B, m < J
+// (B = blockDim.x, B*J = nfft/2).  Bins 0 (DC) and nfft/2 (Nyquist) come from prep_kernel.
+// Shared memory: two FFT buffers of nfft complex doubles; the spectra alias the second one unless rays
+// are common to all traces (then they must survive the per-trace FFTs); layer constants behind them.
+// ------------------------------------------------------------------------------------------------
+template <int J, int BMAX, int MINB>
+__global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
+                                                             const double* __restrict__ lc_in,
+                                                             const double* __restrict__ rc_in) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
@@ -172,174 +299,61 @@ __global__ void __launch_bounds__(BMAX) forward_kernel(const DevConfig cfg, cons
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
 
-  // ---- shared memory carve-up ----
   double2* s_buf0 = reinterpret_cast<double2*>(smem_raw);
   double2* s_buf1 = s_buf0 + n;
-  double2* s_fr = s_buf1 + n;          // [nh] unfiltered radial spectrum (or deconvolved RF spectrum)
-  double2* s_fv = s_fr + (nh + 1);     // [nh] unfiltered vertical spectrum
-  LayerConst* s_lc = reinterpret_cast<LayerConst*>(s_fv + (nh + 1));
-  double* s_z = reinterpret_cast<double*>(s_lc + km);
-  double* s_dvp = s_z + km;
-  double* s_dvs = s_dvp + km;
-  double* s_alpha = s_dvs + km;
-  double* s_beta = s_alpha + (km + 1);
-  double* s_rho = s_beta + (km + 1);
-  double* s_h = s_rho + (km + 1);
-  double* s_xi = s_h + (km + 1);
-  double* s_eta = s_xi + (km + 1);
-  double* s_red = s_eta + (km + 1);    // [32]
-  __shared__ HalfSpace s_hs;
-  __shared__ Water s_w;
-  __shared__ int s_valid;
-  __shared__ double s_tp;
+  double2* s_fr = cfg.ray_common ? s_buf1 + n : s_buf1;   // [nh] unfiltered radial spectrum (or deconvolved RF spectrum)
+  double2* s_fv = s_fr + (nh + 1);                        // [nh] unfiltered vertical spectrum   (2*(nh+1) <= n + 4)
+  double* s_tail = reinterpret_cast<double*>((cfg.ray_common ? s_fv + (nh + 1) : s_buf1 + n + 4));
+  LayerConst* s_lc = reinterpret_cast<LayerConst*>(s_tail);
+  RayConst* s_rc = reinterpret_cast<RayConst*>(s_lc + km);
+  double* s_red = reinterpret_cast<double*>(s_rc + 1);     // [32]
 
-  const int k = mb.k[c];
-  const double p = cfg.rayp[t0];
+  // ---- stage the constants of this (model, ray) ----
+  {
+    const double* src = rc_in + (size_t)item * RC_DOUBLES;
+    double* dst = reinterpret_cast<double*>(s_rc);
+    for (int i = tid; i < RC_DOUBLES; i += nthr) dst[i] = src[i];
+  }
+  __syncthreads();
+  const int k = s_rc->k;
+  {
+    const double* src = lc_in + (size_t)item * km * LC_DOUBLES;
+    double* dst = reinterpret_cast<double*>(s_lc);
+    for (int i = tid; i < k * LC_DOUBLES; i += nthr) dst[i] = src[i];
+  }
+  __syncthreads();
   const int ipha = cfg.ipha[t0];
 
-  // ---- format_model (src/model.f90:175-290): rank sort of the k interfaces ----
-  if (tid == 0) s_valid = 1;
-  double* tz = reinterpret_cast<double*>(s_buf0);  // scratch: unsorted copies
-  double* tp_ = tz + km;
-  double* ts_ = tp_ + km;
-  for (int i = tid; i < k; i += nthr) {
-    tz[i] = mb.z[(size_t)i * C + c];
-    tp_[i] = mb.dvp[(size_t)i * C + c];
-    ts_[i] = mb.dvs[(size_t)i * C + c];
-  }
-  __syncthreads();
-  for (int i = tid; i < k; i += nthr) {
-    const double zi = tz[i];
-    int r = 0;
-    for (int j = 0; j < k; ++j) r += (tz[j] < zi) || (tz[j] == zi && j < i);
-    s_z[r] = zi;
-    s_dvp[r] = tp_[i];
-    s_dvs[r] = ts_[i];
-  }
-  __syncthreads();
-  for (int l = tid; l <= k; l += nthr) {
-    double zc, h, dvs_l, dvp_l;
-    if (l == 0) {
-      zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, s_z[0]));
-      h = __dsub_rn(s_z[0], cfg.sdep);
-      dvs_l = s_dvs[0]; dvp_l = s_dvp[0];
-    } else if (l < k) {
-      zc = __dmul_rn(0.5, __dadd_rn(s_z[l], s_z[l - 1]));
-      h = __dsub_rn(s_z[l], s_z[l - 1]);
-      dvs_l = s_dvs[l]; dvp_l = s_dvp[l];
-    } else {
-      zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, s_z[k - 1]));
-      h = 999.0;
-      dvs_l = mb.dvs[(size_t)(km - 1) * C + c];
-      dvp_l = mb.dvp[(size_t)(km - 1) * C + c];
-    }
-    double a, b;
-    bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
-    if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
-    else if (l < k) ok = ok && !(h < cfg.h_min);           // src/model.f90:257
-    s_alpha[l] = a; s_beta[l] = b; s_rho[l] = vp_to_rho(a); s_h[l] = h;
-    if (!ok) s_valid = 0;
-    // ---- per-layer propagator constants for this ray ----
-    const double beta2 = b * b, p2 = p * p;
-    const double bp = 1.0 - 2.0 * beta2 * p2;
-    const double eta = sqrt(1.0 / beta2 - p2);
-    const double xi = sqrt(1.0 / (a * a) - p2);
-    const double rho = s_rho[l];
-    s_xi[l] = xi; s_eta[l] = eta;
-    if (l < k) {
-      LayerConst L;
-      L.thx = cfg.domg * xi * h;
-      L.the = cfg.domg * eta * h;
-      sincos((double)nthr * L.thx, &L.sbx, &L.cbx);
-      sincos((double)nthr * L.the, &L.sbe, &L.cbe);
-      sincos((double)1.0e-5f * xi * h, &L.dsx, &L.dcx);
-      sincos((double)1.0e-5f * eta * h, &L.dse, &L.dce);
-      L.g = 2.0 * beta2 * p2;
-      L.bp = bp;
-      L.c12a = -p * bp / xi;            L.c12b = 2.0 * p * beta2 * eta;
-      L.c21a = 2.0 * p * beta2 * xi;    L.c21b = -p * bp / eta;
-      L.c13a = p2 / (xi * rho);         L.c13b = eta / rho;
-      L.c24a = xi / rho;                L.c24b = p2 / (eta * rho);
-      L.c31a = -4.0 * rho * beta2 * beta2 * p2 * xi;   L.c31b = -rho * bp * bp / eta;
-      L.c42a = -rho * bp * bp / xi;                    L.c42b = -4.0 * rho * beta2 * beta2 * p2 * eta;
-      L.c14 = p / rho;
-      L.c41 = 2.0 * beta2 * rho * p * bp;
-      s_lc[l] = L;
-    } else {  // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors
-      HalfSpace H;
-      H.e11 = beta2 * p / a;
-      H.e12 = bp / (2.0 * a * xi);
-      H.e13 = p / (2.0 * rho * a * xi);
-      H.e14 = 1.0 / (2.0 * rho * a);
-      H.e21 = bp / (2.0 * b * eta);
-      H.e22 = b * p;
-      H.e23 = 1.0 / (2.0 * rho * b);
-      H.e24 = p / (2.0 * rho * b * eta);
-      s_hs = H;
-    }
-  }
-  if (tid == 0) {  // water layer (src/model.f90:201-207, src/forward.f90:424-442)
-    Water W;
-    W.present = cfg.sdep > 0.0;
-    if (W.present) {
-      const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
-      const double xiw = sqrt(1.0 / (aw * aw) - p * p);
-      W.thw = cfg.domg * xiw * hw;
-      sincos((double)nthr * W.thw, &W.sbw, &W.cbw);
-      sincos((double)1.0e-5f * xiw * hw, &W.dsw, &W.dcw);
-      W.rw = rhow / xiw;
-    } else {
-      W.thw = 0.0; W.cbw = 1.0; W.sbw = 0.0; W.rw = 0.0; W.dcw = 1.0; W.dsw = 0.0;
-    }
-    s_w = W;
-  }
-  __syncthreads();
-  if (tid == 0) {  // direct_arrival (src/forward.f90:474-491), summed in layer order
-    double t = 0.0;
-    if (cfg.deconv_mode == 0) {
-      const double* sl = ipha == 1 ? s_xi : s_eta;
-      for (int l = 0; l < k; ++l) t = t + s_h[l] * sl[l];
-    }
-    s_tp = t;
-    if (out.is_valid && t0 == 0) out.is_valid[c] = (uint8_t)s_valid;
-  }
-
-  // ---- propagator product: thread handles bins j = tid + m*nthr (m < J); thread 0 also the Nyquist ----
+  // ---- propagator product over the solid layers, top down ----
   double ya[J][4], yb[J][4], cwv[J];
-  double yae[4] = {1.0, 0.0, 0.0, 0.0}, ybe[4], cwe;
   {
-    const Water W = s_w;
+    const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw, rw = s_rc->rw;
     double cw, sw;
-    sincos((double)tid * W.thw, &sw, &cw);
+    sincos((double)tid * thw, &sw, &cw);
 #pragma unroll
     for (int m = 0; m < J; ++m) {
-      double ucw = cw, usw = sw;
-      if (m == 0 && tid == 0) { ucw = W.dcw; usw = W.dsw; }
       ya[m][0] = 1.0; ya[m][1] = 0.0; ya[m][2] = 0.0; ya[m][3] = 0.0;
-      yb[m][0] = 0.0; yb[m][1] = ucw; yb[m][2] = 0.0; yb[m][3] = -W.rw * usw;
-      cwv[m] = ucw;
-      rot(cw, sw, W.cbw, W.sbw);
+      yb[m][0] = 0.0; yb[m][1] = cw; yb[m][2] = 0.0; yb[m][3] = -rw * sw;
+      cwv[m] = cw;
+      rot(cw, sw, cbw, sbw);
     }
-    ybe[0] = 0.0; ybe[1] = cw; ybe[2] = 0.0; ybe[3] = -W.rw * sw;
-    cwe = cw;
   }
   for (int l = 0; l < k; ++l) {
-    const LayerConst L = s_lc[l];
+    const LayerConst& L = s_lc[l];
     double c1, s1, c2, s2;
     sincos((double)tid * L.thx, &s1, &c1);
     sincos((double)tid * L.the, &s2, &c2);
 #pragma unroll
     for (int m = 0; m < J; ++m) {
-      double uc1 = c1, us1 = s1, uc2 = c2, us2 = s2;
-      if (m == 0 && tid == 0) { uc1 = L.dcx; us1 = L.dsx; uc2 = L.dce; us2 = L.dse; }
-      layer_step(L, uc1, us1, uc2, us2, ya[m], yb[m]);
-      rot(c1, s1, L.cbx, L.sbx);
-      rot(c2, s2, L.cbe, L.sbe);
+      layer_step(L, c1, s1, c2, s2, ya[m], yb[m]);
+      if (m + 1 < J) {
+        rot(c1, s1, L.cbx, L.sbx);
+        rot(c2, s2, L.cbe, L.sbe);
+      }
     }
-    if (tid == 0) layer_step(L, c1, s1, c2, s2, yae, ybe);
   }
   {
-    const HalfSpace H = s_hs;
+    const HalfSpace H = s_rc->hs;
 #pragma unroll
     for (int m = 0; m < J; ++m) {
       double2 fr, fv;
@@ -347,11 +361,9 @@ __global__ void __launch_bounds__(BMAX) forward_kernel(const DevConfig cfg, cons
       s_fr[tid + m * nthr] = fr;
       s_fv[tid + m * nthr] = fv;
     }
-    if (tid == 0) {
-      double2 fr, fv;
-      surface_response(H, yae, ybe, cwe, ipha, fr, fv);
-      s_fr[nh - 1] = fr;
-      s_fv[nh - 1] = fv;
+    if (tid == 0) {  // the two bins off the regular grid
+      s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
+      s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
     }
   }
   __syncthreads();
@@ -365,21 +377,27 @@ __global__ void __launch_bounds__(BMAX) forward_kernel(const DevConfig cfg, cons
     mx = block_max(mx, s_red, tid, nthr);
     const double wlvl = 0.001 * mx;
     double2 keep[J + 1];
-    int cnt = 0;
-    for (int j = tid; j < nh; j += nthr) {
-      const double2 x = xs[j], y = ys[j];
-      const double amp = x.x * x.x + x.y * x.y;
-      const double d = fmax(amp, wlvl);
-      keep[cnt++] = make_double2((y.x * x.x + y.y * x.y) / d, (y.y * x.x - y.x * x.y) / d);
+#pragma unroll
+    for (int q = 0; q < J + 1; ++q) {
+      const int j = tid + q * nthr;
+      if (j < nh) {
+        const double2 x = xs[j], y = ys[j];
+        const double amp = x.x * x.x + x.y * x.y;
+        const double d = fmax(amp, wlvl);
+        keep[q] = make_double2((y.x * x.x + y.y * x.y) / d, (y.y * x.x - y.x * x.y) / d);
+      }
     }
     __syncthreads();
-    cnt = 0;
-    for (int j = tid; j < nh; j += nthr) s_fr[j] = keep[cnt++];
+#pragma unroll
+    for (int q = 0; q < J + 1; ++q) {
+      const int j = tid + q * nthr;
+      if (j < nh) s_fr[j] = keep[q];
+    }
     __syncthreads();
   }
 
   // ---- per trace: filter -> inverse FFT -> shift / normalise -> outputs ----
-  const double tp = s_tp;
+  const double tp = s_rc->tp;
   const int S = cfg.nsmp, Sp = cfg.nsmp_pad;
   const int t_begin = cfg.ray_common ? 0 : t0, t_end = cfg.ray_common ? cfg.ntrc : t0 + 1;
   for (int t = t_begin; t < t_end; ++t) {
@@ -476,22 +494,19 @@ __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, in
 
 size_t forward_smem_bytes(const DevConfig& cfg) {
   const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
-  return sizeof(double2) * (2 * n + 2 * (nh + 1)) + sizeof(LayerConst) * km + sizeof(double) * (3 * km + 6 * (km + 1) + 32);
+  const size_t spectra = cfg.ray_common ? 2 * (nh + 1) : 4;   // aliased onto the second FFT buffer otherwise
+  return sizeof(double2) * (2 * n + spectra) + sizeof(LayerConst) * km + sizeof(RayConst) + sizeof(double) * 32;
 }
 
-template <int J, int BMAX>
-int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, int nthr, cudaStream_t stream) {
+template <int J, int BMAX, int MINB>
+int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
+                     const double* rc, int nthr, cudaStream_t stream) {
   const size_t smem = forward_smem_bytes(cfg);
-  static size_t configured = 0;
-  if (smem > configured) {
-    RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long grid = (long long)n_models * ntr_eff;
-  if (grid == 0) return RFINV_OK;
-  forward_kernel<J, BMAX><<<(unsigned)grid, nthr, smem, stream>>>(cfg, mb, out);
+  forward_kernel<J, BMAX, MINB><<<(unsigned)grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -505,14 +520,29 @@ int rfinv_forward_bins_per_thread(int nfft) {
   return 8;
 }
 
-int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, cudaStream_t stream) {
+size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
+  const long long ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
+  return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES);
+}
+
+// scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
+int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
+                         cudaStream_t stream) {
   const int J = rfinv_forward_bins_per_thread(cfg.nfft);
   const int nthr = (cfg.nfft / 2) / J;
+  const int n_models = mb.active ? mb.n_active : mb.C;
+  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
+  const long long n_items = (long long)n_models * ntr_eff;
+  if (n_items == 0) return RFINV_OK;
+  double* lc = scratch;
+  double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
+  prep_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, stream>>>(cfg, mb, lc, rc, out.is_valid, (int)n_items, ntr_eff, nthr);
+  RFINV_CUDA_CHECK(cudaGetLastError());
   switch (J) {
-    case 1: return launch_forward_t<1, 32>(cfg, mb, out, nthr, stream);
-    case 2: return launch_forward_t<2, 64>(cfg, mb, out, nthr, stream);
-    case 4: return launch_forward_t<4, 128>(cfg, mb, out, nthr, stream);
-    default: return launch_forward_t<8, 256>(cfg, mb, out, nthr, stream);
+    case 1: return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, nthr, stream);
+    case 2: return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, nthr, stream);
+    case 4: return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
+    default: return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
   }
 }
 

@@ -90,7 +90,10 @@ struct EvalOutputs {
   double* rft_full;   // [C][ntrc][nfft]      complete RF, the reference's prop_rft (optional)
   uint8_t* is_valid;  // [C]                  format_model's flag (optional)
 };
-int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, cudaStream_t stream);
+// prep_kernel + forward_kernel.  scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles in HBM
+size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models);
+int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
+                         cudaStream_t stream);
 // phi[ntrc][C] = m^T R^-1 m per trace and model
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
                           int n_active, cudaStream_t stream);

@@ -24,7 +24,7 @@ struct rfinv_handle {
   int cap = 0;
   int* d_k = nullptr;
   double *d_z = nullptr, *d_dvp = nullptr, *d_dvs = nullptr, *d_sig = nullptr, *d_stage = nullptr;
-  double *d_misfit = nullptr, *d_phi = nullptr, *d_logl = nullptr, *d_rft_full = nullptr;
+  double *d_misfit = nullptr, *d_phi = nullptr, *d_logl = nullptr, *d_rft_full = nullptr, *d_scratch = nullptr;
   uint8_t* d_valid = nullptr;
   size_t cap_rft_full = 0;
   int launches = 0;
