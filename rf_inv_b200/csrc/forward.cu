@@ -18,7 +18,31 @@
 // distinct entries of B_l are two-term combinations of cos/sin of (w xi h, w eta h).  The four
 // trigonometric values per layer-frequency come from one sincos pair per thread and layer, advanced
 // across the thread's J frequencies by a fixed rotation (frequencies of a thread are equally spaced).
+#include <cstdlib>
 #include "rfinv_common.cuh"
+
+#ifdef RFINV_PHASE_TIMING
+// Debug build only (tools/phase_timing.py): per-phase cycle totals of forward_kernel, summed over CTAs.
+__device__ unsigned long long g_phase[16];
+#define PHASE_MARK(i)                                                            \
+  do {                                                                           \
+    if (tid == 0) {                                                              \
+      const long long now__ = clock64();                                         \
+      atomicAdd(&g_phase[i], (unsigned long long)(now__ - t_phase__));           \
+      t_phase__ = now__;                                                         \
+    }                                                                            \
+  } while (0)
+#define PHASE_INIT() long long t_phase__ = clock64(); if (tid == 0) atomicAdd(&g_phase[15], 1ULL)
+extern "C" int rfinv_debug_get_phases(unsigned long long* out) {
+  cudaError_t e = cudaMemcpyFromSymbol(out, g_phase, sizeof(g_phase));
+  unsigned long long zero[16] = {0};
+  cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
+  return e == cudaSuccess ? 0 : 2;
+}
+#else
+#define PHASE_MARK(i) do { } while (0)
+#define PHASE_INIT() do { } while (0)
+#endif
 
 namespace {
 
@@ -97,8 +121,8 @@ __device__ __forceinline__ void surface_response(const HalfSpace& H, const doubl
   const double2 B4 = make_double2(fma(H.e21, yb[0], -H.e24 * yb[3]), fma(H.e22, yb[1], H.e23 * yb[2]));
   const double2 p = cmul(A3, B4), q = cmul(B3, A4);
   const double2 dl = make_double2(p.x - q.x, p.y - q.y);
-  const double nrm = dl.x * dl.x + dl.y * dl.y;
-  const double2 inv = make_double2(dl.x / nrm, -dl.y / nrm);
+  const double rn = 1.0 / (dl.x * dl.x + dl.y * dl.y);
+  const double2 inv = make_double2(dl.x * rn, -dl.y * rn);
   double2 ur, uz;
   if (ipha >= 0) {
     ur = cmul(B4, inv);
@@ -227,10 +251,16 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
   if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
 }
 
-// In-place-pair Stockham inverse FFT (sign +, unnormalised) of n complex points in shared memory.
+// exp(+2 pi i m / n) for m < 3n/4 from the quarter-wave table twq[r] = exp(+2 pi i r / n), r < n/4
+__device__ __forceinline__ double2 twiddle(const double2* twq, int m, int qmask, int qshift) {
+  const double2 w = twq[m & qmask];
+  const int q = m >> qshift;
+  return q == 0 ? w : (q == 1 ? make_double2(-w.y, w.x) : make_double2(-w.x, -w.y));
+}
+
+// Stockham inverse FFT (sign +, unnormalised) of n complex points in shared memory, ping-pong x <-> y.
 // Returns the buffer holding the result.
-__device__ double2* fft_inverse(double2* x, double2* y, int n, int log2n, const double2* __restrict__ tw, int tid,
-                                int nthr) {
+__device__ double2* fft_inverse(double2* x, double2* y, int n, int log2n, const double2* twq, int tid, int nthr) {
   int Ns = 1;
   if (log2n & 1) {  // one radix-2 pass (no twiddles at Ns = 1)
     const int half = n >> 1;
@@ -243,16 +273,16 @@ __device__ double2* fft_inverse(double2* x, double2* y, int n, int log2n, const 
     double2* t = x; x = y; y = t;
     Ns = 2;
   }
-  const int quarter = n >> 2;
+  const int quarter = n >> 2, qmask = quarter - 1, qshift = log2n - 2;
   while (Ns < n) {
     const int tstep = n / (4 * Ns);
     for (int j = tid; j < quarter; j += nthr) {
       const int k = j & (Ns - 1);
       double2 v0 = x[j], v1 = x[j + quarter], v2 = x[j + 2 * quarter], v3 = x[j + 3 * quarter];
       if (Ns > 1) {
-        v1 = cmul(v1, __ldg(&tw[k * tstep]));
-        v2 = cmul(v2, __ldg(&tw[2 * k * tstep]));
-        v3 = cmul(v3, __ldg(&tw[3 * k * tstep]));
+        v1 = cmul(v1, twiddle(twq, k * tstep, qmask, qshift));
+        v2 = cmul(v2, twiddle(twq, 2 * k * tstep, qmask, qshift));
+        v3 = cmul(v3, twiddle(twq, 3 * k * tstep, qmask, qshift));
       }
       const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
       const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
@@ -299,29 +329,56 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
 
-  double2* s_buf0 = reinterpret_cast<double2*>(smem_raw);
-  double2* s_buf1 = s_buf0 + n;
-  double2* s_fr = cfg.ray_common ? s_buf1 + n : s_buf1;   // [nh] unfiltered radial spectrum (or deconvolved RF spectrum)
-  double2* s_fv = s_fr + (nh + 1);                        // [nh] unfiltered vertical spectrum   (2*(nh+1) <= n + 4)
-  double* s_tail = reinterpret_cast<double*>((cfg.ray_common ? s_fv + (nh + 1) : s_buf1 + n + 4));
+  // layout: [buf1 | buf0 ... trig tables may extend past buf0 | (spectra if rays are common) | layer consts | ray consts]
+  const int n_hi = nthr >> 4;                         // table split: tid = 16*hi + lo
+  const int tab_per_layer = 2 * (16 + n_hi);          // double2 entries per layer: (xi | eta) x (lo | hi)
+  const size_t tab_entries = (size_t)km * tab_per_layer;
+  const size_t region0 = tab_entries > (size_t)n ? tab_entries : (size_t)n;   // buf0 region also hosts the tables
+  double2* s_buf1 = reinterpret_cast<double2*>(smem_raw);
+  double2* s_buf0 = s_buf1 + n + 4;
+  double2* s_tab = s_buf0;                            // dead before buf0 is first written (Z build)
+  double2* s_fr = cfg.ray_common ? s_buf0 + region0 : s_buf1;   // [nh] unfiltered radial spectrum (or deconvolved RF spectrum)
+  double2* s_fv = s_fr + (nh + 1);                              // [nh] unfiltered vertical spectrum   (2*(nh+1) = n + 4)
+  double* s_tail = reinterpret_cast<double*>(s_buf0 + region0 + (cfg.ray_common ? 2 * (nh + 1) : 0));
   LayerConst* s_lc = reinterpret_cast<LayerConst*>(s_tail);
   RayConst* s_rc = reinterpret_cast<RayConst*>(s_lc + km);
   double* s_red = reinterpret_cast<double*>(s_rc + 1);     // [32]
+  double2* s_twq = reinterpret_cast<double2*>(s_red + 32); // [n/4] quarter-wave twiddles
 
-  // ---- stage the constants of this (model, ray) ----
+  PHASE_INIT();
+  // ---- stage the constants of this (model, ray): one round trip to L2/HBM ----
+  int k = mb.k[c];
+  k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);   // same clamp as prep_kernel
   {
     const double* src = rc_in + (size_t)item * RC_DOUBLES;
     double* dst = reinterpret_cast<double*>(s_rc);
     for (int i = tid; i < RC_DOUBLES; i += nthr) dst[i] = src[i];
+    const double* src2 = lc_in + (size_t)item * km * LC_DOUBLES;
+    double* dst2 = reinterpret_cast<double*>(s_lc);
+    for (int i = tid; i < k * LC_DOUBLES; i += nthr) dst2[i] = src2[i];
+    for (int i = tid; i < (n >> 2); i += nthr) s_twq[i] = cfg.tw[i];
   }
   __syncthreads();
-  const int k = s_rc->k;
-  {
-    const double* src = lc_in + (size_t)item * km * LC_DOUBLES;
-    double* dst = reinterpret_cast<double*>(s_lc);
-    for (int i = tid; i < k * LC_DOUBLES; i += nthr) dst[i] = src[i];
+  PHASE_MARK(0);
+  // ---- two-level rotation tables: cos/sin(tid*theta) = rot(lo[tid & 15], hi[tid >> 4]) ----
+  // per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
+  // One thread per (layer, angle, level): one sincos, then a chain of rotations (<= 15 steps, error ~1e-15).
+  for (int task = tid; task < 4 * k; task += nthr) {
+    const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
+    const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
+    const int cnt = level ? n_hi : 16;
+    double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
+    double sb, cb;
+    sincos(th, &sb, &cb);
+    double cc = 1.0, ss = 0.0;
+    dst[0] = make_double2(1.0, 0.0);
+    for (int i = 1; i < cnt; ++i) {
+      rot(cc, ss, cb, sb);
+      dst[i] = make_double2(cc, ss);
+    }
   }
   __syncthreads();
+  PHASE_MARK(1);
   const int ipha = cfg.ipha[t0];
 
   // ---- propagator product over the solid layers, top down ----
@@ -338,11 +395,16 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       rot(cw, sw, cbw, sbw);
     }
   }
+  const int t_lo = tid & 15, t_hi = 16 + (tid >> 4);
   for (int l = 0; l < k; ++l) {
     const LayerConst& L = s_lc[l];
+    const double2* tab = s_tab + l * tab_per_layer;
     double c1, s1, c2, s2;
-    sincos((double)tid * L.thx, &s1, &c1);
-    sincos((double)tid * L.the, &s2, &c2);
+    {
+      const double2 a = tab[t_lo], b = tab[t_hi], c = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
+      c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
+      c2 = c.x; s2 = c.y; rot(c2, s2, d.x, d.y);
+    }
 #pragma unroll
     for (int m = 0; m < J; ++m) {
       layer_step(L, c1, s1, c2, s2, ya[m], yb[m]);
@@ -352,6 +414,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       }
     }
   }
+  PHASE_MARK(2);
   {
     const HalfSpace H = s_rc->hs;
 #pragma unroll
@@ -367,6 +430,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     }
   }
   __syncthreads();
+  PHASE_MARK(3);
 
   // ---- water-level deconvolution (src/forward.f90:148-153, 447-470): overwrites s_fr with rff ----
   if (cfg.deconv_mode == 1) {
@@ -417,7 +481,9 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       }
     }
     __syncthreads();
-    const double2* res = fft_inverse(s_buf0, s_buf1, n, cfg.log2n, cfg.tw, tid, nthr);
+    PHASE_MARK(4);
+    const double2* res = fft_inverse(s_buf0, s_buf1, n, cfg.log2n, s_twq, tid, nthr);
+    PHASE_MARK(5);
     double fac = 1.0;
     if (cfg.deconv_mode == 0) {  // src/forward.f90:197-203
       double mx = -INFINITY;
@@ -432,17 +498,13 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     double* smp = out.rft_smp ? out.rft_smp + ((size_t)t * C + c) * S : nullptr;
     double* full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
     const double* __restrict__ obs = cfg.obs + (size_t)t * S;
+    const double scale = cfg.deconv_mode == 0 ? 1.0 / fac : 1.0;
+    const int nmask = n - 1;
     for (int i = tid; i < nout; i += nthr) {
-      int src;
       double v;
-      if (ipha == 1) {
-        src = (i - npre) % n; if (src < 0) src += n;
-        v = res[src].x;
-      } else {
-        src = (npre - i - 1) % n; if (src < 0) src += n;
-        v = -res[src].x;
-      }
-      if (cfg.deconv_mode == 0) v = v / fac;
+      if (ipha == 1) v = res[(i - npre) & nmask].x;       // src/forward.f90:178-184 (n is a power of two)
+      else v = -res[(npre - i - 1) & nmask].x;            // src/forward.f90:187-193
+      v *= scale;
       if (i < S) {
         mis[i] = v - obs[i];
         if (smp) smp[i] = v;
@@ -450,6 +512,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       if (full) full[i] = v;
     }
     __syncthreads();
+    PHASE_MARK(6);
   }
 }
 
@@ -492,16 +555,18 @@ __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, in
   is_valid[c] = (uint8_t)valid;
 }
 
-size_t forward_smem_bytes(const DevConfig& cfg) {
+size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
-  const size_t spectra = cfg.ray_common ? 2 * (nh + 1) : 4;   // aliased onto the second FFT buffer otherwise
-  return sizeof(double2) * (2 * n + spectra) + sizeof(LayerConst) * km + sizeof(RayConst) + sizeof(double) * 32;
+  const size_t tab_entries = km * 2 * (16 + (nthr >> 4));
+  const size_t region0 = tab_entries > n ? tab_entries : n;
+  const size_t spectra = cfg.ray_common ? 2 * (nh + 1) : 0;   // aliased onto buf1 otherwise
+  return sizeof(double2) * (n + 4 + region0 + spectra + n / 4) + sizeof(LayerConst) * km + sizeof(RayConst) + sizeof(double) * 32;
 }
 
 template <int J, int BMAX, int MINB>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
                      const double* rc, int nthr, cudaStream_t stream) {
-  const size_t smem = forward_smem_bytes(cfg);
+  const size_t smem = forward_smem_bytes(cfg, nthr);
   RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
@@ -541,7 +606,11 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   switch (J) {
     case 1: return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, nthr, stream);
     case 2: return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, nthr, stream);
-    case 4: return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
+    case 4: {
+      static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
+      if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
+      return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, nthr, stream);
+    }
     default: return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
   }
 }
