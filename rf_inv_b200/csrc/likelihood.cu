@@ -9,96 +9,140 @@
 
 namespace {
 
-constexpr int TM = 64;   // chains per CTA
-constexpr int TN = 64;   // columns of R^-1 per tile
-constexpr int TK = 16;   // k-slab
-constexpr int QF_THREADS = 256;
+constexpr int TM = 64;    // chains per CTA
+constexpr int TN = 64;    // columns of R^-1 per tile
+constexpr int TK = 16;    // k-slab per pipeline stage
+constexpr int LDS_STRIDE = TK + 4;   // doubles; (row*20 + k) mod 16 distinct over an 8x4 fragment: conflict-free LDS.64
+constexpr int QF_THREADS = 128;      // 4 warps, each owns a 32 x 32 sub-tile
 
-// CTA = 64 chains of one trace; loops over column tiles jt and k tiles kt <= jt.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// CTA = 64 chains of one trace.  For every column tile jt of the symmetric R^-1 it accumulates
+//   Y(64 x 64) = 2 * sum_{kt<jt} M[:,kt] R[kt,jt]  +  M[:,jt] R[jt,jt]          (DMMA, fp64 accumulate)
+// and folds it into phi with the row-dot  phi += sum_cols Y .* M[:,jt].  Both MMA operands are read as
+// "row-major, k contiguous": M[chain][k] and, by symmetry, R[col][k].  Fixed summation order, no atomics.
 __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cfg, int C, const double* __restrict__ misfit,
                                                               double* __restrict__ phi, const int* __restrict__ active,
                                                               int n_active) {
-  __shared__ double sA[TK][TM + 4];   // M tile, k-major
-  __shared__ double sB[TK][TN + 4];   // R^-1 tile
+  __shared__ __align__(16) double sA[2][TM * LDS_STRIDE];
+  __shared__ __align__(16) double sB[2][TN * LDS_STRIDE];
   __shared__ int s_rows[TM];
+  __shared__ double s_part[2][TM];
   const int t = blockIdx.y;
   const int Sp = cfg.nsmp_pad;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile origin: rows wm*32, cols wn*32
   const int n_rows = active ? n_active : C;
   const int row0 = blockIdx.x * TM;
   if (tid < TM) {
-    const int r = row0 + tid;
-    s_rows[tid] = r < n_rows ? (active ? active[r] : r) : -1;
+    int r = row0 + tid;
+    r = r < n_rows ? r : n_rows - 1;                // clamp: duplicates are computed but never written
+    s_rows[tid] = active ? active[r] : r;
   }
   __syncthreads();
   const double* __restrict__ Mt = misfit + (size_t)t * C * Sp;
   const double* __restrict__ Rt = cfg.r_inv + (size_t)t * Sp * Sp;
-  const int tx = tid & 15, ty = tid >> 4;   // thread owns rows ty*4..+3, cols tx*4..+3 of the 64x64 tile
-  double phi_acc[4] = {0.0, 0.0, 0.0, 0.0};
   const int ntile = Sp / TN;
-  // load indices: A tile 64 rows x 16 k: thread loads 4 consecutive k of one row; B tile 16 k x 64 cols
-  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
-  const int b_k = tid >> 4, b_col = (tid & 15) * 4;
-  const int a_src = s_rows[a_row];
+  // global -> smem copy assignment: 64 rows x 16 doubles = 512 x 16 B per operand, 4 per thread each
+  const double* a_src[4];
+  int cp_off[4], cp_row[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int id = tid + q * QF_THREADS;            // 0..511
+    const int row = id >> 3, seg = id & 7;          // 8 segments of 2 doubles per row
+    cp_row[q] = row;
+    cp_off[q] = row * LDS_STRIDE + seg * 2;
+    a_src[q] = Mt + (size_t)s_rows[row] * Sp + seg * 2;
+  }
+  const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates
+  double phi_acc[4] = {0.0, 0.0, 0.0, 0.0};         // rows wm*32 + 8*i + fr
+
   for (int jt = 0; jt < ntile; ++jt) {
-    double acc[4][4];
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    const int k_end = (jt + 1) * TN;
-    for (int k0 = 0; k0 < k_end; k0 += TK) {
-      if (k0 == jt * TN && jt > 0) {  // entering the diagonal tile: everything so far counts twice
+      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    const int nk = (jt + 1) * (TN / TK);            // k-slabs up to and including the diagonal tile
+    const double* b_base = Rt + (size_t)(jt * TN) * Sp;
+    // prologue: stage 0
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      cp_async16(&sA[0][cp_off[q]], a_src[q]);
+      cp_async16(&sB[0][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + (cp_off[q] - cp_row[q] * LDS_STRIDE));
+    }
+    cp_async_commit();
+    for (int ks = 0; ks < nk; ++ks) {
+      const int cur = ks & 1;
+      if (ks + 1 < nk) {
+        const int k0 = (ks + 1) * TK;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          cp_async16(&sA[cur ^ 1][cp_off[q]], a_src[q] + k0);
+          cp_async16(&sB[cur ^ 1][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + k0 + (cp_off[q] - cp_row[q] * LDS_STRIDE));
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      if (ks == jt * (TN / TK) && jt > 0) {         // entering the diagonal tile: what came before counts twice
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] *= 2.0;
+          for (int j = 0; j < 4; ++j) { acc[i][j][0] *= 2.0; acc[i][j][1] *= 2.0; }
       }
-      double av[4] = {0.0, 0.0, 0.0, 0.0};
-      if (a_src >= 0) {
-        const double2* src = reinterpret_cast<const double2*>(Mt + (size_t)a_src * Sp + k0 + a_k);
-        const double2 v0 = src[0], v1 = src[1];
-        av[0] = v0.x; av[1] = v0.y; av[2] = v1.x; av[3] = v1.y;
-      }
-      const double2* bsrc = reinterpret_cast<const double2*>(Rt + (size_t)(k0 + b_k) * Sp + jt * TN + b_col);
-      const double2 b0 = bsrc[0], b1 = bsrc[1];
-      __syncthreads();
+      const double* A = &sA[cur][(wm * 32 + fr) * LDS_STRIDE + fk];
+      const double* B = &sB[cur][(wn * 32 + fr) * LDS_STRIDE + fk];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) sA[a_k + q][a_row] = av[q];
-      sB[b_k][b_col] = b0.x; sB[b_k][b_col + 1] = b0.y; sB[b_k][b_col + 2] = b1.x; sB[b_k][b_col + 3] = b1.y;
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < TK; ++kk) {
+      for (int kk = 0; kk < TK; kk += 4) {
         double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = sA[kk][ty * 4 + i];
+        for (int i = 0; i < 4; ++i) a[i] = A[i * 8 * LDS_STRIDE + kk];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = sB[kk][tx * 4 + j];
+        for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDS_STRIDE + kk];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
+      __syncthreads();
     }
-    // epilogue of this column tile: phi += sum_j acc[i][j] * M[row_i][jt*TN + col_j]
+    // row-dot with M[:, jt]: lane holds Y[row = 8i + fr][col = 8j + 2*fk + {0,1}] of its warp sub-tile
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int src = s_rows[ty * 4 + i];
-      if (src >= 0) {
-        const double2* mp = reinterpret_cast<const double2*>(Mt + (size_t)src * Sp + jt * TN + tx * 4);
-        const double2 m0 = mp[0], m1 = mp[1];
-        phi_acc[i] += acc[i][0] * m0.x + acc[i][1] * m0.y + acc[i][2] * m1.x + acc[i][3] * m1.y;
+      const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 32 + 2 * fk;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
+        phi_acc[i] = fma(acc[i][j][0], m.x, phi_acc[i]);
+        phi_acc[i] = fma(acc[i][j][1], m.y, phi_acc[i]);
       }
     }
   }
-  // reduce over the 16 threads (tx) that share rows: they are 16 consecutive lanes
+  // reduce over the 4 lanes sharing a row, then over the two warps (wn) covering the 64 columns
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     double v = phi_acc[i];
-    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int src = s_rows[ty * 4 + i];
-    if (tx == 0 && src >= 0) phi[(size_t)t * C + src] = v;
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (fk == 0) s_part[wn][wm * 32 + 8 * i + fr] = v;
   }
+  __syncthreads();
+  if (tid < TM && row0 + tid < n_rows) phi[(size_t)t * C + s_rows[tid]] = s_part[0][tid] + s_part[1][tid];
 }
 
 __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restrict__ phi, const double* __restrict__ sig,
