@@ -143,6 +143,40 @@ int32_t rfinv_get_timing(rfinv_handle* h, double* ms);
  * loops on all SMs, best of a few repetitions; TFLOP/s.                                           */
 int32_t rfinv_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);
 
+/* ---- parallel tempering (device-resident chains) ---------------------------------------------------
+ * The job consists of `nproc_total` virtual ranks (= MPI ranks of the reference: cfg.nchains chains and ONE
+ * mt19937 stream each, seeded iseed + r*r*10000 + 23*r, src/rf_inv.f90:75).  This handle owns the ranks
+ * [rank_begin, rank_begin + rank_count); with several processes every process must own the same number of
+ * ranks and process q owns [q*rank_count, (q+1)*rank_count).                                               */
+/* init_model + init_sig + init_rft + temperatures (src/rf_inv.f90:86-91), on device. */
+int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, int32_t rank_count);
+/* Number of proposal types (src/pt_mcmc.f90:311-365): 4 (+1 if vp_mode) (+1 if a sigma is solved). */
+int32_t rfinv_pt_ntype(rfinv_handle* h);
+/* Keep per-iteration logs for the next `cap_iters` iterations (0 disables): accept flags, proposal types, swaps. */
+int32_t rfinv_pt_set_logging(rfinv_handle* h, int32_t cap_iters);
+/* pt_control (src/pt_mcmc.f90:468-576) for n_iter iterations when this handle owns ALL ranks. */
+int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter);
+/* Multi-process iteration, step 1: every chain proposes, is evaluated and accepted/rejected; fills this
+ * process's swap table [temps(Cl) | logL(Cl) | next uniform of each local stream (G) | itarget1, itarget2]. */
+int32_t rfinv_pt_local_step(rfinv_handle* h);
+/* Device pointer and length (doubles) of the swap table: the payload of the per-iteration all-gather. */
+int32_t rfinv_pt_swap_table(rfinv_handle* h, uint64_t* dev_ptr, int32_t* n_doubles);
+/* Step 2: `gathered_dev_ptr` holds the `world` tables in process order (device memory); every process evaluates
+ * the one global swap proposal of the iteration identically (src/pt_mcmc.f90:501-571) and updates its chains. */
+int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t world);
+/* Host copies of the local chain state, chain-major like the Fortran arrays (any pointer may be NULL):
+ * k[Cl], z[Cl][k_max-1], dvp[Cl][k_max], dvs[Cl][k_max], sig[Cl][ntrc], logl[Cl], temps[Cl]. */
+int32_t rfinv_pt_get_state(rfinv_handle* h, int32_t* k, double* z, double* dvp, double* dvs, double* sig, double* logl,
+                           double* temps);
+/* nprop[ntype], naccept[ntype] of the non-tempered chains (src/pt_mcmc.f90:196-198), likelihood_hist[0..n_hist)
+ * (sum of logL over the local non-tempered chains per iteration, :199-200), forward evaluations executed. */
+int32_t rfinv_pt_get_counters(rfinv_handle* h, int64_t* nprop, int64_t* naccept, double* likelihood_hist, int32_t n_hist,
+                              int64_t* n_eval);
+int32_t rfinv_pt_iterations_done(rfinv_handle* h);
+/* Logs kept by rfinv_pt_set_logging: flags[n][Cl] (-1 null proposal, 0 rejected, 1 accepted), itypes[n][Cl]
+ * (1-based), swaps[n][3] (itarget1, itarget2, accepted). */
+int32_t rfinv_pt_get_log(rfinv_handle* h, int8_t* flags, int8_t* itypes, int32_t* swaps, int32_t* n_logged);
+
 #ifdef __cplusplus
 }
 #endif

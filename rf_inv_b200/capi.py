@@ -40,6 +40,17 @@ SIGNATURES = {
     "rfinv_set_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_get_timing": (C.c_int32, [C.c_void_p, dp]),
     "rfinv_measure_fp64_peak": (C.c_int32, [C.c_int32, dp, dp]),
+    "rfinv_pt_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "rfinv_pt_ntype": (C.c_int32, [C.c_void_p]),
+    "rfinv_pt_set_logging": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rfinv_pt_run": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rfinv_pt_local_step": (C.c_int32, [C.c_void_p]),
+    "rfinv_pt_swap_table": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), i32p]),
+    "rfinv_pt_apply_swap": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_int32]),
+    "rfinv_pt_get_state": (C.c_int32, [C.c_void_p, i32p, dp, dp, dp, dp, dp, dp]),
+    "rfinv_pt_get_counters": (C.c_int32, [C.c_void_p, i64p, i64p, dp, C.c_int32, i64p]),
+    "rfinv_pt_iterations_done": (C.c_int32, [C.c_void_p]),
+    "rfinv_pt_get_log": (C.c_int32, [C.c_void_p, i8p, i8p, i32p, i32p]),
 }
 
 _lib = None

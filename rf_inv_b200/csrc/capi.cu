@@ -197,16 +197,17 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
                               const int* active, int n_active) {
   // misfit scratch is sized by capacity; its [t][c] stride uses the C of this call
   ModelBatch mb;
-  mb.C = C; mb.k = k; mb.z = z; mb.dvp = dvp; mb.dvs = dvs; mb.sig = sig; mb.active = active; mb.n_active = n_active;
+  mb.C = C; mb.k = k; mb.z = z; mb.dvp = dvp; mb.dvs = dvs; mb.sig = sig; mb.active = active; mb.n_active = n_active; mb.n_active_dev = nullptr;
   EvalOutputs out;
-  out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_full = rft_full; out.is_valid = is_valid;
+  out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_smp_alt = nullptr; out.slot = nullptr; out.slot_invert = 0;
+  out.rft_full = rft_full; out.is_valid = is_valid;
   int st;
   launches = 0;
   if (timing) cudaEventRecord(ev[0], stream);
   if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream)) != RFINV_OK) return st;
   launches += 2;
   if (timing) cudaEventRecord(ev[1], stream);
-  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, stream)) != RFINV_OK) return st;
+  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, nullptr, stream)) != RFINV_OK) return st;
   ++launches;
   if (timing) cudaEventRecord(ev[2], stream);
   if (logl) {
@@ -459,7 +460,7 @@ int32_t rfinv_format_model_batch(rfinv_handle* h, int32_t C, const int32_t* k, c
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_out, sizeof(double) * (size_t)C * stride * 4));
   RFINV_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * (size_t)C * stride * 4, h->stream));
   ModelBatch mb;
-  mb.C = C; mb.k = h->d_k; mb.z = h->d_z; mb.dvp = h->d_dvp; mb.dvs = h->d_dvs; mb.sig = h->d_sig; mb.active = nullptr; mb.n_active = 0;
+  mb.C = C; mb.k = h->d_k; mb.z = h->d_z; mb.dvp = h->d_dvp; mb.dvs = h->d_dvs; mb.sig = h->d_sig; mb.active = nullptr; mb.n_active = 0; mb.n_active_dev = nullptr;
   const size_t blk = (size_t)C * stride;
   st = rfinv_launch_format_model(h->dc, mb, d_nlay, d_out, d_out + blk, d_out + 2 * blk, d_out + 3 * blk, h->d_valid, h->stream);
   if (st == RFINV_OK) {

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
                                                    int n_items, int ntr_eff, int nthr_fwd) {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= n_items) return;
+  if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
   const int km = cfg.k_max, C = mb.C;
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const int item = blockIdx.x;
+  if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;   // grid is sized for the upper bound
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
 
@@ -495,7 +497,9 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
     const int nout = out.rft_full ? n : S;
     double* mis = out.misfit + ((size_t)t * C + c) * Sp;
-    double* smp = out.rft_smp ? out.rft_smp + ((size_t)t * C + c) * S : nullptr;
+    double* smp_base = out.rft_smp;
+    if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
+    double* smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
     double* full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
     const double* __restrict__ obs = cfg.obs + (size_t)t * S;
     const double scale = cfg.deconv_mode == 0 ? 1.0 / fac : 1.0;

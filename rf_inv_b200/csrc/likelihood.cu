@@ -35,7 +35,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // "row-major, k contiguous": M[chain][k] and, by symmetry, R[col][k].  Fixed summation order, no atomics.
 __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cfg, int C, const double* __restrict__ misfit,
                                                               double* __restrict__ phi, const int* __restrict__ active,
-                                                              int n_active) {
+                                                              int n_active, const int* __restrict__ n_active_dev) {
   __shared__ __align__(16) double sA[2][TM * LDS_STRIDE];
   __shared__ __align__(16) double sB[2][TN * LDS_STRIDE];
   __shared__ int s_rows[TM];
@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
   const int Sp = cfg.nsmp_pad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile origin: rows wm*32, cols wn*32
-  const int n_rows = active ? n_active : C;
+  const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
   const int row0 = blockIdx.x * TM;
+  if (row0 >= n_rows) return;
   if (tid < TM) {
     int r = row0 + tid;
     r = r < n_rows ? r : n_rows - 1;                // clamp: duplicates are computed but never written
@@ -161,11 +162,11 @@ __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restri
 }  // namespace
 
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
-                          int n_active, cudaStream_t stream) {
+                          int n_active, const int* n_active_dev, cudaStream_t stream) {
   const int n_rows = active ? n_active : C;
   if (n_rows == 0) return RFINV_OK;
   dim3 grid((n_rows + TM - 1) / TM, cfg.ntrc);
-  quadform_kernel<<<grid, QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, active, n_active);
+  quadform_kernel<<<grid, QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, active, n_active, n_active_dev);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }

@@ -1,4 +1,651 @@
-// Parallel-tempering MCMC on device (filled in below).
+// Parallel-tempering reversible-jump MCMC on device: the caller of the forward+likelihood path.
+//
+// Replaces, with all chain state resident in HBM (structure of arrays, chain fastest):
+//   init_model        src/model.f90:43-107        init_sig     src/likelihood.f90:107-139
+//   init_rft          src/likelihood.f90:143-163  temperatures src/pt_mcmc.f90:444-452
+//   mcmc              src/pt_mcmc.f90:54-201      judge_mcmc   src/pt_mcmc.f90:600-621
+//   pt_control        src/pt_mcmc.f90:468-576     judge_pt     src/pt_mcmc.f90:580-595
+//   mt19937 grnd      src/mt19937.f90:78-130      gauss        src/math.f90:34-50
+//   laplace, log_prior_ratio                      src/prior.f90:36-123
+//
+// RNG semantics: the reference has ONE mt19937 stream per MPI rank, shared by the
+// `nchains` chains of that rank.  A "virtual rank" here = nchains chains + one 624-word MT state, seeded
+// iseed + r*r*10000 + 23*r.  The number of draws a chain step consumes never depends on the forward result, so
+// per iteration one thread per virtual rank runs the serial proposal pass (draws, proposal, validity, the
+// acceptance uniform), then ALL forward+likelihood evaluations run batched, then acceptance is parallel.
+#include <vector>
+#include <cstring>
 #include "rfinv_handle.h"
+#include "rfinv_pt.h"
 
-void rfinv_handle::free_pt() {}
+namespace {
+
+constexpr double PI2 = 2.0 * 3.1415926535897931;  // src/math.f90:37
+
+// ---------------- mt19937 (src/mt19937.f90): state word i of stream r at mt[i*G + r] ----------------
+struct Mt {
+  uint32_t* mt;
+  int stride, mti;
+  __device__ Mt(uint32_t* base, int G, int r, int mti_) : mt(base + r), stride(G), mti(mti_) {}
+  __device__ uint32_t& w(int i) { return mt[(size_t)i * stride]; }
+  __device__ void reload() {  // src/mt19937.f90:96-116
+    for (int kk = 0; kk < 624; ++kk) {
+      const uint32_t y = (w(kk) & 0x80000000u) | (w(kk == 623 ? 0 : kk + 1) & 0x7fffffffu);
+      w(kk) = w(kk + 397 < 624 ? kk + 397 : kk + 397 - 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    mti = 0;
+  }
+  __device__ static double temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return (double)y / 4294967296.0;  // src/mt19937.f90:125-129: [0,1)
+  }
+  __device__ double grnd() {
+    if (mti >= 624) reload();
+    return temper(w(mti++));
+  }
+  __device__ double peek() {  // next output without consuming it
+    if (mti >= 624) reload();
+    return temper(w(mti));
+  }
+};
+
+__device__ double gauss(Mt& g) {  // src/math.f90:34-50: cosine branch only, exactly two draws
+  double v1 = g.grnd();
+  const double v2 = g.grnd();
+  if (v1 == 0.0) v1 = (double)1.0e-16f;
+  return __dmul_rn(sqrt(__dmul_rn(-2.0, log(v1))), cos(__dmul_rn(PI2, v2)));
+}
+
+__device__ double laplace(Mt& g) {  // src/prior.f90:57-123; +,-,*,/ only: bit-exact without FMA contraction
+  const double d = 0.69314718055994529;
+  double u1 = g.grnd();
+  const double u1p = __dmul_rn(2.0, u1);
+  double u1pp, a = 0.0, w, val;
+  int i_sign;
+  if (u1p < 1.0) { i_sign = 1; u1pp = __dsub_rn(1.0, u1p); } else { i_sign = -1; u1pp = __dsub_rn(2.0, u1p); }
+  for (;;) {
+    const double u1ppp = __dmul_rn(2.0, u1pp);
+    if (u1ppp >= 1.0) { u1 = __dsub_rn(u1ppp, 1.0); break; }
+    a = __dadd_rn(a, d);
+    u1pp = u1ppp;
+  }
+  for (;;) {
+    w = __dmul_rn(d, u1);
+    val = __dmul_rn((double)i_sign, __dadd_rn(a, w));
+    int k = 1;
+    for (;;) {
+      const double u2 = g.grnd();
+      if (u2 >= w) { u1 = __ddiv_rn(__dsub_rn(u2, w), __dsub_rn(1.0, w)); break; }
+      w = u2;
+      ++k;
+    }
+    if (k & 1) break;
+  }
+  return val;
+}
+
+__device__ double prior_draw(Mt& g, int prior_mode) { return prior_mode == 1 ? laplace(g) : gauss(g); }
+
+__device__ double log_prior_ratio(double x_new, double x_old, double dev, int prior_mode) {  // src/prior.f90:36-53
+  if (prior_mode == 1) return __ddiv_rn(-__dsub_rn(fabs(x_new), fabs(x_old)), dev);
+  return __ddiv_rn(-__dsub_rn(__dmul_rn(x_new, x_new), __dmul_rn(x_old, x_old)), __dmul_rn(__dmul_rn(2.0, dev), dev));
+}
+
+// format_model's validity flag (src/model.f90:175-290) for one model held in thread-local arrays.
+__device__ bool model_valid(const DevConfig& cfg, int k, const double* zin, const double* dvpin, const double* dvsin,
+                            double dvp_half, double dvs_half) {
+  double z[RFINV_MAX_K], dp[RFINV_MAX_K], ds[RFINV_MAX_K];
+  for (int i = 0; i < k; ++i) { z[i] = zin[i]; dp[i] = dvpin[i]; ds[i] = dvsin[i]; }
+  for (int i = 1; i < k; ++i) {
+    const double a = z[i], b = dp[i], d = ds[i];
+    int m = i - 1;
+    while (m >= 0 && z[m] > a) { z[m + 1] = z[m]; dp[m + 1] = dp[m]; ds[m + 1] = ds[m]; --m; }
+    z[m + 1] = a; dp[m + 1] = b; ds[m + 1] = d;
+  }
+  bool valid = true;
+  for (int l = 0; l <= k; ++l) {
+    double zc, h, dvs_l, dvp_l;
+    if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, z[0])); h = __dsub_rn(z[0], cfg.sdep); dvs_l = ds[0]; dvp_l = dp[0]; }
+    else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(z[l], z[l - 1])); h = __dsub_rn(z[l], z[l - 1]); dvs_l = ds[l]; dvp_l = dp[l]; }
+    else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, z[k - 1])); h = 999.0; dvs_l = dvs_half; dvp_l = dvp_half; }
+    double a, b;
+    bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
+    if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));
+    else if (l < k) ok = ok && !(h < cfg.h_min);
+    valid = valid && ok;
+  }
+  return valid;
+}
+
+// ---------------- init: sgrnd + init_model + init_sig + temperatures, one thread per virtual rank ----------------
+__global__ void pt_init_kernel(const DevConfig cfg, const PtDev p) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.G) return;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  const uint32_t grank = (uint32_t)(p.rank_begin + r);
+  Mt g(p.mt, p.G, r, 624);
+  {  // sgrnd, src/mt19937.f90:78-90; seed src/rf_inv.f90:75 (wraps like default-integer arithmetic)
+    uint32_t s = (uint32_t)p.iseed + grank * grank * 10000u + 23u * grank;
+    g.w(0) = s;
+    for (int i = 1; i < 624; ++i) { s = 69069u * s; g.w(i) = s; }
+  }
+  double z[RFINV_MAX_K], dvp[RFINV_MAX_K], dvs[RFINV_MAX_K];
+  for (int ic = 0; ic < p.nchains; ++ic) {  // init_model, src/model.f90:62-95
+    const int c = r * p.nchains + ic;
+    int kk = 1;
+    bool valid = false;
+    // the reference zeroes z/dvp/dvs once (src/model.f90:59-61); entries written by a rejected draw stay in place
+    for (int i = 0; i < km; ++i) { z[i] = 0.0; dvp[i] = 0.0; dvs[i] = 0.0; }
+    while (!valid) {
+      kk = cfg.k_min + (int)(g.grnd() * (double)(cfg.k_max - cfg.k_min));
+      for (int i = 0; i < kk; ++i) z[i] = __dadd_rn(cfg.z_min, __dmul_rn(g.grnd(), __dsub_rn(cfg.z_max, cfg.z_min)));
+      for (int i = 0; i < kk; ++i) {
+        dvs[i] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvs_prior);
+        dvp[i] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvp_prior);
+      }
+      dvs[km - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvs_prior);
+      dvp[km - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvp_prior);
+      valid = model_valid(cfg, kk, z, dvp, dvs, dvp[km - 1], dvs[km - 1]);
+    }
+    p.k[c] = kk;
+    for (int i = 0; i < km - 1; ++i) p.z[(size_t)i * Cl + c] = z[i];
+    for (int i = 0; i < km; ++i) { p.dvp[(size_t)i * Cl + c] = dvp[i]; p.dvs[(size_t)i * Cl + c] = dvs[i]; }
+  }
+  for (int ic = 0; ic < p.nchains; ++ic)  // init_sig, src/likelihood.f90:117-126
+    for (int t = 0; t < T; ++t) {
+      const int c = r * p.nchains + ic;
+      p.sig[(size_t)t * Cl + c] = p.sig_mode[t]
+          ? __dadd_rn(p.sig_min[t], __dmul_rn(g.grnd(), __dsub_rn(p.sig_max[t], p.sig_min[t]))) : p.sig_min[t];
+    }
+  for (int ic = 0; ic < p.nchains; ++ic) {  // src/pt_mcmc.f90:447-452
+    const int c = r * p.nchains + ic;
+    p.temps[c] = ic < p.ncool ? 1.0 : exp(__dmul_rn(g.grnd(), log(p.t_high)));
+  }
+  p.mti[r] = g.mti;
+}
+
+// ---------------- proposal pass: mcmc, src/pt_mcmc.f90:77-169 + the draws of judge_mcmc :611-615 ----------------
+__global__ void pt_propose_kernel(const DevConfig cfg, const PtDev p) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.G) return;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  Mt g(p.mt, p.G, r, p.mti[r]);
+  double pz[RFINV_MAX_K], pdvp[RFINV_MAX_K], pdvs[RFINV_MAX_K], psig[RFINV_MAX_TRC];
+  for (int ic = 0; ic < p.nchains; ++ic) {
+    const int c = r * p.nchains + ic;
+    int pk = p.k[c];
+    for (int i = 0; i < km - 1; ++i) pz[i] = p.z[(size_t)i * Cl + c];
+    pz[km - 1] = 0.0;
+    for (int i = 0; i < km; ++i) { pdvp[i] = p.dvp[(size_t)i * Cl + c]; pdvs[i] = p.dvs[(size_t)i * Cl + c]; }
+    for (int t = 0; t < T; ++t) psig[t] = p.sig[(size_t)t * Cl + c];
+    double log_prior12 = 0.0;
+    bool null_flag = false;
+    const int itype = (int)(g.grnd() * (double)p.ntype) + 1;
+    if (itype == p.it_birth) {
+      pk = pk + 1;
+      if (pk < km) {
+        pdvp[pk - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvp_prior);
+        pdvs[pk - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvs_prior);
+        pz[pk - 1] = __dadd_rn(cfg.z_min, __dmul_rn(g.grnd(), __dsub_rn(cfg.z_max, cfg.z_min)));
+      } else null_flag = true;
+    } else if (itype == p.it_death) {
+      pk = pk - 1;
+      if (pk >= cfg.k_min) {
+        const int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
+        for (int il = itarget; il <= pk; ++il) {
+          pdvp[il - 1] = p.dvp[(size_t)il * Cl + c];
+          pdvs[il - 1] = p.dvs[(size_t)il * Cl + c];
+          pz[il - 1] = p.z[(size_t)il * Cl + c];
+        }
+        pdvp[pk] = 0.0; pdvs[pk] = 0.0; pz[pk] = 0.0;
+      } else null_flag = true;
+    } else if (itype == p.it_z) {
+      const int itarget = (int)(g.grnd() * (double)pk) + 1;
+      pz[itarget - 1] = __dadd_rn(pz[itarget - 1], __dmul_rn(gauss(g), p.dev_z));
+      if (pz[itarget - 1] < cfg.z_min || pz[itarget - 1] > cfg.z_max) null_flag = true;
+    } else if (itype == p.it_dvs) {
+      int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
+      if (itarget == pk + 1) itarget = km;
+      pdvs[itarget - 1] = __dadd_rn(pdvs[itarget - 1], __dmul_rn(gauss(g), p.dev_dvs));
+      log_prior12 = log_prior_ratio(pdvs[itarget - 1], p.dvs[(size_t)(itarget - 1) * Cl + c], p.dvs_prior, cfg.prior_mode);
+    } else if (itype == p.it_dvp) {
+      int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
+      if (itarget == pk + 1) itarget = km;
+      pdvp[itarget - 1] = __dadd_rn(pdvp[itarget - 1], __dmul_rn(gauss(g), p.dev_dvp));
+      log_prior12 = log_prior_ratio(pdvp[itarget - 1], p.dvp[(size_t)(itarget - 1) * Cl + c], p.dvp_prior, cfg.prior_mode);
+    } else if (itype == p.it_sig) {
+      const int itarget = p.isig_trc[(int)(g.grnd() * (double)p.nsig_trc)];
+      psig[itarget] = __dadd_rn(psig[itarget], __dmul_rn(gauss(g), p.dev_sig));
+      if (psig[itarget] < p.sig_min[itarget] || psig[itarget] > p.sig_max[itarget]) null_flag = true;
+    }
+    if (!null_flag && !model_valid(cfg, pk, pz, pdvp, pdvs, pdvp[km - 1], pdvs[km - 1])) null_flag = true;
+    double log_r = 0.0;
+    if (!null_flag) {  // judge_mcmc draws (src/pt_mcmc.f90:610-615): independent of the likelihood
+      double rr;
+      do { rr = g.grnd(); } while (!(rr >= 2.220446049250313e-16));
+      log_r = log(rr);
+    }
+    p.pk[c] = pk;
+    for (int i = 0; i < km - 1; ++i) p.pz[(size_t)i * Cl + c] = pz[i];
+    for (int i = 0; i < km; ++i) { p.pdvp[(size_t)i * Cl + c] = pdvp[i]; p.pdvs[(size_t)i * Cl + c] = pdvs[i]; }
+    for (int t = 0; t < T; ++t) p.psig[(size_t)t * Cl + c] = psig[t];
+    p.itype[c] = (int8_t)itype;
+    p.pflag[c] = (int8_t)(null_flag ? -1 : (itype == p.it_sig ? 2 : 1));  // 1: forward needed, 2: cached RF (fwd_flag false)
+    p.log_r[c] = log_r;
+    p.log_prior12[c] = log_prior12;
+  }
+  p.mti[r] = g.mti;
+}
+
+// ordered compaction of the chains that need a forward evaluation (single CTA, deterministic)
+__global__ void pt_compact_kernel(const PtDev p) {
+  __shared__ int s_cnt[1024];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < p.Cl; start += nthr) {
+    const int c = start + tid;
+    const int f = (c < p.Cl && p.pflag[c] == 1) ? 1 : 0;
+    s_cnt[tid] = f;
+    __syncthreads();
+    for (int o = 1; o < nthr; o <<= 1) {  // inclusive scan
+      const int v = tid >= o ? s_cnt[tid - o] : 0;
+      __syncthreads();
+      s_cnt[tid] += v;
+      __syncthreads();
+    }
+    if (f) p.active[s_base + s_cnt[tid] - 1] = c;
+    __syncthreads();
+    if (tid == nthr - 1) s_base += s_cnt[tid];
+    __syncthreads();
+  }
+  if (tid == 0) { *p.n_active = s_base; *p.n_eval += (unsigned long long)s_base; }
+}
+
+// ---------------- acceptance: src/pt_mcmc.f90:178-201, one thread per chain ----------------
+__global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p, int log_slot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.Cl) return;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  const int flag = p.pflag[c];
+  const double temp = p.temps[c];
+  int yn = 0;
+  if (flag != -1) {
+    double ll = 0.0;
+    for (int t = 0; t < T; ++t) {  // src/likelihood.f90:94-96; sigma-only proposals reuse the cached phi (same rft, same obs)
+      const double ph = flag == 1 ? p.pphi[(size_t)t * Cl + c] : p.phi[(size_t)t * Cl + c];
+      const double s = p.psig[(size_t)t * Cl + c];
+      ll = __dsub_rn(__dsub_rn(ll, __ddiv_rn(__dmul_rn(0.5, ph), __dmul_rn(s, s))), __dmul_rn((double)cfg.nsmp, log(s)));
+    }
+    const double del_s = __dadd_rn(__ddiv_rn(__dsub_rn(ll, p.logl[c]), temp), p.log_prior12[c]);  // src/pt_mcmc.f90:608
+    yn = p.log_r[c] <= del_s;
+    if (yn) {
+      p.logl[c] = ll;
+      p.k[c] = p.pk[c];
+      for (int i = 0; i < km - 1; ++i) p.z[(size_t)i * Cl + c] = p.pz[(size_t)i * Cl + c];
+      for (int i = 0; i < km; ++i) { p.dvp[(size_t)i * Cl + c] = p.pdvp[(size_t)i * Cl + c]; p.dvs[(size_t)i * Cl + c] = p.pdvs[(size_t)i * Cl + c]; }
+      for (int t = 0; t < T; ++t) p.sig[(size_t)t * Cl + c] = p.psig[(size_t)t * Cl + c];
+      if (flag == 1) {
+        for (int t = 0; t < T; ++t) p.phi[(size_t)t * Cl + c] = p.pphi[(size_t)t * Cl + c];
+        p.slot[c] ^= 1;  // the proposal's RF samples were written to the other slot
+      }
+    }
+  }
+  if (temp <= 1.0 + (double)1.0e-6f) {  // src/pt_mcmc.f90:196-201
+    atomicAdd(&p.nprop[p.itype[c] - 1], 1ULL);
+    if (yn) atomicAdd(&p.naccept[p.itype[c] - 1], 1ULL);
+  }
+  if (p.log_flags && log_slot >= 0) {
+    p.log_flags[(size_t)log_slot * Cl + c] = (int8_t)(flag == -1 ? -1 : yn);
+    p.log_itypes[(size_t)log_slot * Cl + c] = p.itype[c];
+  }
+}
+
+// likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200); fixed-order tree sum
+__global__ void pt_lhist_kernel(const PtDev p, double* out) {
+  __shared__ double s[1024];
+  const int tid = threadIdx.x;
+  double acc = 0.0;
+  const int per = (p.Cl + blockDim.x - 1) / blockDim.x;
+  for (int i = 0; i < per; ++i) {
+    const int c = tid * per + i;
+    if (c < p.Cl && p.temps[c] <= 1.0 + (double)1.0e-6f) acc += p.logl[c];
+  }
+  s[tid] = acc;
+  __syncthreads();
+  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+    if (tid < o) s[tid] += s[tid + o];
+    __syncthreads();
+  }
+  if (tid == 0) *out = s[0];
+}
+
+// Swap table of this process (src/pt_mcmc.f90:501-571 needs (T, logL) of two chains anywhere in the job):
+//   [0,Cl) temps | [Cl,2Cl) logL | [2Cl,2Cl+G) next uniform of every local stream | +0,+1: itarget1, itarget2 (-1 if
+//   this process does not own virtual rank 0).  The owner of rank 0 draws the pair first (consuming its stream).
+__global__ void pt_table_kernel(const PtDev p, double* table) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0) {
+    double t1 = -1.0, t2 = -1.0;
+    if (p.rank_begin == 0 && p.nchains >= 2) {
+      Mt g(p.mt, p.G, 0, p.mti[0]);
+      const int n_all = p.nproc_total * p.nchains;
+      const int i1 = (int)(g.grnd() * (double)n_all);
+      int i2;
+      do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
+      p.mti[0] = g.mti;
+      t1 = i1; t2 = i2;
+    }
+    table[2 * p.Cl + p.G] = t1;
+    table[2 * p.Cl + p.G + 1] = t2;
+  }
+  for (int c = tid; c < p.Cl; c += gridDim.x * blockDim.x) {
+    table[c] = p.temps[c];
+    table[p.Cl + c] = p.logl[c];
+  }
+}
+__global__ void pt_peek_kernel(const PtDev p, double* table) {  // after pt_table_kernel: stream 0 has advanced
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.G) return;
+  Mt g(p.mt, p.G, r, p.mti[r]);
+  table[2 * p.Cl + r] = g.peek();
+  p.mti[r] = g.mti;  // a peek may have reloaded the state (mti 624 -> 0); nothing is consumed
+}
+
+// judge_pt (src/pt_mcmc.f90:580-595) evaluated identically by every process from the gathered tables.
+__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len, int log_slot) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  if (p.nchains < 2) return;
+  const int G = p.G, Cl = p.Cl;
+  const double* t0 = gathered;  // process 0 owns virtual rank 0
+  const int i1 = (int)t0[2 * Cl + G], i2 = (int)t0[2 * Cl + G + 1];
+  const int own1 = i1 / Cl, own2 = i2 / Cl, l1 = i1 - own1 * Cl, l2 = i2 - own2 * Cl;
+  const double* ta = gathered + (size_t)own1 * table_len;
+  const double* tb = gathered + (size_t)own2 * table_len;
+  const double temp1 = ta[l1], temp2 = tb[l2], e1 = ta[Cl + l1], e2 = tb[Cl + l2];
+  const int rank1_local = l1 / p.nchains;
+  const double u = ta[2 * Cl + rank1_local];
+  const double del_s = __dmul_rn(__dsub_rn(e2, e1), __dsub_rn(__ddiv_rn(1.0, temp1), __ddiv_rn(1.0, temp2)));
+  const int yn = log(u) <= del_s;
+  const int me = p.rank_begin / G;
+  if (me == own1) {
+    p.mti[rank1_local] += 1;  // the stream of rank1 consumed the judge_pt uniform
+    if (yn) p.temps[l1] = temp2;
+  }
+  if (me == own2 && yn) p.temps[l2] = temp1;
+  if (p.log_swaps && log_slot >= 0) {
+    p.log_swaps[3 * log_slot] = i1; p.log_swaps[3 * log_slot + 1] = i2; p.log_swaps[3 * log_slot + 2] = yn;
+  }
+}
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  RFINV_CUDA_CHECK(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
+  RFINV_CUDA_CHECK(cudaMemset(*p, 0, sizeof(T) * (n ? n : 1)));
+  return RFINV_OK;
+}
+
+}  // namespace
+
+void rfinv_handle::free_pt() {
+  if (!pt) return;
+  PtDev& d = pt->dev;
+  cudaFree(d.mt); cudaFree(d.mti); cudaFree(d.k); cudaFree(d.z); cudaFree(d.dvp); cudaFree(d.dvs); cudaFree(d.sig);
+  cudaFree(d.logl); cudaFree(d.temps); cudaFree(d.phi); cudaFree(d.slot); cudaFree(d.rft_smp[0]); cudaFree(d.rft_smp[1]);
+  cudaFree(d.pk); cudaFree(d.pz); cudaFree(d.pdvp); cudaFree(d.pdvs); cudaFree(d.psig); cudaFree(d.pphi); cudaFree(d.log_r);
+  cudaFree(d.log_prior12); cudaFree(d.itype); cudaFree(d.pflag); cudaFree(d.active); cudaFree(d.n_active);
+  cudaFree(d.nprop); cudaFree(d.naccept); cudaFree(d.n_eval);
+  cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
+  cudaFree(pt->d_lhist); cudaFree(pt->d_table);
+  delete pt;
+  pt = nullptr;
+}
+
+static int pt_require(rfinv_handle* h, const char* who) {
+  if (!h) { rfinv_set_error("%s: handle is NULL", who); return RFINV_ERR_ARG; }
+  if (!h->pt) { rfinv_set_error("%s: call rfinv_pt_init first", who); return RFINV_ERR_STATE; }
+  return RFINV_OK;
+}
+
+// forward + quadratic form for the chains in `active` (or all), proposal or current state
+static int pt_eval(rfinv_handle* h, bool proposal, bool all) {
+  PtState* s = h->pt;
+  PtDev& d = s->dev;
+  ModelBatch mb;
+  mb.C = d.Cl;
+  mb.k = proposal ? d.pk : d.k; mb.z = proposal ? d.pz : d.z; mb.dvp = proposal ? d.pdvp : d.dvp;
+  mb.dvs = proposal ? d.pdvs : d.dvs; mb.sig = proposal ? d.psig : d.sig;
+  mb.active = all ? nullptr : d.active; mb.n_active = all ? 0 : d.Cl; mb.n_active_dev = all ? nullptr : d.n_active;
+  EvalOutputs out;
+  out.misfit = h->d_misfit; out.rft_smp = d.rft_smp[0]; out.rft_smp_alt = d.rft_smp[1]; out.slot = d.slot;
+  out.slot_invert = proposal ? 1 : 0; out.rft_full = nullptr; out.is_valid = nullptr;
+  int st;
+  if ((st = rfinv_launch_forward(h->dc, mb, out, h->d_scratch, h->stream)) != RFINV_OK) return st;
+  return rfinv_launch_quadform(h->dc, d.Cl, h->d_misfit, proposal ? d.pphi : d.phi, mb.active, mb.n_active, mb.n_active_dev,
+                               h->stream);
+}
+
+extern "C" {
+
+int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, int32_t rank_count) {
+  if (!h) { rfinv_set_error("rfinv_pt_init: handle is NULL"); return RFINV_ERR_ARG; }
+  const rfinv_config& c = h->cfg;
+  if (nproc_total < 1 || rank_begin < 0 || rank_count < 1 || rank_begin + rank_count > nproc_total ||
+      (rank_begin % rank_count) != 0 || (nproc_total % rank_count) != 0) {
+    rfinv_set_error("rfinv_pt_init: ranks must be split evenly: nproc_total=%d rank_begin=%d rank_count=%d", nproc_total,
+                    rank_begin, rank_count);
+    return RFINV_ERR_ARG;
+  }
+  if (c.nchains < 1 || c.ncool < 0 || c.ncool > c.nchains || (c.prior_mode != 1 && c.prior_mode != 2)) {
+    rfinv_set_error("rfinv_pt_init: need 0 <= ncool <= nchains, nchains >= 1, prior_mode 1 or 2");
+    return RFINV_ERR_ARG;
+  }
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  h->free_pt();
+  PtState* s = new PtState();
+  h->pt = s;
+  PtDev& d = s->dev;
+  std::memset(&d, 0, sizeof(d));
+  const int km = c.k_max, T = c.ntrc, S = c.nsmp;
+  d.nproc_total = nproc_total; d.rank_begin = rank_begin; d.G = rank_count; d.nchains = c.nchains; d.Cl = rank_count * c.nchains;
+  d.ncool = c.ncool; d.iseed = c.iseed; d.t_high = c.t_high;
+  d.dev_z = c.dev_z; d.dev_dvs = c.dev_dvs; d.dev_dvp = c.dev_dvp; d.dev_sig = c.dev_sig;
+  d.dvs_prior = c.dvs_prior; d.dvp_prior = c.dvp_prior;
+  // proposal types, src/pt_mcmc.f90:311-365
+  d.ntype = 4; d.it_birth = 1; d.it_death = 2; d.it_z = 3; d.it_dvs = 4;
+  if (c.vp_mode == 1) { d.ntype++; d.it_dvp = d.ntype; } else d.it_dvp = -1;
+  d.nsig_trc = 0;
+  for (int t = 0; t < T; ++t) {
+    d.sig_min[t] = c.sig_min[t]; d.sig_max[t] = c.sig_max[t];
+    d.sig_mode[t] = (c.sig_max[t] - c.sig_min[t] > (double)1.0e-5f) ? 1 : 0;  // src/params.f90:262
+    if (d.sig_mode[t]) d.isig_trc[d.nsig_trc++] = t;
+  }
+  if (d.nsig_trc > 0) { d.ntype++; d.it_sig = d.ntype; } else d.it_sig = -1;
+  const size_t Cl = d.Cl, G = d.G;
+  int st;
+#define A(x) if ((st = (x)) != RFINV_OK) { h->free_pt(); return st; }
+  A(dalloc(&d.mt, 624 * G)); A(dalloc(&d.mti, G));
+  A(dalloc(&d.k, Cl)); A(dalloc(&d.z, Cl * (km - 1))); A(dalloc(&d.dvp, Cl * km)); A(dalloc(&d.dvs, Cl * km));
+  A(dalloc(&d.sig, Cl * T)); A(dalloc(&d.logl, Cl)); A(dalloc(&d.temps, Cl)); A(dalloc(&d.phi, Cl * T)); A(dalloc(&d.slot, Cl));
+  A(dalloc(&d.rft_smp[0], Cl * T * S)); A(dalloc(&d.rft_smp[1], Cl * T * S));
+  A(dalloc(&d.pk, Cl)); A(dalloc(&d.pz, Cl * (km - 1))); A(dalloc(&d.pdvp, Cl * km)); A(dalloc(&d.pdvs, Cl * km));
+  A(dalloc(&d.psig, Cl * T)); A(dalloc(&d.pphi, Cl * T)); A(dalloc(&d.log_r, Cl)); A(dalloc(&d.log_prior12, Cl));
+  A(dalloc(&d.itype, Cl)); A(dalloc(&d.pflag, Cl)); A(dalloc(&d.active, Cl)); A(dalloc(&d.n_active, 1));
+  A(dalloc(&d.nprop, 8)); A(dalloc(&d.naccept, 8)); A(dalloc(&d.n_eval, 1));
+  s->table_len = (int)(2 * Cl + G + 2);
+  A(dalloc(&s->d_table, (size_t)s->table_len));
+  s->cap_lhist = c.nburn + c.niter > 0 ? c.nburn + c.niter : 1024;
+  A(dalloc(&s->d_lhist, (size_t)s->cap_lhist));
+  A(h->ensure_capacity(d.Cl));
+#undef A
+  pt_init_kernel<<<(d.G + 63) / 64, 64, 0, h->stream>>>(h->dc, d);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  // init_rft, src/likelihood.f90:143-163: forward + likelihood of every initial model
+  if ((st = pt_eval(h, /*proposal=*/false, /*all=*/true)) != RFINV_OK) return st;
+  if ((st = rfinv_launch_loglik(h->dc, d.Cl, d.phi, d.sig, d.logl, h->stream)) != RFINV_OK) return st;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  s->it_done = 0;
+  s->n_eval = d.Cl;
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_ntype(rfinv_handle* h) { return (h && h->pt) ? h->pt->dev.ntype : -1; }
+
+int32_t rfinv_pt_set_logging(rfinv_handle* h, int32_t cap_iters) {
+  int st = pt_require(h, "rfinv_pt_set_logging");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  PtDev& d = s->dev;
+  cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
+  d.log_flags = nullptr; d.log_itypes = nullptr; d.log_swaps = nullptr;
+  s->log_cap = 0; s->log_used = 0;
+  if (cap_iters > 0) {
+    if ((st = dalloc(&d.log_flags, (size_t)cap_iters * d.Cl)) != RFINV_OK) return st;
+    if ((st = dalloc(&d.log_itypes, (size_t)cap_iters * d.Cl)) != RFINV_OK) return st;
+    if ((st = dalloc(&d.log_swaps, (size_t)cap_iters * 3)) != RFINV_OK) return st;
+    s->log_cap = cap_iters;
+  }
+  return RFINV_OK;
+}
+
+// Everything of one iteration except the swap decision: proposal pass, batched evaluation, acceptance,
+// likelihood history, and this process's swap table.
+int32_t rfinv_pt_local_step(rfinv_handle* h) {
+  int st = pt_require(h, "rfinv_pt_local_step");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  PtDev& d = s->dev;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  cudaStream_t q = h->stream;
+  if (s->it_done >= s->cap_lhist) {  // grow the likelihood history
+    double* nl = nullptr;
+    const int ncap = s->cap_lhist * 2;
+    if ((st = dalloc(&nl, (size_t)ncap)) != RFINV_OK) return st;
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(nl, s->d_lhist, sizeof(double) * s->cap_lhist, cudaMemcpyDeviceToDevice, q));
+    RFINV_CUDA_CHECK(cudaStreamSynchronize(q));
+    cudaFree(s->d_lhist);
+    s->d_lhist = nl; s->cap_lhist = ncap;
+  }
+  const int log_slot = (s->log_cap > 0 && s->log_used < s->log_cap) ? s->log_used : -1;
+  pt_propose_kernel<<<(d.G + 63) / 64, 64, 0, q>>>(h->dc, d);
+  pt_compact_kernel<<<1, 1024, 0, q>>>(d);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
+  pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d, log_slot);
+  pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist + s->it_done);
+  pt_table_kernel<<<(d.Cl + 255) / 256, 256, 0, q>>>(d, s->d_table);
+  pt_peek_kernel<<<(d.G + 63) / 64, 64, 0, q>>>(d, s->d_table);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  s->pending_log_slot = log_slot;
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_swap_table(rfinv_handle* h, uint64_t* dev_ptr, int32_t* n_doubles) {
+  int st = pt_require(h, "rfinv_pt_swap_table");
+  if (st != RFINV_OK) return st;
+  if (dev_ptr) *dev_ptr = reinterpret_cast<uint64_t>(h->pt->d_table);
+  if (n_doubles) *n_doubles = h->pt->table_len;
+  return RFINV_OK;
+}
+
+// gathered: `world` tables back to back, in process order (process q owns virtual ranks [q*G, (q+1)*G))
+int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t world) {
+  int st = pt_require(h, "rfinv_pt_apply_swap");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  if (world * s->dev.G != s->dev.nproc_total) {
+    rfinv_set_error("rfinv_pt_apply_swap: world=%d inconsistent with nproc_total=%d, rank_count=%d", world, s->dev.nproc_total, s->dev.G);
+    return RFINV_ERR_ARG;
+  }
+  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len,
+                                          s->pending_log_slot);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  if (s->pending_log_slot >= 0) s->log_used++;
+  s->it_done++;
+  return RFINV_OK;
+}
+
+// single-process run: pt_control's loop (src/pt_mcmc.f90:488-572)
+int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter) {
+  int st = pt_require(h, "rfinv_pt_run");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  if (s->dev.G != s->dev.nproc_total) {
+    rfinv_set_error("rfinv_pt_run: this handle holds %d of %d ranks; drive rfinv_pt_local_step/apply_swap instead", s->dev.G,
+                    s->dev.nproc_total);
+    return RFINV_ERR_STATE;
+  }
+  for (int it = 0; it < n_iter; ++it) {
+    if ((st = rfinv_pt_local_step(h)) != RFINV_OK) return st;
+    if ((st = rfinv_pt_apply_swap(h, reinterpret_cast<uint64_t>(s->d_table), 1)) != RFINV_OK) return st;
+  }
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_get_state(rfinv_handle* h, int32_t* k, double* z, double* dvp, double* dvs, double* sig, double* logl,
+                           double* temps) {
+  int st = pt_require(h, "rfinv_pt_get_state");
+  if (st != RFINV_OK) return st;
+  PtDev& d = h->pt->dev;
+  const int km = h->cfg.k_max, T = h->cfg.ntrc, Cl = d.Cl;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  std::vector<double> tmp;
+  auto fetch = [&](const double* src, double* dst, int len) -> int {  // device [len][Cl] -> host [Cl][len]
+    if (!dst) return RFINV_OK;
+    tmp.resize((size_t)len * Cl);
+    RFINV_CUDA_CHECK(cudaMemcpy(tmp.data(), src, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < len; ++i)
+      for (int c = 0; c < Cl; ++c) dst[(size_t)c * len + i] = tmp[(size_t)i * Cl + c];
+    return RFINV_OK;
+  };
+  if (k) RFINV_CUDA_CHECK(cudaMemcpy(k, d.k, sizeof(int) * Cl, cudaMemcpyDeviceToHost));
+  if ((st = fetch(d.z, z, km - 1)) != RFINV_OK) return st;
+  if ((st = fetch(d.dvp, dvp, km)) != RFINV_OK) return st;
+  if ((st = fetch(d.dvs, dvs, km)) != RFINV_OK) return st;
+  if ((st = fetch(d.sig, sig, T)) != RFINV_OK) return st;
+  if (logl) RFINV_CUDA_CHECK(cudaMemcpy(logl, d.logl, sizeof(double) * Cl, cudaMemcpyDeviceToHost));
+  if (temps) RFINV_CUDA_CHECK(cudaMemcpy(temps, d.temps, sizeof(double) * Cl, cudaMemcpyDeviceToHost));
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_get_counters(rfinv_handle* h, int64_t* nprop, int64_t* naccept, double* likelihood_hist, int32_t n_hist,
+                              int64_t* n_eval) {
+  int st = pt_require(h, "rfinv_pt_get_counters");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (nprop) RFINV_CUDA_CHECK(cudaMemcpy(nprop, s->dev.nprop, sizeof(int64_t) * s->dev.ntype, cudaMemcpyDeviceToHost));
+  if (naccept) RFINV_CUDA_CHECK(cudaMemcpy(naccept, s->dev.naccept, sizeof(int64_t) * s->dev.ntype, cudaMemcpyDeviceToHost));
+  if (likelihood_hist && n_hist > 0) {
+    const int n = n_hist < s->it_done ? n_hist : s->it_done;
+    RFINV_CUDA_CHECK(cudaMemcpy(likelihood_hist, s->d_lhist, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  }
+  if (n_eval) {
+    unsigned long long ne = 0;
+    RFINV_CUDA_CHECK(cudaMemcpy(&ne, s->dev.n_eval, sizeof(ne), cudaMemcpyDeviceToHost));
+    *n_eval = s->n_eval + (long long)ne;
+  }
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_iterations_done(rfinv_handle* h) { return (h && h->pt) ? h->pt->it_done : -1; }
+
+int32_t rfinv_pt_get_log(rfinv_handle* h, int8_t* flags, int8_t* itypes, int32_t* swaps, int32_t* n_logged) {
+  int st = pt_require(h, "rfinv_pt_get_log");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  const size_t n = (size_t)s->log_used * s->dev.Cl;
+  if (flags && n) RFINV_CUDA_CHECK(cudaMemcpy(flags, s->dev.log_flags, n, cudaMemcpyDeviceToHost));
+  if (itypes && n) RFINV_CUDA_CHECK(cudaMemcpy(itypes, s->dev.log_itypes, n, cudaMemcpyDeviceToHost));
+  if (swaps && s->log_used) RFINV_CUDA_CHECK(cudaMemcpy(swaps, s->dev.log_swaps, sizeof(int32_t) * 3 * s->log_used, cudaMemcpyDeviceToHost));
+  if (n_logged) *n_logged = s->log_used;
+  return RFINV_OK;
+}
+
+}  // extern "C"

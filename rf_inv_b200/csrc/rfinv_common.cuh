@@ -38,7 +38,8 @@ struct ModelBatch {
   const double* dvs;            // [k_max][C]
   const double* sig;            // [ntrc][C]
   const int* active;            // optional list of model indices to evaluate (nullptr = all)
-  int n_active;
+  int n_active;                 // length of `active` (upper bound when n_active_dev is set)
+  const int* n_active_dev;      // optional: actual length of `active`, resident on device (grids are sized by n_active)
 };
 
 // Fortran NINT (round half away from zero)
@@ -87,6 +88,9 @@ void rfinv_set_error(const char* fmt, ...);
 struct EvalOutputs {
   double* misfit;     // [ntrc][C][nsmp_pad]  rft(1:nsmp) - obs, zero padded          (required)
   double* rft_smp;    // [ntrc][C][nsmp]      first nsmp samples of the RF (optional)
+  double* rft_smp_alt;  // second buffer of the same shape: model c writes to (slot[c] ^ slot_invert) ? alt : rft_smp
+  const uint8_t* slot;  // optional, with rft_smp_alt
+  int slot_invert;
   double* rft_full;   // [C][ntrc][nfft]      complete RF, the reference's prop_rft (optional)
   uint8_t* is_valid;  // [C]                  format_model's flag (optional)
 };
@@ -96,7 +100,7 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
                          cudaStream_t stream);
 // phi[ntrc][C] = m^T R^-1 m per trace and model
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
-                          int n_active, cudaStream_t stream);
+                          int n_active, const int* n_active_dev, cudaStream_t stream);
 // logl[c] = sum_t -0.5 phi/sig^2 - nsmp log(sig)   (src/likelihood.f90:94-96)
 int rfinv_launch_loglik(const DevConfig& cfg, int C, const double* phi, const double* sig, double* logl,
                         cudaStream_t stream);

@@ -1,0 +1,41 @@
+// Device-resident parallel-tempering state (pt.cu).
+#pragma once
+#include "rfinv_common.cuh"
+
+// Passed to the PT kernels by value.  Arrays are chain-fastest: x[i*Cl + c].
+struct PtDev {
+  int nproc_total, rank_begin, G, nchains, Cl, ncool, iseed;
+  int ntype, it_birth, it_death, it_z, it_dvs, it_dvp, it_sig, nsig_trc;
+  int isig_trc[RFINV_MAX_TRC], sig_mode[RFINV_MAX_TRC];
+  double sig_min[RFINV_MAX_TRC], sig_max[RFINV_MAX_TRC];
+  double t_high, dev_z, dev_dvs, dev_dvp, dev_sig, dvs_prior, dvp_prior;
+  // mt19937 streams, one per virtual rank: mt[i*G + r]
+  uint32_t* mt;
+  int* mti;
+  // current state
+  int* k;
+  double *z, *dvp, *dvs, *sig, *logl, *temps, *phi;   // [k_max-1|k_max|k_max|ntrc][Cl], [Cl], [Cl], [ntrc][Cl]
+  uint8_t* slot;                                      // which rft_smp buffer holds the current RF of chain c
+  double* rft_smp[2];                                 // [ntrc][Cl][nsmp] x 2 (current / proposal, selected by slot)
+  // proposal
+  int* pk;
+  double *pz, *pdvp, *pdvs, *psig, *pphi, *log_r, *log_prior12;
+  int8_t *itype, *pflag;                              // pflag: -1 null proposal, 1 forward needed, 2 cached RF
+  int* active;                                        // compacted list of chains with pflag == 1
+  int* n_active;
+  unsigned long long *nprop, *naccept, *n_eval;       // counters of the non-tempered chains; evaluations executed
+  // optional per-iteration logs (tests)
+  int8_t *log_flags, *log_itypes;
+  int32_t* log_swaps;
+};
+
+struct PtState {
+  PtDev dev;
+  int it_done = 0;
+  int cap_lhist = 0;
+  double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
+  double* d_table = nullptr;   // swap table of this process
+  int table_len = 0;
+  int log_cap = 0, log_used = 0, pending_log_slot = -1;
+  long long n_eval = 0;
+};

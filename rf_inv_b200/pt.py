@@ -1,0 +1,112 @@
+"""Host driver of the device-resident parallel-tempering MCMC (mirror of pt_control, src/pt_mcmc.f90:468-576).
+
+Single GPU: ``ParallelTempering(cfg, nproc).run(n)``.  Several GPUs (one process per GPU, torch.distributed):
+virtual ranks are split contiguously over processes; per iteration each process runs ``local_step`` and the
+swap tables -- per-chain (temperature, logL) pairs plus the pair-selection draws -- are exchanged with ONE
+all-gather (NCCL over NVLink on GPUs); every process then evaluates the same swap decision.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import capi
+from .config import RFConfig
+from .evaluator import Evaluator, _p
+
+
+def split_ranks(nproc_total: int, world: int, rank: int):
+    """Contiguous, even split of the virtual ranks over processes: (rank_begin, rank_count)."""
+    if nproc_total % world != 0:
+        raise ValueError(f"nproc_total={nproc_total} must be divisible by the number of processes {world}")
+    per = nproc_total // world
+    return rank * per, per
+
+
+class ParallelTempering:
+    def __init__(self, cfg: RFConfig, nproc_total: int, device: int = 0, world: int = 1, rank: int = 0,
+                 evaluator: Optional[Evaluator] = None):
+        self.cfg = cfg
+        self.nproc_total = nproc_total
+        self.world, self.rank = world, rank
+        self.rank_begin, self.rank_count = split_ranks(nproc_total, world, rank)
+        self.ev = evaluator or Evaluator(cfg, device=device)
+        self._lib = self.ev._lib
+        capi.check(self._lib.rfinv_pt_init(self.ev.handle, nproc_total, self.rank_begin, self.rank_count))
+        self.n_local = self.rank_count * cfg.nchains
+        self.ntype = int(self._lib.rfinv_pt_ntype(self.ev.handle))
+        self._gather_buf = None
+
+    def close(self):
+        self.ev.close()
+
+    # -- single process ---------------------------------------------------------------------------
+    def run(self, n_iter: int) -> None:
+        if self.world != 1:
+            raise RuntimeError("run() is the single-process driver; use run_distributed()")
+        capi.check(self._lib.rfinv_pt_run(self.ev.handle, int(n_iter)))
+
+    # -- one process per GPU ----------------------------------------------------------------------
+    def swap_table(self):
+        ptr, n = C.c_uint64(0), C.c_int32(0)
+        capi.check(self._lib.rfinv_pt_swap_table(self.ev.handle, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def run_distributed(self, n_iter: int, dist, torch) -> None:
+        """pt_control with the per-iteration exchange done by torch.distributed (NCCL all-gather)."""
+        ptr, n = self.swap_table()
+        dev = torch.device("cuda", self.ev.device)
+        if self._gather_buf is None:
+            self._gather_buf = torch.empty(self.world * n, dtype=torch.float64, device=dev)
+        # zero-copy view of the library's table
+        table = _tensor_from_ptr(torch, ptr, n, dev)
+        for _ in range(n_iter):
+            capi.check(self._lib.rfinv_pt_local_step(self.ev.handle))
+            dist.all_gather_into_tensor(self._gather_buf, table)
+            capi.check(self._lib.rfinv_pt_apply_swap(self.ev.handle, self._gather_buf.data_ptr(), self.world))
+        self.ev.synchronize()
+
+    # -- results ----------------------------------------------------------------------------------
+    def set_logging(self, cap_iters: int) -> None:
+        capi.check(self._lib.rfinv_pt_set_logging(self.ev.handle, int(cap_iters)))
+
+    @property
+    def iterations_done(self) -> int:
+        return int(self._lib.rfinv_pt_iterations_done(self.ev.handle))
+
+    def state(self) -> Dict[str, np.ndarray]:
+        cfg, n = self.cfg, self.n_local
+        out = dict(k=np.empty(n, dtype=np.int32), z=np.empty((n, cfg.k_max - 1)), dvp=np.empty((n, cfg.k_max)),
+                   dvs=np.empty((n, cfg.k_max)), sig=np.empty((n, cfg.ntrc)), logl=np.empty(n), temps=np.empty(n))
+        capi.check(self._lib.rfinv_pt_get_state(self.ev.handle, _p(out["k"], capi.i32p), _p(out["z"], capi.dp),
+                                                _p(out["dvp"], capi.dp), _p(out["dvs"], capi.dp), _p(out["sig"], capi.dp),
+                                                _p(out["logl"], capi.dp), _p(out["temps"], capi.dp)))
+        return out
+
+    def counters(self) -> Dict[str, np.ndarray]:
+        n_it = self.iterations_done
+        nprop = np.zeros(self.ntype, dtype=np.int64); nacc = np.zeros(self.ntype, dtype=np.int64)
+        hist = np.zeros(max(n_it, 1)); n_eval = C.c_int64(0)
+        capi.check(self._lib.rfinv_pt_get_counters(self.ev.handle, _p(nprop, capi.i64p), _p(nacc, capi.i64p),
+                                                   _p(hist, capi.dp), n_it, C.byref(n_eval)))
+        return dict(nprop=nprop, naccept=nacc, likelihood_hist=hist[:n_it], n_eval=n_eval.value)
+
+    def log(self, cap_iters: int):
+        flags = np.zeros((cap_iters, self.n_local), dtype=np.int8)
+        itypes = np.zeros((cap_iters, self.n_local), dtype=np.int8)
+        swaps = np.zeros((cap_iters, 3), dtype=np.int32)
+        n = C.c_int32(0)
+        capi.check(self._lib.rfinv_pt_get_log(self.ev.handle, _p(flags, capi.i8p), _p(itypes, capi.i8p),
+                                              _p(swaps, capi.i32p), C.byref(n)))
+        return flags[:n.value], itypes[:n.value], swaps[:n.value]
+
+
+def _tensor_from_ptr(torch, ptr: int, n: int, dev):
+    """float64 torch view of `n` doubles of device memory owned by the library (no copy)."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(h, device=dev)
