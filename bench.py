@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--chains", type=int, default=0, help="models per GPU per step")
     ap.add_argument("--cpu-sample", type=int, default=0, help="models in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pt-iters", type=int, default=20, help="timed PT-MCMC iterations (0 = skip the PT leg)")
     return ap.parse_args()
 
 
@@ -252,6 +253,43 @@ def main():
     e2e_value = world * chains * args.steps / e2e_total
     assert np.array_equal(ll_host, logl.cpu().numpy()), "host and device entry points disagree"
 
+    # ---- PT-MCMC leg: iterations/s of pt_control with every chain on device (second half of BASELINE.json's metric) ----
+    pt_info = None
+    if args.pt_iters > 0:
+        from rf_inv_b200.pt import ParallelTempering
+        nch = cfg.nchains
+        nproc_total = world * max(1, chains // nch)
+        pt = ParallelTempering(cfg, nproc_total, device=local_rank, world=world, rank=rank)
+        pt.ev.set_stream(stream.cuda_stream)
+
+        def pt_iters(n):
+            if world == 1:
+                pt.run(n)
+            else:
+                pt.run_distributed(n, dist, torch)
+
+        pt_iters(3)
+        barrier()
+        n_eval0 = pt.counters()["n_eval"]
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        pt_iters(args.pt_iters)
+        e1.record(stream)
+        e1.synchronize()
+        pt_ms = e0.elapsed_time(e1)
+        n_eval = pt.counters()["n_eval"] - n_eval0
+        k_pt = float(np.mean(pt.state()["k"]))
+        tt = torch.tensor([pt_ms, float(n_eval)], dtype=torch.float64, device=dev)
+        if world > 1:
+            mx = tt.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tt.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            pt_ms, n_eval = float(mx[0].item()), float(sm[1].item())
+        pt_info = {"iters_per_s": args.pt_iters / (pt_ms * 1e-3), "chain_steps_per_s": world * pt.n_local * args.pt_iters / (pt_ms * 1e-3),
+                   "forward_evals_per_s": n_eval / (pt_ms * 1e-3), "iters": args.pt_iters, "chains_total": world * pt.n_local,
+                   "virtual_ranks": nproc_total, "chains_per_rank": nch, "k_mean_after": round(k_pt, 2),
+                   "exchange": "none (single process)" if world == 1 else "one NCCL all-gather of (T, logL, next-uniform) tables per iteration"}
+        pt.close()
+
     if rank == 0:
         # ---- roofline of the dominant kernel (forward_kernel): algorithmic fp64 flop / CUDA-event time ----
         dfma, dmma = C.c_double(0), C.c_double(0)
@@ -277,6 +315,7 @@ def main():
                          "flop_per_eval": fl, "kernel_ms": {"forward": km[0], "quadform": km[1], "loglik": km[2]},
                          "quadform_tflops": qf_achieved, "whole_step_tflops": whole, "whole_step_frac": whole / peak},
             "wall_s_timed_region": t_wall,
+            "pt": pt_info,
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))

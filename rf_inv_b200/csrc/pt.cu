@@ -29,6 +29,7 @@ struct Mt {
   __device__ Mt(uint32_t* base, int G, int r, int mti_) : mt(base + r), stride(G), mti(mti_) {}
   __device__ uint32_t& w(int i) { return mt[(size_t)i * stride]; }
   __device__ void reload() {  // src/mt19937.f90:96-116
+#pragma unroll 8
     for (int kk = 0; kk < 624; ++kk) {
       const uint32_t y = (w(kk) & 0x80000000u) | (w(kk == 623 ? 0 : kk + 1) & 0x7fffffffu);
       w(kk) = w(kk + 397 < 624 ? kk + 397 : kk + 397 - 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -177,9 +178,13 @@ __global__ void pt_propose_kernel(const DevConfig cfg, const PtDev p) {
   for (int ic = 0; ic < p.nchains; ++ic) {
     const int c = r * p.nchains + ic;
     int pk = p.k[c];
-    for (int i = 0; i < km - 1; ++i) pz[i] = p.z[(size_t)i * Cl + c];
+#pragma unroll 8
+    for (int i = 0; i < km - 1; ++i) pz[i] = __ldg(&p.z[(size_t)i * Cl + c]);
     pz[km - 1] = 0.0;
-    for (int i = 0; i < km; ++i) { pdvp[i] = p.dvp[(size_t)i * Cl + c]; pdvs[i] = p.dvs[(size_t)i * Cl + c]; }
+#pragma unroll 8
+    for (int i = 0; i < km; ++i) pdvp[i] = __ldg(&p.dvp[(size_t)i * Cl + c]);
+#pragma unroll 8
+    for (int i = 0; i < km; ++i) pdvs[i] = __ldg(&p.dvs[(size_t)i * Cl + c]);
     for (int t = 0; t < T; ++t) psig[t] = p.sig[(size_t)t * Cl + c];
     double log_prior12 = 0.0;
     bool null_flag = false;

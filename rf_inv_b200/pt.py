@@ -103,6 +103,30 @@ class ParallelTempering:
         return flags[:n.value], itypes[:n.value], swaps[:n.value]
 
 
+def build_table(temps, logl, peeks, pair=(-1, -1)) -> np.ndarray:
+    """Host-side layout of one process's swap table (what pt_table_kernel / pt_peek_kernel write)."""
+    return np.concatenate([np.asarray(temps, dtype=np.float64), np.asarray(logl, dtype=np.float64),
+                           np.asarray(peeks, dtype=np.float64), np.asarray(pair, dtype=np.float64)])
+
+
+def decode_swap(gathered: np.ndarray, world: int, n_local: int, ranks_local: int, nchains: int):
+    """Host mirror of pt_swap_kernel (judge_pt, src/pt_mcmc.f90:580-595) on the gathered tables; used by the
+    CPU (gloo) tests of the exchange protocol and for diagnostics.  Returns (itarget1, itarget2, accepted,
+    owner1, local1, owner2, local2)."""
+    import math
+    tl = 2 * n_local + ranks_local + 2
+    tabs = np.asarray(gathered, dtype=np.float64).reshape(world, tl)
+    i1, i2 = int(tabs[0, 2 * n_local + ranks_local]), int(tabs[0, 2 * n_local + ranks_local + 1])
+    own1, l1 = divmod(i1, n_local)
+    own2, l2 = divmod(i2, n_local)
+    temp1, temp2 = tabs[own1, l1], tabs[own2, l2]
+    e1, e2 = tabs[own1, n_local + l1], tabs[own2, n_local + l2]
+    u = tabs[own1, 2 * n_local + l1 // nchains]
+    del_s = (e2 - e1) * (1.0 / temp1 - 1.0 / temp2)
+    yn = (math.log(u) if u > 0.0 else -math.inf) <= del_s
+    return i1, i2, bool(yn), own1, l1, own2, l2
+
+
 def _tensor_from_ptr(torch, ptr: int, n: int, dev):
     """float64 torch view of `n` doubles of device memory owned by the library (no copy)."""
     class _Holder:
