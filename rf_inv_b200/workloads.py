@@ -135,12 +135,19 @@ def to_soa(models: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
                 dvs=np.ascontiguousarray(models["dvs"].T), sig=np.ascontiguousarray(models["sig"].T))
 
 
-def flops_per_eval(cfg: RFConfig, k_mean: float, rank_r: Tuple[float, ...] = None) -> Dict[str, float]:
-    """Algorithmic fp64 flop per forward+likelihood evaluation (constants from DESIGN.md):
-    W_min = Tf*nh*(a_l*k + a_0) + T*5*n*log2(n) + sum_t (S^2 + 3S)   [symmetric dense quadratic form]."""
+def flops_per_eval(cfg: RFConfig, k_mean: float) -> Dict[str, float]:
+    """Algorithmic fp64 flop per forward+likelihood evaluation (SURVEY.md 8d's W_min with the
+    constants replaced by an exact count of the structure-exploiting algorithm):
+
+      W = Tf*nh*(95*k + 70) + T*5*n*log2(n) + T*(S^2 + 3*S)
+
+    per layer and frequency: 27 flop for the 10 distinct entries of the real 4x4 propagator (8 two-term
+    combinations + 1 difference + 2 scalings), 56 for two real 4-vector products, 12 to advance the two
+    (cos, sin) pairs by rotation; per frequency: 70 for E^-1 rows, boundary condition, complex division, filter;
+    one packed complex inverse FFT per trace; symmetric quadratic form S(S+1)/2 MAC + row dot."""
     Tf = 1 if cfg.is_ray_common else cfg.ntrc
     n, nh, S, T = cfg.nfft, cfg.nh, cfg.nsmp, cfg.ntrc
-    prop = Tf * nh * (103.0 * k_mean + 60.0)
+    prop = Tf * nh * (95.0 * k_mean + 70.0)
     fft = T * 5.0 * n * np.log2(n)
     quad = T * (1.0 * S * S + 3.0 * S)
     return dict(propagator=prop, fft=fft, quadform=quad, total=prop + fft + quad)
