@@ -177,6 +177,37 @@ int32_t rfinv_pt_iterations_done(rfinv_handle* h);
  * (1-based), swaps[n][3] (itarget1, itarget2, accepted). */
 int32_t rfinv_pt_get_log(rfinv_handle* h, int8_t* flags, int8_t* itypes, int32_t* swaps, int32_t* n_logged);
 
+/* Posterior bookkeeping of the non-tempered chains, recorded every ncorr iterations after nburn
+ * (src/pt_mcmc.f90:204-286); local sums of this handle.  Layouts: nk[k_max], nz[nbin_z], nsig[ntrc][nbin_sig],
+ * namp[ntrc][nsmp][nbin_amp], nvpz[nbin_vp][nbin_z], nvsz[nbin_vs][nbin_z], nvpvsz[nbin_vpvs][nbin_z], *_mean[nbin_z].
+ * Requires cfg.niter > 0 and all nbin_* > 0 at rfinv_pt_init.  Any pointer may be NULL. */
+int32_t rfinv_pt_get_hist(rfinv_handle* h, int64_t* nmod, int64_t* nk, int64_t* nz, int64_t* nsig, int64_t* namp,
+                          int64_t* nvpz, int64_t* nvsz, int64_t* nvpvsz, double* vp_mean, double* vs_mean,
+                          double* vpvs_mean);
+/* Recorded models (all_models): vp_model/vs_model [n_models][nbin_z]. */
+int32_t rfinv_pt_get_models(rfinv_handle* h, int64_t max_models, double* vp_model, double* vs_model, int64_t* n_models);
+
+/* ---- file formats either side of the path (host only, no CUDA) ---------------------------------------
+ * params.in (positional, '#' comment lines; src/params.f90:101-405), SAC traces cut to [T_START, T_END]
+ * (src/params.f90:422-476), reference velocity model (src/model.f90:109-171).                        */
+typedef struct rfinv_problem rfinv_problem;
+int32_t rfinv_problem_load(const char* params_path, const char* base_dir, rfinv_problem** out);
+void rfinv_problem_free(rfinv_problem* p);
+/* The configuration read (pointers owned by the problem; r_inv is NULL). */
+const rfinv_config* rfinv_problem_config(const rfinv_problem* p);
+const char* rfinv_problem_out_dir(const rfinv_problem* p);
+double rfinv_problem_t_end(const rfinv_problem* p);
+/* <out_dir>/params.in.copy and <input_dir>/inputNN, the side outputs of get_params / read_obs. */
+int32_t rfinv_problem_write_copies(const rfinv_problem* p, const char* out_dir, const char* input_dir);
+/* output_results (src/mcmc_out.f90:97-318): writes all_models, likelihood, num_interface.ppd, syn_trace.ppd,
+ * interface_depth.ppd, sigma.ppd, vs_z.ppd, vp_z.ppd, vpvs_z.ppd, vs_z.mean, vp_z.mean, vpvs_z.mean into out_dir
+ * from job-wide sums (the caller reduces over processes, like the reference's mpi_reduce at :52-93). */
+int32_t rfinv_write_outputs(const rfinv_config* c, const char* out_dir, int32_t nproc_total, int64_t nmod, const int64_t* nk,
+                            const int64_t* nz, const int64_t* nsig, const int64_t* namp, const int64_t* nvpz,
+                            const int64_t* nvsz, const int64_t* nvpvsz, const double* vp_mean, const double* vs_mean,
+                            const double* vpvs_mean, const double* likelihood_hist, int32_t n_hist, const double* vp_model,
+                            const double* vs_model, int64_t n_models);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,16 @@ SIGNATURES = {
     "rfinv_pt_get_counters": (C.c_int32, [C.c_void_p, i64p, i64p, dp, C.c_int32, i64p]),
     "rfinv_pt_iterations_done": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_get_log": (C.c_int32, [C.c_void_p, i8p, i8p, i32p, i32p]),
+    "rfinv_pt_get_hist": (C.c_int32, [C.c_void_p, i64p, i64p, i64p, i64p, i64p, i64p, i64p, i64p, dp, dp, dp]),
+    "rfinv_pt_get_models": (C.c_int32, [C.c_void_p, C.c_int64, dp, dp, i64p]),
+    "rfinv_problem_load": (C.c_int32, [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "rfinv_problem_free": (None, [C.c_void_p]),
+    "rfinv_problem_config": (C.POINTER(RfinvConfigC), [C.c_void_p]),
+    "rfinv_problem_out_dir": (C.c_char_p, [C.c_void_p]),
+    "rfinv_problem_t_end": (C.c_double, [C.c_void_p]),
+    "rfinv_problem_write_copies": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "rfinv_write_outputs": (C.c_int32, [C.POINTER(RfinvConfigC), C.c_char_p, C.c_int32, C.c_int64, i64p, i64p, i64p, i64p, i64p,
+                                        i64p, i64p, dp, dp, dp, dp, C.c_int32, dp, dp, C.c_int64]),
 }
 
 _lib = None

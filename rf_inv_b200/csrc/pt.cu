@@ -387,6 +387,136 @@ __global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world,
   }
 }
 
+// ordered numbering of the non-tempered chains (deterministic slot of each recorded model in all_models)
+__global__ void pt_coldscan_kernel(const PtDev p) {
+  __shared__ int s_cnt[1024];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < p.Cl; start += nthr) {
+    const int c = start + tid;
+    const int f = (c < p.Cl && p.temps[c] <= 1.0 + (double)1.0e-6f) ? 1 : 0;
+    s_cnt[tid] = f;
+    __syncthreads();
+    for (int o = 1; o < nthr; o <<= 1) {
+      const int v = tid >= o ? s_cnt[tid - o] : 0;
+      __syncthreads();
+      s_cnt[tid] += v;
+      __syncthreads();
+    }
+    if (c < p.Cl) p.cold_ordinal[c] = f ? s_base + s_cnt[tid] - 1 : -1;
+    __syncthreads();
+    if (tid == nthr - 1) s_base += s_cnt[tid];
+    __syncthreads();
+  }
+  if (tid == 0) *p.cold_count = s_base;
+}
+
+// Posterior bookkeeping of one non-tempered chain per CTA (src/pt_mcmc.f90:204-286).
+__global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
+  const int c = blockIdx.x;
+  const int ord = p.cold_ordinal[c];
+  if (ord < 0) return;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc, S = cfg.nsmp;
+  __shared__ double s_alpha[RFINV_MAX_LAY], s_beta[RFINV_MAX_LAY], s_top[RFINV_MAX_LAY + 1];
+  __shared__ int s_iz1[RFINV_MAX_LAY + 1], s_nlay;
+  const double dbin_amp = (p.amp_max - p.amp_min) / p.nbin_amp, dbin_vp = (cfg.vp_max - cfg.vp_min) / p.nbin_vp;
+  const double dbin_vs = (cfg.vs_max - cfg.vs_min) / p.nbin_vs, dbin_z = (cfg.z_max - 0.0) / p.nbin_z;
+  const double dbin_vpvs = (cfg.vpvs_max - cfg.vpvs_min) / p.nbin_vpvs;
+  const int k = p.k[c];
+  const long long imod = (long long)(*p.nmod) + ord;   // nmod is advanced by pt_record_finish_kernel
+  if (tid == 0) {
+    atomicAdd(&p.nk[k - 1], 1ULL);
+    for (int t = 0; t < T; ++t)
+      if (p.sig_mode[t]) {
+        const double dbs = (p.sig_max[t] - p.sig_min[t]) / p.nbin_sig;
+        const int ibin = (int)((p.sig[(size_t)t * Cl + c] - p.sig_min[t]) / dbs) + 1;
+        if (ibin >= 1 && ibin <= p.nbin_sig) atomicAdd(&p.nsig[(size_t)t * p.nbin_sig + ibin - 1], 1ULL);
+      }
+    for (int il = 1; il <= k - 1; ++il) {  // first k-1 interfaces in stored order (src/pt_mcmc.f90:224-227)
+      const int ibin = (int)((p.z[(size_t)(il - 1) * Cl + c] - cfg.z_min) / dbin_z) + 1;
+      if (ibin >= 1 && ibin <= p.nbin_z) atomicAdd(&p.nz[ibin - 1], 1ULL);
+    }
+    // format_model (src/model.f90:175-290) of the current state
+    double z[RFINV_MAX_K], dp[RFINV_MAX_K], ds[RFINV_MAX_K];
+    for (int i = 0; i < k; ++i) { z[i] = p.z[(size_t)i * Cl + c]; dp[i] = p.dvp[(size_t)i * Cl + c]; ds[i] = p.dvs[(size_t)i * Cl + c]; }
+    for (int i = 1; i < k; ++i) {
+      const double a = z[i], b = dp[i], d = ds[i];
+      int m = i - 1;
+      while (m >= 0 && z[m] > a) { z[m + 1] = z[m]; dp[m + 1] = dp[m]; ds[m + 1] = ds[m]; --m; }
+      z[m + 1] = a; dp[m + 1] = b; ds[m + 1] = d;
+    }
+    int n = 0;
+    double tmpz = 0.0;
+    if (cfg.sdep > 0.0) {
+      s_alpha[n] = 1.5; s_beta[n] = -999.0; s_top[n] = tmpz; s_iz1[n] = (int)(tmpz / dbin_z) + 1;
+      tmpz = __dadd_rn(tmpz, cfg.sdep); ++n;
+    }
+    for (int l = 0; l <= k; ++l) {
+      double zc, h, dvs_l, dvp_l;
+      if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, z[0])); h = __dsub_rn(z[0], cfg.sdep); dvs_l = ds[0]; dvp_l = dp[0]; }
+      else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(z[l], z[l - 1])); h = __dsub_rn(z[l], z[l - 1]); dvs_l = ds[l]; dvp_l = dp[l]; }
+      else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, z[k - 1])); h = 999.0;
+             dvs_l = p.dvs[(size_t)(km - 1) * Cl + c]; dvp_l = p.dvp[(size_t)(km - 1) * Cl + c]; }
+      double a, b;
+      layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
+      s_alpha[n] = a; s_beta[n] = b; s_top[n] = tmpz;
+      s_iz1[n] = (int)(__ddiv_rn(tmpz, dbin_z)) + 1;
+      tmpz = __dadd_rn(tmpz, h);
+      ++n;
+    }
+    s_iz1[n] = p.nbin_z + 1;   // iz2 of the half space (src/pt_mcmc.f90:243)
+    s_nlay = n;
+  }
+  __syncthreads();
+  const int nlay = s_nlay;
+  // each depth bin belongs to exactly one layer: iz1(l) <= iz < iz1(l+1)
+  for (int iz = 1 + tid; iz <= p.nbin_z; iz += nthr) {
+    int l = 0;
+    while (l + 1 < nlay && iz >= s_iz1[l + 1]) ++l;
+    if (iz < s_iz1[l]) continue;
+    const double a = s_alpha[l], b = s_beta[l];
+    int ivp = (int)((a - cfg.vp_min) / dbin_vp) + 1;
+    int ivs = (int)((b - cfg.vs_min) / dbin_vs) + 1;
+    if (ivs < 1) ivs = 1;
+    int ivpvs = (int)(((a / b) - cfg.vpvs_min) / dbin_vpvs) + 1;
+    if (ivpvs < 1) ivpvs = 1;
+    if (ivpvs > p.nbin_vpvs) ivpvs = p.nbin_vpvs;
+    if (ivp > p.nbin_vp) ivp = p.nbin_vp;    // the reference would write out of bounds
+    if (ivp < 1) ivp = 1;
+    if (ivs > p.nbin_vs) ivs = p.nbin_vs;
+    atomicAdd(&p.nvpz[(size_t)(ivp - 1) * p.nbin_z + iz - 1], 1ULL);
+    atomicAdd(&p.vp_mean[iz - 1], a);
+    atomicAdd(&p.nvsz[(size_t)(ivs - 1) * p.nbin_z + iz - 1], 1ULL);
+    atomicAdd(&p.nvpvsz[(size_t)(ivpvs - 1) * p.nbin_z + iz - 1], 1ULL);
+    double vs_rec;
+    if (b > 0.0) {
+      atomicAdd(&p.vpvs_mean[iz - 1], a / b);
+      atomicAdd(&p.vs_mean[iz - 1], b);
+      vs_rec = b;
+    } else {  // src/pt_mcmc.f90:260-263: assignment, not accumulation (ocean layer)
+      p.vpvs_mean[iz - 1] = cfg.vpvs_min;
+      p.vs_mean[iz - 1] = cfg.vs_min;
+      vs_rec = cfg.vs_min;
+    }
+    if (p.vp_model && imod < p.cap_models) {
+      p.vp_model[(size_t)imod * p.nbin_z + iz - 1] = a;
+      p.vs_model[(size_t)imod * p.nbin_z + iz - 1] = vs_rec;
+    }
+  }
+  // RF amplitude histogram (src/pt_mcmc.f90:271-284) from the cached RF samples of the current state
+  const double* rft = p.slot[c] ? p.rft_smp[1] : p.rft_smp[0];
+  for (int i = tid; i < T * S; i += nthr) {
+    const int t = i / S, it = i - t * S;
+    int ibin = (int)((rft[((size_t)t * Cl + c) * S + it] - p.amp_min) / dbin_amp) + 1;
+    if (ibin < 1) ibin = 1; else if (ibin > p.nbin_amp) ibin = p.nbin_amp;
+    atomicAdd(&p.namp[((size_t)t * S + it) * p.nbin_amp + ibin - 1], 1ULL);
+  }
+}
+__global__ void pt_record_finish_kernel(const PtDev p) { *p.nmod += (unsigned long long)*p.cold_count; }
+
 template <typename T>
 int dalloc(T** p, size_t n) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)p, sizeof(T) * (n ? n : 1)));
@@ -405,6 +535,8 @@ void rfinv_handle::free_pt() {
   cudaFree(d.log_prior12); cudaFree(d.itype); cudaFree(d.pflag); cudaFree(d.active); cudaFree(d.n_active);
   cudaFree(d.nprop); cudaFree(d.naccept); cudaFree(d.n_eval);
   cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
+  cudaFree(d.nk); cudaFree(d.nz); cudaFree(d.nsig); cudaFree(d.namp); cudaFree(d.nvpz); cudaFree(d.nvsz); cudaFree(d.nvpvsz); cudaFree(d.nmod);
+  cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count);
   cudaFree(pt->d_lhist); cudaFree(pt->d_table);
   delete pt;
   pt = nullptr;
@@ -481,6 +613,23 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   A(dalloc(&d.psig, Cl * T)); A(dalloc(&d.pphi, Cl * T)); A(dalloc(&d.log_r, Cl)); A(dalloc(&d.log_prior12, Cl));
   A(dalloc(&d.itype, Cl)); A(dalloc(&d.pflag, Cl)); A(dalloc(&d.active, Cl)); A(dalloc(&d.n_active, 1));
   A(dalloc(&d.nprop, 8)); A(dalloc(&d.naccept, 8)); A(dalloc(&d.n_eval, 1));
+  d.nburn = c.nburn; d.ncorr = c.ncorr > 0 ? c.ncorr : 1;
+  d.nbin_z = c.nbin_z; d.nbin_vs = c.nbin_vs; d.nbin_vp = c.nbin_vp; d.nbin_vpvs = c.nbin_vpvs; d.nbin_sig = c.nbin_sig;
+  d.nbin_amp = c.nbin_amp; d.amp_min = c.amp_min; d.amp_max = c.amp_max;
+  s->record = c.nbin_z > 0 && c.nbin_vs > 0 && c.nbin_vp > 0 && c.nbin_vpvs > 0 && c.nbin_sig > 0 && c.nbin_amp > 0 && c.niter > 0;
+  if (s->record) {
+    A(dalloc(&d.nk, (size_t)km)); A(dalloc(&d.nz, (size_t)c.nbin_z)); A(dalloc(&d.nsig, (size_t)c.nbin_sig * T));
+    A(dalloc(&d.namp, (size_t)c.nbin_amp * S * T)); A(dalloc(&d.nvpz, (size_t)c.nbin_z * c.nbin_vp));
+    A(dalloc(&d.nvsz, (size_t)c.nbin_z * c.nbin_vs)); A(dalloc(&d.nvpvsz, (size_t)c.nbin_z * c.nbin_vpvs)); A(dalloc(&d.nmod, 1));
+    A(dalloc(&d.vp_mean, (size_t)c.nbin_z)); A(dalloc(&d.vs_mean, (size_t)c.nbin_z)); A(dalloc(&d.vpvs_mean, (size_t)c.nbin_z));
+    A(dalloc(&d.cold_ordinal, Cl)); A(dalloc(&d.cold_count, 1));
+    // all_models: the reference allocates nbin_z x (nchains*niter/ncorr) per rank (src/pt_mcmc.f90:405-406)
+    const long long want = (long long)(c.niter / d.ncorr) * (long long)Cl;
+    if (want > 0 && (double)want * c.nbin_z * 16.0 <= 8.0e9) {
+      d.cap_models = want;
+      A(dalloc(&d.vp_model, (size_t)want * c.nbin_z)); A(dalloc(&d.vs_model, (size_t)want * c.nbin_z));
+    }
+  }
   s->table_len = (int)(2 * Cl + G + 2);
   A(dalloc(&s->d_table, (size_t)s->table_len));
   s->cap_lhist = c.nburn + c.niter > 0 ? c.nburn + c.niter : 1024;
@@ -542,6 +691,14 @@ int32_t rfinv_pt_local_step(rfinv_handle* h) {
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
   pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d, log_slot);
   pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist + s->it_done);
+  {
+    const int it = s->it_done + 1;  // 1-based iteration number (src/pt_mcmc.f90:204-205)
+    if (s->record && it > d.nburn && it % d.ncorr == 0) {
+      pt_coldscan_kernel<<<1, 1024, 0, q>>>(d);
+      pt_record_kernel<<<d.Cl, 128, 0, q>>>(h->dc, d);
+      pt_record_finish_kernel<<<1, 1, 0, q>>>(d);
+    }
+  }
   pt_table_kernel<<<(d.Cl + 255) / 256, 256, 0, q>>>(d, s->d_table);
   pt_peek_kernel<<<(d.G + 63) / 64, 64, 0, q>>>(d, s->d_table);
   RFINV_CUDA_CHECK(cudaGetLastError());
@@ -635,6 +792,45 @@ int32_t rfinv_pt_get_counters(rfinv_handle* h, int64_t* nprop, int64_t* naccept,
     RFINV_CUDA_CHECK(cudaMemcpy(&ne, s->dev.n_eval, sizeof(ne), cudaMemcpyDeviceToHost));
     *n_eval = s->n_eval + (long long)ne;
   }
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_get_hist(rfinv_handle* h, int64_t* nmod, int64_t* nk, int64_t* nz, int64_t* nsig, int64_t* namp,
+                          int64_t* nvpz, int64_t* nvsz, int64_t* nvpvsz, double* vp_mean, double* vs_mean,
+                          double* vpvs_mean) {
+  int st = pt_require(h, "rfinv_pt_get_hist");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  if (!s->record) { rfinv_set_error("rfinv_pt_get_hist: bookkeeping disabled (needs niter > 0 and all nbin_* > 0)"); return RFINV_ERR_STATE; }
+  const rfinv_config& c = h->cfg;
+  PtDev& d = s->dev;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+#define G64(dst, src, n) if (dst) RFINV_CUDA_CHECK(cudaMemcpy(dst, src, sizeof(int64_t) * (size_t)(n), cudaMemcpyDeviceToHost))
+#define GD(dst, src, n) if (dst) RFINV_CUDA_CHECK(cudaMemcpy(dst, src, sizeof(double) * (size_t)(n), cudaMemcpyDeviceToHost))
+  G64(nmod, d.nmod, 1); G64(nk, d.nk, c.k_max); G64(nz, d.nz, c.nbin_z); G64(nsig, d.nsig, c.nbin_sig * c.ntrc);
+  G64(namp, d.namp, (size_t)c.nbin_amp * c.nsmp * c.ntrc); G64(nvpz, d.nvpz, c.nbin_z * c.nbin_vp);
+  G64(nvsz, d.nvsz, c.nbin_z * c.nbin_vs); G64(nvpvsz, d.nvpvsz, c.nbin_z * c.nbin_vpvs);
+  GD(vp_mean, d.vp_mean, c.nbin_z); GD(vs_mean, d.vs_mean, c.nbin_z); GD(vpvs_mean, d.vpvs_mean, c.nbin_z);
+#undef G64
+#undef GD
+  return RFINV_OK;
+}
+
+// recorded models (all_models): vp_model/vs_model [n_models][nbin_z]; n_models = min(nmod, capacity)
+int32_t rfinv_pt_get_models(rfinv_handle* h, int64_t max_models, double* vp_model, double* vs_model, int64_t* n_models) {
+  int st = pt_require(h, "rfinv_pt_get_models");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  PtDev& d = s->dev;
+  if (!s->record || !d.vp_model) { if (n_models) *n_models = 0; return RFINV_OK; }
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  unsigned long long nm = 0;
+  RFINV_CUDA_CHECK(cudaMemcpy(&nm, d.nmod, sizeof(nm), cudaMemcpyDeviceToHost));
+  long long n = (long long)nm < d.cap_models ? (long long)nm : d.cap_models;
+  if (n > max_models) n = max_models;
+  if (n > 0 && vp_model) RFINV_CUDA_CHECK(cudaMemcpy(vp_model, d.vp_model, sizeof(double) * (size_t)n * d.nbin_z, cudaMemcpyDeviceToHost));
+  if (n > 0 && vs_model) RFINV_CUDA_CHECK(cudaMemcpy(vs_model, d.vs_model, sizeof(double) * (size_t)n * d.nbin_z, cudaMemcpyDeviceToHost));
+  if (n_models) *n_models = n;
   return RFINV_OK;
 }
 

@@ -24,6 +24,14 @@ struct PtDev {
   int* active;                                        // compacted list of chains with pflag == 1
   int* n_active;
   unsigned long long *nprop, *naccept, *n_eval;       // counters of the non-tempered chains; evaluations executed
+  // posterior bookkeeping of the non-tempered chains (src/pt_mcmc.f90:204-286); layouts as in rfinv_pt_get_hist
+  int nburn, ncorr, nbin_z, nbin_vs, nbin_vp, nbin_vpvs, nbin_sig, nbin_amp;
+  double amp_min, amp_max;
+  unsigned long long *nk, *nz, *nsig, *namp, *nvpz, *nvsz, *nvpvsz, *nmod;
+  double *vp_mean, *vs_mean, *vpvs_mean;
+  double *vp_model, *vs_model;                        // [cap_models][nbin_z] (all_models), may be null
+  long long cap_models;
+  int *cold_ordinal, *cold_count;                     // ordered numbering of the chains recorded this iteration
   // optional per-iteration logs (tests)
   int8_t *log_flags, *log_itypes;
   int32_t* log_swaps;
@@ -38,4 +46,5 @@ struct PtState {
   int table_len = 0;
   int log_cap = 0, log_used = 0, pending_log_slot = -1;
   long long n_eval = 0;
+  bool record = false;
 };

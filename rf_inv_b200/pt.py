@@ -93,6 +93,28 @@ class ParallelTempering:
                                                    _p(hist, capi.dp), n_it, C.byref(n_eval)))
         return dict(nprop=nprop, naccept=nacc, likelihood_hist=hist[:n_it], n_eval=n_eval.value)
 
+    def hist(self) -> Dict[str, np.ndarray]:
+        """Posterior bookkeeping of the local non-tempered chains (src/pt_mcmc.f90:204-286)."""
+        c = self.cfg
+        o = dict(nk=np.zeros(c.k_max, np.int64), nz=np.zeros(c.nbin_z, np.int64), nsig=np.zeros((c.ntrc, c.nbin_sig), np.int64),
+                 namp=np.zeros((c.ntrc, c.nsmp, c.nbin_amp), np.int64), nvpz=np.zeros((c.nbin_vp, c.nbin_z), np.int64),
+                 nvsz=np.zeros((c.nbin_vs, c.nbin_z), np.int64), nvpvsz=np.zeros((c.nbin_vpvs, c.nbin_z), np.int64),
+                 vp_mean=np.zeros(c.nbin_z), vs_mean=np.zeros(c.nbin_z), vpvs_mean=np.zeros(c.nbin_z))
+        nmod = C.c_int64(0)
+        capi.check(self._lib.rfinv_pt_get_hist(self.ev.handle, C.byref(nmod), *[_p(o[n], capi.i64p) for n in
+                                               ("nk", "nz", "nsig", "namp", "nvpz", "nvsz", "nvpvsz")],
+                                               *[_p(o[n], capi.dp) for n in ("vp_mean", "vs_mean", "vpvs_mean")]))
+        o["nmod"] = int(nmod.value)
+        return o
+
+    def models(self):
+        """Recorded models of the local non-tempered chains: (vp_model, vs_model) [n_models][nbin_z] (all_models)."""
+        cap = max(1, (self.cfg.niter // max(self.cfg.ncorr, 1)) * self.n_local)
+        vp = np.zeros((cap, self.cfg.nbin_z)); vs = np.zeros((cap, self.cfg.nbin_z))
+        n = C.c_int64(0)
+        capi.check(self._lib.rfinv_pt_get_models(self.ev.handle, cap, _p(vp, capi.dp), _p(vs, capi.dp), C.byref(n)))
+        return vp[:n.value], vs[:n.value]
+
     def log(self, cap_iters: int):
         flags = np.zeros((cap_iters, self.n_local), dtype=np.int8)
         itypes = np.zeros((cap_iters, self.n_local), dtype=np.int8)

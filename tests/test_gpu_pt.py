@@ -122,3 +122,66 @@ def test_split_driver_matches_single_driver():
         assert np.array_equal(np.concatenate([s[key] for s in st2]), st1[key]), key
     for p in parts:
         p.close()
+
+
+def test_posterior_bookkeeping_matches_oracle():
+    """nk, nz, nsig, namp, nvpz, nvsz, nvpvsz (integers: exact) and the profile means (1e-12) of the
+    non-tempered chains, recorded every ncorr iterations after nburn (src/pt_mcmc.f90:204-286)."""
+    cfg = helpers.small_config(sdep=2.0, nfft=128, nsmp=64, nchains=4, ncool=2, t_high=8.0, nburn=20, niter=100, ncorr=5,
+                               sig_min=[0.005, 0.01], sig_max=[0.05, 0.01], nbin_z=40, nbin_vs=25, nbin_vp=20,
+                               nbin_vpvs=30, nbin_sig=10, nbin_amp=32, vp_mode=1, iseed=31337)
+    cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
+    nproc, n_iter = 5, 120
+    pt = ParallelTempering(cfg, nproc)
+    pt.set_logging(n_iter)
+    pt.run(n_iter)
+    hg = pt.hist()
+    vp_g, vs_g = pt.models()
+    flags_g = pt.log(n_iter)[0]
+    pt.close()
+    orc = oracle_c.OraclePT(cfg, nproc)
+    flags_o, _, _ = orc.run(n_iter, record=True)
+    ho = orc.hist()
+    nmod_o = orc.counters(n_iter)["nmod"]
+    assert np.array_equal(flags_g, flags_o)
+    assert hg["nmod"] == nmod_o == 20 * nproc * cfg.ncool
+    for key in ("nk", "nz", "nsig", "namp", "nvpz", "nvsz", "nvpvsz"):
+        assert np.array_equal(hg[key], ho[key]), key
+        assert hg[key].sum() > 0, key
+    for key in ("vp_mean", "vs_mean", "vpvs_mean"):
+        assert np.allclose(hg[key], ho[key], rtol=1e-12, atol=0), key
+    # ocean bins carry the reference's assignment quirk (src/pt_mcmc.f90:260-263)
+    assert hg["vs_mean"][0] == cfg.vs_min and hg["vpvs_mean"][0] == cfg.vpvs_min
+    assert vp_g.shape == (hg["nmod"], cfg.nbin_z) and (vs_g[:, 0] == cfg.vs_min).all()
+
+
+def test_run_driver_writes_reference_output_set(tmp_path):
+    """params.in + SAC + velmod in, the reference's 12 output files out (src/rf_inv.f90:28-108, src/mcmc_out.f90)."""
+    import os
+    from rf_inv_b200 import io as rio, run as rrun
+    cfg = helpers.attach_obs_and_rinv(workloads.make_config("sample"), noise=0.01)
+    d = tmp_path
+    (d / "data").mkdir(); (d / "model").mkdir()
+    for t in range(2):
+        rio.write_sac(str(d / "data" / f"s{t + 1}.trc"), cfg.obs[t], cfg.delta, 0.0)
+    with open(d / "model" / "ref.velmod", "w") as f:
+        for i in range(61):
+            f.write(f"{0.5 * i} 5.00 2.89\n")
+    vals = ["'./rslt'", 40, 120, 10, 5, 1, 15.0, 12345678, 2, 0.06, 0.08, 4.0, 4.0, 1, 1, 256, "'data/s1.trc'", "'data/s2.trc'",
+            "0.0 5.0", 0, 2.0, '"model/ref.velmod"', 0, "1 10", "0.0 20.0", 0.05, 2, 2.0, 0.2, "0.01 0.01", "0.01 0.01", 0.02, 0.02,
+            0.02, 0.002, 100, 50, 50, 100, 50, 100, "-0.8 0.8", "0.1 8.6", "0.001 5.0", "0.0 5.0"]
+    (d / "params.in").write_text("# test problem in the reference's params.in format\n" + "\n".join(str(v) for v in vals) + "\n")
+    hist, cnt = rrun.run(str(d / "params.in"), nproc=4, verbose=False)
+    out = d / "rslt"
+    expected = {"params.in.copy", "all_models", "likelihood", "num_interface.ppd", "syn_trace.ppd", "interface_depth.ppd",
+                "sigma.ppd", "vs_z.ppd", "vp_z.ppd", "vpvs_z.ppd", "vs_z.mean", "vp_z.mean", "vpvs_z.mean"}
+    assert expected <= set(os.listdir(out))
+    assert os.path.exists(d / "input01") and os.path.exists(d / "input02")
+    assert hist["nmod"] == 12 * 4 and cnt["nprop"].sum() == 160 * 4
+    lk = np.loadtxt(out / "likelihood")
+    assert lk.shape == (160, 2) and np.isfinite(lk).all()
+    nk = np.loadtxt(out / "num_interface.ppd")
+    assert abs(nk[:, 1].sum() - 1.0) < 1e-12
+    syn = np.loadtxt(out / "syn_trace.ppd")
+    assert syn.shape == (2 * 101 * 100, 4) and abs(syn[:100, 2].sum() - 1.0) < 1e-3
+    assert os.path.getsize(out / "sigma.ppd") == 0                    # sigma fixed for both traces: nothing written
