@@ -22,17 +22,41 @@ namespace {
 
 constexpr double PI2 = 2.0 * 3.1415926535897931;  // src/math.f90:37
 
-// ---------------- mt19937 (src/mt19937.f90): state word i of stream r at mt[i*G + r] ----------------
+// ---------------- mt19937 (src/mt19937.f90): state word i of stream r at mt[r*624 + i] ----------------
+// Two ways to drive a stream: by one thread (init, swap) or by a whole warp in lock step (proposal pass): all lanes
+// then execute the same draws on replicated scalars and the 624-word reload is done cooperatively.
 struct Mt {
   uint32_t* mt;
-  int stride, mti;
-  __device__ Mt(uint32_t* base, int G, int r, int mti_) : mt(base + r), stride(G), mti(mti_) {}
-  __device__ uint32_t& w(int i) { return mt[(size_t)i * stride]; }
+  int mti;
+  bool warp;   // true: called by all 32 lanes of a warp in lock step
+  __device__ Mt(uint32_t* base, int r, int mti_, bool warp_ = false) : mt(base + (size_t)r * 624), mti(mti_), warp(warp_) {}
+  __device__ uint32_t& w(int i) { return mt[i]; }
+  __device__ static uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
   __device__ void reload() {  // src/mt19937.f90:96-116
-#pragma unroll 8
-    for (int kk = 0; kk < 624; ++kk) {
-      const uint32_t y = (w(kk) & 0x80000000u) | (w(kk == 623 ? 0 : kk + 1) & 0x7fffffffu);
-      w(kk) = w(kk + 397 < 624 ? kk + 397 : kk + 397 - 624) ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    if (!warp) {
+      for (int kk = 0; kk < 624; ++kk) w(kk) = twist(w(kk), w(kk == 623 ? 0 : kk + 1), w(kk + 397 < 624 ? kk + 397 : kk - 227));
+    } else {
+      // new[kk] depends on old[kk], old[kk+1] and on old[kk+397] (kk < 227) or new[kk-227]: batches of <= 227
+      // consecutive words are independent.  Read everything of a 32-word round first, then write.
+      const int lane = threadIdx.x & 31;
+      const int bounds[4] = {0, 227, 454, 623};
+      for (int b = 0; b < 3; ++b)
+        for (int base = bounds[b]; base < bounds[b + 1]; base += 32) {
+          const int kk = base + lane;
+          const bool act = kk < bounds[b + 1];
+          uint32_t v = 0;
+          if (act) v = twist(w(kk), w(kk + 1), w(kk + 397 < 624 ? kk + 397 : kk - 227));
+          __syncwarp();
+          if (act) w(kk) = v;
+          __syncwarp();
+        }
+      const uint32_t last = twist(w(623), w(0), w(396));
+      __syncwarp();
+      if (lane == 0) w(623) = last;
+      __syncwarp();
     }
     mti = 0;
   }
@@ -127,7 +151,7 @@ __global__ void pt_init_kernel(const DevConfig cfg, const PtDev p) {
   if (r >= p.G) return;
   const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
   const uint32_t grank = (uint32_t)(p.rank_begin + r);
-  Mt g(p.mt, p.G, r, 624);
+  Mt g(p.mt, r, 624);
   {  // sgrnd, src/mt19937.f90:78-90; seed src/rf_inv.f90:75 (wraps like default-integer arithmetic)
     uint32_t s = (uint32_t)p.iseed + grank * grank * 10000u + 23u * grank;
     g.w(0) = s;
@@ -169,80 +193,148 @@ __global__ void pt_init_kernel(const DevConfig cfg, const PtDev p) {
 }
 
 // ---------------- proposal pass: mcmc, src/pt_mcmc.f90:77-169 + the draws of judge_mcmc :611-615 ----------------
-__global__ void pt_propose_kernel(const DevConfig cfg, const PtDev p) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// One WARP per virtual rank, chains of the rank in order (they share the stream).  All lanes execute the same draws
+// on replicated scalars (no divergence); the model arrays are distributed: lane holds elements `lane` and `lane+32`.
+__device__ __forceinline__ double lane_get(double v0, double v1, int idx) {  // element idx of a distributed array
+  const double a = __shfl_sync(0xffffffffu, v0, idx & 31), b = __shfl_sync(0xffffffffu, v1, idx & 31);
+  return idx < 32 ? a : b;
+}
+__device__ __forceinline__ void lane_set(double& v0, double& v1, int idx, double val, int lane) {
+  if (lane == (idx & 31)) { if (idx < 32) v0 = val; else v1 = val; }
+}
+
+// format_model's validity flag (src/model.f90:175-290), warp-parallel: the layer below interface i is described by
+// z_i and its predecessor (largest interface depth below z_i, or the sea floor), no sort needed.
+__device__ bool model_valid_warp(const DevConfig& cfg, int k, double z0, double z1, double p0, double p1, double s0,
+                                 double s1, double dvp_half, double dvs_half, int lane) {
+  const int i0 = lane, i1 = lane + 32;
+  double prev0 = -INFINITY, prev1 = -INFINITY, zmax = -INFINITY;
+  for (int j = 0; j < k; ++j) {
+    const double zj = lane_get(z0, z1, j);
+    if (zj < z0 || (zj == z0 && j < i0)) prev0 = fmax(prev0, zj);
+    if (zj < z1 || (zj == z1 && j < i1)) prev1 = fmax(prev1, zj);
+    zmax = fmax(zmax, zj);
+  }
+  bool ok = true;
+  for (int slot = 0; slot < 2; ++slot) {
+    const int i = slot ? i1 : i0;
+    if (i >= k) continue;
+    const double zi = slot ? z1 : z0, prev = slot ? prev1 : prev0;
+    const bool top = prev == -INFINITY;
+    const double below = top ? cfg.sdep : prev;
+    const double zc = __dmul_rn(0.5, top ? __dadd_rn(cfg.sdep, zi) : __dadd_rn(zi, prev));
+    const double h = __dsub_rn(zi, below);
+    double a, b;
+    bool lok = layer_velocity(cfg, zc, slot ? s1 : s0, slot ? p1 : p0, a, b);
+    if (top) lok = lok && !(h < __dmul_rn(0.125, a));
+    else lok = lok && !(h < cfg.h_min);
+    ok = ok && lok;
+  }
+  if (lane == 0) {  // half space
+    double a, b;
+    ok = layer_velocity(cfg, __dmul_rn(0.5, __dadd_rn(cfg.z_max, zmax)), dvs_half, dvp_half, a, b) && ok;
+  }
+  return __all_sync(0xffffffffu, ok);
+}
+
+__global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (r >= p.G) return;
   const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
-  Mt g(p.mt, p.G, r, p.mti[r]);
-  double pz[RFINV_MAX_K], pdvp[RFINV_MAX_K], pdvs[RFINV_MAX_K], psig[RFINV_MAX_TRC];
+  Mt g(p.mt, r, p.mti[r], /*warp=*/true);
+  __syncwarp();
+  const bool has1 = lane + 32 < km;
   for (int ic = 0; ic < p.nchains; ++ic) {
     const int c = r * p.nchains + ic;
     int pk = p.k[c];
-#pragma unroll 8
-    for (int i = 0; i < km - 1; ++i) pz[i] = __ldg(&p.z[(size_t)i * Cl + c]);
-    pz[km - 1] = 0.0;
-#pragma unroll 8
-    for (int i = 0; i < km; ++i) pdvp[i] = __ldg(&p.dvp[(size_t)i * Cl + c]);
-#pragma unroll 8
-    for (int i = 0; i < km; ++i) pdvs[i] = __ldg(&p.dvs[(size_t)i * Cl + c]);
-    for (int t = 0; t < T; ++t) psig[t] = p.sig[(size_t)t * Cl + c];
+    // current state, distributed (element km-1 of z does not exist: 0)
+    double z0 = lane < km - 1 ? p.z[(size_t)lane * Cl + c] : 0.0;
+    double z1 = lane + 32 < km - 1 ? p.z[(size_t)(lane + 32) * Cl + c] : 0.0;
+    double dp0 = lane < km ? p.dvp[(size_t)lane * Cl + c] : 0.0, dp1 = has1 ? p.dvp[(size_t)(lane + 32) * Cl + c] : 0.0;
+    double ds0 = lane < km ? p.dvs[(size_t)lane * Cl + c] : 0.0, ds1 = has1 ? p.dvs[(size_t)(lane + 32) * Cl + c] : 0.0;
+    double sg = lane < T ? p.sig[(size_t)lane * Cl + c] : 0.0;
+    const double cz0 = z0, cz1 = z1, cdp0 = dp0, cdp1 = dp1, cds0 = ds0, cds1 = ds1;  // the chain's current values
     double log_prior12 = 0.0;
     bool null_flag = false;
     const int itype = (int)(g.grnd() * (double)p.ntype) + 1;
     if (itype == p.it_birth) {
       pk = pk + 1;
       if (pk < km) {
-        pdvp[pk - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvp_prior);
-        pdvs[pk - 1] = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvs_prior);
-        pz[pk - 1] = __dadd_rn(cfg.z_min, __dmul_rn(g.grnd(), __dsub_rn(cfg.z_max, cfg.z_min)));
+        const double nvp = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvp_prior);
+        const double nvs = __dmul_rn(prior_draw(g, cfg.prior_mode), p.dvs_prior);
+        const double nz = __dadd_rn(cfg.z_min, __dmul_rn(g.grnd(), __dsub_rn(cfg.z_max, cfg.z_min)));
+        lane_set(dp0, dp1, pk - 1, nvp, lane);
+        lane_set(ds0, ds1, pk - 1, nvs, lane);
+        lane_set(z0, z1, pk - 1, nz, lane);
       } else null_flag = true;
     } else if (itype == p.it_death) {
       pk = pk - 1;
       if (pk >= cfg.k_min) {
         const int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
-        for (int il = itarget; il <= pk; ++il) {
-          pdvp[il - 1] = p.dvp[(size_t)il * Cl + c];
-          pdvs[il - 1] = p.dvs[(size_t)il * Cl + c];
-          pz[il - 1] = p.z[(size_t)il * Cl + c];
-        }
-        pdvp[pk] = 0.0; pdvs[pk] = 0.0; pz[pk] = 0.0;
+        // prop(il) = cur(il+1) for il = itarget..pk (1-based); prop(pk+1) = 0
+        // (all shuffles are executed by every lane; selection happens afterwards)
+        const double dz0 = __shfl_down_sync(0xffffffffu, cz0, 1), nz0b = __shfl_sync(0xffffffffu, cz1, 0);
+        const double dq0 = __shfl_down_sync(0xffffffffu, cdp0, 1), np0b = __shfl_sync(0xffffffffu, cdp1, 0);
+        const double dr0 = __shfl_down_sync(0xffffffffu, cds0, 1), ns0b = __shfl_sync(0xffffffffu, cds1, 0);
+        const double nz1 = __shfl_down_sync(0xffffffffu, cz1, 1), np1 = __shfl_down_sync(0xffffffffu, cdp1, 1);
+        const double ns1 = __shfl_down_sync(0xffffffffu, cds1, 1);
+        const double nz0 = dz0, np0 = dq0, ns0 = dr0;
+        const int e0 = lane, e1 = lane + 32;  // 0-based element indices; shift range [itarget-1, pk-1], zero at pk
+        if (e0 >= itarget - 1 && e0 <= pk - 1) { z0 = lane < 31 ? nz0 : nz0b; dp0 = lane < 31 ? np0 : np0b; ds0 = lane < 31 ? ns0 : ns0b; }
+        if (e1 >= itarget - 1 && e1 <= pk - 1) { z1 = lane < 31 ? nz1 : 0.0; dp1 = lane < 31 ? np1 : 0.0; ds1 = lane < 31 ? ns1 : 0.0; }
+        if (e0 == pk) { z0 = 0.0; dp0 = 0.0; ds0 = 0.0; }
+        if (e1 == pk) { z1 = 0.0; dp1 = 0.0; ds1 = 0.0; }
       } else null_flag = true;
     } else if (itype == p.it_z) {
       const int itarget = (int)(g.grnd() * (double)pk) + 1;
-      pz[itarget - 1] = __dadd_rn(pz[itarget - 1], __dmul_rn(gauss(g), p.dev_z));
-      if (pz[itarget - 1] < cfg.z_min || pz[itarget - 1] > cfg.z_max) null_flag = true;
+      const double nz = __dadd_rn(lane_get(z0, z1, itarget - 1), __dmul_rn(gauss(g), p.dev_z));
+      lane_set(z0, z1, itarget - 1, nz, lane);
+      if (nz < cfg.z_min || nz > cfg.z_max) null_flag = true;
     } else if (itype == p.it_dvs) {
       int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
       if (itarget == pk + 1) itarget = km;
-      pdvs[itarget - 1] = __dadd_rn(pdvs[itarget - 1], __dmul_rn(gauss(g), p.dev_dvs));
-      log_prior12 = log_prior_ratio(pdvs[itarget - 1], p.dvs[(size_t)(itarget - 1) * Cl + c], p.dvs_prior, cfg.prior_mode);
+      const double old = lane_get(ds0, ds1, itarget - 1);
+      const double nv = __dadd_rn(old, __dmul_rn(gauss(g), p.dev_dvs));
+      lane_set(ds0, ds1, itarget - 1, nv, lane);
+      log_prior12 = log_prior_ratio(nv, old, p.dvs_prior, cfg.prior_mode);
     } else if (itype == p.it_dvp) {
       int itarget = (int)(g.grnd() * (double)(pk + 1)) + 1;
       if (itarget == pk + 1) itarget = km;
-      pdvp[itarget - 1] = __dadd_rn(pdvp[itarget - 1], __dmul_rn(gauss(g), p.dev_dvp));
-      log_prior12 = log_prior_ratio(pdvp[itarget - 1], p.dvp[(size_t)(itarget - 1) * Cl + c], p.dvp_prior, cfg.prior_mode);
+      const double old = lane_get(dp0, dp1, itarget - 1);
+      const double nv = __dadd_rn(old, __dmul_rn(gauss(g), p.dev_dvp));
+      lane_set(dp0, dp1, itarget - 1, nv, lane);
+      log_prior12 = log_prior_ratio(nv, old, p.dvp_prior, cfg.prior_mode);
     } else if (itype == p.it_sig) {
       const int itarget = p.isig_trc[(int)(g.grnd() * (double)p.nsig_trc)];
-      psig[itarget] = __dadd_rn(psig[itarget], __dmul_rn(gauss(g), p.dev_sig));
-      if (psig[itarget] < p.sig_min[itarget] || psig[itarget] > p.sig_max[itarget]) null_flag = true;
+      const double nv = __dadd_rn(__shfl_sync(0xffffffffu, sg, itarget), __dmul_rn(gauss(g), p.dev_sig));
+      if (lane == itarget) sg = nv;
+      if (nv < p.sig_min[itarget] || nv > p.sig_max[itarget]) null_flag = true;
     }
-    if (!null_flag && !model_valid(cfg, pk, pz, pdvp, pdvs, pdvp[km - 1], pdvs[km - 1])) null_flag = true;
+    if (!null_flag) {
+      const double dvp_half = lane_get(dp0, dp1, km - 1), dvs_half = lane_get(ds0, ds1, km - 1);
+      if (!model_valid_warp(cfg, pk, z0, z1, dp0, dp1, ds0, ds1, dvp_half, dvs_half, lane)) null_flag = true;
+    }
     double log_r = 0.0;
     if (!null_flag) {  // judge_mcmc draws (src/pt_mcmc.f90:610-615): independent of the likelihood
       double rr;
       do { rr = g.grnd(); } while (!(rr >= 2.220446049250313e-16));
       log_r = log(rr);
     }
-    p.pk[c] = pk;
-    for (int i = 0; i < km - 1; ++i) p.pz[(size_t)i * Cl + c] = pz[i];
-    for (int i = 0; i < km; ++i) { p.pdvp[(size_t)i * Cl + c] = pdvp[i]; p.pdvs[(size_t)i * Cl + c] = pdvs[i]; }
-    for (int t = 0; t < T; ++t) p.psig[(size_t)t * Cl + c] = psig[t];
-    p.itype[c] = (int8_t)itype;
-    p.pflag[c] = (int8_t)(null_flag ? -1 : (itype == p.it_sig ? 2 : 1));  // 1: forward needed, 2: cached RF (fwd_flag false)
-    p.log_r[c] = log_r;
-    p.log_prior12[c] = log_prior12;
+    if (lane < km - 1) p.pz[(size_t)lane * Cl + c] = z0;
+    if (lane + 32 < km - 1) p.pz[(size_t)(lane + 32) * Cl + c] = z1;
+    if (lane < km) { p.pdvp[(size_t)lane * Cl + c] = dp0; p.pdvs[(size_t)lane * Cl + c] = ds0; }
+    if (has1) { p.pdvp[(size_t)(lane + 32) * Cl + c] = dp1; p.pdvs[(size_t)(lane + 32) * Cl + c] = ds1; }
+    if (lane < T) p.psig[(size_t)lane * Cl + c] = sg;
+    if (lane == 0) {
+      p.pk[c] = pk;
+      p.itype[c] = (int8_t)itype;
+      p.pflag[c] = (int8_t)(null_flag ? -1 : (itype == p.it_sig ? 2 : 1));  // 1: forward needed, 2: cached RF (fwd_flag false)
+      p.log_r[c] = log_r;
+      p.log_prior12[c] = log_prior12;
+    }
   }
-  p.mti[r] = g.mti;
+  if (lane == 0) p.mti[r] = g.mti;
 }
 
 // ordered compaction of the chains that need a forward evaluation (single CTA, deterministic)
@@ -332,33 +424,30 @@ __global__ void pt_lhist_kernel(const PtDev p, double* out) {
 // Swap table of this process (src/pt_mcmc.f90:501-571 needs (T, logL) of two chains anywhere in the job):
 //   [0,Cl) temps | [Cl,2Cl) logL | [2Cl,2Cl+G) next uniform of every local stream | +0,+1: itarget1, itarget2 (-1 if
 //   this process does not own virtual rank 0).  The owner of rank 0 draws the pair first (consuming its stream).
-__global__ void pt_table_kernel(const PtDev p, double* table) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid == 0) {
+// One warp per virtual rank (cooperative mt19937 reload), plus a grid-stride copy of temps / logL.
+__global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* table) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = gtid >> 5, lane = threadIdx.x & 31;
+  for (int c = gtid; c < p.Cl; c += gridDim.x * blockDim.x) {
+    table[c] = p.temps[c];
+    table[p.Cl + c] = p.logl[c];
+  }
+  if (r >= p.G) return;
+  Mt g(p.mt, r, p.mti[r], /*warp=*/true);
+  __syncwarp();
+  if (r == 0) {
     double t1 = -1.0, t2 = -1.0;
     if (p.rank_begin == 0 && p.nchains >= 2) {
-      Mt g(p.mt, p.G, 0, p.mti[0]);
       const int n_all = p.nproc_total * p.nchains;
       const int i1 = (int)(g.grnd() * (double)n_all);
       int i2;
       do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
-      p.mti[0] = g.mti;
       t1 = i1; t2 = i2;
     }
-    table[2 * p.Cl + p.G] = t1;
-    table[2 * p.Cl + p.G + 1] = t2;
+    if (lane == 0) { table[2 * p.Cl + p.G] = t1; table[2 * p.Cl + p.G + 1] = t2; }
   }
-  for (int c = tid; c < p.Cl; c += gridDim.x * blockDim.x) {
-    table[c] = p.temps[c];
-    table[p.Cl + c] = p.logl[c];
-  }
-}
-__global__ void pt_peek_kernel(const PtDev p, double* table) {  // after pt_table_kernel: stream 0 has advanced
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= p.G) return;
-  Mt g(p.mt, p.G, r, p.mti[r]);
-  table[2 * p.Cl + r] = g.peek();
-  p.mti[r] = g.mti;  // a peek may have reloaded the state (mti 624 -> 0); nothing is consumed
+  const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
+  if (lane == 0) { table[2 * p.Cl + r] = u; p.mti[r] = g.mti; }
 }
 
 // judge_pt (src/pt_mcmc.f90:580-595) evaluated identically by every process from the gathered tables.
@@ -685,7 +774,7 @@ int32_t rfinv_pt_local_step(rfinv_handle* h) {
     s->d_lhist = nl; s->cap_lhist = ncap;
   }
   const int log_slot = (s->log_cap > 0 && s->log_used < s->log_cap) ? s->log_used : -1;
-  pt_propose_kernel<<<(d.G + 63) / 64, 64, 0, q>>>(h->dc, d);
+  pt_propose_kernel<<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d);
   pt_compact_kernel<<<1, 1024, 0, q>>>(d);
   RFINV_CUDA_CHECK(cudaGetLastError());
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
@@ -699,8 +788,10 @@ int32_t rfinv_pt_local_step(rfinv_handle* h) {
       pt_record_finish_kernel<<<1, 1, 0, q>>>(d);
     }
   }
-  pt_table_kernel<<<(d.Cl + 255) / 256, 256, 0, q>>>(d, s->d_table);
-  pt_peek_kernel<<<(d.G + 63) / 64, 64, 0, q>>>(d, s->d_table);
+  {
+    const int nb_rank = (d.G * 32 + 127) / 128, nb_copy = (d.Cl + 127) / 128;
+    pt_table_kernel<<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table);
+  }
   RFINV_CUDA_CHECK(cudaGetLastError());
   s->pending_log_slot = log_slot;
   return RFINV_OK;
