@@ -1,0 +1,38 @@
+"""Parity report quoted with every benchmark: max relative error of rft and logL of the CUDA path vs the
+C oracle on >= 1000 random models per configuration, and fixed-seed PT sequence identity on C1.  Run on the GPU box:
+    python tools/parity_report.py > gpurun_out/parity_report.json"""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import numpy as np
+import helpers, oracle_c
+from rf_inv_b200 import workloads
+from rf_inv_b200.evaluator import Evaluator
+from rf_inv_b200.pt import ParallelTempering
+
+out = {"tolerance": 1e-9, "configs": {}}
+for name, n in [("sample", 1024), ("c2", 1024), ("c3", 1024), ("c4", 1024), ("c4_laplace", 1024), ("c5", 1024), ("target", 1024)]:
+    cfg = helpers.attach_obs_and_rinv(workloads.make_config(name), noise=0.01)
+    m = workloads.draw_models(cfg, n, seed=2024, dvs_scale=0.5)
+    t0 = time.time()
+    ll_o, rft_o, val_o = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    t_cpu = time.time() - t0
+    with Evaluator(cfg) as ev:
+        ll_g, rft_g, val_g = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True, want_valid=True)
+    out["configs"][name] = {"models": n, "nfft": cfg.nfft, "ntrc": cfg.ntrc, "k_max": cfg.k_max, "nsmp": cfg.nsmp,
+                            "rft_max_rel_err": helpers.rel_err_rft(rft_g, rft_o),
+                            "logl_max_rel_err": helpers.logl_err(cfg, ll_g, ll_o, m["sig"]),
+                            "valid_flags_equal": bool(np.array_equal(val_g, val_o)), "nan_logl": int(np.isnan(ll_g).sum()),
+                            "oracle_seconds": round(t_cpu, 2)}
+cfg = helpers.attach_obs_and_rinv(workloads.make_config("sample"), noise=0.01)
+n_iter, nproc = 500, 20
+pt = ParallelTempering(cfg, nproc); pt.set_logging(n_iter); pt.run(n_iter)
+fl, ty, sw = pt.log(n_iter); cnt = pt.counters(); st = pt.state(); pt.close()
+orc = oracle_c.OraclePT(cfg, nproc); ofl, oty, osw = orc.run(n_iter); ocnt = orc.counters(n_iter); ost = orc.state()
+out["pt_fixed_seed_C1"] = {"iterations": n_iter, "chains": nproc * cfg.nchains,
+                           "accept_flags_identical": bool(np.array_equal(fl, ofl)), "proposal_types_identical": bool(np.array_equal(ty, oty)),
+                           "swaps_identical": bool(np.array_equal(sw, osw)), "nprop": cnt["nprop"].tolist(), "naccept": cnt["naccept"].tolist(),
+                           "nprop_oracle": ocnt["nprop"].tolist(), "naccept_oracle": ocnt["naccept"].tolist(),
+                           "logl_max_rel_err": helpers.logl_err(cfg, st["logl"], ost["logl"], ost["sig"]),
+                           "first_divergence_iteration": int(np.argmax((fl != ofl).any(axis=1))) if (fl != ofl).any() else None}
+print(json.dumps(out, indent=1))
