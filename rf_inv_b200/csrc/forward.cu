@@ -12,12 +12,16 @@
 // Arithmetic re-design.  The reference multiplies dense complex 4x4 layer
 // matrices P_l and then E^-1 * prod(P_l); only rows 3,4 x columns 1,2 (and 4 with a water layer) of the
 // result are used.  P_l has a fixed checkerboard real/imaginary structure: P = D S B S^-1 D^-1 with
-// D = diag(1,i,1,i), S = diag(1,1,w,w) (w = angular frequency) and B REAL and free of explicit w.  So we
-// propagate two REAL 4-vectors (columns e1 and the free-surface / water-layer combination of e2,e4)
-// from the top layer down, y <- B_l y: 32 FMA per layer-frequency instead of 64 complex MACs, and the 10
-// distinct entries of B_l are two-term combinations of cos/sin of (w xi h, w eta h).  The four
-// trigonometric values per layer-frequency come from one sincos pair per thread and layer, advanced
-// across the thread's J frequencies by a fixed rotation (frequencies of a thread are equally spaced).
+// D = diag(1,i,1,i), S = diag(1,1,w,w) (w = angular frequency) and B REAL and free of explicit w, so two
+// REAL 4-vectors (column e1 and the free-surface / water-layer combination of e2,e4) are propagated from
+// the top layer down.  B_l itself is never formed: B_l = V_l R_l V_l^-1, with R_l two plane rotations by
+// (w xi h, w eta h) -- the standing P and S waves of the layer -- and V_l frequency independent with two
+// decoupled 2x2 blocks (components {1,4} and {2,3}).  The vectors are carried in wave coordinates
+// w = V_l^-1 y; a layer is "rotate both pairs", an interface is "apply the two 2x2 blocks of
+// V_{l+1}^-1 V_l", and the free per-layer scale of the P and S coordinates is chosen so that the {1,4}
+// block has a unit diagonal.  Per layer and frequency: 2 x 14 FP64 instructions for the two vectors plus
+// 8 to advance the two (cos, sin) pairs.  The trigonometric values come from two-level rotation tables
+// per layer, advanced across the thread's J frequencies by a fixed rotation (equally spaced bins).
 #include <cstdlib>
 #include "rfinv_common.cuh"
 
@@ -46,24 +50,21 @@ extern "C" int rfinv_debug_get_phases(unsigned long long* out) {
 
 namespace {
 
-// Per (model, ray, solid layer) constants of the real propagator B_l, written by prep_kernel.
+// Per (model, ray, solid layer) constants, written by prep_kernel.
 struct LayerConst {
   double thx, the;            // domg*xi*h, domg*eta*h : phase advance per frequency bin
   double cbx, sbx, cbe, sbe;  // rotation by B*thx, B*the (B = threads per CTA = frequency stride of a thread)
-  double g, bp;               // 2 beta^2 p^2, 1 - 2 beta^2 p^2
-  double c12a, c12b, c21a, c21b, c13a, c13b, c24a, c24b, c31a, c31b, c42a, c42b;
-  double c14, c41;
+  double t12, t21;            // interface to the next layer, {1,4} block [[1, t12], [t21, 1]] on (P, S) coordinates
+  double u11, u12, u21, u22;  // interface to the next layer, {2,3} block
 };
-constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 22
-
-struct HalfSpace {
-  double e11, e12, e13, e14, e21, e22, e23, e24;  // E^-1 rows 3,4 with the 1/w factors removed
-};
+constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 12
 
 // Per (model, ray) constants written by prep_kernel.
 struct RayConst {
-  HalfSpace hs;
-  double thw, cbw, sbw, rw;   // water layer: phase per bin, stride rotation, rho_w/xi_w
+  double h14[4], h23[4];      // rows 3,4 of E^-1 (1/w factors removed) times the last solid layer's basis, per block
+  double a1, b1;              // start vector e1 in the wave coordinates of the top solid layer
+  double q1a, q1b, q2a, q2b;  // start vector (0, cw, 0, -rw sw): (a1,b1) = sw*(q1a,q1b), (a2,b2) = cw*(q2a,q2b)
+  double thw, cbw, sbw;       // water layer: phase per bin, stride rotation
   double tp;                  // direct-arrival delay (src/forward.f90:474-491)
   double2 edge[4];            // fr, fv at the DC pseudo-frequency and at Nyquist
   int k, valid;
@@ -77,34 +78,27 @@ __device__ __forceinline__ void rot(double& c, double& s, double cb, double sb) 
   s = s2;
 }
 
-// y <- B y for the two propagated vectors; (c1,s1) = cos/sin(w xi h), (c2,s2) = cos/sin(w eta h)
-__device__ __forceinline__ void layer_step(const LayerConst& L, double c1, double s1, double c2, double s2, double* ya,
-                                           double* yb) {
-  const double d = c1 - c2;
-  const double b11 = fma(L.g, c1, L.bp * c2);
-  const double b22 = fma(L.bp, c1, L.g * c2);
-  const double b12 = fma(L.c12a, s1, L.c12b * s2);
-  const double b21 = fma(L.c21a, s1, L.c21b * s2);
-  const double b13 = fma(L.c13a, s1, L.c13b * s2);
-  const double b24 = fma(L.c24a, s1, L.c24b * s2);
-  const double b31 = fma(L.c31a, s1, L.c31b * s2);
-  const double b42 = fma(L.c42a, s1, L.c42b * s2);
-  const double b14 = L.c14 * d;
-  const double b41 = L.c41 * d;
-  {
-    const double y1 = ya[0], y2 = ya[1], y3 = ya[2], y4 = ya[3];
-    ya[0] = fma(b14, y4, fma(b13, y3, fma(b12, y2, b11 * y1)));
-    ya[1] = fma(b24, y4, fma(-b14, y3, fma(b22, y2, b21 * y1)));
-    ya[2] = fma(-b21, y4, fma(b11, y3, fma(-b41, y2, b31 * y1)));
-    ya[3] = fma(b22, y4, fma(-b12, y3, fma(b42, y2, b41 * y1)));
-  }
-  {
-    const double y1 = yb[0], y2 = yb[1], y3 = yb[2], y4 = yb[3];
-    yb[0] = fma(b14, y4, fma(b13, y3, fma(b12, y2, b11 * y1)));
-    yb[1] = fma(b24, y4, fma(-b14, y3, fma(b22, y2, b21 * y1)));
-    yb[2] = fma(-b21, y4, fma(b11, y3, fma(-b41, y2, b31 * y1)));
-    yb[3] = fma(b22, y4, fma(-b12, y3, fma(b42, y2, b41 * y1)));
-  }
+// One vector in wave coordinates: (a1, a2) the standing P wave, (b1, b2) the standing S wave of the layer.
+// Physical components {1,4} depend on (a1, b1) only, components {2,3} on (a2, b2) only.
+struct Wave { double a1, a2, b1, b2; };
+
+// the layer itself: rotate the P pair by w xi h = (c1,s1) and the S pair by w eta h = (c2,s2)
+__device__ __forceinline__ void wave_rotate(Wave& w, double c1, double s1, double c2, double s2) {
+  const double a1 = fma(-s1, w.a2, c1 * w.a1);
+  const double a2 = fma(s1, w.a1, c1 * w.a2);
+  const double b1 = fma(-s2, w.b2, c2 * w.b1);
+  const double b2 = fma(s2, w.b1, c2 * w.b2);
+  w.a1 = a1; w.a2 = a2; w.b1 = b1; w.b2 = b2;
+}
+
+// the interface below it: coordinates of the same displacement-stress vector in the next layer's basis
+__device__ __forceinline__ void wave_interface(Wave& w, double t12, double t21, double u11, double u12, double u21,
+                                               double u22) {
+  const double a1 = fma(t12, w.b1, w.a1);
+  const double b1 = fma(t21, w.a1, w.b1);
+  const double a2 = fma(u12, w.b2, u11 * w.a2);
+  const double b2 = fma(u22, w.b2, u21 * w.a2);
+  w.a1 = a1; w.a2 = a2; w.b1 = b1; w.b2 = b2;
 }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -112,13 +106,14 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 }
 
 // Boundary conditions (src/forward.f90:267-287) in the scaled real basis, then the sign conventions of
-// calc_rf (src/forward.f90:145-146): fr = conj(ur), fv = -conj(uz).
-__device__ __forceinline__ void surface_response(const HalfSpace& H, const double* ya, const double* yb, double cw,
-                                                 int ipha, double2& fr, double2& fv) {
-  const double2 A3 = make_double2(fma(H.e11, ya[0], H.e14 * ya[3]), fma(-H.e12, ya[1], H.e13 * ya[2]));
-  const double2 A4 = make_double2(fma(H.e21, ya[0], -H.e24 * ya[3]), fma(H.e22, ya[1], H.e23 * ya[2]));
-  const double2 B3 = make_double2(fma(H.e11, yb[0], H.e14 * yb[3]), fma(-H.e12, yb[1], H.e13 * yb[2]));
-  const double2 B4 = make_double2(fma(H.e21, yb[0], -H.e24 * yb[3]), fma(H.e22, yb[1], H.e23 * yb[2]));
+// calc_rf (src/forward.f90:145-146): fr = conj(ur), fv = -conj(uz).  (A3, A4) / (B3, B4) are rows 3,4 of
+// E^-1 prod(P) applied to the two propagated vectors: real parts from the {1,4} block, imaginary parts from {2,3}.
+__device__ __forceinline__ void surface_response(const double* h14, const double* h23, const Wave& wa, const Wave& wb,
+                                                 double cw, int ipha, double2& fr, double2& fv) {
+  const double2 A3 = make_double2(fma(h14[0], wa.a1, h14[1] * wa.b1), fma(h23[0], wa.a2, h23[1] * wa.b2));
+  const double2 A4 = make_double2(fma(h14[2], wa.a1, h14[3] * wa.b1), fma(h23[2], wa.a2, h23[3] * wa.b2));
+  const double2 B3 = make_double2(fma(h14[0], wb.a1, h14[1] * wb.b1), fma(h23[0], wb.a2, h23[1] * wb.b2));
+  const double2 B4 = make_double2(fma(h14[2], wb.a1, h14[3] * wb.b1), fma(h23[2], wb.a2, h23[3] * wb.b2));
   const double2 p = cmul(A3, B4), q = cmul(B3, A4);
   const double2 dl = make_double2(p.x - q.x, p.y - q.y);
   const double rn = 1.0 / (dl.x * dl.x + dl.y * dl.y);
@@ -138,11 +133,25 @@ __device__ __forceinline__ void surface_response(const HalfSpace& H, const doubl
   fv = make_double2(-uz.x, uz.y);
 }
 
+// 2x2 helpers, row-major m[4] = {m11, m12, m21, m22}
+__device__ __forceinline__ void mat2_mul(const double* a, const double* b, double* c) {
+  const double c0 = fma(a[0], b[0], a[1] * b[2]), c1 = fma(a[0], b[1], a[1] * b[3]);
+  const double c2 = fma(a[2], b[0], a[3] * b[2]), c3 = fma(a[2], b[1], a[3] * b[3]);
+  c[0] = c0; c[1] = c1; c[2] = c2; c[3] = c3;
+}
+
 // ------------------------------------------------------------------------------------------------
 // prep_kernel: one thread per (model, ray).  format_model (src/model.f90:175-290), the per-layer
-// constants of the real propagator for this ray, half-space / water-layer constants, the direct-arrival
-// delay, and the two bins that do not fit the regular frequency grid of forward_kernel: the DC
-// pseudo-frequency omega = 1.0e-5 (src/forward.f90:246-248) and the Nyquist bin.
+// constants of the wave-coordinate propagator for this ray (rotation angles, interface blocks),
+// half-space / water-layer constants, the direct-arrival delay, and the two bins that do not fit the
+// regular frequency grid of forward_kernel: the DC pseudo-frequency omega = 1.0e-5
+// (src/forward.f90:246-248) and the Nyquist bin.
+//
+// Basis of a solid layer (columns = standing P wave, standing S wave; rows = components {1,4} / {2,3}):
+//   V14 = [[p, 1], [rho bp, -2 rho beta^2 p]],          V14^-1 = [[2 beta^2 p, 1/rho], [bp, -p/rho]]
+//   V23 = [[xi, -p/eta], [-2 rho beta^2 p xi, -rho bp/eta]],   V23^-1 = [[bp/xi, -p/(rho xi)], [-2 beta^2 p eta, -eta/rho]]
+// with bp = 1 - 2 beta^2 p^2; B_l = V R V^-1 reproduces layer_matrix_sol (src/forward.f90:385-421).
+// The basis of layer l is scaled by (sP, sS) on its (P, S) columns so that V14_l^-1 V14_{l-1} has a unit diagonal.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                    double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
@@ -168,29 +177,27 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
     z[m + 1] = a; dp[m + 1] = b; ds[m + 1] = d;
   }
   RayConst R;
-  // water layer (src/model.f90:201-207, src/forward.f90:424-442) and start vectors of the two edge bins
-  double ya0[4] = {1.0, 0.0, 0.0, 0.0}, yb0[4], ya1[4] = {1.0, 0.0, 0.0, 0.0}, yb1[4], cw0 = 1.0, cw1 = 1.0;
+  // water layer (src/model.f90:201-207, src/forward.f90:424-442): cos/sin of the two edge bins
+  double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
   const double nyq = (double)(cfg.nfft / 2);
   if (cfg.sdep > 0.0) {
     const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
     const double xiw = sqrt(1.0 / (aw * aw) - p * p);
     R.thw = cfg.domg * xiw * hw;
     sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
-    R.rw = rhow / xiw;
-    double sw;
-    sincos((double)1.0e-5f * xiw * hw, &sw, &cw0);
-    yb0[0] = 0.0; yb0[1] = cw0; yb0[2] = 0.0; yb0[3] = -R.rw * sw;
-    sincos(nyq * R.thw, &sw, &cw1);
-    yb1[0] = 0.0; yb1[1] = cw1; yb1[2] = 0.0; yb1[3] = -R.rw * sw;
+    rw = rhow / xiw;
+    sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
+    sincos(nyq * R.thw, &sw1, &cw1);
   } else {
-    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0; R.rw = 0.0;
-    yb0[0] = 0.0; yb0[1] = 1.0; yb0[2] = 0.0; yb0[3] = 0.0;
-    yb1[0] = 0.0; yb1[1] = 1.0; yb1[2] = 0.0; yb1[3] = 0.0;
+    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
   }
   bool valid = true;
   double tp = 0.0;
   LayerConst* lc = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km;
   const double p2 = __dmul_rn(p, p);
+  Wave ea0, eb0, ea1, eb1;                 // the two vectors at the DC pseudo-frequency (0) and at Nyquist (1)
+  double v14[4], v23[4];                   // scaled basis blocks of the previous layer
+  LayerConst L;
   for (int l = 0; l <= k; ++l) {
     double zc, h, dvs_l, dvp_l;
     if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, z[0])); h = __dsub_rn(z[0], cfg.sdep); dvs_l = ds[0]; dvp_l = dp[0]; }
@@ -209,42 +216,62 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
     const double xi = sqrt(__dsub_rn(__ddiv_rn(1.0, __dmul_rn(a, a)), p2));    // src/forward.f90:396
     if (l < k) {
       if (cfg.deconv_mode == 0) tp = __dadd_rn(tp, __dmul_rn(h, ipha == 1 ? xi : eta));  // src/forward.f90:489-491
-      LayerConst L;
+      const double g2 = 2.0 * beta2 * p;   // 2 beta^2 p
+      const double i14[4] = {g2, 1.0 / rho, bp, -p / rho};                               // V14^-1
+      const double i23[4] = {bp / xi, -p / (rho * xi), -g2 * eta, -eta / rho};           // V23^-1
+      if (l == 0) {
+        // start vectors in layer 0's coordinates: e1, and (0, cw, 0, -rw sw) for a unit pressure-free / water top
+        R.a1 = i14[0]; R.b1 = i14[2];
+        R.q1a = -rw * i14[1]; R.q1b = -rw * i14[3];
+        R.q2a = i23[0]; R.q2b = i23[2];
+        ea0.a1 = R.a1; ea0.b1 = R.b1; ea0.a2 = 0.0; ea0.b2 = 0.0; ea1 = ea0;
+        eb0.a1 = sw0 * R.q1a; eb0.b1 = sw0 * R.q1b; eb0.a2 = cw0 * R.q2a; eb0.b2 = cw0 * R.q2b;
+        eb1.a1 = sw1 * R.q1a; eb1.b1 = sw1 * R.q1b; eb1.a2 = cw1 * R.q2a; eb1.b2 = cw1 * R.q2b;
+        v14[0] = p; v14[1] = 1.0; v14[2] = rho * bp; v14[3] = -rho * g2;
+        v23[0] = xi; v23[1] = -p / eta; v23[2] = -rho * g2 * xi; v23[3] = -rho * bp / eta;
+      } else {
+        // interface l-1 -> l; new scales (sP, sS) = diagonal of the unscaled {1,4} block
+        double t14[4], t23[4];
+        mat2_mul(i14, v14, t14);
+        mat2_mul(i23, v23, t23);
+        const double sP = t14[0], sS = t14[3];
+        L.t12 = t14[1] / sP; L.t21 = t14[2] / sS;
+        L.u11 = t23[0] / sP; L.u12 = t23[1] / sP; L.u21 = t23[2] / sS; L.u22 = t23[3] / sS;
+        lc[l - 1] = L;
+        wave_interface(ea0, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
+        wave_interface(eb0, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
+        wave_interface(ea1, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
+        wave_interface(eb1, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
+        v14[0] = p * sP; v14[1] = sS; v14[2] = rho * bp * sP; v14[3] = -rho * g2 * sS;
+        v23[0] = xi * sP; v23[1] = -p / eta * sS; v23[2] = -rho * g2 * xi * sP; v23[3] = -rho * bp / eta * sS;
+      }
       L.thx = cfg.domg * xi * h;
       L.the = cfg.domg * eta * h;
       sincos((double)nthr_fwd * L.thx, &L.sbx, &L.cbx);
       sincos((double)nthr_fwd * L.the, &L.sbe, &L.cbe);
-      L.g = 2.0 * beta2 * p2;
-      L.bp = bp;
-      L.c12a = -p * bp / xi;            L.c12b = 2.0 * p * beta2 * eta;
-      L.c21a = 2.0 * p * beta2 * xi;    L.c21b = -p * bp / eta;
-      L.c13a = p2 / (xi * rho);         L.c13b = eta / rho;
-      L.c24a = xi / rho;                L.c24b = p2 / (eta * rho);
-      L.c31a = -4.0 * rho * beta2 * beta2 * p2 * xi;   L.c31b = -rho * bp * bp / eta;
-      L.c42a = -rho * bp * bp / xi;                    L.c42b = -4.0 * rho * beta2 * beta2 * p2 * eta;
-      L.c14 = p / rho;
-      L.c41 = 2.0 * beta2 * rho * p * bp;
-      lc[l] = L;
+      L.t12 = 0.0; L.t21 = 0.0; L.u11 = 1.0; L.u12 = 0.0; L.u21 = 0.0; L.u22 = 1.0;
       double c1, s1, c2, s2;
       sincos((double)1.0e-5f * xi * h, &s1, &c1);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
       sincos((double)1.0e-5f * eta * h, &s2, &c2);
-      layer_step(L, c1, s1, c2, s2, ya0, yb0);
+      wave_rotate(ea0, c1, s1, c2, s2);
+      wave_rotate(eb0, c1, s1, c2, s2);
       sincos(nyq * L.thx, &s1, &c1);
       sincos(nyq * L.the, &s2, &c2);
-      layer_step(L, c1, s1, c2, s2, ya1, yb1);
-    } else {  // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors
-      R.hs.e11 = beta2 * p / a;
-      R.hs.e12 = bp / (2.0 * a * xi);
-      R.hs.e13 = p / (2.0 * rho * a * xi);
-      R.hs.e14 = 1.0 / (2.0 * rho * a);
-      R.hs.e21 = bp / (2.0 * b * eta);
-      R.hs.e22 = b * p;
-      R.hs.e23 = 1.0 / (2.0 * rho * b);
-      R.hs.e24 = p / (2.0 * rho * b * eta);
+      wave_rotate(ea1, c1, s1, c2, s2);
+      wave_rotate(eb1, c1, s1, c2, s2);
+    } else {
+      lc[k - 1] = L;   // the last solid layer has no in-loop interface: the half space follows
+      // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the basis
+      const double e11 = beta2 * p / a, e12 = bp / (2.0 * a * xi), e13 = p / (2.0 * rho * a * xi), e14 = 1.0 / (2.0 * rho * a);
+      const double e21 = bp / (2.0 * b * eta), e22 = b * p, e23 = 1.0 / (2.0 * rho * b), e24 = p / (2.0 * rho * b * eta);
+      const double r14[4] = {e11, e14, e21, -e24};
+      const double r23[4] = {-e12, e13, e22, e23};
+      mat2_mul(r14, v14, R.h14);
+      mat2_mul(r23, v23, R.h23);
     }
   }
-  surface_response(R.hs, ya0, yb0, cw0, ipha, R.edge[0], R.edge[1]);
-  surface_response(R.hs, ya1, yb1, cw1, ipha, R.edge[2], R.edge[3]);
+  surface_response(R.h14, R.h23, ea0, eb0, cw0, ipha, R.edge[0], R.edge[1]);
+  surface_response(R.h14, R.h23, ea1, eb1, cw1, ipha, R.edge[2], R.edge[3]);
   R.tp = tp;
   R.k = k;
   R.valid = valid;
@@ -348,51 +375,66 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   double2* s_twq = reinterpret_cast<double2*>(s_red + 32); // [n/4] quarter-wave twiddles
 
   PHASE_INIT();
-  // ---- stage the constants of this (model, ray): one round trip to L2/HBM ----
-  int k = mb.k[c];
-  k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);   // same clamp as prep_kernel
+  // ---- stage the constants of this (model, ray): one round trip to L2/HBM, no dependent loads ----
   {
     const double* src = rc_in + (size_t)item * RC_DOUBLES;
     double* dst = reinterpret_cast<double*>(s_rc);
     for (int i = tid; i < RC_DOUBLES; i += nthr) dst[i] = src[i];
-    const double* src2 = lc_in + (size_t)item * km * LC_DOUBLES;
-    double* dst2 = reinterpret_cast<double*>(s_lc);
-    for (int i = tid; i < k * LC_DOUBLES; i += nthr) dst2[i] = src2[i];
-    for (int i = tid; i < (n >> 2); i += nthr) s_twq[i] = cfg.tw[i];
+    const double2* src2 = reinterpret_cast<const double2*>(lc_in + (size_t)item * km * LC_DOUBLES);
+    double2* dst2 = reinterpret_cast<double2*>(s_lc);
+    for (int i = tid; i < km * (LC_DOUBLES / 2); i += nthr) dst2[i] = src2[i];   // all k_max layers: k is not known yet
+    // quarter-wave twiddles: asynchronous copy, consumed only by the FFT after the layer loop
+    for (int i = tid; i < (n >> 2); i += nthr) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(&s_twq[i]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(cfg.tw + i));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
   }
   __syncthreads();
+  const int k = s_rc->k;
   PHASE_MARK(0);
   // ---- two-level rotation tables: cos/sin(tid*theta) = rot(lo[tid & 15], hi[tid >> 4]) ----
   // per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
-  // One thread per (layer, angle, level): one sincos, then a chain of rotations (<= 15 steps, error ~1e-15).
+  // One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
+  // independent rotations inside a level (error ~1e-16 * log2(16)).
   for (int task = tid; task < 4 * k; task += nthr) {
     const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
     const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
     const int cnt = level ? n_hi : 16;
     double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
-    double sb, cb;
-    sincos(th, &sb, &cb);
-    double cc = 1.0, ss = 0.0;
-    dst[0] = make_double2(1.0, 0.0);
-    for (int i = 1; i < cnt; ++i) {
-      rot(cc, ss, cb, sb);
-      dst[i] = make_double2(cc, ss);
+    double2 e[16];
+    e[0] = make_double2(1.0, 0.0);
+    sincos(th, &e[1].y, &e[1].x);
+#pragma unroll
+    for (int len = 2; len < 16; len <<= 1) {
+      e[len] = e[len >> 1];
+      rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
+#pragma unroll
+      for (int j = 1; j < len; ++j) {
+        e[len + j] = e[j];
+        rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) dst[i] = e[i];
   }
   __syncthreads();
   PHASE_MARK(1);
   const int ipha = cfg.ipha[t0];
 
-  // ---- propagator product over the solid layers, top down ----
-  double ya[J][4], yb[J][4], cwv[J];
+  // ---- propagator product over the solid layers, top down, in wave coordinates ----
+  Wave wa[J], wb[J];
+  double cwv[J];
   {
-    const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw, rw = s_rc->rw;
+    const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
+    const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
     double cw, sw;
     sincos((double)tid * thw, &sw, &cw);
 #pragma unroll
     for (int m = 0; m < J; ++m) {
-      ya[m][0] = 1.0; ya[m][1] = 0.0; ya[m][2] = 0.0; ya[m][3] = 0.0;
-      yb[m][0] = 0.0; yb[m][1] = cw; yb[m][2] = 0.0; yb[m][3] = -rw * sw;
+      wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
+      wb[m].a1 = sw * q1a; wb[m].b1 = sw * q1b; wb[m].a2 = cw * q2a; wb[m].b2 = cw * q2b;
       cwv[m] = cw;
       rot(cw, sw, cbw, sbw);
     }
@@ -407,29 +449,48 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
       c2 = c.x; s2 = c.y; rot(c2, s2, d.x, d.y);
     }
+    const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
+    if (l + 1 < k) {
 #pragma unroll
-    for (int m = 0; m < J; ++m) {
-      layer_step(L, c1, s1, c2, s2, ya[m], yb[m]);
-      if (m + 1 < J) {
-        rot(c1, s1, L.cbx, L.sbx);
-        rot(c2, s2, L.cbe, L.sbe);
+      for (int m = 0; m < J; ++m) {
+        wave_rotate(wa[m], c1, s1, c2, s2);
+        wave_rotate(wb[m], c1, s1, c2, s2);
+        wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
+        wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
+        if (m + 1 < J) {
+          rot(c1, s1, L.cbx, L.sbx);
+          rot(c2, s2, L.cbe, L.sbe);
+        }
+      }
+    } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
+#pragma unroll
+      for (int m = 0; m < J; ++m) {
+        wave_rotate(wa[m], c1, s1, c2, s2);
+        wave_rotate(wb[m], c1, s1, c2, s2);
+        if (m + 1 < J) {
+          rot(c1, s1, L.cbx, L.sbx);
+          rot(c2, s2, L.cbe, L.sbe);
+        }
       }
     }
   }
   PHASE_MARK(2);
   {
-    const HalfSpace H = s_rc->hs;
+    double h14[4], h23[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
 #pragma unroll
     for (int m = 0; m < J; ++m) {
       double2 fr, fv;
-      surface_response(H, ya[m], yb[m], cwv[m], ipha, fr, fv);
+      surface_response(h14, h23, wa[m], wb[m], cwv[m], ipha, fr, fv);
       s_fr[tid + m * nthr] = fr;
       s_fv[tid + m * nthr] = fv;
     }
-    if (tid == 0) {  // the two bins off the regular grid
-      s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
-      s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
-    }
+  }
+  __syncthreads();
+  if (tid == 0) {  // the two bins off the regular grid (after the barrier: bin 0 is also written above)
+    s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
+    s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
   }
   __syncthreads();
   PHASE_MARK(3);
@@ -482,6 +543,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
         s_buf0[n - j] = make_double2(xr.x + xv.y, xv.x - xr.y);
       }
     }
+    asm volatile("cp.async.wait_all;\n" ::);   // quarter-wave twiddles have landed (own copies; barrier publishes them)
     __syncthreads();
     PHASE_MARK(4);
     const double2* res = fft_inverse(s_buf0, s_buf1, n, cfg.log2n, s_twq, tid, nthr);
@@ -570,7 +632,8 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
 template <int J, int BMAX, int MINB>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
                      const double* rc, int nthr, cudaStream_t stream) {
-  const size_t smem = forward_smem_bytes(cfg, nthr);
+  static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
+  const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
   RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
@@ -583,6 +646,11 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
 }  // namespace
 
 int rfinv_forward_bins_per_thread(int nfft) {
+  static const int forced = getenv("RFINV_FWD_J") ? atoi(getenv("RFINV_FWD_J")) : 0;   // tuning knob
+  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
+    const int nthr = (nfft / 2) / forced;
+    if (nthr >= 32 && nthr <= 256 && (nthr & 15) == 0) return forced;
+  }
   if (nfft <= 64) return 1;
   if (nfft <= 256) return 2;
   if (nfft <= 1024) return 4;
@@ -607,16 +675,22 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
   prep_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, stream>>>(cfg, mb, lc, rc, out.is_valid, (int)n_items, ntr_eff, nthr);
   RFINV_CUDA_CHECK(cudaGetLastError());
-  switch (J) {
-    case 1: return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, nthr, stream);
-    case 2: return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, nthr, stream);
-    case 4: {
-      static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
-      if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
-      return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, nthr, stream);
-    }
-    default: return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
+  static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
+  if (J == 1) {
+    if (nthr <= 32) return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, nthr, stream);
+    return launch_forward_t<1, 256, 2>(cfg, mb, out, lc, rc, nthr, stream);
   }
+  if (J == 2) {
+    if (nthr <= 64) return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, nthr, stream);
+    return launch_forward_t<2, 256, 2>(cfg, mb, out, lc, rc, nthr, stream);
+  }
+  if (J == 4) {
+    if (nthr > 128) return launch_forward_t<4, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
+    if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
+    return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, nthr, stream);
+  }
+  if (nthr <= 64) return launch_forward_t<8, 64, 4>(cfg, mb, out, lc, rc, nthr, stream);
+  return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
 }
 
 int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,
