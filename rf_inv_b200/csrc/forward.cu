@@ -155,8 +155,9 @@ __device__ __forceinline__ void mat2_mul(const double* a, const double* b, doubl
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                    double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
-                                                   int n_items, int ntr_eff, int nthr_fwd) {
+                                                   int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item == 0) *counter = 0;   // work counter of the forward_kernel launch that follows on the same stream
   if (item >= n_items) return;
   if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
@@ -279,53 +280,103 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
   if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
 }
 
-// exp(+2 pi i m / n) for m < 3n/4 from the quarter-wave table twq[r] = exp(+2 pi i r / n), r < n/4
+// exp(+2 pi i m / n) for 0 <= m < n from the quarter-wave table twq[r] = exp(+2 pi i r / n), r < n/4
 __device__ __forceinline__ double2 twiddle(const double2* twq, int m, int qmask, int qshift) {
   const double2 w = twq[m & qmask];
-  const int q = m >> qshift;
-  return q == 0 ? w : (q == 1 ? make_double2(-w.y, w.x) : make_double2(-w.x, -w.y));
+  const int q = m >> qshift;   // w * i^q : (x,y), (-y,x), (-x,-y), (y,-x)
+  double2 r = (q & 1) ? make_double2(w.y, w.x) : w;
+  if (q == 1 || q == 2) r.x = -r.x;
+  if (q >= 2) r.y = -r.y;
+  return r;
 }
 
-// Stockham inverse FFT (sign +, unnormalised) of n complex points in shared memory, ping-pong x <-> y.
-// Returns the buffer holding the result.
-__device__ double2* fft_inverse(double2* x, double2* y, int n, int log2n, const double2* twq, int tid, int nthr) {
-  int Ns = 1;
-  if (log2n & 1) {  // one radix-2 pass (no twiddles at Ns = 1)
-    const int half = n >> 1;
-    for (int j = tid; j < half; j += nthr) {
-      const double2 a = x[j], b = x[j + half];
-      y[2 * j] = make_double2(a.x + b.x, a.y + b.y);
-      y[2 * j + 1] = make_double2(a.x - b.x, a.y - b.y);
-    }
-    __syncthreads();
-    double2* t = x; x = y; y = t;
-    Ns = 2;
+// Position of logical element p in the padded FFT buffer: one pad element per 8, so that "8 consecutive
+// elements per thread" (last radix-8 stage) and "consecutive elements across threads" are both conflict free.
+__device__ __forceinline__ int fpad(int p) { return p + (p >> 3); }
+__host__ __device__ inline size_t fft_buf_elems(size_t n) { return n + (n >> 3) + 1; }
+
+// 8-point inverse DFT in registers: v[q] <- sum_r v[r] exp(+2 pi i q r / 8)
+__device__ __forceinline__ void dft8(double2* v) {
+  const double hs = 0.70710678118654752440;
+  double2 e0, e1, e2, e3, o0, o1, o2, o3;
+  {
+    const double2 a = make_double2(v[0].x + v[4].x, v[0].y + v[4].y), b = make_double2(v[0].x - v[4].x, v[0].y - v[4].y);
+    const double2 c = make_double2(v[2].x + v[6].x, v[2].y + v[6].y), d = make_double2(-(v[2].y - v[6].y), v[2].x - v[6].x);
+    e0 = make_double2(a.x + c.x, a.y + c.y); e1 = make_double2(b.x + d.x, b.y + d.y);
+    e2 = make_double2(a.x - c.x, a.y - c.y); e3 = make_double2(b.x - d.x, b.y - d.y);
   }
-  const int quarter = n >> 2, qmask = quarter - 1, qshift = log2n - 2;
-  while (Ns < n) {
-    const int tstep = n / (4 * Ns);
-    for (int j = tid; j < quarter; j += nthr) {
-      const int k = j & (Ns - 1);
-      double2 v0 = x[j], v1 = x[j + quarter], v2 = x[j + 2 * quarter], v3 = x[j + 3 * quarter];
-      if (Ns > 1) {
-        v1 = cmul(v1, twiddle(twq, k * tstep, qmask, qshift));
-        v2 = cmul(v2, twiddle(twq, 2 * k * tstep, qmask, qshift));
-        v3 = cmul(v3, twiddle(twq, 3 * k * tstep, qmask, qshift));
+  {
+    const double2 a = make_double2(v[1].x + v[5].x, v[1].y + v[5].y), b = make_double2(v[1].x - v[5].x, v[1].y - v[5].y);
+    const double2 c = make_double2(v[3].x + v[7].x, v[3].y + v[7].y), d = make_double2(-(v[3].y - v[7].y), v[3].x - v[7].x);
+    o0 = make_double2(a.x + c.x, a.y + c.y);
+    const double2 t1 = make_double2(b.x + d.x, b.y + d.y), t2 = make_double2(a.x - c.x, a.y - c.y);
+    const double2 t3 = make_double2(b.x - d.x, b.y - d.y);
+    o1 = make_double2((t1.x - t1.y) * hs, (t1.x + t1.y) * hs);     // * (1 + i)/sqrt 2
+    o2 = make_double2(-t2.y, t2.x);                                // * i
+    o3 = make_double2(-(t3.x + t3.y) * hs, (t3.x - t3.y) * hs);    // * (-1 + i)/sqrt 2
+  }
+  v[0] = make_double2(e0.x + o0.x, e0.y + o0.y); v[4] = make_double2(e0.x - o0.x, e0.y - o0.y);
+  v[1] = make_double2(e1.x + o1.x, e1.y + o1.y); v[5] = make_double2(e1.x - o1.x, e1.y - o1.y);
+  v[2] = make_double2(e2.x + o2.x, e2.y + o2.y); v[6] = make_double2(e2.x - o2.x, e2.y - o2.y);
+  v[3] = make_double2(e3.x + o3.x, e3.y + o3.y); v[7] = make_double2(e3.x - o3.x, e3.y - o3.y);
+}
+
+// In-place decimation-in-frequency inverse FFT (sign +, unnormalised) of n complex points in the padded shared
+// buffer: radix-8 stages while the sub-transform length N >= 8, then one radix-4 or radix-2 stage.  Every stage
+// stores output q of a butterfly at bit-reversed digit position, so element f of the result ends up at logical
+// position bitreverse(f).  One barrier per stage.  Returns the maximum imaginary part over all outputs seen by
+// this thread (the vertical trace rides in the imaginary part).
+__device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2* twq, int tid, int nthr) {
+  const int qmask = (n >> 2) - 1, qshift = log2n - 2;
+  double vmax = -INFINITY;
+  int N = n;
+  for (; N >= 8; N >>= 3) {
+    const int stride = N >> 3, tmul = n / N;
+    const bool last = (N == 8);
+    for (int j = tid; j < (n >> 3); j += nthr) {
+      const int o = j & (stride - 1), base = ((j - o) << 3) + o;
+      double2 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) v[r] = buf[fpad(base + r * stride)];
+      dft8(v);
+      if (!last) {
+        const int m1 = o * tmul;
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], twiddle(twq, q * m1, qmask, qshift));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) vmax = fmax(vmax, v[q].y);
       }
-      const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
-      const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y);
-      const double2 a3 = make_double2(-(v1.y - v3.y), v1.x - v3.x);  // i*(v1 - v3)
-      const int j0 = ((j - k) << 2) + k;
-      y[j0] = make_double2(a0.x + a2.x, a0.y + a2.y);
-      y[j0 + Ns] = make_double2(a1.x + a3.x, a1.y + a3.y);
-      y[j0 + 2 * Ns] = make_double2(a0.x - a2.x, a0.y - a2.y);
-      y[j0 + 3 * Ns] = make_double2(a1.x - a3.x, a1.y - a3.y);
+      buf[fpad(base)] = v[0];              buf[fpad(base + 4 * stride)] = v[1];
+      buf[fpad(base + 2 * stride)] = v[2]; buf[fpad(base + 6 * stride)] = v[3];
+      buf[fpad(base + stride)] = v[4];     buf[fpad(base + 5 * stride)] = v[5];
+      buf[fpad(base + 3 * stride)] = v[6]; buf[fpad(base + 7 * stride)] = v[7];
     }
     __syncthreads();
-    double2* t = x; x = y; y = t;
-    Ns <<= 2;
   }
-  return x;
+  if (N == 4) {
+    for (int j = tid; j < (n >> 2); j += nthr) {
+      const int base = j << 2;
+      const double2 v0 = buf[fpad(base)], v1 = buf[fpad(base + 1)], v2 = buf[fpad(base + 2)], v3 = buf[fpad(base + 3)];
+      const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
+      const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y), a3 = make_double2(-(v1.y - v3.y), v1.x - v3.x);
+      const double2 r0 = make_double2(a0.x + a2.x, a0.y + a2.y), r1 = make_double2(a1.x + a3.x, a1.y + a3.y);
+      const double2 r2 = make_double2(a0.x - a2.x, a0.y - a2.y), r3 = make_double2(a1.x - a3.x, a1.y - a3.y);
+      vmax = fmax(fmax(vmax, r0.y), fmax(fmax(r1.y, r2.y), r3.y));
+      buf[fpad(base)] = r0; buf[fpad(base + 2)] = r1; buf[fpad(base + 1)] = r2; buf[fpad(base + 3)] = r3;
+    }
+    __syncthreads();
+  } else if (N == 2) {
+    for (int j = tid; j < (n >> 1); j += nthr) {
+      const int base = j << 1;
+      const double2 a = buf[fpad(base)], b = buf[fpad(base + 1)];
+      const double2 r0 = make_double2(a.x + b.x, a.y + b.y), r1 = make_double2(a.x - b.x, a.y - b.y);
+      vmax = fmax(vmax, fmax(r0.y, r1.y));
+      buf[fpad(base)] = r0; buf[fpad(base + 1)] = r1;
+    }
+    __syncthreads();
+  }
+  return vmax;
 }
 
 __device__ __forceinline__ double block_max(double v, double* scratch, int tid, int nthr) {
@@ -339,246 +390,287 @@ __device__ __forceinline__ double block_max(double v, double* scratch, int tid, 
   return r;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
 // ------------------------------------------------------------------------------------------------
-// forward_kernel: one CTA per (model, ray); thread `tid` owns frequency bins j = tid + m*B, m < J
+// forward_kernel: persistent CTAs, one (model, ray) item at a time, items handed out by an atomic counter
+// (the work per item is proportional to its layer count).  The constants of the next item are fetched with
+// cp.async while the current one is computed.  Thread `tid` owns frequency bins j = tid + m*B, m < J
 // (B = blockDim.x, B*J = nfft/2).  Bins 0 (DC) and nfft/2 (Nyquist) come from prep_kernel.
-// Shared memory: two FFT buffers of nfft complex doubles; the spectra alias the second one unless rays
-// are common to all traces (then they must survive the per-trace FFTs); layer constants behind them.
+// Shared memory: one region that first holds the trigonometric tables of the layer loop and then the padded
+// in-place FFT buffer; the unfiltered spectra only when they must outlive one FFT (common rays) or feed the
+// water-level deconvolution; two sets of layer / ray constants; quarter-wave twiddles.
 // ------------------------------------------------------------------------------------------------
 template <int J, int BMAX, int MINB>
 __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
                                                              const double* __restrict__ lc_in,
-                                                             const double* __restrict__ rc_in) {
+                                                             const double* __restrict__ rc_in, int* __restrict__ counter) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ int s_next;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  const int item = blockIdx.x;
-  if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;   // grid is sized for the upper bound
-  const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
-  const int c = mb.active ? mb.active[ci] : ci;
+  const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * ntr_eff;
+  const bool general = cfg.ray_common || cfg.deconv_mode == 1;   // spectra staged in shared memory
 
-  // layout: [buf1 | buf0 ... trig tables may extend past buf0 | (spectra if rays are common) | layer consts | ray consts]
   const int n_hi = nthr >> 4;                         // table split: tid = 16*hi + lo
   const int tab_per_layer = 2 * (16 + n_hi);          // double2 entries per layer: (xi | eta) x (lo | hi)
   const size_t tab_entries = (size_t)km * tab_per_layer;
-  const size_t region0 = tab_entries > (size_t)n ? tab_entries : (size_t)n;   // buf0 region also hosts the tables
-  double2* s_buf1 = reinterpret_cast<double2*>(smem_raw);
-  double2* s_buf0 = s_buf1 + n + 4;
-  double2* s_tab = s_buf0;                            // dead before buf0 is first written (Z build)
-  double2* s_fr = cfg.ray_common ? s_buf0 + region0 : s_buf1;   // [nh] unfiltered radial spectrum (or deconvolved RF spectrum)
-  double2* s_fv = s_fr + (nh + 1);                              // [nh] unfiltered vertical spectrum   (2*(nh+1) = n + 4)
-  double* s_tail = reinterpret_cast<double*>(s_buf0 + region0 + (cfg.ray_common ? 2 * (nh + 1) : 0));
-  LayerConst* s_lc = reinterpret_cast<LayerConst*>(s_tail);
-  RayConst* s_rc = reinterpret_cast<RayConst*>(s_lc + km);
-  double* s_red = reinterpret_cast<double*>(s_rc + 1);     // [32]
-  double2* s_twq = reinterpret_cast<double2*>(s_red + 32); // [n/4] quarter-wave twiddles
+  const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
+  double2* s_buf = reinterpret_cast<double2*>(smem_raw);
+  double2* s_tab = s_buf;                             // dead before the FFT buffer is first written
+  double2* s_fr = s_buf + region0;                    // [nh+1] unfiltered radial spectrum (or deconvolved RF spectrum)
+  double2* s_fv = s_fr + (nh + 1);                    // [nh+1] unfiltered vertical spectrum
+  double2* s_twq = s_fr + (general ? 2 * (nh + 1) : 0);   // [n/4] quarter-wave twiddles
+  double* s_red = reinterpret_cast<double*>(s_twq + (n >> 2));   // [32]
+  RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 32);     // [2]
+  LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
 
-  PHASE_INIT();
-  // ---- stage the constants of this (model, ray): one round trip to L2/HBM, no dependent loads ----
-  {
-    const double* src = rc_in + (size_t)item * RC_DOUBLES;
-    double* dst = reinterpret_cast<double*>(s_rc);
-    for (int i = tid; i < RC_DOUBLES; i += nthr) dst[i] = src[i];
+  auto prefetch = [&](int item, int slot) {
+    const double2* src = reinterpret_cast<const double2*>(rc_in + (size_t)item * RC_DOUBLES);
+    double2* dst = reinterpret_cast<double2*>(s_rc2 + slot);
+    for (int i = tid; i < RC_DOUBLES / 2; i += nthr) cp_async16(dst + i, src + i);
     const double2* src2 = reinterpret_cast<const double2*>(lc_in + (size_t)item * km * LC_DOUBLES);
-    double2* dst2 = reinterpret_cast<double2*>(s_lc);
-    for (int i = tid; i < km * (LC_DOUBLES / 2); i += nthr) dst2[i] = src2[i];   // all k_max layers: k is not known yet
-    // quarter-wave twiddles: asynchronous copy, consumed only by the FFT after the layer loop
-    for (int i = tid; i < (n >> 2); i += nthr) {
-      const unsigned d = (unsigned)__cvta_generic_to_shared(&s_twq[i]);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(cfg.tw + i));
-    }
-    asm volatile("cp.async.commit_group;\n" ::);
-  }
-  __syncthreads();
-  const int k = s_rc->k;
-  PHASE_MARK(0);
-  // ---- two-level rotation tables: cos/sin(tid*theta) = rot(lo[tid & 15], hi[tid >> 4]) ----
-  // per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
-  // One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
-  // independent rotations inside a level (error ~1e-16 * log2(16)).
-  for (int task = tid; task < 4 * k; task += nthr) {
-    const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
-    const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
-    const int cnt = level ? n_hi : 16;
-    double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
-    double2 e[16];
-    e[0] = make_double2(1.0, 0.0);
-    sincos(th, &e[1].y, &e[1].x);
-#pragma unroll
-    for (int len = 2; len < 16; len <<= 1) {
-      e[len] = e[len >> 1];
-      rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
-#pragma unroll
-      for (int j = 1; j < len; ++j) {
-        e[len + j] = e[j];
-        rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < cnt) dst[i] = e[i];
-  }
-  __syncthreads();
-  PHASE_MARK(1);
-  const int ipha = cfg.ipha[t0];
+    double2* dst2 = reinterpret_cast<double2*>(s_lc2 + (size_t)slot * km);
+    for (int i = tid; i < km * (LC_DOUBLES / 2); i += nthr) cp_async16(dst2 + i, src2 + i);   // all k_max layers: k is not known yet
+  };
 
-  // ---- propagator product over the solid layers, top down, in wave coordinates ----
-  Wave wa[J], wb[J];
-  double cwv[J];
-  {
-    const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
-    const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
-    double cw, sw;
-    sincos((double)tid * thw, &sw, &cw);
-#pragma unroll
-    for (int m = 0; m < J; ++m) {
-      wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
-      wb[m].a1 = sw * q1a; wb[m].b1 = sw * q1b; wb[m].a2 = cw * q2a; wb[m].b2 = cw * q2b;
-      cwv[m] = cw;
-      rot(cw, sw, cbw, sbw);
-    }
-  }
+  // Three items in flight per CTA: `item` is computed, the constants of `next` are being fetched, and the index
+  // after that is on its way back from the atomic counter (thread 0 holds it in a register until the end of the
+  // iteration, so nobody waits for the round trip).
+  int item = blockIdx.x, slot = 0;
+  if (item >= n_items) return;
+  for (int i = tid; i < (n >> 2); i += nthr) cp_async16(&s_twq[i], cfg.tw + i);
+  prefetch(item, 0);
+  asm volatile("cp.async.commit_group;\n" ::);
+  if (tid == 0) s_next = (int)gridDim.x + atomicAdd(counter, 1);
+
+  const int S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
   const int t_lo = tid & 15, t_hi = 16 + (tid >> 4);
-  for (int l = 0; l < k; ++l) {
-    const LayerConst& L = s_lc[l];
-    const double2* tab = s_tab + l * tab_per_layer;
-    double c1, s1, c2, s2;
+
+  while (item < n_items) {
+    PHASE_INIT();
+    asm volatile("cp.async.wait_all;\n" ::);
+    __syncthreads();   // constants of `item` (and, the first time, the twiddles) have landed; s_next is visible
+    const int next = s_next;
+    if (next < n_items) prefetch(next, slot ^ 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    int next2 = 0;
+    if (tid == 0) next2 = (int)gridDim.x + atomicAdd(counter, 1);
+    const RayConst* s_rc = s_rc2 + slot;
+    const LayerConst* s_lc = s_lc2 + (size_t)slot * km;
+    const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
+    const int c = mb.active ? mb.active[ci] : ci;
+    const int k = s_rc->k;
+    const int ipha = cfg.ipha[t0];
+    PHASE_MARK(0);
+    // ---- two-level rotation tables: cos/sin(tid*theta) = rot(lo[tid & 15], hi[tid >> 4]) ----
+    // per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
+    // One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
+    // independent rotations inside a level (error ~1e-16 * log2(16)).
+    for (int task = tid; task < 4 * k; task += nthr) {
+      const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
+      const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
+      const int cnt = level ? n_hi : 16;
+      double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
+      double2 e[16];
+      e[0] = make_double2(1.0, 0.0);
+      sincos(th, &e[1].y, &e[1].x);
+#pragma unroll
+      for (int len = 2; len < 16; len <<= 1) {
+        e[len] = e[len >> 1];
+        rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
+#pragma unroll
+        for (int j = 1; j < len; ++j) {
+          e[len + j] = e[j];
+          rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i < cnt) dst[i] = e[i];
+    }
+    __syncthreads();
+    PHASE_MARK(1);
+
+    // ---- propagator product over the solid layers, top down, in wave coordinates ----
+    Wave wa[J], wb[J];
     {
-      const double2 a = tab[t_lo], b = tab[t_hi], c = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
-      c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
-      c2 = c.x; s2 = c.y; rot(c2, s2, d.x, d.y);
-    }
-    const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
-    if (l + 1 < k) {
+      const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
+      const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
+      double cw = 1.0, sw = 0.0;
+      if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
 #pragma unroll
       for (int m = 0; m < J; ++m) {
-        wave_rotate(wa[m], c1, s1, c2, s2);
-        wave_rotate(wb[m], c1, s1, c2, s2);
-        wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
-        wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
-        if (m + 1 < J) {
-          rot(c1, s1, L.cbx, L.sbx);
-          rot(c2, s2, L.cbe, L.sbe);
+        wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
+        wb[m].a1 = sw * q1a; wb[m].b1 = sw * q1b; wb[m].a2 = cw * q2a; wb[m].b2 = cw * q2b;
+        rot(cw, sw, cbw, sbw);
+      }
+    }
+    for (int l = 0; l < k; ++l) {
+      const LayerConst& L = s_lc[l];
+      const double2* tab = s_tab + l * tab_per_layer;
+      double c1, s1, c2, s2;
+      {
+        const double2 a = tab[t_lo], b = tab[t_hi], cc = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
+        c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
+        c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
+      }
+      if (l + 1 < k) {
+        const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
+#pragma unroll
+        for (int m = 0; m < J; ++m) {
+          wave_rotate(wa[m], c1, s1, c2, s2);
+          wave_rotate(wb[m], c1, s1, c2, s2);
+          wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
+          wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
+          if (m + 1 < J) {
+            rot(c1, s1, L.cbx, L.sbx);
+            rot(c2, s2, L.cbe, L.sbe);
+          }
+        }
+      } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
+#pragma unroll
+        for (int m = 0; m < J; ++m) {
+          wave_rotate(wa[m], c1, s1, c2, s2);
+          wave_rotate(wb[m], c1, s1, c2, s2);
+          if (m + 1 < J) {
+            rot(c1, s1, L.cbx, L.sbx);
+            rot(c2, s2, L.cbe, L.sbe);
+          }
         }
       }
-    } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
+    }
+    PHASE_MARK(2);
+    __syncthreads();   // the trigonometric tables are dead: their region becomes the FFT buffer
+
+    // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
+    {
+      double h14[4], h23[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
+      const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
+      double cw = 1.0, sw = 0.0;
+      if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
+      const double* __restrict__ flt = cfg.flt + (size_t)t0 * nh;
 #pragma unroll
       for (int m = 0; m < J; ++m) {
-        wave_rotate(wa[m], c1, s1, c2, s2);
-        wave_rotate(wb[m], c1, s1, c2, s2);
-        if (m + 1 < J) {
-          rot(c1, s1, L.cbx, L.sbx);
-          rot(c2, s2, L.cbe, L.sbe);
+        const int j = tid + m * nthr;
+        double2 fr, fv;
+        surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
+        rot(cw, sw, cbw, sbw);
+        if (general) {
+          if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
+        } else if (j > 0) {
+          // packed spectrum Z = X_r + i X_v with Hermitian extension (src/forward.f90:168, 199)
+          const double f = flt[j];
+          const double2 xv = make_double2(fv.x * f, fv.y * f);
+          const double2 xr = ipha == 1 ? make_double2(fr.x * f, fr.y * f) : xv;
+          s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
+          s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
+        }
+      }
+      if (tid == 0) {  // the two bins off the regular grid
+        if (general) {
+          s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
+          s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
+        } else {       // c2r ignores the imaginary parts of DC and Nyquist
+          const double f0 = flt[0], f1 = flt[nh - 1];
+          const double2 r0 = ipha == 1 ? s_rc->edge[0] : s_rc->edge[1], r1 = ipha == 1 ? s_rc->edge[2] : s_rc->edge[3];
+          s_buf[fpad(0)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
+          s_buf[fpad(nh - 1)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
         }
       }
     }
-  }
-  PHASE_MARK(2);
-  {
-    double h14[4], h23[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
-#pragma unroll
-    for (int m = 0; m < J; ++m) {
-      double2 fr, fv;
-      surface_response(h14, h23, wa[m], wb[m], cwv[m], ipha, fr, fv);
-      s_fr[tid + m * nthr] = fr;
-      s_fv[tid + m * nthr] = fv;
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {  // the two bins off the regular grid (after the barrier: bin 0 is also written above)
-    s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
-    s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
-  }
-  __syncthreads();
-  PHASE_MARK(3);
+    __syncthreads();
+    PHASE_MARK(3);
 
-  // ---- water-level deconvolution (src/forward.f90:148-153, 447-470): overwrites s_fr with rff ----
-  if (cfg.deconv_mode == 1) {
-    const double2* xs = ipha == 1 ? s_fv : s_fr;  // denominator spectrum
-    const double2* ys = ipha == 1 ? s_fr : s_fv;
-    double mx = -INFINITY;
-    for (int j = tid; j < nh; j += nthr) mx = fmax(mx, xs[j].x * xs[j].x + xs[j].y * xs[j].y);
-    mx = block_max(mx, s_red, tid, nthr);
-    const double wlvl = 0.001 * mx;
-    double2 keep[J + 1];
-#pragma unroll
-    for (int q = 0; q < J + 1; ++q) {
-      const int j = tid + q * nthr;
-      if (j < nh) {
-        const double2 x = xs[j], y = ys[j];
-        const double amp = x.x * x.x + x.y * x.y;
-        const double d = fmax(amp, wlvl);
-        keep[q] = make_double2((y.x * x.x + y.y * x.y) / d, (y.y * x.x - y.x * x.y) / d);
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < J + 1; ++q) {
-      const int j = tid + q * nthr;
-      if (j < nh) s_fr[j] = keep[q];
-    }
-    __syncthreads();
-  }
-
-  // ---- per trace: filter -> inverse FFT -> shift / normalise -> outputs ----
-  const double tp = s_rc->tp;
-  const int S = cfg.nsmp, Sp = cfg.nsmp_pad;
-  const int t_begin = cfg.ray_common ? 0 : t0, t_end = cfg.ray_common ? cfg.ntrc : t0 + 1;
-  for (int t = t_begin; t < t_end; ++t) {
-    const double* __restrict__ flt = cfg.flt + (size_t)t * nh;
-    const double2* src_r = (cfg.deconv_mode == 1 || ipha == 1) ? s_fr : s_fv;  // rff
-    // packed spectrum Z = X_r + i X_v with Hermitian extension (c2r ignores Im of DC and Nyquist)
-    for (int j = tid; j < nh; j += nthr) {
-      const double f = flt[j];
-      const double2 xr = make_double2(src_r[j].x * f, src_r[j].y * f);
-      double2 xv = make_double2(0.0, 0.0);
-      if (cfg.deconv_mode == 0) xv = make_double2(s_fv[j].x * f, s_fv[j].y * f);
-      if (j == 0 || j == nh - 1) {
-        s_buf0[j] = make_double2(xr.x, xv.x);
-      } else {
-        s_buf0[j] = make_double2(xr.x - xv.y, xr.y + xv.x);
-        s_buf0[n - j] = make_double2(xr.x + xv.y, xv.x - xr.y);
-      }
-    }
-    asm volatile("cp.async.wait_all;\n" ::);   // quarter-wave twiddles have landed (own copies; barrier publishes them)
-    __syncthreads();
-    PHASE_MARK(4);
-    const double2* res = fft_inverse(s_buf0, s_buf1, n, cfg.log2n, s_twq, tid, nthr);
-    PHASE_MARK(5);
-    double fac = 1.0;
-    if (cfg.deconv_mode == 0) {  // src/forward.f90:197-203
+    // ---- water-level deconvolution (src/forward.f90:148-153, 447-470): overwrites s_fr with rff ----
+    if (cfg.deconv_mode == 1) {
+      const double2* xs = ipha == 1 ? s_fv : s_fr;  // denominator spectrum
+      const double2* ys = ipha == 1 ? s_fr : s_fv;
       double mx = -INFINITY;
-      for (int i = tid; i < n; i += nthr) mx = fmax(mx, res[i].y);
-      fac = block_max(mx, s_red, tid, nthr);
-    }
-    int npre;
-    if (ipha == 1) npre = f_nint((-cfg.t_start - tp) / cfg.delta);   // src/forward.f90:177
-    else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
-    const int nout = out.rft_full ? n : S;
-    double* mis = out.misfit + ((size_t)t * C + c) * Sp;
-    double* smp_base = out.rft_smp;
-    if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
-    double* smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
-    double* full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
-    const double* __restrict__ obs = cfg.obs + (size_t)t * S;
-    const double scale = cfg.deconv_mode == 0 ? 1.0 / fac : 1.0;
-    const int nmask = n - 1;
-    for (int i = tid; i < nout; i += nthr) {
-      double v;
-      if (ipha == 1) v = res[(i - npre) & nmask].x;       // src/forward.f90:178-184 (n is a power of two)
-      else v = -res[(npre - i - 1) & nmask].x;            // src/forward.f90:187-193
-      v *= scale;
-      if (i < S) {
-        mis[i] = v - obs[i];
-        if (smp) smp[i] = v;
+      for (int j = tid; j < nh; j += nthr) mx = fmax(mx, xs[j].x * xs[j].x + xs[j].y * xs[j].y);
+      mx = block_max(mx, s_red, tid, nthr);
+      const double wlvl = 0.001 * mx;
+      double2 keep[J + 1];
+#pragma unroll
+      for (int q = 0; q < J + 1; ++q) {
+        const int j = tid + q * nthr;
+        if (j < nh) {
+          const double2 x = xs[j], y = ys[j];
+          const double amp = x.x * x.x + x.y * x.y;
+          const double d = fmax(amp, wlvl);
+          keep[q] = make_double2((y.x * x.x + y.y * x.y) / d, (y.y * x.x - y.x * x.y) / d);
+        }
       }
-      if (full) full[i] = v;
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < J + 1; ++q) {
+        const int j = tid + q * nthr;
+        if (j < nh) s_fr[j] = keep[q];
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    PHASE_MARK(6);
+
+    // ---- per trace: filter -> inverse FFT -> shift / normalise -> outputs ----
+    const double tp = s_rc->tp;
+    const int t_begin = cfg.ray_common ? 0 : t0, t_end = cfg.ray_common ? cfg.ntrc : t0 + 1;
+    for (int t = t_begin; t < t_end; ++t) {
+      if (general) {
+        const double* __restrict__ flt = cfg.flt + (size_t)t * nh;
+        const double2* src_r = (cfg.deconv_mode == 1 || ipha == 1) ? s_fr : s_fv;  // rff
+        for (int j = tid; j < nh; j += nthr) {
+          const double f = flt[j];
+          const double2 xr = make_double2(src_r[j].x * f, src_r[j].y * f);
+          double2 xv = make_double2(0.0, 0.0);
+          if (cfg.deconv_mode == 0) xv = make_double2(s_fv[j].x * f, s_fv[j].y * f);
+          if (j == 0 || j == nh - 1) {
+            s_buf[fpad(j)] = make_double2(xr.x, xv.x);
+          } else {
+            s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
+            s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
+          }
+        }
+        __syncthreads();
+      }
+      PHASE_MARK(4);
+      double mx = fft_inverse_dif(s_buf, n, cfg.log2n, s_twq, tid, nthr);
+      PHASE_MARK(5);
+      double scale = 1.0;
+      if (cfg.deconv_mode == 0) scale = 1.0 / block_max(mx, s_red, tid, nthr);  // src/forward.f90:197-203
+      int npre;
+      if (ipha == 1) npre = f_nint((-cfg.t_start - tp) / cfg.delta);   // src/forward.f90:177
+      else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
+      const int nout = out.rft_full ? n : S;
+      double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
+      double* smp_base = out.rft_smp;
+      if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
+      double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
+      double* __restrict__ full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
+      const double* __restrict__ obs = cfg.obs + (size_t)t * S;
+#pragma unroll 4
+      for (int i = tid; i < nout; i += nthr) {
+        // element f of the transform sits at bit-reversed position (n is a power of two)
+        const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
+                                : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
+        double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
+        if (ipha != 1) v = -v;
+        if (i < S) {
+          mis[i] = v - __ldg(obs + i);
+          if (smp) smp[i] = v;
+        }
+        if (full) full[i] = v;
+      }
+      if (tid == 0 && t + 1 == t_end) s_next = next2;
+      __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables
+      PHASE_MARK(6);
+    }
+    item = next;
+    slot ^= 1;
   }
 }
 
@@ -624,21 +716,29 @@ __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, in
 size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
   const size_t tab_entries = km * 2 * (16 + (nthr >> 4));
-  const size_t region0 = tab_entries > n ? tab_entries : n;
-  const size_t spectra = cfg.ray_common ? 2 * (nh + 1) : 0;   // aliased onto buf1 otherwise
-  return sizeof(double2) * (n + 4 + region0 + spectra + n / 4) + sizeof(LayerConst) * km + sizeof(RayConst) + sizeof(double) * 32;
+  const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
+  const bool general = cfg.ray_common || cfg.deconv_mode == 1;
+  const size_t spectra = general ? 2 * (nh + 1) : 0;
+  return sizeof(double2) * (region0 + spectra + n / 4) + sizeof(double) * 32 + 2 * sizeof(RayConst) + 2 * sizeof(LayerConst) * km;
 }
 
 template <int J, int BMAX, int MINB>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
-                     const double* rc, int nthr, cudaStream_t stream) {
+                     const double* rc, int* counter, int nthr, cudaStream_t stream) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
   RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, n_sm = 0, per_sm = 0;
+  RFINV_CUDA_CHECK(cudaGetDevice(&dev));
+  RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB>, nthr, smem));
+  if (per_sm < 1) { rfinv_set_error("forward_kernel does not fit on an SM (%zu bytes of shared memory)", smem); return RFINV_ERR_CUDA; }
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  const long long grid = (long long)n_models * ntr_eff;
-  forward_kernel<J, BMAX, MINB><<<(unsigned)grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc);
+  const long long items = (long long)n_models * ntr_eff;
+  const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
+  const unsigned grid = (unsigned)(items < resident ? items : resident);
+  forward_kernel<J, BMAX, MINB><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -659,7 +759,7 @@ int rfinv_forward_bins_per_thread(int nfft) {
 
 size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
   const long long ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES);
+  return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES) + 2;   // + the work counter
 }
 
 // scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
@@ -673,24 +773,27 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   if (n_items == 0) return RFINV_OK;
   double* lc = scratch;
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
-  prep_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, stream>>>(cfg, mb, lc, rc, out.is_valid, (int)n_items, ntr_eff, nthr);
+  int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
+  prep_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
   RFINV_CUDA_CHECK(cudaGetLastError());
   static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
   if (J == 1) {
-    if (nthr <= 32) return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, nthr, stream);
-    return launch_forward_t<1, 256, 2>(cfg, mb, out, lc, rc, nthr, stream);
+    if (nthr <= 32) return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    return launch_forward_t<1, 256, 2>(cfg, mb, out, lc, rc, counter, nthr, stream);
   }
   if (J == 2) {
-    if (nthr <= 64) return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, nthr, stream);
-    return launch_forward_t<2, 256, 2>(cfg, mb, out, lc, rc, nthr, stream);
+    if (nthr <= 64) return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    if (minb == 3) return launch_forward_t<2, 256, 3>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    return launch_forward_t<2, 256, 2>(cfg, mb, out, lc, rc, counter, nthr, stream);
   }
   if (J == 4) {
-    if (nthr > 128) return launch_forward_t<4, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
-    if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, nthr, stream);
-    return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, nthr, stream);
+    if (nthr > 128) return launch_forward_t<4, 256, 1>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    if (minb == 5) return launch_forward_t<4, 128, 5>(cfg, mb, out, lc, rc, counter, nthr, stream);
+    return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, counter, nthr, stream);
   }
-  if (nthr <= 64) return launch_forward_t<8, 64, 4>(cfg, mb, out, lc, rc, nthr, stream);
-  return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, nthr, stream);
+  if (nthr <= 64) return launch_forward_t<8, 64, 4>(cfg, mb, out, lc, rc, counter, nthr, stream);
+  return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, counter, nthr, stream);
 }
 
 int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,

@@ -9,7 +9,8 @@ capi._lib = capi.load(so)
 from rf_inv_b200.evaluator import Evaluator
 cfg = workloads.make_config("target")
 cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
-m = workloads.draw_models(cfg, 16384, seed=100, dvs_scale=0.3)
+nC = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+m = workloads.draw_models(cfg, nC, seed=100, dvs_scale=0.3)
 with Evaluator(cfg) as ev:
     capi.check(capi._lib.rfinv_set_timing(ev.handle, 1))
     ts = []
