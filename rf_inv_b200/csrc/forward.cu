@@ -141,23 +141,49 @@ __device__ __forceinline__ void mat2_mul(const double* a, const double* b, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// prep_kernel: one thread per (model, ray).  format_model (src/model.f90:175-290), the per-layer
-// constants of the wave-coordinate propagator for this ray (rotation angles, interface blocks),
-// half-space / water-layer constants, the direct-arrival delay, and the two bins that do not fit the
-// regular frequency grid of forward_kernel: the DC pseudo-frequency omega = 1.0e-5
-// (src/forward.f90:246-248) and the Nyquist bin.
+// prep_kernel: one WARP per (model, ray), lane <-> layer.  format_model (src/model.f90:175-290), the per-layer
+// constants of the wave-coordinate propagator for this ray (rotation angles, interface blocks), half-space /
+// water-layer constants, the direct-arrival delay, and the two bins that do not fit the regular frequency grid
+// of forward_kernel: the DC pseudo-frequency omega = 1.0e-5 (src/forward.f90:246-248) and the Nyquist bin.
 //
 // Basis of a solid layer (columns = standing P wave, standing S wave; rows = components {1,4} / {2,3}):
 //   V14 = [[p, 1], [rho bp, -2 rho beta^2 p]],          V14^-1 = [[2 beta^2 p, 1/rho], [bp, -p/rho]]
 //   V23 = [[xi, -p/eta], [-2 rho beta^2 p xi, -rho bp/eta]],   V23^-1 = [[bp/xi, -p/(rho xi)], [-2 beta^2 p eta, -eta/rho]]
 // with bp = 1 - 2 beta^2 p^2; B_l = V R V^-1 reproduces layer_matrix_sol (src/forward.f90:385-421).
-// The basis of layer l is scaled by (sP, sS) on its (P, S) columns so that V14_l^-1 V14_{l-1} has a unit diagonal.
+// The basis of layer l is scaled by (sP_l, sS_l) on its (P, S) columns so that T14_l = V14_l^-1 V14_{l-1} has a
+// unit diagonal: with tau = (unscaled V_l^-1)(unscaled V_{l-1}), sP_l = prod tau14[0][0], sS_l = prod tau14[1][1]
+// (warp prefix products), and the interface constants only need the ratio r = sS/sP of the layer above.
+//
+// Phases (warp-synchronous, staged through shared memory): rank sort of the interfaces; per-layer physics, all
+// transcendental functions included, one layer per lane; prefix products and interface constants; then the only
+// serial part: lanes 0-3 carry the four edge-bin vectors down the stack while lane 4 sums the delay in the
+// reference's order.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
-                                                   double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
-                                                   int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item == 0) *counter = 0;   // work counter of the forward_kernel launch that follows on the same stream
+struct PrepLayer {
+  double v14[4], v23[4];   // unscaled basis blocks of this layer
+  double tr[8];            // cos, sin of (w xi h), (w eta h) at the DC pseudo-frequency, then at Nyquist
+  double ic[6];            // t12, t21, u11, u12, u21, u22 of the interface below this layer
+  double tpterm, pad;
+};
+constexpr int PREP_WARPS = 4;
+__host__ __device__ inline size_t prep_smem_doubles_per_warp(int km) { return (size_t)6 * km + (size_t)(km + 1) * (sizeof(PrepLayer) / sizeof(double)); }
+
+__device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclusive prefix product, fixed order
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double y = __shfl_up_sync(0xffffffffu, x, o);
+    if (lane >= o) x *= y;
+  }
+  return x;
+}
+
+__global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
+                                                              double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
+                                                              int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
+  extern __shared__ __align__(16) double prep_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * PREP_WARPS + warp;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;   // work counter of the forward_kernel launch that follows on the same stream
   if (item >= n_items) return;
   if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
@@ -167,43 +193,33 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
   k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
   const double p = cfg.rayp[t0];
   const int ipha = cfg.ipha[t0];
-  double z[RFINV_MAX_K], dp[RFINV_MAX_K], ds[RFINV_MAX_K];
-  for (int i = 0; i < k; ++i) {
-    z[i] = mb.z[(size_t)i * C + c]; dp[i] = mb.dvp[(size_t)i * C + c]; ds[i] = mb.dvs[(size_t)i * C + c];
+  double* zu = prep_smem + (size_t)warp * prep_smem_doubles_per_warp(km);   // unsorted z, dvp, dvs, then sorted
+  double *du = zu + km, *su = du + km, *zs = su + km, *dps = zs + km, *dss = dps + km;
+  PrepLayer* PL = reinterpret_cast<PrepLayer*>(dss + km);
+
+  // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
+  for (int i = lane; i < k; i += 32) {
+    zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
   }
-  for (int i = 1; i < k; ++i) {  // src/sort.f90:34-68 (any correct sort; keys are distinct)
-    const double a = z[i], b = dp[i], d = ds[i];
-    int m = i - 1;
-    while (m >= 0 && z[m] > a) { z[m + 1] = z[m]; dp[m + 1] = dp[m]; ds[m + 1] = ds[m]; --m; }
-    z[m + 1] = a; dp[m + 1] = b; ds[m + 1] = d;
+  __syncwarp();
+  for (int i = lane; i < k; i += 32) {
+    const double zi = zu[i];
+    int rank = 0;
+    for (int j = 0; j < k; ++j) { const double zj = zu[j]; rank += (zj < zi || (zj == zi && j < i)) ? 1 : 0; }
+    zs[rank] = zi; dps[rank] = du[i]; dss[rank] = su[i];
   }
-  RayConst R;
-  // water layer (src/model.f90:201-207, src/forward.f90:424-442): cos/sin of the two edge bins
-  double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
-  const double nyq = (double)(cfg.nfft / 2);
-  if (cfg.sdep > 0.0) {
-    const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
-    const double xiw = sqrt(1.0 / (aw * aw) - p * p);
-    R.thw = cfg.domg * xiw * hw;
-    sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
-    rw = rhow / xiw;
-    sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
-    sincos(nyq * R.thw, &sw1, &cw1);
-  } else {
-    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
-  }
-  bool valid = true;
-  double tp = 0.0;
-  LayerConst* lc = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km;
+  __syncwarp();
+
+  // ---- per-layer physics, one layer per lane ----
   const double p2 = __dmul_rn(p, p);
-  Wave ea0, eb0, ea1, eb1;                 // the two vectors at the DC pseudo-frequency (0) and at Nyquist (1)
-  double v14[4], v23[4];                   // scaled basis blocks of the previous layer
-  LayerConst L;
-  for (int l = 0; l <= k; ++l) {
+  const double nyq = (double)(cfg.nfft / 2);
+  bool valid = true;
+  double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane k & 31)
+  for (int l = lane; l <= k; l += 32) {
     double zc, h, dvs_l, dvp_l;
-    if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, z[0])); h = __dsub_rn(z[0], cfg.sdep); dvs_l = ds[0]; dvp_l = dp[0]; }
-    else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(z[l], z[l - 1])); h = __dsub_rn(z[l], z[l - 1]); dvs_l = ds[l]; dvp_l = dp[l]; }
-    else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, z[k - 1])); h = 999.0;
+    if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
+    else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
+    else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
            dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; }
     double a, b;
     bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
@@ -216,68 +232,142 @@ __global__ void __launch_bounds__(128) prep_kernel(const DevConfig cfg, const Mo
     const double eta = sqrt(__dsub_rn(__ddiv_rn(1.0, beta2), p2));              // src/forward.f90:395
     const double xi = sqrt(__dsub_rn(__ddiv_rn(1.0, __dmul_rn(a, a)), p2));    // src/forward.f90:396
     if (l < k) {
-      if (cfg.deconv_mode == 0) tp = __dadd_rn(tp, __dmul_rn(h, ipha == 1 ? xi : eta));  // src/forward.f90:489-491
+      PrepLayer& Q = PL[l];
       const double g2 = 2.0 * beta2 * p;   // 2 beta^2 p
-      const double i14[4] = {g2, 1.0 / rho, bp, -p / rho};                               // V14^-1
-      const double i23[4] = {bp / xi, -p / (rho * xi), -g2 * eta, -eta / rho};           // V23^-1
-      if (l == 0) {
-        // start vectors in layer 0's coordinates: e1, and (0, cw, 0, -rw sw) for a unit pressure-free / water top
-        R.a1 = i14[0]; R.b1 = i14[2];
-        R.q1a = -rw * i14[1]; R.q1b = -rw * i14[3];
-        R.q2a = i23[0]; R.q2b = i23[2];
-        ea0.a1 = R.a1; ea0.b1 = R.b1; ea0.a2 = 0.0; ea0.b2 = 0.0; ea1 = ea0;
-        eb0.a1 = sw0 * R.q1a; eb0.b1 = sw0 * R.q1b; eb0.a2 = cw0 * R.q2a; eb0.b2 = cw0 * R.q2b;
-        eb1.a1 = sw1 * R.q1a; eb1.b1 = sw1 * R.q1b; eb1.a2 = cw1 * R.q2a; eb1.b2 = cw1 * R.q2b;
-        v14[0] = p; v14[1] = 1.0; v14[2] = rho * bp; v14[3] = -rho * g2;
-        v23[0] = xi; v23[1] = -p / eta; v23[2] = -rho * g2 * xi; v23[3] = -rho * bp / eta;
-      } else {
-        // interface l-1 -> l; new scales (sP, sS) = diagonal of the unscaled {1,4} block
-        double t14[4], t23[4];
-        mat2_mul(i14, v14, t14);
-        mat2_mul(i23, v23, t23);
-        const double sP = t14[0], sS = t14[3];
-        L.t12 = t14[1] / sP; L.t21 = t14[2] / sS;
-        L.u11 = t23[0] / sP; L.u12 = t23[1] / sP; L.u21 = t23[2] / sS; L.u22 = t23[3] / sS;
-        lc[l - 1] = L;
-        wave_interface(ea0, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
-        wave_interface(eb0, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
-        wave_interface(ea1, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
-        wave_interface(eb1, L.t12, L.t21, L.u11, L.u12, L.u21, L.u22);
-        v14[0] = p * sP; v14[1] = sS; v14[2] = rho * bp * sP; v14[3] = -rho * g2 * sS;
-        v23[0] = xi * sP; v23[1] = -p / eta * sS; v23[2] = -rho * g2 * xi * sP; v23[3] = -rho * bp / eta * sS;
-      }
-      L.thx = cfg.domg * xi * h;
-      L.the = cfg.domg * eta * h;
-      sincos((double)nthr_fwd * L.thx, &L.sbx, &L.cbx);
-      sincos((double)nthr_fwd * L.the, &L.sbe, &L.cbe);
-      L.t12 = 0.0; L.t21 = 0.0; L.u11 = 1.0; L.u12 = 0.0; L.u21 = 0.0; L.u22 = 1.0;
-      double c1, s1, c2, s2;
-      sincos((double)1.0e-5f * xi * h, &s1, &c1);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
-      sincos((double)1.0e-5f * eta * h, &s2, &c2);
-      wave_rotate(ea0, c1, s1, c2, s2);
-      wave_rotate(eb0, c1, s1, c2, s2);
-      sincos(nyq * L.thx, &s1, &c1);
-      sincos(nyq * L.the, &s2, &c2);
-      wave_rotate(ea1, c1, s1, c2, s2);
-      wave_rotate(eb1, c1, s1, c2, s2);
+      Q.v14[0] = p; Q.v14[1] = 1.0; Q.v14[2] = rho * bp; Q.v14[3] = -rho * g2;
+      Q.v23[0] = xi; Q.v23[1] = -p / eta; Q.v23[2] = -rho * g2 * xi; Q.v23[3] = -rho * bp / eta;
+      Q.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(h, ipha == 1 ? xi : eta) : 0.0;   // src/forward.f90:489-491
+      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + l;
+      const double thx = cfg.domg * xi * h, the = cfg.domg * eta * h;
+      L->thx = thx; L->the = the;
+      double sn, cs;
+      sincos((double)nthr_fwd * thx, &sn, &cs); L->cbx = cs; L->sbx = sn;
+      sincos((double)nthr_fwd * the, &sn, &cs); L->cbe = cs; L->sbe = sn;
+      sincos((double)1.0e-5f * xi * h, &Q.tr[1], &Q.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
+      sincos((double)1.0e-5f * eta * h, &Q.tr[3], &Q.tr[2]);
+      sincos(nyq * thx, &Q.tr[5], &Q.tr[4]);
+      sincos(nyq * the, &Q.tr[7], &Q.tr[6]);
     } else {
-      lc[k - 1] = L;   // the last solid layer has no in-loop interface: the half space follows
-      // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the basis
-      const double e11 = beta2 * p / a, e12 = bp / (2.0 * a * xi), e13 = p / (2.0 * rho * a * xi), e14 = 1.0 / (2.0 * rho * a);
-      const double e21 = bp / (2.0 * b * eta), e22 = b * p, e23 = 1.0 / (2.0 * rho * b), e24 = p / (2.0 * rho * b * eta);
-      const double r14[4] = {e11, e14, e21, -e24};
-      const double r23[4] = {-e12, e13, e22, e23};
-      mat2_mul(r14, v14, R.h14);
-      mat2_mul(r23, v23, R.h23);
+      hs_a = a; hs_b = b; hs_rho = rho; hs_xi = xi; hs_eta = eta; hs_bp = bp; hs_beta2 = beta2;
     }
   }
-  surface_response(R.h14, R.h23, ea0, eb0, cw0, ipha, R.edge[0], R.edge[1]);
-  surface_response(R.h14, R.h23, ea1, eb1, cw1, ipha, R.edge[2], R.edge[3]);
-  R.tp = tp;
-  R.k = k;
-  R.valid = valid;
-  reinterpret_cast<RayConst*>(rc_out)[item] = R;
-  if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
+  valid = __all_sync(0xffffffffu, valid);
+  __syncwarp();
+
+  // ---- interfaces l-1 -> l (l = 1..k-1): tau = V_l^-1 V_{l-1} unscaled, prefix products of its {1,4} diagonal ----
+  double carryP = 1.0, carryS = 1.0;      // scale products of the slots already done
+  double sP_last = 1.0, sS_last = 1.0;    // scales of the last solid layer k-1
+  for (int base = 0; base < k; base += 32) {
+    const int l = base + lane;
+    double t14[4] = {1.0, 0.0, 0.0, 1.0}, t23[4] = {1.0, 0.0, 0.0, 1.0};
+    if (l >= 1 && l < k) {
+      // V_l^-1 from this layer's own blocks: V14 = [[p,1],[m,n]] has determinant -rho, V23 determinant -rho xi/eta
+      const PrepLayer& Q = PL[l];
+      const double d14 = Q.v14[0] * Q.v14[3] - Q.v14[1] * Q.v14[2], d23 = Q.v23[0] * Q.v23[3] - Q.v23[1] * Q.v23[2];
+      const double i14[4] = {Q.v14[3] / d14, -Q.v14[1] / d14, -Q.v14[2] / d14, Q.v14[0] / d14};
+      const double i23[4] = {Q.v23[3] / d23, -Q.v23[1] / d23, -Q.v23[2] / d23, Q.v23[0] / d23};
+      mat2_mul(i14, PL[l - 1].v14, t14);
+      mat2_mul(i23, PL[l - 1].v23, t23);
+    }
+    const double sP = carryP * warp_scan_mul(t14[0], lane), sS = carryS * warp_scan_mul(t14[3], lane);   // scales of layer l
+    double sPp = __shfl_up_sync(0xffffffffu, sP, 1), sSp = __shfl_up_sync(0xffffffffu, sS, 1);           // scales of layer l-1
+    if (lane == 0) { sPp = carryP; sSp = carryS; }
+    if (l >= 1 && l < k) {
+      double* ic = PL[l - 1].ic;
+      ic[0] = t14[1] * sSp / sP; ic[1] = t14[2] * sPp / sS;
+      ic[2] = t23[0] * sPp / sP; ic[3] = t23[1] * sSp / sP; ic[4] = t23[2] * sPp / sS; ic[5] = t23[3] * sSp / sS;
+      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (l - 1);
+      L->t12 = ic[0]; L->t21 = ic[1]; L->u11 = ic[2]; L->u12 = ic[3]; L->u21 = ic[4]; L->u22 = ic[5];
+    }
+    const int last_lane = (k - 1 - base) < 31 ? (k - 1 - base) : 31;   // highest lane of this slot holding a solid layer
+    carryP = __shfl_sync(0xffffffffu, sP, last_lane);
+    carryS = __shfl_sync(0xffffffffu, sS, last_lane);
+    sP_last = carryP; sS_last = carryS;
+  }
+  if (lane == 0) {   // the last solid layer has no in-loop interface: the half space follows
+    LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (k - 1);
+    L->t12 = 0.0; L->t21 = 0.0; L->u11 = 1.0; L->u12 = 0.0; L->u21 = 0.0; L->u22 = 1.0;
+  }
+  __syncwarp();
+
+  // ---- ray constants: half space, water layer, start vectors ----
+  RayConst R;
+  double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
+  if (cfg.sdep > 0.0) {   // water layer (src/model.f90:201-207, src/forward.f90:424-442)
+    const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
+    const double xiw = sqrt(1.0 / (aw * aw) - p * p);
+    R.thw = cfg.domg * xiw * hw;
+    sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
+    rw = rhow / xiw;
+    sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
+    sincos(nyq * R.thw, &sw1, &cw1);
+  } else {
+    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
+  }
+  {
+    // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the scaled basis of
+    // the last solid layer
+    const int src_lane = k & 31;
+    const double a = __shfl_sync(0xffffffffu, hs_a, src_lane), b = __shfl_sync(0xffffffffu, hs_b, src_lane);
+    const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
+    const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
+    const double beta2 = __shfl_sync(0xffffffffu, hs_beta2, src_lane);
+    const double e11 = beta2 * p / a, e12 = bp / (2.0 * a * xi), e13 = p / (2.0 * rho * a * xi), e14 = 1.0 / (2.0 * rho * a);
+    const double e21 = bp / (2.0 * b * eta), e22 = b * p, e23 = 1.0 / (2.0 * rho * b), e24 = p / (2.0 * rho * b * eta);
+    const double r14[4] = {e11, e14, e21, -e24};
+    const double r23[4] = {-e12, e13, e22, e23};
+    const PrepLayer& Q = PL[k - 1];
+    const double v14[4] = {Q.v14[0] * sP_last, Q.v14[1] * sS_last, Q.v14[2] * sP_last, Q.v14[3] * sS_last};
+    const double v23[4] = {Q.v23[0] * sP_last, Q.v23[1] * sS_last, Q.v23[2] * sP_last, Q.v23[3] * sS_last};
+    mat2_mul(r14, v14, R.h14);
+    mat2_mul(r23, v23, R.h23);
+  }
+  {
+    // start vectors in layer 0's coordinates (scale 1): e1, and (0, cw, 0, -rw sw) for a free / water-loaded surface
+    const PrepLayer& Q = PL[0];
+    const double d14 = Q.v14[0] * Q.v14[3] - Q.v14[1] * Q.v14[2], d23 = Q.v23[0] * Q.v23[3] - Q.v23[1] * Q.v23[2];
+    R.a1 = Q.v14[3] / d14; R.b1 = -Q.v14[2] / d14;                 // V14^-1 (1, 0)^T
+    R.q1a = -rw * (-Q.v14[1] / d14); R.q1b = -rw * (Q.v14[0] / d14);   // -rw V14^-1 (0, 1)^T
+    R.q2a = Q.v23[3] / d23; R.q2b = -Q.v23[2] / d23;               // V23^-1 (1, 0)^T
+  }
+
+  // ---- serial part: lanes 0..3 carry (vector a | b) x (DC | Nyquist) down the stack; lane 4 sums the delay ----
+  Wave w;
+  {
+    const bool is_b = lane & 1, is_nyq = (lane >> 1) & 1;
+    const double cw = is_nyq ? cw1 : cw0, sw = is_nyq ? sw1 : sw0;
+    if (!is_b) { w.a1 = R.a1; w.b1 = R.b1; w.a2 = 0.0; w.b2 = 0.0; }
+    else { w.a1 = sw * R.q1a; w.b1 = sw * R.q1b; w.a2 = cw * R.q2a; w.b2 = cw * R.q2b; }
+    double tp = 0.0;
+    if (lane < 4) {
+      const int o = is_nyq ? 4 : 0;
+      for (int l = 0; l < k; ++l) {
+        const PrepLayer& Q = PL[l];
+        wave_rotate(w, Q.tr[o], Q.tr[o + 1], Q.tr[o + 2], Q.tr[o + 3]);
+        if (l + 1 < k) wave_interface(w, Q.ic[0], Q.ic[1], Q.ic[2], Q.ic[3], Q.ic[4], Q.ic[5]);
+      }
+    } else if (lane == 4) {
+      for (int l = 0; l < k; ++l) tp = __dadd_rn(tp, PL[l].tpterm);
+    }
+    R.tp = __shfl_sync(0xffffffffu, tp, 4);
+  }
+  {
+    // gather the four vectors on every lane; lane 0 finishes the two edge bins
+    Wave wv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      wv[i].a1 = __shfl_sync(0xffffffffu, w.a1, i); wv[i].a2 = __shfl_sync(0xffffffffu, w.a2, i);
+      wv[i].b1 = __shfl_sync(0xffffffffu, w.b1, i); wv[i].b2 = __shfl_sync(0xffffffffu, w.b2, i);
+    }
+    if (lane == 0) {
+      surface_response(R.h14, R.h23, wv[0], wv[1], cw0, ipha, R.edge[0], R.edge[1]);
+      surface_response(R.h14, R.h23, wv[2], wv[3], cw1, ipha, R.edge[2], R.edge[3]);
+      R.k = k;
+      R.valid = valid;
+      reinterpret_cast<RayConst*>(rc_out)[item] = R;
+      if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
+    }
+  }
 }
 
 // exp(+2 pi i m / n) for 0 <= m < n from the quarter-wave table twq[r] = exp(+2 pi i r / n), r < n/4
@@ -326,7 +416,9 @@ __device__ __forceinline__ void dft8(double2* v) {
 // stores output q of a butterfly at bit-reversed digit position, so element f of the result ends up at logical
 // position bitreverse(f).  One barrier per stage.  Returns the maximum imaginary part over all outputs seen by
 // this thread (the vertical trace rides in the imaginary part).
-__device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2* twq, int tid, int nthr) {
+struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+template <class Sync>
+__device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2* twq, int tid, int nthr, Sync sync) {
   const int qmask = (n >> 2) - 1, qshift = log2n - 2;
   double vmax = -INFINITY;
   int N = n;
@@ -352,7 +444,7 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       buf[fpad(base + stride)] = v[4];     buf[fpad(base + 5 * stride)] = v[5];
       buf[fpad(base + 3 * stride)] = v[6]; buf[fpad(base + 7 * stride)] = v[7];
     }
-    __syncthreads();
+    sync();
   }
   if (N == 4) {
     for (int j = tid; j < (n >> 2); j += nthr) {
@@ -365,7 +457,7 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       vmax = fmax(fmax(vmax, r0.y), fmax(fmax(r1.y, r2.y), r3.y));
       buf[fpad(base)] = r0; buf[fpad(base + 2)] = r1; buf[fpad(base + 1)] = r2; buf[fpad(base + 3)] = r3;
     }
-    __syncthreads();
+    sync();
   } else if (N == 2) {
     for (int j = tid; j < (n >> 1); j += nthr) {
       const int base = j << 1;
@@ -374,16 +466,17 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       vmax = fmax(vmax, fmax(r0.y, r1.y));
       buf[fpad(base)] = r0; buf[fpad(base + 1)] = r1;
     }
-    __syncthreads();
+    sync();
   }
   return vmax;
 }
 
-__device__ __forceinline__ double block_max(double v, double* scratch, int tid, int nthr) {
+template <class Sync>
+__device__ __forceinline__ double block_max(double v, double* scratch, int tid, int nthr, Sync sync) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
+  sync();
   if ((tid & 31) == 0) scratch[tid >> 5] = v;
-  __syncthreads();
+  sync();
   const int nw = (nthr + 31) >> 5;
   double r = scratch[0];
   for (int i = 1; i < nw; ++i) r = fmax(r, scratch[i]);
@@ -393,6 +486,161 @@ __device__ __forceinline__ double block_max(double v, double* scratch, int tid, 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src));
+}
+
+// Two-level rotation tables of one item: cos/sin(t*theta) = rot(lo[t & 15], hi[t >> 4]) for t < 16*n_hi.
+// Per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
+// One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
+// independent rotations inside a level (error ~1e-16 * log2(16)).
+__device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerConst* s_lc, int k, int n_hi, int tid, int nthr) {
+  const int tab_per_layer = 2 * (16 + n_hi);
+  for (int task = tid; task < 4 * k; task += nthr) {
+    const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
+    const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
+    const int cnt = level ? n_hi : 16;
+    double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
+    double2 e[16];
+    e[0] = make_double2(1.0, 0.0);
+    sincos(th, &e[1].y, &e[1].x);
+#pragma unroll
+    for (int len = 2; len < 16; len <<= 1) {
+      e[len] = e[len >> 1];
+      rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
+#pragma unroll
+      for (int j = 1; j < len; ++j) {
+        e[len + j] = e[j];
+        rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < cnt) dst[i] = e[i];
+  }
+}
+
+// Propagator product over the k solid layers, top down, in wave coordinates, for the J bins tid + m*nthr of this thread.
+template <int J>
+__device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, int k, int n_hi,
+                                          int tid, Wave* wa, Wave* wb) {
+  const int tab_per_layer = 2 * (16 + n_hi);
+  {
+    const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
+    const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
+    double cw = 1.0, sw = 0.0;
+    if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
+#pragma unroll
+    for (int m = 0; m < J; ++m) {
+      wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
+      wb[m].a1 = sw * q1a; wb[m].b1 = sw * q1b; wb[m].a2 = cw * q2a; wb[m].b2 = cw * q2b;
+      rot(cw, sw, cbw, sbw);
+    }
+  }
+  const int t_lo = tid & 15, t_hi = 16 + (tid >> 4);
+  for (int l = 0; l < k; ++l) {
+    const LayerConst& L = s_lc[l];
+    const double2* tab = s_tab + l * tab_per_layer;
+    double c1, s1, c2, s2;
+    {
+      const double2 a = tab[t_lo], b = tab[t_hi], cc = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
+      c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
+      c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
+    }
+    if (l + 1 < k) {
+      const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
+#pragma unroll
+      for (int m = 0; m < J; ++m) {
+        wave_rotate(wa[m], c1, s1, c2, s2);
+        wave_rotate(wb[m], c1, s1, c2, s2);
+        wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
+        wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
+        if (m + 1 < J) {
+          rot(c1, s1, L.cbx, L.sbx);
+          rot(c2, s2, L.cbe, L.sbe);
+        }
+      }
+    } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
+#pragma unroll
+      for (int m = 0; m < J; ++m) {
+        wave_rotate(wa[m], c1, s1, c2, s2);
+        wave_rotate(wb[m], c1, s1, c2, s2);
+        if (m + 1 < J) {
+          rot(c1, s1, L.cbx, L.sbx);
+          rot(c2, s2, L.cbe, L.sbe);
+        }
+      }
+    }
+  }
+}
+
+// Surface response of the thread's J bins.  STAGE = false: straight into the packed, filtered spectrum
+// Z = X_r + i X_v with Hermitian extension (src/forward.f90:168, 199) in the padded FFT buffer; STAGE = true: the
+// unfiltered spectra go to s_fr / s_fv (common rays, water-level deconvolution).  Thread 0 adds the two edge bins.
+template <int J, bool STAGE>
+__device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int ipha, int n, int nh,
+                                                 int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
+                                                 double2* s_fr, double2* s_fv) {
+  double h14[4], h23[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
+  const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
+  double cw = 1.0, sw = 0.0;
+  if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
+#pragma unroll
+  for (int m = 0; m < J; ++m) {
+    const int j = tid + m * nthr;
+    double2 fr, fv;
+    surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
+    rot(cw, sw, cbw, sbw);
+    if (STAGE) {
+      if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
+    } else if (j > 0) {
+      const double f = flt[j];
+      const double2 xv = make_double2(fv.x * f, fv.y * f);
+      const double2 xr = ipha == 1 ? make_double2(fr.x * f, fr.y * f) : xv;
+      s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
+      s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
+    }
+  }
+  if (tid == 0) {  // the two bins off the regular grid
+    if (STAGE) {
+      s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
+      s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
+    } else {       // c2r ignores the imaginary parts of DC and Nyquist
+      const double f0 = flt[0], f1 = flt[nh - 1];
+      const double2 r0 = ipha == 1 ? s_rc->edge[0] : s_rc->edge[1], r1 = ipha == 1 ? s_rc->edge[2] : s_rc->edge[3];
+      s_buf[fpad(0)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
+      s_buf[fpad(nh - 1)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
+    }
+  }
+}
+
+// Shift / sign / normalise the transformed trace (src/forward.f90:176-203) and write misfit, cached samples and
+// (optionally) the complete RF.  Element f of the transform sits at bit-reversed position (n is a power of two).
+__device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOutputs& out, const double2* s_buf, int C, int c,
+                                              int t, int ipha, double tp, double scale, int tid, int nthr) {
+  const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
+  int npre;
+  if (ipha == 1) npre = f_nint((-cfg.t_start - tp) / cfg.delta);   // src/forward.f90:177
+  else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
+  const int nout = out.rft_full ? n : S;
+  double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
+  double* smp_base = out.rft_smp;
+  if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
+  double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
+  double* __restrict__ full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
+  const double* __restrict__ obs = cfg.obs + (size_t)t * S;
+#pragma unroll 4
+  for (int i = tid; i < nout; i += nthr) {
+    const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
+                            : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
+    double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
+    if (ipha != 1) v = -v;
+    if (i < S) {
+      mis[i] = v - __ldg(obs + i);
+      if (smp) smp[i] = v;
+    }
+    if (full) full[i] = v;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -448,9 +696,6 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   asm volatile("cp.async.commit_group;\n" ::);
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(counter, 1);
 
-  const int S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
-  const int t_lo = tid & 15, t_hi = 16 + (tid >> 4);
-
   while (item < n_items) {
     PHASE_INIT();
     asm volatile("cp.async.wait_all;\n" ::);
@@ -459,7 +704,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     if (next < n_items) prefetch(next, slot ^ 1);
     asm volatile("cp.async.commit_group;\n" ::);
     int next2 = 0;
-    if (tid == 0) next2 = (int)gridDim.x + atomicAdd(counter, 1);
+    if (tid == 0) next2 = atomicAdd(counter, 1);   // consumed at the end of the iteration: nobody waits for the round trip
     const RayConst* s_rc = s_rc2 + slot;
     const LayerConst* s_lc = s_lc2 + (size_t)slot * km;
     const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
@@ -467,124 +712,18 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     const int k = s_rc->k;
     const int ipha = cfg.ipha[t0];
     PHASE_MARK(0);
-    // ---- two-level rotation tables: cos/sin(tid*theta) = rot(lo[tid & 15], hi[tid >> 4]) ----
-    // per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
-    // One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
-    // independent rotations inside a level (error ~1e-16 * log2(16)).
-    for (int task = tid; task < 4 * k; task += nthr) {
-      const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
-      const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
-      const int cnt = level ? n_hi : 16;
-      double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
-      double2 e[16];
-      e[0] = make_double2(1.0, 0.0);
-      sincos(th, &e[1].y, &e[1].x);
-#pragma unroll
-      for (int len = 2; len < 16; len <<= 1) {
-        e[len] = e[len >> 1];
-        rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
-#pragma unroll
-        for (int j = 1; j < len; ++j) {
-          e[len + j] = e[j];
-          rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        if (i < cnt) dst[i] = e[i];
-    }
+    build_trig_tables(s_tab, s_lc, k, n_hi, tid, nthr);
     __syncthreads();
     PHASE_MARK(1);
 
-    // ---- propagator product over the solid layers, top down, in wave coordinates ----
     Wave wa[J], wb[J];
-    {
-      const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
-      const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
-      double cw = 1.0, sw = 0.0;
-      if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
-#pragma unroll
-      for (int m = 0; m < J; ++m) {
-        wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
-        wb[m].a1 = sw * q1a; wb[m].b1 = sw * q1b; wb[m].a2 = cw * q2a; wb[m].b2 = cw * q2b;
-        rot(cw, sw, cbw, sbw);
-      }
-    }
-    for (int l = 0; l < k; ++l) {
-      const LayerConst& L = s_lc[l];
-      const double2* tab = s_tab + l * tab_per_layer;
-      double c1, s1, c2, s2;
-      {
-        const double2 a = tab[t_lo], b = tab[t_hi], cc = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
-        c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
-        c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
-      }
-      if (l + 1 < k) {
-        const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
-#pragma unroll
-        for (int m = 0; m < J; ++m) {
-          wave_rotate(wa[m], c1, s1, c2, s2);
-          wave_rotate(wb[m], c1, s1, c2, s2);
-          wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
-          wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
-          if (m + 1 < J) {
-            rot(c1, s1, L.cbx, L.sbx);
-            rot(c2, s2, L.cbe, L.sbe);
-          }
-        }
-      } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
-#pragma unroll
-        for (int m = 0; m < J; ++m) {
-          wave_rotate(wa[m], c1, s1, c2, s2);
-          wave_rotate(wb[m], c1, s1, c2, s2);
-          if (m + 1 < J) {
-            rot(c1, s1, L.cbx, L.sbx);
-            rot(c2, s2, L.cbe, L.sbe);
-          }
-        }
-      }
-    }
+    propagate<J>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
     PHASE_MARK(2);
     __syncthreads();   // the trigonometric tables are dead: their region becomes the FFT buffer
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
-    {
-      double h14[4], h23[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
-      const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
-      double cw = 1.0, sw = 0.0;
-      if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
-      const double* __restrict__ flt = cfg.flt + (size_t)t0 * nh;
-#pragma unroll
-      for (int m = 0; m < J; ++m) {
-        const int j = tid + m * nthr;
-        double2 fr, fv;
-        surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
-        rot(cw, sw, cbw, sbw);
-        if (general) {
-          if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
-        } else if (j > 0) {
-          // packed spectrum Z = X_r + i X_v with Hermitian extension (src/forward.f90:168, 199)
-          const double f = flt[j];
-          const double2 xv = make_double2(fv.x * f, fv.y * f);
-          const double2 xr = ipha == 1 ? make_double2(fr.x * f, fr.y * f) : xv;
-          s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
-          s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
-        }
-      }
-      if (tid == 0) {  // the two bins off the regular grid
-        if (general) {
-          s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
-          s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
-        } else {       // c2r ignores the imaginary parts of DC and Nyquist
-          const double f0 = flt[0], f1 = flt[nh - 1];
-          const double2 r0 = ipha == 1 ? s_rc->edge[0] : s_rc->edge[1], r1 = ipha == 1 ? s_rc->edge[2] : s_rc->edge[3];
-          s_buf[fpad(0)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
-          s_buf[fpad(nh - 1)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
-        }
-      }
-    }
+    if (general) surface_and_pack<J, true>(s_rc, wa, wb, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv);
+    else surface_and_pack<J, false>(s_rc, wa, wb, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -594,7 +733,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       const double2* ys = ipha == 1 ? s_fr : s_fv;
       double mx = -INFINITY;
       for (int j = tid; j < nh; j += nthr) mx = fmax(mx, xs[j].x * xs[j].x + xs[j].y * xs[j].y);
-      mx = block_max(mx, s_red, tid, nthr);
+      mx = block_max(mx, s_red, tid, nthr, CtaSync());
       const double wlvl = 0.001 * mx;
       double2 keep[J + 1];
 #pragma unroll
@@ -638,34 +777,12 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
         __syncthreads();
       }
       PHASE_MARK(4);
-      double mx = fft_inverse_dif(s_buf, n, cfg.log2n, s_twq, tid, nthr);
+      double mx = fft_inverse_dif(s_buf, n, cfg.log2n, s_twq, tid, nthr, CtaSync());
       PHASE_MARK(5);
       double scale = 1.0;
-      if (cfg.deconv_mode == 0) scale = 1.0 / block_max(mx, s_red, tid, nthr);  // src/forward.f90:197-203
-      int npre;
-      if (ipha == 1) npre = f_nint((-cfg.t_start - tp) / cfg.delta);   // src/forward.f90:177
-      else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
-      const int nout = out.rft_full ? n : S;
-      double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
-      double* smp_base = out.rft_smp;
-      if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
-      double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
-      double* __restrict__ full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
-      const double* __restrict__ obs = cfg.obs + (size_t)t * S;
-#pragma unroll 4
-      for (int i = tid; i < nout; i += nthr) {
-        // element f of the transform sits at bit-reversed position (n is a power of two)
-        const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
-                                : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
-        double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
-        if (ipha != 1) v = -v;
-        if (i < S) {
-          mis[i] = v - __ldg(obs + i);
-          if (smp) smp[i] = v;
-        }
-        if (full) full[i] = v;
-      }
-      if (tid == 0 && t + 1 == t_end) s_next = next2;
+      if (cfg.deconv_mode == 0) scale = 1.0 / block_max(mx, s_red, tid, nthr, CtaSync());  // src/forward.f90:197-203
+      write_outputs(cfg, out, s_buf, C, c, t, ipha, tp, scale, tid, nthr);
+      if (tid == 0 && t + 1 == t_end) s_next = (int)gridDim.x + next2;
       __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables
       PHASE_MARK(6);
     }
@@ -774,7 +891,10 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   double* lc = scratch;
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
   int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
-  prep_kernel<<<(unsigned)((n_items + 127) / 128), 128, 0, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
+  const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+  prep_kernel<<<(unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS), 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter,
+                                                                                                         (int)n_items, ntr_eff, nthr);
   RFINV_CUDA_CHECK(cudaGetLastError());
   static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
   if (J == 1) {
