@@ -68,6 +68,7 @@ struct RayConst {
   double tp;                  // direct-arrival delay (src/forward.f90:474-491)
   double2 edge[4];            // fr, fv at the DC pseudo-frequency and at Nyquist
   int k, valid;
+  int npre, pad_;             // nint((-t_start -/+ tp)/delta): circular shift of the trace (src/forward.f90:177, 186)
 };
 constexpr int RC_DOUBLES = sizeof(RayConst) / sizeof(double);
 
@@ -161,12 +162,24 @@ __device__ __forceinline__ void mat2_mul(const double* a, const double* b, doubl
 // ------------------------------------------------------------------------------------------------
 struct PrepLayer {
   double v14[4], v23[4];   // unscaled basis blocks of this layer
+  double i14[4], i23[4];   // their inverses (closed form)
   double tr[8];            // cos, sin of (w xi h), (w eta h) at the DC pseudo-frequency, then at Nyquist
   double ic[6];            // t12, t21, u11, u12, u21, u22 of the interface below this layer
   double tpterm, pad;
 };
 constexpr int PREP_WARPS = 4;
 __host__ __device__ inline size_t prep_smem_doubles_per_warp(int km) { return (size_t)6 * km + (size_t)(km + 1) * (sizeof(PrepLayer) / sizeof(double)); }
+
+// sin, cos of a small argument (|x| < 0.01: Taylor remainder < 3e-21); falls back to sincos otherwise
+__device__ __forceinline__ void small_sincos(double x, double* sn, double* cs) {
+  if (fabs(x) < 0.01) {
+    const double x2 = x * x;
+    *cs = fma(x2, fma(x2, fma(x2, -1.0 / 720.0, 1.0 / 24.0), -0.5), 1.0);
+    *sn = x * fma(x2, fma(x2, fma(x2, -1.0 / 5040.0, 1.0 / 120.0), -1.0 / 6.0), 1.0);
+  } else {
+    sincos(x, sn, cs);
+  }
+}
 
 __device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclusive prefix product, fixed order
 #pragma unroll
@@ -213,6 +226,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   // ---- per-layer physics, one layer per lane ----
   const double p2 = __dmul_rn(p, p);
   const double nyq = (double)(cfg.nfft / 2);
+  int nyq_doublings = 0;
+  while ((nthr_fwd << nyq_doublings) < cfg.nfft / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d
   bool valid = true;
   double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane k & 31)
   for (int l = lane; l <= k; l += 32) {
@@ -234,8 +249,11 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     if (l < k) {
       PrepLayer& Q = PL[l];
       const double g2 = 2.0 * beta2 * p;   // 2 beta^2 p
+      const double ieta = 1.0 / eta, irho = 1.0 / rho, ixi = 1.0 / xi;
       Q.v14[0] = p; Q.v14[1] = 1.0; Q.v14[2] = rho * bp; Q.v14[3] = -rho * g2;
-      Q.v23[0] = xi; Q.v23[1] = -p / eta; Q.v23[2] = -rho * g2 * xi; Q.v23[3] = -rho * bp / eta;
+      Q.v23[0] = xi; Q.v23[1] = -p * ieta; Q.v23[2] = -rho * g2 * xi; Q.v23[3] = -rho * bp * ieta;
+      Q.i14[0] = g2; Q.i14[1] = irho; Q.i14[2] = bp; Q.i14[3] = -p * irho;
+      Q.i23[0] = bp * ixi; Q.i23[1] = -p * irho * ixi; Q.i23[2] = -g2 * eta; Q.i23[3] = -eta * irho;
       Q.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(h, ipha == 1 ? xi : eta) : 0.0;   // src/forward.f90:489-491
       LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + l;
       const double thx = cfg.domg * xi * h, the = cfg.domg * eta * h;
@@ -243,10 +261,16 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
       double sn, cs;
       sincos((double)nthr_fwd * thx, &sn, &cs); L->cbx = cs; L->sbx = sn;
       sincos((double)nthr_fwd * the, &sn, &cs); L->cbe = cs; L->sbe = sn;
-      sincos((double)1.0e-5f * xi * h, &Q.tr[1], &Q.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
-      sincos((double)1.0e-5f * eta * h, &Q.tr[3], &Q.tr[2]);
-      sincos(nyq * thx, &Q.tr[5], &Q.tr[4]);
-      sincos(nyq * the, &Q.tr[7], &Q.tr[6]);
+      small_sincos((double)1.0e-5f * xi * h, &Q.tr[1], &Q.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
+      small_sincos((double)1.0e-5f * eta * h, &Q.tr[3], &Q.tr[2]);
+      // Nyquist = (nfft/2) bins = nyq_doublings doublings of the stride rotation; its bin carries the smallest
+      // filter weight of the whole spectrum, so the doubled rounding error is immaterial
+      double cn = L->cbx, sn2 = L->sbx, ce = L->cbe, se = L->sbe;
+      for (int d = 0; d < nyq_doublings; ++d) {
+        const double c2 = fma(cn, cn, -sn2 * sn2), s2 = 2.0 * cn * sn2; cn = c2; sn2 = s2;
+        const double c3 = fma(ce, ce, -se * se), s3 = 2.0 * ce * se; ce = c3; se = s3;
+      }
+      Q.tr[4] = cn; Q.tr[5] = sn2; Q.tr[6] = ce; Q.tr[7] = se;
     } else {
       hs_a = a; hs_b = b; hs_rho = rho; hs_xi = xi; hs_eta = eta; hs_bp = bp; hs_beta2 = beta2;
     }
@@ -261,21 +285,18 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     const int l = base + lane;
     double t14[4] = {1.0, 0.0, 0.0, 1.0}, t23[4] = {1.0, 0.0, 0.0, 1.0};
     if (l >= 1 && l < k) {
-      // V_l^-1 from this layer's own blocks: V14 = [[p,1],[m,n]] has determinant -rho, V23 determinant -rho xi/eta
-      const PrepLayer& Q = PL[l];
-      const double d14 = Q.v14[0] * Q.v14[3] - Q.v14[1] * Q.v14[2], d23 = Q.v23[0] * Q.v23[3] - Q.v23[1] * Q.v23[2];
-      const double i14[4] = {Q.v14[3] / d14, -Q.v14[1] / d14, -Q.v14[2] / d14, Q.v14[0] / d14};
-      const double i23[4] = {Q.v23[3] / d23, -Q.v23[1] / d23, -Q.v23[2] / d23, Q.v23[0] / d23};
-      mat2_mul(i14, PL[l - 1].v14, t14);
-      mat2_mul(i23, PL[l - 1].v23, t23);
+      mat2_mul(PL[l].i14, PL[l - 1].v14, t14);
+      mat2_mul(PL[l].i23, PL[l - 1].v23, t23);
     }
     const double sP = carryP * warp_scan_mul(t14[0], lane), sS = carryS * warp_scan_mul(t14[3], lane);   // scales of layer l
     double sPp = __shfl_up_sync(0xffffffffu, sP, 1), sSp = __shfl_up_sync(0xffffffffu, sS, 1);           // scales of layer l-1
     if (lane == 0) { sPp = carryP; sSp = carryS; }
     if (l >= 1 && l < k) {
       double* ic = PL[l - 1].ic;
-      ic[0] = t14[1] * sSp / sP; ic[1] = t14[2] * sPp / sS;
-      ic[2] = t23[0] * sPp / sP; ic[3] = t23[1] * sSp / sP; ic[4] = t23[2] * sPp / sS; ic[5] = t23[3] * sSp / sS;
+      const double rP = 1.0 / sP, rS = 1.0 / sS;
+      const double pp = sPp * rP, sp = sSp * rP, ps = sPp * rS, ss = sSp * rS;
+      ic[0] = t14[1] * sp; ic[1] = t14[2] * ps;
+      ic[2] = t23[0] * pp; ic[3] = t23[1] * sp; ic[4] = t23[2] * ps; ic[5] = t23[3] * ss;
       LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (l - 1);
       L->t12 = ic[0]; L->t21 = ic[1]; L->u11 = ic[2]; L->u12 = ic[3]; L->u21 = ic[4]; L->u22 = ic[5];
     }
@@ -299,7 +320,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     R.thw = cfg.domg * xiw * hw;
     sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
     rw = rhow / xiw;
-    sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
+    small_sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
     sincos(nyq * R.thw, &sw1, &cw1);
   } else {
     R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
@@ -312,8 +333,9 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
     const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
     const double beta2 = __shfl_sync(0xffffffffu, hs_beta2, src_lane);
-    const double e11 = beta2 * p / a, e12 = bp / (2.0 * a * xi), e13 = p / (2.0 * rho * a * xi), e14 = 1.0 / (2.0 * rho * a);
-    const double e21 = bp / (2.0 * b * eta), e22 = b * p, e23 = 1.0 / (2.0 * rho * b), e24 = p / (2.0 * rho * b * eta);
+    const double r1 = 1.0 / (2.0 * rho * a * xi), r2 = 1.0 / (2.0 * rho * b * eta);
+    const double e11 = beta2 * p * (2.0 * rho * xi) * r1, e12 = bp * rho * r1, e13 = p * r1, e14 = xi * r1;
+    const double e21 = bp * rho * r2, e22 = b * p, e23 = eta * r2, e24 = p * r2;
     const double r14[4] = {e11, e14, e21, -e24};
     const double r23[4] = {-e12, e13, e22, e23};
     const PrepLayer& Q = PL[k - 1];
@@ -325,10 +347,9 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   {
     // start vectors in layer 0's coordinates (scale 1): e1, and (0, cw, 0, -rw sw) for a free / water-loaded surface
     const PrepLayer& Q = PL[0];
-    const double d14 = Q.v14[0] * Q.v14[3] - Q.v14[1] * Q.v14[2], d23 = Q.v23[0] * Q.v23[3] - Q.v23[1] * Q.v23[2];
-    R.a1 = Q.v14[3] / d14; R.b1 = -Q.v14[2] / d14;                 // V14^-1 (1, 0)^T
-    R.q1a = -rw * (-Q.v14[1] / d14); R.q1b = -rw * (Q.v14[0] / d14);   // -rw V14^-1 (0, 1)^T
-    R.q2a = Q.v23[3] / d23; R.q2b = -Q.v23[2] / d23;               // V23^-1 (1, 0)^T
+    R.a1 = Q.i14[0]; R.b1 = Q.i14[2];                   // V14^-1 (1, 0)^T
+    R.q1a = -rw * Q.i14[1]; R.q1b = -rw * Q.i14[3];     // -rw V14^-1 (0, 1)^T
+    R.q2a = Q.i23[0]; R.q2b = Q.i23[2];                 // V23^-1 (1, 0)^T
   }
 
   // ---- serial part: lanes 0..3 carry (vector a | b) x (DC | Nyquist) down the stack; lane 4 sums the delay ----
@@ -359,25 +380,47 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
       wv[i].a1 = __shfl_sync(0xffffffffu, w.a1, i); wv[i].a2 = __shfl_sync(0xffffffffu, w.a2, i);
       wv[i].b1 = __shfl_sync(0xffffffffu, w.b1, i); wv[i].b2 = __shfl_sync(0xffffffffu, w.b2, i);
     }
+    {
+      const int e = lane & 1;   // lane parity picks the edge bin: both are finished in one pass
+      double2 fr, fv;
+      const Wave ea = e ? wv[2] : wv[0], eb = e ? wv[3] : wv[1];
+      surface_response(R.h14, R.h23, ea, eb, e ? cw1 : cw0, ipha, fr, fv);
+      R.edge[0].x = __shfl_sync(0xffffffffu, fr.x, 0); R.edge[0].y = __shfl_sync(0xffffffffu, fr.y, 0);
+      R.edge[1].x = __shfl_sync(0xffffffffu, fv.x, 0); R.edge[1].y = __shfl_sync(0xffffffffu, fv.y, 0);
+      R.edge[2].x = __shfl_sync(0xffffffffu, fr.x, 1); R.edge[2].y = __shfl_sync(0xffffffffu, fr.y, 1);
+      R.edge[3].x = __shfl_sync(0xffffffffu, fv.x, 1); R.edge[3].y = __shfl_sync(0xffffffffu, fv.y, 1);
+    }
     if (lane == 0) {
-      surface_response(R.h14, R.h23, wv[0], wv[1], cw0, ipha, R.edge[0], R.edge[1]);
-      surface_response(R.h14, R.h23, wv[2], wv[3], cw1, ipha, R.edge[2], R.edge[3]);
       R.k = k;
       R.valid = valid;
+      R.npre = ipha == 1 ? f_nint((-cfg.t_start - R.tp) / cfg.delta)    // src/forward.f90:177
+                         : f_nint((-cfg.t_start + R.tp) / cfg.delta);   // src/forward.f90:186
+      R.pad_ = 0;
       reinterpret_cast<RayConst*>(rc_out)[item] = R;
       if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
     }
   }
 }
 
-// exp(+2 pi i m / n) for 0 <= m < n from the quarter-wave table twq[r] = exp(+2 pi i r / n), r < n/4
-__device__ __forceinline__ double2 twiddle(const double2* twq, int m, int qmask, int qshift) {
-  const double2 w = twq[m & qmask];
-  const int q = m >> qshift;   // w * i^q : (x,y), (-y,x), (-x,-y), (y,-x)
-  double2 r = (q & 1) ? make_double2(w.y, w.x) : w;
-  if (q == 1 || q == 2) r.x = -r.x;
-  if (q >= 2) r.y = -r.y;
-  return r;
+// Twiddles of the radix-8 DIF stages, one table per stage laid out [q-1][o] (q = 1..7 output index of the butterfly,
+// o < N/8 its offset inside the sub-transform of length N): entry = exp(+2 pi i q o / N).  Consecutive threads read
+// consecutive entries (no bank conflicts, no quadrant logic).  Stages with N = 8 need none.
+__host__ __device__ inline size_t fft_twiddle_entries(size_t n) {
+  size_t e = 0;
+  for (size_t N = n; N > 8; N >>= 3) e += 7 * (N >> 3);
+  return e;
+}
+// fills the tables from the full-circle table tw[m] = exp(+2 pi i m / n) in global memory (once per CTA)
+__device__ __forceinline__ void fill_fft_twiddles(double2* s_tw, const double2* __restrict__ tw, int n, int tid, int nthr) {
+  int off = 0;
+  for (int N = n; N > 8; N >>= 3) {
+    const int stride = N >> 3, tmul = n / N;
+    for (int i = tid; i < 7 * stride; i += nthr) {
+      const int q = i / stride + 1, o = i - (q - 1) * stride;
+      s_tw[off + i] = tw[q * o * tmul];
+    }
+    off += 7 * stride;
+  }
 }
 
 // Position of logical element p in the padded FFT buffer: one pad element per 8, so that "8 consecutive
@@ -414,28 +457,37 @@ __device__ __forceinline__ void dft8(double2* v) {
 // In-place decimation-in-frequency inverse FFT (sign +, unnormalised) of n complex points in the padded shared
 // buffer: radix-8 stages while the sub-transform length N >= 8, then one radix-4 or radix-2 stage.  Every stage
 // stores output q of a butterfly at bit-reversed digit position, so element f of the result ends up at logical
-// position bitreverse(f).  One barrier per stage.  Returns the maximum imaginary part over all outputs seen by
-// this thread (the vertical trace rides in the imaginary part).
+// position bitreverse(f).  One barrier per stage.  Returns the maximum imaginary part over all n outputs (the
+// vertical trace rides in the imaginary part); the block reduction shares the last stage's barrier.
 struct CtaSync { __device__ __forceinline__ void operator()() const { __syncthreads(); } };
+// warp maximum -> s_red[warp]; the caller's next barrier publishes it to the CTA
+__device__ __forceinline__ void publish_max(double v, double* s_red, int tid) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((tid & 31) == 0) s_red[tid >> 5] = v;
+}
+
 template <class Sync>
-__device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2* twq, int tid, int nthr, Sync sync) {
-  const int qmask = (n >> 2) - 1, qshift = log2n - 2;
+__device__ double fft_inverse_dif(double2* buf, int n, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
   double vmax = -INFINITY;
   int N = n;
+  const double2* stw = twq;
   for (; N >= 8; N >>= 3) {
-    const int stride = N >> 3, tmul = n / N;
+    const int stride = N >> 3;
     const bool last = (N == 8);
     for (int j = tid; j < (n >> 3); j += nthr) {
       const int o = j & (stride - 1), base = ((j - o) << 3) + o;
       double2 v[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) v[r] = buf[fpad(base + r * stride)];
-      dft8(v);
       if (!last) {
-        const int m1 = o * tmul;
+        double2 w[7];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], twiddle(twq, q * m1, qmask, qshift));
+        for (int q = 1; q < 8; ++q) w[q - 1] = stw[(q - 1) * stride + o];
+        dft8(v);
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], w[q - 1]);
       } else {
+        dft8(v);
 #pragma unroll
         for (int q = 0; q < 8; ++q) vmax = fmax(vmax, v[q].y);
       }
@@ -444,6 +496,8 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       buf[fpad(base + stride)] = v[4];     buf[fpad(base + 5 * stride)] = v[5];
       buf[fpad(base + 3 * stride)] = v[6]; buf[fpad(base + 7 * stride)] = v[7];
     }
+    stw += 7 * stride;
+    if (last) publish_max(vmax, s_red, tid);   // N == 8: no stage follows
     sync();
   }
   if (N == 4) {
@@ -457,6 +511,7 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       vmax = fmax(fmax(vmax, r0.y), fmax(fmax(r1.y, r2.y), r3.y));
       buf[fpad(base)] = r0; buf[fpad(base + 2)] = r1; buf[fpad(base + 1)] = r2; buf[fpad(base + 3)] = r3;
     }
+    publish_max(vmax, s_red, tid);
     sync();
   } else if (N == 2) {
     for (int j = tid; j < (n >> 1); j += nthr) {
@@ -466,9 +521,13 @@ __device__ double fft_inverse_dif(double2* buf, int n, int log2n, const double2*
       vmax = fmax(vmax, fmax(r0.y, r1.y));
       buf[fpad(base)] = r0; buf[fpad(base + 1)] = r1;
     }
+    publish_max(vmax, s_red, tid);
     sync();
   }
-  return vmax;
+  const int nw = (nthr + 31) >> 5;
+  double r = s_red[0];
+  for (int i = 1; i < nw; ++i) r = fmax(r, s_red[i]);
+  return r;
 }
 
 template <class Sync>
@@ -616,12 +675,10 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
 
 // Shift / sign / normalise the transformed trace (src/forward.f90:176-203) and write misfit, cached samples and
 // (optionally) the complete RF.  Element f of the transform sits at bit-reversed position (n is a power of two).
+constexpr int OBS_PRE = 4;   // observed samples per thread fetched before the FFT
 __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOutputs& out, const double2* s_buf, int C, int c,
-                                              int t, int ipha, double tp, double scale, int tid, int nthr) {
+                                              int t, int ipha, int npre, double scale, const double* obs_pre, int tid, int nthr) {
   const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
-  int npre;
-  if (ipha == 1) npre = f_nint((-cfg.t_start - tp) / cfg.delta);   // src/forward.f90:177
-  else npre = f_nint((-cfg.t_start + tp) / cfg.delta);             // src/forward.f90:186
   const int nout = out.rft_full ? n : S;
   double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
   double* smp_base = out.rft_smp;
@@ -629,12 +686,26 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
   double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
   double* __restrict__ full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
   const double* __restrict__ obs = cfg.obs + (size_t)t * S;
-#pragma unroll 4
-  for (int i = tid; i < nout; i += nthr) {
+  auto sample = [&](int i) {
     const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
                             : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
-    double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
-    if (ipha != 1) v = -v;
+    const double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
+    return ipha == 1 ? v : -v;
+  };
+#pragma unroll
+  for (int q = 0; q < OBS_PRE; ++q) {
+    const int i = tid + q * nthr;
+    if (i < nout) {
+      const double v = sample(i);
+      if (i < S) {
+        mis[i] = v - obs_pre[q];
+        if (smp) smp[i] = v;
+      }
+      if (full) full[i] = v;
+    }
+  }
+  for (int i = tid + OBS_PRE * nthr; i < nout; i += nthr) {
+    const double v = sample(i);
     if (i < S) {
       mis[i] = v - __ldg(obs + i);
       if (smp) smp[i] = v;
@@ -672,8 +743,8 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   double2* s_tab = s_buf;                             // dead before the FFT buffer is first written
   double2* s_fr = s_buf + region0;                    // [nh+1] unfiltered radial spectrum (or deconvolved RF spectrum)
   double2* s_fv = s_fr + (nh + 1);                    // [nh+1] unfiltered vertical spectrum
-  double2* s_twq = s_fr + (general ? 2 * (nh + 1) : 0);   // [n/4] quarter-wave twiddles
-  double* s_red = reinterpret_cast<double*>(s_twq + (n >> 2));   // [32]
+  double2* s_twq = s_fr + (general ? 2 * (nh + 1) : 0);   // per-stage FFT twiddle tables
+  double* s_red = reinterpret_cast<double*>(s_twq + fft_twiddle_entries(n));   // [32]
   RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 32);     // [2]
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
 
@@ -691,7 +762,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   // iteration, so nobody waits for the round trip).
   int item = blockIdx.x, slot = 0;
   if (item >= n_items) return;
-  for (int i = tid; i < (n >> 2); i += nthr) cp_async16(&s_twq[i], cfg.tw + i);
+  fill_fft_twiddles(s_twq, cfg.tw, n, tid, nthr);
   prefetch(item, 0);
   asm volatile("cp.async.commit_group;\n" ::);
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(counter, 1);
@@ -756,7 +827,6 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     }
 
     // ---- per trace: filter -> inverse FFT -> shift / normalise -> outputs ----
-    const double tp = s_rc->tp;
     const int t_begin = cfg.ray_common ? 0 : t0, t_end = cfg.ray_common ? cfg.ntrc : t0 + 1;
     for (int t = t_begin; t < t_end; ++t) {
       if (general) {
@@ -777,11 +847,17 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
         __syncthreads();
       }
       PHASE_MARK(4);
-      double mx = fft_inverse_dif(s_buf, n, cfg.log2n, s_twq, tid, nthr, CtaSync());
+      double obs_pre[OBS_PRE];
+      const double* __restrict__ obs_t = cfg.obs + (size_t)t * cfg.nsmp;
+#pragma unroll
+      for (int q = 0; q < OBS_PRE; ++q) {   // observed samples of this thread's outputs: in flight during the FFT
+        const int i = tid + q * nthr;
+        obs_pre[q] = i < cfg.nsmp ? __ldg(obs_t + i) : 0.0;
+      }
+      const double mx = fft_inverse_dif(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
       PHASE_MARK(5);
-      double scale = 1.0;
-      if (cfg.deconv_mode == 0) scale = 1.0 / block_max(mx, s_red, tid, nthr, CtaSync());  // src/forward.f90:197-203
-      write_outputs(cfg, out, s_buf, C, c, t, ipha, tp, scale, tid, nthr);
+      const double scale = cfg.deconv_mode == 0 ? 1.0 / mx : 1.0;   // src/forward.f90:197-203
+      write_outputs(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
       if (tid == 0 && t + 1 == t_end) s_next = (int)gridDim.x + next2;
       __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables
       PHASE_MARK(6);
@@ -836,7 +912,8 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
   const bool general = cfg.ray_common || cfg.deconv_mode == 1;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
-  return sizeof(double2) * (region0 + spectra + n / 4) + sizeof(double) * 32 + 2 * sizeof(RayConst) + 2 * sizeof(LayerConst) * km;
+  return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 32 + 2 * sizeof(RayConst) +
+         2 * sizeof(LayerConst) * km;
 }
 
 template <int J, int BMAX, int MINB>
