@@ -107,6 +107,20 @@ def attach_obs_via_cuda(cfg, Evaluator):
     return cfg
 
 
+def cpu_sample_size(cfg, models, target_s, cap):
+    """Number of models that keep one CPU pass near `target_s` seconds (calibrated on a 64-model probe)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_c
+    cores = oracle_c.num_threads()
+    probe = min(max(4 * cores, 64), cap)
+    sub = {k: v[:probe] for k, v in models.items()}
+    oracle_c.eval_batch(cfg, sub["k"], sub["z"], sub["dvp"], sub["dvs"], sub["sig"], want_rft=False, nthreads=cores)
+    t0 = time.perf_counter()
+    oracle_c.eval_batch(cfg, sub["k"], sub["z"], sub["dvp"], sub["dvs"], sub["sig"], want_rft=False, nthreads=cores)
+    rate = probe / max(time.perf_counter() - t0, 1e-6)
+    return int(min(cap, max(probe, rate * target_s)))
+
+
 def cpu_arm(cfg, models, n_sample, steps, warmup):
     """Times the C restatement of the reference algorithm (oracle/) on all host cores: evals/s."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -135,10 +149,12 @@ def run_reference(args):
     cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
     import oracle_c
     cores = oracle_c.num_threads()
-    n_sample = args.cpu_sample or max(cores * 8, 256)
-    models = make_inputs(cfg, n_sample, seed=100)
-    k_mean = float(np.mean(models["k"]))
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    models = make_inputs(cfg, min(chains, 16384), seed=100)
+    # bounded sample: about 20 s of CPU work over the whole --steps/--warmup run
+    n_sample = args.cpu_sample or cpu_sample_size(cfg, models, 20.0 / (steps + warmup), len(models["k"]))
+    models = {k: v[:n_sample] for k, v in models.items()}
+    k_mean = float(np.mean(models["k"]))
     val, cores, sec = cpu_arm(cfg, models, n_sample, steps, warmup)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -301,6 +317,16 @@ def main():
         achieved = fwd_flop / (km[0] * 1e-3) * 1e-12
         qf_achieved = fl["quadform"] * chains / (km[1] * 1e-3) * 1e-12
         whole = fl["total"] * chains * args.steps / (float(np.sum(step_ms)) * 1e-3) * 1e-12
+        # share of the FP64 pipe's issue slots the forward path fills (an FP64 instruction holds the pipe for the time of
+        # one FMA whether or not it is one): instructions x 2 flop-slots / time / peak
+        slot_frac = fl["forward_fp64_instructions"] * 2.0 * chains / (km[0] * 1e-3) * 1e-12 / peak
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "forward_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            if tj.get("workload") == args.workload and tj.get("chains") == chains:
+                traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -309,7 +335,10 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "kernel": "forward_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "fp64_issue_slot_frac": slot_frac,
+                         "note": "FP64-pipe bound (arithmetic intensity > 100 flop/B, DRAM < 2% of peak): `achieved` = algorithmic "
+                                 "flop of prep_kernel + forward_kernel / their CUDA-event time; `traffic` = ncu dram bytes of one "
+                                 "forward_kernel launch at this shape (profiles/forward_kernel_traffic.json)",
                          "peak_source": "measured live: rfinv_measure_fp64_peak (max of DFMA %.1f / DMMA %.1f TFLOP/s); "
                                         "MEASURED_PEAKS.json has no FP64 figure" % (dfma.value, dmma.value),
                          "flop_per_eval": fl, "kernel_ms": {"forward": km[0], "quadform": km[1], "loglik": km[2]},
@@ -321,7 +350,7 @@ def main():
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
             import oracle_c
             cores = oracle_c.num_threads()
-            n_sample = args.cpu_sample or max(cores * 8, 256)
+            n_sample = args.cpu_sample or cpu_sample_size(cfg, models, 5.0, chains)   # ~15 s of CPU work in 3 passes
             val, cores, sec = cpu_arm(cfg, models, min(n_sample, chains), 2, 1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {min(n_sample, chains)} models of the same batch, {sec:.2f} s per pass, "

@@ -136,21 +136,29 @@ def to_soa(models: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
 
 
 def flops_per_eval(cfg: RFConfig, k_mean: float) -> Dict[str, float]:
-    """Algorithmic fp64 flop per forward+likelihood evaluation (SURVEY.md 8d's W_min with the
-    constants replaced by an exact count of the structure-exploiting algorithm):
+    """Algorithmic fp64 flop per forward+likelihood evaluation: an exact count of the algorithm the
+    kernels execute (an FMA is 2 flop, a multiply / add / divide 1), not of the reference's dense complex form:
 
-      W = Tf*nh*(95*k + 70) + T*5*n*log2(n) + T*(S^2 + 3*S)
+      W = Tf*nh*(56*k + 56) + T*5*n*log2(n) + T*(S^2 + 3*S)
 
-    per layer and frequency: 27 flop for the 10 distinct entries of the real 4x4 propagator (8 two-term
-    combinations + 1 difference + 2 scalings), 56 for two real 4-vector products, 12 to advance the two
-    (cos, sin) pairs by rotation; per frequency: 70 for E^-1 rows, boundary condition, complex division, filter;
-    one packed complex inverse FFT per trace; symmetric quadratic form S(S+1)/2 MAC + row dot."""
+    per layer and frequency bin (wave coordinates, rf_inv_b200/csrc/forward.cu): two plane rotations for each of the
+    two propagated vectors (2 x (4 mul + 4 fma) = 24 flop), the 2x2 interface blocks with unit {1,4} diagonal
+    (2 x (2 fma + 2 mul + 2 fma) = 20), one rotation of each (cos, sin) pair to the bin (2 x (2 mul + 2 fma) = 12):
+    56 flop in 36 FP64 instructions; the last solid layer has no interface (-20).  Per bin: rows 3,4 of E^-1, the
+    boundary condition with one complex division, sign conventions, Gaussian filter, Hermitian packing: 76.
+    One packed complex inverse FFT per trace (the customary 5 n log2 n); symmetric quadratic form S(S+1)/2 MAC + row dot.
+    SURVEY.md 8d's W_min (110 k + 100 per bin) and the reference's W_ref (570 k + 550) are reported next to it."""
     Tf = 1 if cfg.is_ray_common else cfg.ntrc
     n, nh, S, T = cfg.nfft, cfg.nh, cfg.nsmp, cfg.ntrc
-    prop = Tf * nh * (95.0 * k_mean + 70.0)
+    prop = Tf * nh * (56.0 * k_mean + 56.0)
     fft = T * 5.0 * n * np.log2(n)
     quad = T * (1.0 * S * S + 3.0 * S)
-    return dict(propagator=prop, fft=fft, quadform=quad, total=prop + fft + quad)
+    w_min_survey = Tf * nh * (110.0 * k_mean + 100.0) + fft + T * (2.0 * S * S + 3.0 * S)
+    w_ref = Tf * nh * (570.0 * k_mean + 550.0) + fft + T * (2.0 * S * S + 3.0 * S)
+    # FP64 instructions the forward path issues per evaluation (each occupies one issue slot of the FP64 pipe, FMA or not)
+    fwd_instr = Tf * nh * (36.0 * k_mean + 40.0) + T * (3.0 * (n / 8) * 84.0 + (n / 2) * 4.0)
+    return dict(propagator=prop, fft=fft, quadform=quad, total=prop + fft + quad, survey_w_min=w_min_survey,
+                reference_as_written=w_ref, forward_fp64_instructions=fwd_instr)
 
 
 def lapack_r_inv(cfg: RFConfig) -> np.ndarray:
