@@ -107,11 +107,20 @@ def attach_obs_via_cuda(cfg, Evaluator):
     return cfg
 
 
+def host_cores():
+    """Host threads the CPU arm uses: every core this process may run on (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which must not throttle the CPU baseline)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_size(cfg, models, target_s, cap):
     """Number of models that keep one CPU pass near `target_s` seconds (calibrated on a 64-model probe)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
-    cores = oracle_c.num_threads()
+    cores = host_cores()
     probe = min(max(4 * cores, 64), cap)
     sub = {k: v[:probe] for k, v in models.items()}
     oracle_c.eval_batch(cfg, sub["k"], sub["z"], sub["dvp"], sub["dvs"], sub["sig"], want_rft=False, nthreads=cores)
@@ -125,7 +134,7 @@ def cpu_arm(cfg, models, n_sample, steps, warmup):
     """Times the C restatement of the reference algorithm (oracle/) on all host cores: evals/s."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_c
-    cores = oracle_c.num_threads()
+    cores = host_cores()
     sub = {k: v[:n_sample] for k, v in models.items()}
     times = []
     for i in range(warmup + steps):
@@ -148,7 +157,7 @@ def run_reference(args):
     import helpers
     cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
     import oracle_c
-    cores = oracle_c.num_threads()
+    cores = host_cores()
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
     models = make_inputs(cfg, min(chains, 16384), seed=100)
     # bounded sample: about 20 s of CPU work over the whole --steps/--warmup run
@@ -348,8 +357,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             sys.path.insert(0, os.path.join(ROOT, "oracle"))
-            import oracle_c
-            cores = oracle_c.num_threads()
+            cores = host_cores()
             n_sample = args.cpu_sample or cpu_sample_size(cfg, models, 5.0, chains)   # ~15 s of CPU work in 3 passes
             val, cores, sec = cpu_arm(cfg, models, min(n_sample, chains), 2, 1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
