@@ -3,6 +3,7 @@
 // point that evaluates models launches the CUDA kernels or fails with RFINV_ERR_CUDA.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -34,6 +35,39 @@ void build_filter(const rfinv_config& c, std::vector<double>& flt) {
       flt[(size_t)t * nh + i] = std::exp(-(q * q)) / fac_norm;
     }
   }
+}
+
+// Band limit of the forward kernel.  The Gaussian filter (src/forward.f90:95-119) multiplies every spectrum before the
+// inverse FFT; bins whose total weight is below 2^-52 of the filter's mass change no bit of the fp64 trace and are not
+// propagated.  forward_kernel computes bins in groups of `nthr` (thread t owns bins t + m*nthr): jbins[t] = number of
+// groups kept for trace t, rounded up to a value the kernel is instantiated for.  Full band when the water-level
+// deconvolution is on (its water level is the maximum over all bins) or RFINV_FULL_BAND=1.
+void band_limits(DevConfig& d, const std::vector<double>& flt) {
+  const int nh = d.nh, jfull = rfinv_forward_bins_per_thread(d.nfft), nthr = (d.nfft / 2) / jfull;
+  static const bool full_band = getenv("RFINV_FULL_BAND") && atoi(getenv("RFINV_FULL_BAND")) != 0;
+  const int allowed[6] = {1, 2, 3, 4, 6, 8};
+  d.jb_max = 1;
+  for (int t = 0; t < d.ntrc; ++t) {
+    int g = jfull;
+    if (!full_band && d.deconv_mode == 0) {
+      const double* f = flt.data() + (size_t)t * nh;
+      double total = 0.0;
+      for (int j = 0; j < nh; ++j) total += f[j];
+      double tail = 0.0;
+      g = jfull;
+      // largest cut (in whole groups) whose tail -- bins g*nthr .. nh-1 -- stays below 2^-52 of the total
+      for (int cand = jfull - 1; cand >= 1; --cand) {
+        tail = 0.0;
+        for (int j = cand * nthr; j < nh; ++j) tail += f[j];
+        if (tail <= total * 2.220446049250313e-16) g = cand; else break;
+      }
+    }
+    int r = jfull;
+    for (int i = 5; i >= 0; --i) if (allowed[i] >= g && allowed[i] <= jfull) r = allowed[i];
+    d.jbins[t] = r;
+    if (r > d.jb_max) d.jb_max = r;
+  }
+  if (d.ray_common) for (int t = 0; t < d.ntrc; ++t) d.jbins[t] = d.jb_max;   // one propagation serves every trace
 }
 
 // exp(+2 pi i m / n), exact symmetries of the octants
@@ -283,6 +317,7 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
 
   std::vector<double> flt;
   build_filter(*cfg, flt);
+  band_limits(d, flt);
   std::vector<double2> tw;
   build_twiddles(cfg->nfft, tw);
   // R^-1: symmetrised (the quadratic form only sees the symmetric part) and zero padded to the tile

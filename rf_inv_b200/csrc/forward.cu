@@ -631,12 +631,26 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
   }
 }
 
-// Surface response of the thread's J bins.  STAGE = false: straight into the packed, filtered spectrum
+// Runs the layer loop for the first jm (<= JB) bin groups of the thread; jm takes the values band_limits() hands out.
+template <int JB, bool MIXED>
+__device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, int k,
+                                                 int n_hi, int tid, Wave* wa, Wave* wb) {
+  if (!MIXED || jm >= JB) { propagate<JB>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+  if constexpr (MIXED) {
+  if constexpr (JB > 6) if (jm == 6) { propagate<6>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 4) if (jm == 4) { propagate<4>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 3) if (jm == 3) { propagate<3>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 2) if (jm == 2) { propagate<2>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 1) propagate<1>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
+  }
+}
+
+// Surface response of the thread's first J bin groups (the groups above them are zero filled).  STAGE = false: straight into the packed, filtered spectrum
 // Z = X_r + i X_v with Hermitian extension (src/forward.f90:168, 199) in the padded FFT buffer; STAGE = true: the
 // unfiltered spectra go to s_fr / s_fv (common rays, water-level deconvolution).  Thread 0 adds the two edge bins.
 template <int J, bool STAGE>
-__device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int ipha, int n, int nh,
-                                                 int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
+__device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha,
+                                                 int n, int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
                                                  double2* s_fr, double2* s_fv) {
   double h14[4], h23[4];
 #pragma unroll
@@ -659,6 +673,11 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
       s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
       s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
     }
+  }
+  for (int m = J; m < jfull; ++m) {    // bins above the band limit of this trace (band_limits(), capi.cu)
+    const int j = tid + m * nthr;
+    if (STAGE) { s_fr[j] = make_double2(0.0, 0.0); s_fv[j] = make_double2(0.0, 0.0); }
+    else { s_buf[fpad(j)] = make_double2(0.0, 0.0); s_buf[fpad(n - j)] = make_double2(0.0, 0.0); }
   }
   if (tid == 0) {  // the two bins off the regular grid
     if (STAGE) {
@@ -714,16 +733,33 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
   }
 }
 
+template <int JB, bool STAGE, bool MIXED>
+__device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha, int n,
+                                               int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
+                                               double2* s_fr, double2* s_fv) {
+#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv)
+  if (!MIXED || jm >= JB) { SURF(JB); return; }
+  if constexpr (MIXED) {
+  if constexpr (JB > 6) if (jm == 6) { SURF(6); return; }
+  if constexpr (JB > 4) if (jm == 4) { SURF(4); return; }
+  if constexpr (JB > 3) if (jm == 3) { SURF(3); return; }
+  if constexpr (JB > 2) if (jm == 2) { SURF(2); return; }
+  if constexpr (JB > 1) SURF(1);
+  }
+#undef SURF
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward_kernel: persistent CTAs, one (model, ray) item at a time, items handed out by an atomic counter
 // (the work per item is proportional to its layer count).  The constants of the next item are fetched with
-// cp.async while the current one is computed.  Thread `tid` owns frequency bins j = tid + m*B, m < J
-// (B = blockDim.x, B*J = nfft/2).  Bins 0 (DC) and nfft/2 (Nyquist) come from prep_kernel.
+// cp.async while the current one is computed.  Thread `tid` owns frequency bins j = tid + m*B, m < nfft/2/B
+// (B = blockDim.x), of which only the first cfg.jbins[trace] <= J groups carry signal through the Gaussian filter
+// (band_limits(), capi.cu) and are propagated.  Bins 0 (DC) and nfft/2 (Nyquist) come from prep_kernel.
 // Shared memory: one region that first holds the trigonometric tables of the layer loop and then the padded
 // in-place FFT buffer; the unfiltered spectra only when they must outlive one FFT (common rays) or feed the
 // water-level deconvolution; two sets of layer / ray constants; quarter-wave twiddles.
 // ------------------------------------------------------------------------------------------------
-template <int J, int BMAX, int MINB>
+template <int J, int BMAX, int MINB, bool MIXED>
 __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
                                                              const double* __restrict__ lc_in,
                                                              const double* __restrict__ rc_in, int* __restrict__ counter) {
@@ -787,14 +823,16 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     __syncthreads();
     PHASE_MARK(1);
 
+    const int jm = MIXED ? cfg.jbins[t0] : J;   // bin groups with signal for this trace (<= J; MIXED: it varies by trace)
     Wave wa[J], wb[J];
-    propagate<J>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
+    propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
     PHASE_MARK(2);
     __syncthreads();   // the trigonometric tables are dead: their region becomes the FFT buffer
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
-    if (general) surface_and_pack<J, true>(s_rc, wa, wb, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv);
-    else surface_and_pack<J, false>(s_rc, wa, wb, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv);
+    const int jfull = (n >> 1) / nthr;
+    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv);
+    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -916,23 +954,23 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
          2 * sizeof(LayerConst) * km;
 }
 
-template <int J, int BMAX, int MINB>
+template <int J, int BMAX, int MINB, bool MIXED>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
                      const double* rc, int* counter, int nthr, cudaStream_t stream) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
-  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, per_sm = 0;
   RFINV_CUDA_CHECK(cudaGetDevice(&dev));
   RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB>, nthr, smem));
+  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED>, nthr, smem));
   if (per_sm < 1) { rfinv_set_error("forward_kernel does not fit on an SM (%zu bytes of shared memory)", smem); return RFINV_ERR_CUDA; }
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long items = (long long)n_models * ntr_eff;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  forward_kernel<J, BMAX, MINB><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
+  forward_kernel<J, BMAX, MINB, MIXED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -940,11 +978,6 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
 }  // namespace
 
 int rfinv_forward_bins_per_thread(int nfft) {
-  static const int forced = getenv("RFINV_FWD_J") ? atoi(getenv("RFINV_FWD_J")) : 0;   // tuning knob
-  if (forced == 1 || forced == 2 || forced == 4 || forced == 8) {
-    const int nthr = (nfft / 2) / forced;
-    if (nthr >= 32 && nthr <= 256 && (nthr & 15) == 0) return forced;
-  }
   if (nfft <= 64) return 1;
   if (nfft <= 256) return 2;
   if (nfft <= 1024) return 4;
@@ -973,24 +1006,28 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   prep_kernel<<<(unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS), 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter,
                                                                                                          (int)n_items, ntr_eff, nthr);
   RFINV_CUDA_CHECK(cudaGetLastError());
-  static const int minb = getenv("RFINV_FWD_MINB") ? atoi(getenv("RFINV_FWD_MINB")) : 4;   // tuning knob (CTAs per SM)
-  if (J == 1) {
-    if (nthr <= 32) return launch_forward_t<1, 32, 8>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    return launch_forward_t<1, 256, 2>(cfg, mb, out, lc, rc, counter, nthr, stream);
+  // kernel variant: <bin groups per thread that are propagated (band limit), upper bound of threads per CTA, CTAs per SM>
+  const int JB = cfg.jb_max;
+  bool mixed = false;   // traces with different band limits: the kernel picks the loop length per item
+  for (int t = 0; t < cfg.ntrc; ++t) mixed = mixed || cfg.jbins[t] != JB;
+#define FWD(JJ, BB, MM)                                                                                   \
+  do {                                                                                                    \
+    if (mixed || JJ != JB) return launch_forward_t<JJ, BB, MM, true>(cfg, mb, out, lc, rc, counter, nthr, stream); \
+    return launch_forward_t<JJ, BB, MM, false>(cfg, mb, out, lc, rc, counter, nthr, stream);              \
+  } while (0)
+  if (nthr <= 32) { if (JB <= 1) FWD(1, 32, 8); FWD(2, 32, 8); }
+  if (nthr <= 64) { if (JB <= 2) FWD(2, 64, 6); FWD(4, 64, 6); }
+  if (nthr <= 128) {
+    if (JB <= 2) FWD(2, 128, 6);
+    static const int minb3 = getenv("RFINV_FWD_MINB3") ? atoi(getenv("RFINV_FWD_MINB3")) : 4;   // tuning knob
+    if (JB <= 3) { if (minb3 == 5) FWD(3, 128, 5); FWD(3, 128, 4); }
+    if (JB <= 4) FWD(4, 128, 4);
+    if (JB <= 6) FWD(6, 128, 2);
+    FWD(8, 128, 2);
   }
-  if (J == 2) {
-    if (nthr <= 64) return launch_forward_t<2, 64, 6>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    if (minb == 3) return launch_forward_t<2, 256, 3>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    return launch_forward_t<2, 256, 2>(cfg, mb, out, lc, rc, counter, nthr, stream);
-  }
-  if (J == 4) {
-    if (nthr > 128) return launch_forward_t<4, 256, 1>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    if (minb <= 3) return launch_forward_t<4, 128, 3>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    if (minb == 5) return launch_forward_t<4, 128, 5>(cfg, mb, out, lc, rc, counter, nthr, stream);
-    return launch_forward_t<4, 128, 4>(cfg, mb, out, lc, rc, counter, nthr, stream);
-  }
-  if (nthr <= 64) return launch_forward_t<8, 64, 4>(cfg, mb, out, lc, rc, counter, nthr, stream);
-  return launch_forward_t<8, 256, 1>(cfg, mb, out, lc, rc, counter, nthr, stream);
+  if (JB <= 4) FWD(4, 256, 2);
+  FWD(8, 256, 1);
+#undef FWD
 }
 
 int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,

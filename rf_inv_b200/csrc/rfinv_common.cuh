@@ -21,6 +21,8 @@ struct DevConfig {
   double domg;                  // 2 pi / (nfft * delta), src/forward.f90:241
   double rayp[RFINV_MAX_TRC];
   int ipha[RFINV_MAX_TRC];
+  int jbins[RFINV_MAX_TRC];     // frequency-bin groups (of blockDim bins each) of forward_kernel that carry signal for the trace
+  int jb_max;                   // largest jbins[]: picks the kernel variant
   const double* flt;            // [ntrc][nh]   Gaussian filter, src/forward.f90:95-119
   const double2* tw;            // [nfft]       exp(+2 pi i m / nfft)
   const double* obs;            // [ntrc][nsmp]
@@ -98,6 +100,8 @@ struct EvalOutputs {
 size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models);
 int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
                          cudaStream_t stream);
+// bins per thread of forward_kernel for the full band (threads per CTA = nfft/2 / this)
+int rfinv_forward_bins_per_thread(int nfft);
 // phi[ntrc][C] = m^T R^-1 m per trace and model
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
                           int n_active, const int* n_active_dev, cudaStream_t stream);
