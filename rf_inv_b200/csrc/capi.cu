@@ -214,13 +214,17 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_logl, sizeof(double) * Cz));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_valid, Cz));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_scratch, sizeof(double) * rfinv_forward_scratch_doubles(dc, C)));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_qpart, sizeof(double) * rfinv_quadform_partial_doubles(dc, C)));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_qcnt, sizeof(int) * rfinv_quadform_counter_ints(dc, C)));
+  RFINV_CUDA_CHECK(cudaMemset(d_qcnt, 0, sizeof(int) * rfinv_quadform_counter_ints(dc, C)));
   cap = C;
   return RFINV_OK;
 }
 
 void rfinv_handle::free_workspace() {
   cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage);
-  cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch);
+  cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch); cudaFree(d_qpart); cudaFree(d_qcnt);
+  d_qpart = nullptr; d_qcnt = nullptr;
   d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = d_scratch = nullptr;
   d_valid = nullptr;
   cap = 0; cap_rft_full = 0;
@@ -241,7 +245,7 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream)) != RFINV_OK) return st;
   launches += 2;
   if (timing) cudaEventRecord(ev[1], stream);
-  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, active, n_active, nullptr, stream)) != RFINV_OK) return st;
+  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, d_qpart, d_qcnt, active, n_active, nullptr, stream)) != RFINV_OK) return st;
   ++launches;
   if (timing) cudaEventRecord(ev[2], stream);
   if (logl) {

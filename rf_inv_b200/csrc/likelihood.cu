@@ -29,121 +29,151 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// CTA = 64 chains of one trace.  For every column tile jt of the symmetric R^-1 it accumulates
+// Work item = (64 chains, one trace, one column tile jt of the symmetric R^-1).  It accumulates
 //   Y(64 x 64) = 2 * sum_{kt<jt} M[:,kt] R[kt,jt]  +  M[:,jt] R[jt,jt]          (DMMA, fp64 accumulate)
-// and folds it into phi with the row-dot  phi += sum_cols Y .* M[:,jt].  Both MMA operands are read as
-// "row-major, k contiguous": M[chain][k] and, by symmetry, R[col][k].  Fixed summation order, no atomics.
+// and the row-dot  sum_cols Y .* M[:,jt]  -> partial[jt][t][chain].  Both MMA operands are read as "row-major,
+// k contiguous": M[chain][k] and, by symmetry, R[col][k].  The cost of an item grows with jt, so persistent CTAs
+// take items from an atomic counter, largest first.  The CTA that delivers the last of the ntile partials of a
+// (64 chains, trace) block sums them in the fixed order jt = 0..ntile-1 into phi: no floating-point atomics, results
+// are bit-identical from run to run whatever the schedule.
 __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cfg, int C, const double* __restrict__ misfit,
-                                                              double* __restrict__ phi, const int* __restrict__ active,
-                                                              int n_active, const int* __restrict__ n_active_dev) {
+                                                              double* __restrict__ phi, double* __restrict__ partial,
+                                                              int* __restrict__ arrivals, int* __restrict__ work,
+                                                              const int* __restrict__ active, int n_active,
+                                                              const int* __restrict__ n_active_dev) {
   __shared__ __align__(16) double sA[2][TM * LDS_STRIDE];
   __shared__ __align__(16) double sB[2][TN * LDS_STRIDE];
   __shared__ int s_rows[TM];
   __shared__ double s_part[2][TM];
-  const int t = blockIdx.y;
-  const int Sp = cfg.nsmp_pad;
+  __shared__ int s_next, s_last;
+  const int Sp = cfg.nsmp_pad, T = cfg.ntrc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile origin: rows wm*32, cols wn*32
   const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
-  const int row0 = blockIdx.x * TM;
-  if (row0 >= n_rows) return;
-  if (tid < TM) {
-    int r = row0 + tid;
-    r = r < n_rows ? r : n_rows - 1;                // clamp: duplicates are computed but never written
-    s_rows[tid] = active ? active[r] : r;
-  }
-  __syncthreads();
-  const double* __restrict__ Mt = misfit + (size_t)t * C * Sp;
-  const double* __restrict__ Rt = cfg.r_inv + (size_t)t * Sp * Sp;
+  const int n_rb_grid = ((active ? n_active : C) + TM - 1) / TM;   // row blocks the item index space is built on
   const int ntile = Sp / TN;
-  // global -> smem copy assignment: 64 rows x 16 doubles = 512 x 16 B per operand, 4 per thread each
-  const double* a_src[4];
-  int cp_off[4], cp_row[4];
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int id = tid + q * QF_THREADS;            // 0..511
-    const int row = id >> 3, seg = id & 7;          // 8 segments of 2 doubles per row
-    cp_row[q] = row;
-    cp_off[q] = row * LDS_STRIDE + seg * 2;
-    a_src[q] = Mt + (size_t)s_rows[row] * Sp + seg * 2;
-  }
+  const int n_items = ntile * T * n_rb_grid;
   const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates
-  double phi_acc[4] = {0.0, 0.0, 0.0, 0.0};         // rows wm*32 + 8*i + fr
-
-  for (int jt = 0; jt < ntile; ++jt) {
-    double acc[4][4][2];
+  if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
+  int item = blockIdx.x;
+  while (item < n_items) {
+    const int jt = ntile - 1 - item / (T * n_rb_grid);       // largest column tiles first
+    const int rem = item % (T * n_rb_grid);
+    const int t = rem / n_rb_grid, rb = rem - t * n_rb_grid;
+    const int row0 = rb * TM;
+    __syncthreads();                                // previous item is done with s_rows / s_part; s_next is visible
+    const int next = s_next;
+    int next_raw = 0;
+    if (tid == 0) next_raw = atomicAdd(work, 1);    // consumed at the end of the item
+    if (row0 < n_rows) {
+      if (tid < TM) {
+        int r = row0 + tid;
+        r = r < n_rows ? r : n_rows - 1;            // clamp: duplicates are computed but never written
+        s_rows[tid] = active ? active[r] : r;
+      }
+      __syncthreads();
+      const double* __restrict__ Mt = misfit + (size_t)t * C * Sp;
+      const double* __restrict__ Rt = cfg.r_inv + (size_t)t * Sp * Sp;
+      // global -> smem copy assignment: 64 rows x 16 doubles = 512 x 16 B per operand, 4 per thread each
+      const double* a_src[4];
+      int cp_off[4], cp_row[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int q = 0; q < 4; ++q) {
+        const int id = tid + q * QF_THREADS;        // 0..511
+        const int row = id >> 3, seg = id & 7;      // 8 segments of 2 doubles per row
+        cp_row[q] = row;
+        cp_off[q] = row * LDS_STRIDE + seg * 2;
+        a_src[q] = Mt + (size_t)s_rows[row] * Sp + seg * 2;
+      }
+      double acc[4][4][2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    const int nk = (jt + 1) * (TN / TK);            // k-slabs up to and including the diagonal tile
-    const double* b_base = Rt + (size_t)(jt * TN) * Sp;
-    // prologue: stage 0
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      cp_async16(&sA[0][cp_off[q]], a_src[q]);
-      cp_async16(&sB[0][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + (cp_off[q] - cp_row[q] * LDS_STRIDE));
-    }
-    cp_async_commit();
-    for (int ks = 0; ks < nk; ++ks) {
-      const int cur = ks & 1;
-      if (ks + 1 < nk) {
-        const int k0 = (ks + 1) * TK;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      const int nk = (jt + 1) * (TN / TK);          // k-slabs up to and including the diagonal tile
+      const double* b_base = Rt + (size_t)(jt * TN) * Sp;
+      // prologue: stage 0
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          cp_async16(&sA[cur ^ 1][cp_off[q]], a_src[q] + k0);
-          cp_async16(&sB[cur ^ 1][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + k0 + (cp_off[q] - cp_row[q] * LDS_STRIDE));
+      for (int q = 0; q < 4; ++q) {
+        cp_async16(&sA[0][cp_off[q]], a_src[q]);
+        cp_async16(&sB[0][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + (cp_off[q] - cp_row[q] * LDS_STRIDE));
+      }
+      cp_async_commit();
+      for (int ks = 0; ks < nk; ++ks) {
+        const int cur = ks & 1;
+        if (ks + 1 < nk) {
+          const int k0 = (ks + 1) * TK;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cp_async16(&sA[cur ^ 1][cp_off[q]], a_src[q] + k0);
+            cp_async16(&sB[cur ^ 1][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + k0 + (cp_off[q] - cp_row[q] * LDS_STRIDE));
+          }
+          cp_async_commit();
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
         }
-        cp_async_commit();
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
+        __syncthreads();
+        if (ks == jt * (TN / TK) && jt > 0) {       // entering the diagonal tile: what came before counts twice
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { acc[i][j][0] *= 2.0; acc[i][j][1] *= 2.0; }
+        }
+        const double* A = &sA[cur][(wm * 32 + fr) * LDS_STRIDE + fk];
+        const double* B = &sB[cur][(wn * 32 + fr) * LDS_STRIDE + fk];
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = A[i * 8 * LDS_STRIDE + kk];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDS_STRIDE + kk];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncthreads();
+      }
+      // row-dot with M[:, jt]: lane holds Y[row = 8i + fr][col = 8j + 2*fk + {0,1}] of its warp sub-tile
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 32 + 2 * fk;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
+          v = fma(acc[i][j][0], m.x, v);
+          v = fma(acc[i][j][1], m.y, v);
+        }
+        // reduce over the 4 lanes sharing a row; the two warps (wn) covering the 64 columns meet in shared memory
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (fk == 0) s_part[wn][wm * 32 + 8 * i + fr] = v;
       }
       __syncthreads();
-      if (ks == jt * (TN / TK) && jt > 0) {         // entering the diagonal tile: what came before counts twice
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { acc[i][j][0] *= 2.0; acc[i][j][1] *= 2.0; }
-      }
-      const double* A = &sA[cur][(wm * 32 + fr) * LDS_STRIDE + fk];
-      const double* B = &sB[cur][(wn * 32 + fr) * LDS_STRIDE + fk];
-#pragma unroll
-      for (int kk = 0; kk < TK; kk += 4) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = A[i * 8 * LDS_STRIDE + kk];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDS_STRIDE + kk];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      }
+      double* part_t = partial + (size_t)t * C;                      // [jt][T][C], indexed by chain
+      const size_t jstride = (size_t)T * C;
+      if (tid < TM && row0 + tid < n_rows) part_t[(size_t)jt * jstride + s_rows[tid]] = s_part[0][tid] + s_part[1][tid];
+      __threadfence();
       __syncthreads();
-    }
-    // row-dot with M[:, jt]: lane holds Y[row = 8i + fr][col = 8j + 2*fk + {0,1}] of its warp sub-tile
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 32 + 2 * fk;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
-        phi_acc[i] = fma(acc[i][j][0], m.x, phi_acc[i]);
-        phi_acc[i] = fma(acc[i][j][1], m.y, phi_acc[i]);
+      if (tid == 0) s_last = (atomicAdd(&arrivals[t * n_rb_grid + rb], 1) == ntile - 1);
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        if (tid < TM && row0 + tid < n_rows) {
+          const int c = s_rows[tid];
+          double v = 0.0;
+          for (int j = 0; j < ntile; ++j) v += __ldcg(part_t + (size_t)j * jstride + c);   // fixed order
+          phi[(size_t)t * C + c] = v;
+        }
+        if (tid == 0) arrivals[t * n_rb_grid + rb] = 0;              // ready for the next launch
       }
     }
+    if (tid == 0) s_next = (int)gridDim.x + next_raw;
+    item = next;
   }
-  // reduce over the 4 lanes sharing a row, then over the two warps (wn) covering the 64 columns
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double v = phi_acc[i];
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (fk == 0) s_part[wn][wm * 32 + 8 * i + fr] = v;
-  }
-  __syncthreads();
-  if (tid < TM && row0 + tid < n_rows) phi[(size_t)t * C + s_rows[tid]] = s_part[0][tid] + s_part[1][tid];
 }
 
 __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restrict__ phi, const double* __restrict__ sig,
@@ -161,12 +191,31 @@ __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restri
 
 }  // namespace
 
-int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
-                          int n_active, const int* n_active_dev, cudaStream_t stream) {
+size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C) { return (size_t)(cfg.nsmp_pad / TN) * cfg.ntrc * C; }
+size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C) { return (size_t)((C + TM - 1) / TM) * cfg.ntrc + 4; }
+
+// partial: rfinv_quadform_partial_doubles(cfg, C) doubles; counters: rfinv_quadform_counter_ints(cfg, capacity) ints, zeroed
+// once at allocation (the arrival counters reset themselves; the work counter is cleared here before every launch)
+int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, double* partial, int* counters,
+                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream) {
   const int n_rows = active ? n_active : C;
   if (n_rows == 0) return RFINV_OK;
-  dim3 grid((n_rows + TM - 1) / TM, cfg.ntrc);
-  quadform_kernel<<<grid, QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, active, n_active, n_active_dev);
+  const size_t ntile = cfg.nsmp_pad / TN;
+  int* work = counters;
+  int* arrivals = counters + 4;
+  static int per_sm = 0, n_sm = 0;
+  if (per_sm == 0) {
+    int dev = 0;
+    RFINV_CUDA_CHECK(cudaGetDevice(&dev));
+    RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quadform_kernel, QF_THREADS, 0));
+    if (per_sm < 1) per_sm = 1;
+  }
+  const long long items = (long long)ntile * cfg.ntrc * ((n_rows + TM - 1) / TM);
+  const long long resident = (long long)n_sm * per_sm;
+  RFINV_CUDA_CHECK(cudaMemsetAsync(work, 0, sizeof(int), stream));
+  quadform_kernel<<<(unsigned)(items < resident ? items : resident), QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, partial, arrivals, work,
+                                                                                              active, n_active, n_active_dev);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }

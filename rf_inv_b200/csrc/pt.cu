@@ -651,7 +651,7 @@ static int pt_eval(rfinv_handle* h, bool proposal, bool all) {
   out.slot_invert = proposal ? 1 : 0; out.rft_full = nullptr; out.is_valid = nullptr;
   int st;
   if ((st = rfinv_launch_forward(h->dc, mb, out, h->d_scratch, h->stream)) != RFINV_OK) return st;
-  return rfinv_launch_quadform(h->dc, d.Cl, h->d_misfit, proposal ? d.pphi : d.phi, mb.active, mb.n_active, mb.n_active_dev,
+  return rfinv_launch_quadform(h->dc, d.Cl, h->d_misfit, proposal ? d.pphi : d.phi, h->d_qpart, h->d_qcnt, mb.active, mb.n_active, mb.n_active_dev,
                                h->stream);
 }
 

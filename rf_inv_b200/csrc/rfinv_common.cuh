@@ -102,9 +102,12 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
                          cudaStream_t stream);
 // bins per thread of forward_kernel for the full band (threads per CTA = nfft/2 / this)
 int rfinv_forward_bins_per_thread(int nfft);
-// phi[ntrc][C] = m^T R^-1 m per trace and model
-int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, const int* active,
-                          int n_active, const int* n_active_dev, cudaStream_t stream);
+// phi[ntrc][C] = m^T R^-1 m per trace and model.  partial / counters: scratch sized by the two functions below, the
+// counters zeroed at allocation
+size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C);
+size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C);
+int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, double* partial, int* counters,
+                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream);
 // logl[c] = sum_t -0.5 phi/sig^2 - nsmp log(sig)   (src/likelihood.f90:94-96)
 int rfinv_launch_loglik(const DevConfig& cfg, int C, const double* phi, const double* sig, double* logl,
                         cudaStream_t stream);

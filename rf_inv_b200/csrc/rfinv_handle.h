@@ -26,6 +26,8 @@ struct rfinv_handle {
   double *d_z = nullptr, *d_dvp = nullptr, *d_dvs = nullptr, *d_sig = nullptr, *d_stage = nullptr;
   double *d_misfit = nullptr, *d_phi = nullptr, *d_logl = nullptr, *d_rft_full = nullptr, *d_scratch = nullptr;
   uint8_t* d_valid = nullptr;
+  double* d_qpart = nullptr;    // quadform_kernel partial sums
+  int* d_qcnt = nullptr;        // quadform_kernel work / arrival counters
   size_t cap_rft_full = 0;
   int launches = 0;
   bool timing = false;
