@@ -197,3 +197,41 @@ def test_full_size_properties(workload, n_models):
     sub = np.arange(0, n_models, max(1, n_models // 48))
     ll_o, _, _ = oracle_c.eval_batch(cfg, m["k"][sub], m["z"][sub], m["dvp"][sub], m["dvs"][sub], m["sig"][sub], want_rft=False)
     assert helpers.logl_err(cfg, ll[sub], ll_o, m["sig"][sub]) < RTOL
+
+
+def test_band_limit_changes_nothing_above_rounding(tmp_path):
+    """forward_kernel skips frequency-bin groups whose Gaussian-filter weight is below 2^-52 of the filter's mass
+    (band_limits(), capi.cu).  With RFINV_FULL_BAND=1 every bin is propagated: both runs must agree to rounding
+    level (here: 1e-13 of the trace maximum, four orders of magnitude inside the 1e-9 bar), on the target shape
+    (the band limit drops one bin group of four) and on mixed Gaussian widths (2, 3 and 4 groups kept per trace)."""
+    import subprocess
+    import sys
+    script = r'''
+import sys, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import helpers
+from rf_inv_b200 import workloads
+from rf_inv_b200.evaluator import Evaluator
+out = {}
+for name in ("target", "c3"):
+    cfg = workloads.make_config(name)
+    cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
+    m = workloads.draw_models(cfg, 64, seed=5, dvs_scale=0.3)
+    with Evaluator(cfg) as ev:
+        _, rft, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+    out[name] = rft
+np.savez(sys.argv[1], **out)
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)),
+       os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    res = {}
+    for tag, val in (("band", "0"), ("full", "1")):
+        env = dict(os.environ, RFINV_FULL_BAND=val)
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=env)
+        res[tag] = np.load(path)
+    for name in ("target", "c3"):
+        a, b = res["band"][name], res["full"][name]
+        assert np.isfinite(b).all()
+        err = helpers.rel_err_rft(a, b)
+        assert err < 1e-13, (name, err)
+        assert not np.array_equal(a, b) or name != "target"   # the switch really changes the computation
