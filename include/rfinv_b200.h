@@ -127,6 +127,11 @@ int32_t rfinv_format_model_batch(rfinv_handle* h, int32_t C, const int32_t* k, c
                                  const double* dvp, const double* dvs, int32_t* nlay, double* alpha,
                                  double* beta, double* rho, double* hthick, uint8_t* is_valid);
 
+/* out = c2r( r2c(in) * flt(:, trace_of[i]) ) for n_series real series of nfft samples, both transforms unnormalised like
+ * FFTW's: the noise shaping of make_syn (src/make_syn.f90:96-100, plans src/fftw.f90:44-45).  HOST pointers:
+ * trace_of[n_series] (0-based trace whose Gaussian filter is applied), in/out [n_series][nfft].                      */
+int32_t rfinv_filter_traces(rfinv_handle* h, int32_t n_series, const int32_t* trace_of, const double* in, double* out);
+
 /* Copies the R^-1 actually in use back to the host ([ntrc][nsmp][nsmp]). */
 int32_t rfinv_get_r_inv(rfinv_handle* h, double* r_inv);
 /* Waits for all work queued on the handle's stream. */
@@ -150,6 +155,11 @@ int32_t rfinv_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmm
  * ranks and process q owns [q*rank_count, (q+1)*rank_count).                                               */
 /* init_model + init_sig + init_rft + temperatures (src/rf_inv.f90:86-91), on device. */
 int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, int32_t rank_count);
+/* Draws n deviates from the mt19937 stream of local virtual rank `local_rank`, advancing it: kind 0 = grnd()
+ * (src/mt19937.f90:92-130), kind 1 = gauss() (src/math.f90:34-50).  out[n] is a HOST pointer.  With cfg.ncool = cfg.nchains
+ * (no temperature draws) the stream after rfinv_pt_init(h, 1, 0, 1) is where make_syn starts its noise draws
+ * (src/make_syn.f90:52-65, 80-110). */
+int32_t rfinv_pt_draw(rfinv_handle* h, int32_t local_rank, int32_t kind, int32_t n, double* out);
 /* Number of proposal types (src/pt_mcmc.f90:311-365): 4 (+1 if vp_mode) (+1 if a sigma is solved). */
 int32_t rfinv_pt_ntype(rfinv_handle* h);
 /* Keep per-iteration logs for the next `cap_iters` iterations (0 disables): accept flags, proposal types, swaps. */

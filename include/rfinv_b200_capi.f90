@@ -103,6 +103,22 @@ module rfinv_b200_capi
        integer(c_int64_t), intent(out) :: n_eval
      end function rfinv_pt_get_counters
 
+     integer(c_int32_t) function rfinv_pt_draw(handle, local_rank, kind, n, out) bind(C, name="rfinv_pt_draw")
+       import :: c_int32_t, c_ptr, c_double
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: local_rank, kind, n
+       real(c_double), intent(out) :: out(*)
+     end function rfinv_pt_draw
+
+     integer(c_int32_t) function rfinv_filter_traces(handle, n_series, trace_of, in, out) bind(C, name="rfinv_filter_traces")
+       import :: c_int32_t, c_ptr, c_double
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: n_series
+       integer(c_int32_t), intent(in) :: trace_of(*)
+       real(c_double), intent(in) :: in(*)
+       real(c_double), intent(out) :: out(*)
+     end function rfinv_filter_traces
+
      function rfinv_last_error() bind(C, name="rfinv_last_error") result(msg)
        import :: c_ptr
        type(c_ptr) :: msg

@@ -724,3 +724,35 @@ def pt_run(cfg: Config, flt, r_inv, nproc: int, n_tot_iter: Optional[int] = None
             s1.temps[c1] = temp2
         res.swaps.append((itarget1, itarget2, int(yn)))
     return ranks, res
+
+
+def make_syn(cfg: Config):
+    """make_syn.f90:51-161: one random model per chain from the stream sgrnd(iseed) (no rank offset), init_sig, the
+    synthetic RF of chain 1, and per trace a Gaussian white-noise series shaped by the trace's filter
+    (r2c -> *flt -> c2r, both transforms unnormalised: make_syn.f90:96-100).  Returns a dict with the model of chain 1,
+    its layer stack, noise_sigma[T], the filtered noise[T][nfft], rft[T][nsmp] and the noisy traces.
+    The observed data of `cfg` are only used through nsmp / delta, like the reference's read_obs call."""
+    rng = MT19937(cfg.iseed & 0xFFFFFFFF)
+    k, z, dvp, dvs = init_model(cfg, rng)
+    sig = init_sig(cfg, rng)
+    flt = init_filter(cfg)
+    nlay, alpha, beta, rho, h, is_valid = format_model(cfg, int(k[0]), z[:, 0], dvp[:, 0], dvs[:, 0])
+    rft = calc_rf(cfg, flt, nlay, alpha, beta, rho, h)              # [nfft][ntrc]
+    n, T = cfg.nfft, cfg.ntrc
+    noise = np.zeros((T, n)); noise_sigma = np.zeros(T)
+    if cfg.is_ray_common:
+        noise_sigma[:] = rng.grnd() * (cfg.sig_max[0] - cfg.sig_min[0]) + cfg.sig_min[0]
+        white = np.array([gauss(rng) * noise_sigma[0] for _ in range(n)])
+        for t in range(T):
+            noise[t] = c2r(np.fft.rfft(white) * flt[:, t], n)
+    else:
+        for t in range(T):
+            noise_sigma[t] = rng.grnd() * (cfg.sig_max[t] - cfg.sig_min[t]) + cfg.sig_min[t]
+            white = np.array([gauss(rng) * noise_sigma[t] for _ in range(n)])
+            noise[t] = c2r(np.fft.rfft(white) * flt[:, t], n)
+    S = cfg.nsmp
+    clean = rft[:S, :].T.copy()
+    return dict(k=int(k[0]), z=z[:, 0].copy(), dvp=dvp[:, 0].copy(), dvs=dvs[:, 0].copy(), sig=sig[:, 0].copy(), nlay=nlay,
+                alpha=alpha[:nlay].copy(), beta=beta[:nlay].copy(), rho=rho[:nlay].copy(), h=h[:nlay].copy(),
+                noise_sigma=noise_sigma, noise=noise, rft=clean, noisy=clean + noise[:, :S])
+

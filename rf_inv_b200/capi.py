@@ -34,6 +34,7 @@ SIGNATURES = {
     "rfinv_eval_batch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp, dp, dp, dp, dp, u8p]),
     "rfinv_eval_batch_device": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_uint64] * 8),
     "rfinv_format_model_batch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp, dp, i32p, dp, dp, dp, dp, u8p]),
+    "rfinv_filter_traces": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp]),
     "rfinv_get_r_inv": (C.c_int32, [C.c_void_p, dp]),
     "rfinv_synchronize": (C.c_int32, [C.c_void_p]),
     "rfinv_last_launch_count": (C.c_int32, [C.c_void_p]),
@@ -41,6 +42,7 @@ SIGNATURES = {
     "rfinv_get_timing": (C.c_int32, [C.c_void_p, dp]),
     "rfinv_measure_fp64_peak": (C.c_int32, [C.c_int32, dp, dp]),
     "rfinv_pt_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
+    "rfinv_pt_draw": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, dp]),
     "rfinv_pt_ntype": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_set_logging": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_pt_run": (C.c_int32, [C.c_void_p, C.c_int32]),

@@ -458,6 +458,35 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
   return RFINV_OK;
 }
 
+int32_t rfinv_filter_traces(rfinv_handle* h, int32_t n_series, const int32_t* trace_of, const double* in, double* out) {
+  if (!h || n_series < 0 || (n_series > 0 && (!trace_of || !in || !out))) {
+    rfinv_set_error("rfinv_filter_traces: NULL argument");
+    return RFINV_ERR_ARG;
+  }
+  for (int i = 0; i < n_series; ++i)
+    if (trace_of[i] < 0 || trace_of[i] >= h->cfg.ntrc) {
+      rfinv_set_error("rfinv_filter_traces: trace_of[%d]=%d outside [0,ntrc)", i, trace_of[i]);
+      return RFINV_ERR_ARG;
+    }
+  if (n_series == 0) return RFINV_OK;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  const size_t n = (size_t)n_series * h->cfg.nfft;
+  double *d_in = nullptr, *d_out = nullptr;
+  int* d_tr = nullptr;
+  cudaError_t e = cudaMalloc((void**)&d_in, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, sizeof(double) * n);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&d_tr, sizeof(int) * (size_t)n_series);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, in, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_tr, trace_of, sizeof(int) * (size_t)n_series, cudaMemcpyHostToDevice, h->stream);
+  int st = RFINV_OK;
+  if (e == cudaSuccess) st = rfinv_launch_filter_traces(h->dc, n_series, d_in, d_tr, d_out, h->stream);
+  if (e == cudaSuccess && st == RFINV_OK) e = cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && st == RFINV_OK) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_in); cudaFree(d_out); cudaFree(d_tr);
+  if (e != cudaSuccess) { rfinv_set_error("rfinv_filter_traces: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
+  return st;
+}
+
 int32_t rfinv_eval_batch_device(rfinv_handle* h, int32_t C, uint64_t d_k, uint64_t d_z, uint64_t d_dvp, uint64_t d_dvs,
                                 uint64_t d_sig, uint64_t d_logl, uint64_t d_rft_smp, uint64_t d_is_valid) {
   if (!h || C < 0 || (C > 0 && (!d_k || !d_z || !d_dvp || !d_dvs || !d_sig || !d_logl))) {

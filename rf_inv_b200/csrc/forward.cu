@@ -905,6 +905,41 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// filter_traces_kernel: y = c2r( r2c(x) * flt(:, trace) ), both transforms unnormalised like FFTW's -- the noise
+// shaping of make_syn (src/make_syn.f90:96-100; plans src/fftw.f90:44-45).  One CTA per series.  For real x the
+// forward transform is the conjugate of the inverse one, so both directions run through fft_inverse_dif.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg, const double* __restrict__ in,
+                                                           const int* __restrict__ trace_of, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, nthr = blockDim.x, n = cfg.nfft, nh = cfg.nh, brev_shift = 32 - cfg.log2n;
+  double2* b0 = reinterpret_cast<double2*>(smem_raw);
+  double2* b1 = b0 + fft_buf_elems(n);
+  double2* s_tw = b1 + fft_buf_elems(n);
+  double* s_red = reinterpret_cast<double*>(s_tw + fft_twiddle_entries(n));
+  const double* x = in + (size_t)blockIdx.x * n;
+  const double* __restrict__ flt = cfg.flt + (size_t)trace_of[blockIdx.x] * nh;
+  fill_fft_twiddles(s_tw, cfg.tw, n, tid, nthr);
+  for (int i = tid; i < n; i += nthr) b0[fpad(i)] = make_double2(x[i], 0.0);
+  __syncthreads();
+  fft_inverse_dif(b0, n, s_tw, s_red, tid, nthr, CtaSync());
+  for (int f = tid; f < nh; f += nthr) {
+    const double2 v = b0[fpad((int)(__brev((unsigned)f) >> brev_shift))];
+    const double w = flt[f];
+    const double2 y = make_double2(v.x * w, -v.y * w);          // r2c bin f (conjugate), filtered
+    if (f == 0 || f == nh - 1) {
+      b1[fpad(f)] = make_double2(y.x, 0.0);                     // c2r ignores these imaginary parts
+    } else {
+      b1[fpad(f)] = y;
+      b1[fpad(n - f)] = make_double2(y.x, -y.y);
+    }
+  }
+  __syncthreads();
+  fft_inverse_dif(b1, n, s_tw, s_red, tid, nthr, CtaSync());
+  for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad((int)(__brev((unsigned)i) >> brev_shift))].x;
+}
+
 __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, int* nlay_out, double* alpha,
                                     double* beta, double* rho, double* h, uint8_t* is_valid) {
   // One thread per model; used by rfinv_format_model_batch (host diagnostics / parity tests).
@@ -1028,6 +1063,18 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   if (JB <= 4) FWD(4, 256, 2);
   FWD(8, 256, 1);
 #undef FWD
+}
+
+// in / out: [n_series][nfft] in HBM, trace_of[n_series]: which trace's filter shapes the series
+int rfinv_launch_filter_traces(const DevConfig& cfg, int n_series, const double* in, const int* trace_of, double* out,
+                               cudaStream_t stream) {
+  if (n_series == 0) return RFINV_OK;
+  const size_t smem = sizeof(double2) * (2 * fft_buf_elems(cfg.nfft) + fft_twiddle_entries(cfg.nfft)) + sizeof(double) * 32;
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(filter_traces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nthr = cfg.nfft / 8 < 32 ? 32 : (cfg.nfft / 8 > 128 ? 128 : cfg.nfft / 8);
+  filter_traces_kernel<<<n_series, nthr, smem, stream>>>(cfg, in, trace_of, out);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  return RFINV_OK;
 }
 
 int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,

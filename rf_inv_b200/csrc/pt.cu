@@ -192,6 +192,14 @@ __global__ void pt_init_kernel(const DevConfig cfg, const PtDev p) {
   p.mti[r] = g.mti;
 }
 
+// Draws `n` deviates from the stream of local virtual rank r, advancing it: kind 0 = grnd() (src/mt19937.f90:92-130),
+// kind 1 = gauss() (src/math.f90:34-50).  One thread: the stream is sequential.  make_syn's noise (src/make_syn.f90:80-110).
+__global__ void pt_draw_kernel(const PtDev p, int r, int kind, int n, double* out) {
+  Mt g(p.mt, r, p.mti[r]);
+  for (int i = 0; i < n; ++i) out[i] = kind == 1 ? gauss(g) : g.grnd();
+  p.mti[r] = g.mti;
+}
+
 // ---------------- proposal pass: mcmc, src/pt_mcmc.f90:77-169 + the draws of judge_mcmc :611-615 ----------------
 // One WARP per virtual rank, chains of the rank in order (they share the stream).  All lanes execute the same draws
 // on replicated scalars (no divergence); the model arrays are distributed: lane holds elements `lane` and `lane+32`.
@@ -733,6 +741,27 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   s->it_done = 0;
   s->n_eval = d.Cl;
+  return RFINV_OK;
+}
+
+int32_t rfinv_pt_draw(rfinv_handle* h, int32_t local_rank, int32_t kind, int32_t n, double* out) {
+  int st = pt_require(h, "rfinv_pt_draw");
+  if (st != RFINV_OK) return st;
+  PtDev& d = h->pt->dev;
+  if (local_rank < 0 || local_rank >= d.G || kind < 0 || kind > 1 || n < 0 || (n > 0 && !out)) {
+    rfinv_set_error("rfinv_pt_draw: bad argument (local_rank %d of %d, kind %d, n %d)", local_rank, d.G, kind, n);
+    return RFINV_ERR_ARG;
+  }
+  if (n == 0) return RFINV_OK;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  double* d_out = nullptr;
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_out, sizeof(double) * (size_t)n));
+  pt_draw_kernel<<<1, 1, 0, h->stream>>>(d, local_rank, kind, n, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_out);
+  if (e != cudaSuccess) { rfinv_set_error("rfinv_pt_draw: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
   return RFINV_OK;
 }
 

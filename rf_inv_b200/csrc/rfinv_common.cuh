@@ -113,3 +113,6 @@ int rfinv_launch_loglik(const DevConfig& cfg, int C, const double* phi, const do
                         cudaStream_t stream);
 int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* nlay, double* alpha, double* beta,
                               double* rho, double* h, uint8_t* is_valid, cudaStream_t stream);
+// y = c2r(r2c(x) * flt(:, trace_of[series])) for n_series real series of nfft samples (make_syn's noise shaping)
+int rfinv_launch_filter_traces(const DevConfig& cfg, int n_series, const double* in, const int* trace_of, double* out,
+                               cudaStream_t stream);

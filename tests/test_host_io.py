@@ -120,3 +120,15 @@ def test_write_outputs_formats(tmp_path):
     # list-directed reals look like gfortran's: 17 significant digits, 26-column fields
     line = open(out / "interface_depth.ppd").readline().rstrip("\n")
     assert len(line) == 52 and line.startswith("   2.5000000000000000     ")
+
+
+def test_list_directed_real_matches_gfortran_layout():
+    """make_syn's test_vel is written with list-directed output (src/make_syn.f90:73): 26 columns per real(8)."""
+    from rf_inv_b200.make_syn import _ld_real
+    assert _ld_real(5.0) == "   5.0000000000000000     "
+    assert _ld_real(2.5347508187769563) == "   2.5347508187769563     "
+    assert _ld_real(999.0) == "   999.00000000000000     "
+    assert _ld_real(0.125) == "  0.12500000000000000     "
+    assert _ld_real(-999.0) == "  -999.00000000000000     "
+    assert _ld_real(1.0e-5) == "   1.0000000000000001E-005"
+    assert all(len(_ld_real(v)) == 26 for v in (0.0, 3.14, 1e20, -2.5e-7))
