@@ -135,11 +135,39 @@ def to_soa(models: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
                 dvs=np.ascontiguousarray(models["dvs"].T), sig=np.ascontiguousarray(models["sig"].T))
 
 
+def band_bins(cfg: RFConfig):
+    """Frequency bins forward_kernel propagates per trace: mirror of band_limits() in csrc/capi.cu (bin groups whose
+    Gaussian-filter weight is below 2^-52 of the filter mass are zero filled; RFINV_FULL_BAND=1 or the water-level
+    deconvolution keep the full band).  Accounting only -- the library decides for itself."""
+    import os
+    n, nh = cfg.nfft, cfg.nh
+    jfull = 1 if n <= 64 else (2 if n <= 256 else (4 if n <= 1024 else 8))
+    nthr = (n // 2) // jfull
+    allowed = [1, 2, 3, 4, 6, 8]
+    full = os.environ.get("RFINV_FULL_BAND", "0") not in ("", "0") or cfg.deconv_mode == 1
+    groups = []
+    for t in range(cfg.ntrc):
+        g = jfull
+        if not full:
+            omega = np.arange(nh) * 2.0 * np.pi / (cfg.delta * n)
+            f = np.exp(-(omega / (2.0 * cfg.a_gus[t])) ** 2)
+            total = f.sum()
+            for cand in range(jfull - 1, 0, -1):
+                if f[cand * nthr:].sum() <= total * 2.220446049250313e-16:
+                    g = cand
+                else:
+                    break
+        groups.append(min(a for a in allowed if a >= g and a <= jfull) if any(a >= g and a <= jfull for a in allowed) else jfull)
+    if cfg.is_ray_common:
+        groups = [max(groups)] * cfg.ntrc
+    return [min(gr * nthr, n // 2) + 1 for gr in groups], groups
+
+
 def flops_per_eval(cfg: RFConfig, k_mean: float) -> Dict[str, float]:
     """Algorithmic fp64 flop per forward+likelihood evaluation: an exact count of the algorithm the
     kernels execute (an FMA is 2 flop, a multiply / add / divide 1), not of the reference's dense complex form:
 
-      W = Tf*nh*(56*k + 56) + T*5*n*log2(n) + T*(S^2 + 3*S)
+      W = sum_rays nb_ray*(56*k + 56) + T*5*n*log2(n) + T*(S^2 + 3*S),   nb_ray = bins inside the band limit (band_bins)
 
     per layer and frequency bin (wave coordinates, rf_inv_b200/csrc/forward.cu): two plane rotations for each of the
     two propagated vectors (2 x (4 mul + 4 fma) = 24 flop), the 2x2 interface blocks with unit {1,4} diagonal
@@ -150,15 +178,18 @@ def flops_per_eval(cfg: RFConfig, k_mean: float) -> Dict[str, float]:
     SURVEY.md 8d's W_min (110 k + 100 per bin) and the reference's W_ref (570 k + 550) are reported next to it."""
     Tf = 1 if cfg.is_ray_common else cfg.ntrc
     n, nh, S, T = cfg.nfft, cfg.nh, cfg.nsmp, cfg.ntrc
-    prop = Tf * nh * (56.0 * k_mean + 56.0)
+    bins, groups = band_bins(cfg)
+    nb = float(bins[0]) if cfg.is_ray_common else float(sum(bins))   # bins propagated per evaluation (all rays)
+    prop = nb * (56.0 * k_mean + 56.0)
     fft = T * 5.0 * n * np.log2(n)
     quad = T * (1.0 * S * S + 3.0 * S)
     w_min_survey = Tf * nh * (110.0 * k_mean + 100.0) + fft + T * (2.0 * S * S + 3.0 * S)
     w_ref = Tf * nh * (570.0 * k_mean + 550.0) + fft + T * (2.0 * S * S + 3.0 * S)
     # FP64 instructions the forward path issues per evaluation (each occupies one issue slot of the FP64 pipe, FMA or not)
-    fwd_instr = Tf * nh * (36.0 * k_mean + 40.0) + T * (3.0 * (n / 8) * 84.0 + (n / 2) * 4.0)
+    fwd_instr = nb * (36.0 * k_mean + 40.0) + T * (3.0 * (n / 8) * 84.0 + (n / 2) * 4.0)
     return dict(propagator=prop, fft=fft, quadform=quad, total=prop + fft + quad, survey_w_min=w_min_survey,
-                reference_as_written=w_ref, forward_fp64_instructions=fwd_instr)
+                reference_as_written=w_ref, forward_fp64_instructions=fwd_instr, bins_propagated_per_eval=nb,
+                bins_full_band_per_eval=float(Tf * nh), band_groups=groups)
 
 
 def lapack_r_inv(cfg: RFConfig) -> np.ndarray:
