@@ -14,6 +14,7 @@ constexpr int TN = 64;    // columns of R^-1 per tile
 constexpr int TK = 16;    // k-slab per pipeline stage
 constexpr int LDS_STRIDE = TK + 4;   // doubles; (row*20 + k) mod 16 distinct over an 8x4 fragment: conflict-free LDS.64
 constexpr int QF_THREADS = 128;      // 4 warps, each owns a 32 x 32 sub-tile
+constexpr int QF_CHUNK = 384;        // (trace, row block) pairs per scheduling chunk: 384 x 64 rows x 4 KB = 100 MB of misfits at S = 512
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -57,9 +58,14 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
   int item = blockIdx.x;
   while (item < n_items) {
-    const int jt = ntile - 1 - item / (T * n_rb_grid);       // largest column tiles first
-    const int rem = item % (T * n_rb_grid);
-    const int t = rem / n_rb_grid, rb = rem - t * n_rb_grid;
+    // item order: (trace, row block) pairs in chunks of QF_CHUNK (their misfit rows, 64 x Sp doubles each, stay in L2
+    // while the chunk's column tiles are worked through), inside a chunk the largest column tiles first
+    const int nblk = T * n_rb_grid;
+    const int chunk = item / (ntile * QF_CHUNK), local = item - chunk * (ntile * QF_CHUNK);
+    const int cb = min(QF_CHUNK, nblk - chunk * QF_CHUNK);   // blocks in this chunk (the last one may be short)
+    const int jt = ntile - 1 - local / cb;
+    const int blk = chunk * QF_CHUNK + local % cb;
+    const int t = blk / n_rb_grid, rb = blk - t * n_rb_grid;
     const int row0 = rb * TM;
     __syncthreads();                                // previous item is done with s_rows / s_part; s_next is visible
     const int next = s_next;
