@@ -81,47 +81,103 @@ void build_twiddles(int n, std::vector<double2>& tw) {
   if (n % 4 == 0) { tw[n / 4] = make_double2(0.0, 1.0); tw[n / 2] = make_double2(-1.0, 0.0); tw[3 * n / 4] = make_double2(0.0, -1.0); }
 }
 
-// Cyclic Jacobi eigen-decomposition of a symmetric matrix (row-major n x n): A = V diag(w) V^T.
-// Used for init_r_inv when the caller passes no R^-1.  R = r^((i-j)^2) is symmetric positive
-// semi-definite, so its SVD (what the reference asks LAPACK dgesvd for, src/likelihood.f90:197-205) is
-// its eigen-decomposition.
-void jacobi_eigh(std::vector<double>& a, int n, std::vector<double>& w, std::vector<double>& v) {
-  v.assign((size_t)n * n, 0.0);
-  for (int i = 0; i < n; ++i) v[(size_t)i * n + i] = 1.0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    double off = 0.0, diag = 0.0;
-    for (int i = 0; i < n; ++i) {
-      diag += a[(size_t)i * n + i] * a[(size_t)i * n + i];
-      for (int j = i + 1; j < n; ++j) off += a[(size_t)i * n + j] * a[(size_t)i * n + j];
-    }
-    if (off <= 1e-30 * diag) break;
-    for (int p = 0; p < n - 1; ++p)
-      for (int q = p + 1; q < n; ++q) {
-        const double apq = a[(size_t)p * n + q];
-        if (std::fabs(apq) < 1e-300) continue;
-        const double app = a[(size_t)p * n + p], aqq = a[(size_t)q * n + q];
-        const double theta = (aqq - app) / (2.0 * apq);
-        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
-        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
-        for (int k = 0; k < n; ++k) {  // columns p,q
-          const double akp = a[(size_t)k * n + p], akq = a[(size_t)k * n + q];
-          a[(size_t)k * n + p] = cs * akp - sn * akq;
-          a[(size_t)k * n + q] = sn * akp + cs * akq;
-        }
-        for (int k = 0; k < n; ++k) {  // rows p,q
-          const double apk = a[(size_t)p * n + k], aqk = a[(size_t)q * n + k];
-          a[(size_t)p * n + k] = cs * apk - sn * aqk;
-          a[(size_t)q * n + k] = sn * apk + cs * aqk;
-        }
-        for (int k = 0; k < n; ++k) {
-          const double vkp = v[(size_t)k * n + p], vkq = v[(size_t)k * n + q];
-          v[(size_t)k * n + p] = cs * vkp - sn * vkq;
-          v[(size_t)k * n + q] = sn * vkp + cs * vkq;
-        }
+// Eigen-decomposition of a symmetric matrix (row-major n x n): A = V diag(w) V^T, v[i*n + e] = component i of
+// eigenvector e.  Householder tridiagonalisation followed by the implicit QL algorithm (the classical EISPACK
+// tred2 / tql2 pair, O(n^3) with a small constant: ~1 s at n = 1000).  Used (i) for init_r_inv when the caller passes
+// no R^-1 -- R = r^((i-j)^2) is symmetric positive semi-definite, so its SVD (what the reference asks LAPACK dgesvd for,
+// src/likelihood.f90:197-205) is its eigen-decomposition -- and (ii) to factor R^-1 = W W^T for the quadratic form.
+void sym_eigh(std::vector<double>& a, int n, std::vector<double>& w, std::vector<double>& v) {
+  std::vector<double> d(n), e(n);
+  auto V = [&](int i, int j) -> double& { return a[(size_t)i * n + j]; };
+  for (int j = 0; j < n; ++j) d[j] = V(n - 1, j);
+  for (int i = n - 1; i > 0; --i) {   // Householder reduction to tridiagonal form
+    double scale = 0.0, h = 0.0;
+    for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
+    if (scale == 0.0) {
+      e[i] = d[i - 1];
+      for (int j = 0; j < i; ++j) { d[j] = V(i - 1, j); V(i, j) = 0.0; V(j, i) = 0.0; }
+    } else {
+      for (int k = 0; k < i; ++k) { d[k] /= scale; h += d[k] * d[k]; }
+      double f = d[i - 1], g = std::sqrt(h);
+      if (f > 0) g = -g;
+      e[i] = scale * g; h -= f * g; d[i - 1] = f - g;
+      for (int j = 0; j < i; ++j) e[j] = 0.0;
+      for (int j = 0; j < i; ++j) {
+        f = d[j]; V(j, i) = f; g = e[j] + V(j, j) * f;
+        for (int k = j + 1; k <= i - 1; ++k) { g += V(k, j) * d[k]; e[k] += V(k, j) * f; }
+        e[j] = g;
       }
+      f = 0.0;
+      for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
+      const double hh = f / (h + h);
+      for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
+      for (int j = 0; j < i; ++j) {
+        f = d[j]; g = e[j];
+        for (int k = j; k <= i - 1; ++k) V(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = V(i - 1, j); V(i, j) = 0.0;
+      }
+    }
+    d[i] = h;
   }
-  w.resize(n);
-  for (int i = 0; i < n; ++i) w[i] = a[(size_t)i * n + i];
+  for (int i = 0; i < n - 1; ++i) {   // accumulate the transformations
+    V(n - 1, i) = V(i, i); V(i, i) = 1.0;
+    const double h = d[i + 1];
+    if (h != 0.0) {
+      for (int k = 0; k <= i; ++k) d[k] = V(k, i + 1) / h;
+      for (int j = 0; j <= i; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= i; ++k) g += V(k, i + 1) * V(k, j);
+        for (int k = 0; k <= i; ++k) V(k, j) -= g * d[k];
+      }
+    }
+    for (int k = 0; k <= i; ++k) V(k, i + 1) = 0.0;
+  }
+  for (int j = 0; j < n; ++j) { d[j] = V(n - 1, j); V(n - 1, j) = 0.0; }
+  V(n - 1, n - 1) = 1.0; e[0] = 0.0;
+  // implicit QL on the tridiagonal matrix; eigenvectors kept transposed (z[e*n + i]) so the plane rotations stream
+  std::vector<double> z((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) z[(size_t)j * n + i] = V(i, j);
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  double f = 0.0, tst1 = 0.0;
+  const double eps = 2.220446049250313e-16;
+  for (int l = 0; l < n; ++l) {
+    tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
+    int m = l;
+    while (m < n) { if (std::fabs(e[m]) <= eps * tst1) break; ++m; }
+    if (m > l) {
+      int iter = 0;
+      do {
+        ++iter;
+        double g = d[l], p = (d[l + 1] - g) / (2.0 * e[l]), r = std::hypot(p, 1.0);
+        if (p < 0) r = -r;
+        d[l] = e[l] / (p + r); d[l + 1] = e[l] * (p + r);
+        const double dl1 = d[l + 1];
+        double h = g - d[l];
+        for (int i = l + 2; i < n; ++i) d[i] -= h;
+        f += h;
+        p = d[m];
+        double c = 1.0, c2 = c, c3 = c, s = 0.0, s2 = 0.0;
+        const double el1 = e[l + 1];
+        for (int i = m - 1; i >= l; --i) {
+          c3 = c2; c2 = c; s2 = s;
+          g = c * e[i]; h = c * p; r = std::hypot(p, e[i]);
+          e[i + 1] = s * r; s = e[i] / r; c = p / r; p = c * d[i] - s * g;
+          d[i + 1] = h + s * (c * g + s * d[i]);
+          double* zi = &z[(size_t)i * n];
+          double* zi1 = &z[(size_t)(i + 1) * n];
+          for (int k = 0; k < n; ++k) { const double hk = zi1[k]; zi1[k] = s * zi[k] + c * hk; zi[k] = c * zi[k] - s * hk; }
+        }
+        p = -s * s2 * c3 * el1 * e[l] / dl1; e[l] = s * p; d[l] = c * p;
+      } while (std::fabs(e[l]) > eps * tst1 && iter < 200);
+    }
+    d[l] += f; e[l] = 0.0;
+  }
+  w.assign(d.begin(), d.end());
+  v.resize((size_t)n * n);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < n; ++j) v[(size_t)i * n + j] = z[(size_t)j * n + i];
 }
 
 // init_r_inv, src/likelihood.f90:168-241: R^-1 = sum_{s_i > 1e-3} v_i v_i^T / s_i
@@ -142,7 +198,7 @@ void build_r_inv(const rfinv_config& c, std::vector<double>& rinv) {
     a.resize((size_t)S * S);
     for (int i = 0; i < S; ++i)
       for (int j = 0; j < S; ++j) a[(size_t)i * S + j] = std::pow(r, (double)((i - j) * (i - j)));
-    jacobi_eigh(a, S, w, v);
+    sym_eigh(a, S, w, v);
     double* out = &rinv[(size_t)t * S * S];
     for (int e = 0; e < S; ++e) {
       if (!(w[e] > 1.0e-3)) continue;
@@ -332,6 +388,65 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
       for (int j = 0; j < S; ++j)
         rpad[((size_t)t * Sp + i) * Sp + j] =
             0.5 * (h->h_r_inv[((size_t)t * S + i) * S + j] + h->h_r_inv[((size_t)t * S + j) * S + i]);
+  // Factor form of the quadratic form: when the symmetrised R^-1 is positive semi-definite of rank r << S (it is, by
+  // construction: a truncated pseudo-inverse, src/likelihood.f90:212-222), phi = m^T R^-1 m = |W^T m|^2 with
+  // W = V_r diag(sqrt(lambda_r)) costs 2 S r flop instead of S^2 and sums non-negative terms only.  Eigenvalues below
+  // 1e-12 of the largest are rounding residue of the construction (they change phi by < 1e-10 relative) and are
+  // dropped; any eigenvalue below -1e-12 lambda_max, or a rank that does not pay, keeps the dense form for that trace.
+  std::vector<double> wfac;
+  {
+    static const bool force_dense = getenv("RFINV_QF_DENSE") && atoi(getenv("RFINV_QF_DENSE")) != 0;
+    const int ntile_dense = Sp / 64;
+    std::vector<std::vector<double>> Wt(T);      // per trace: [rank][S]
+    std::vector<double> a, w, v;
+    d.qf_tiles_max = 0;
+    int wrows = 64;
+    for (int t = 0; t < T; ++t) {
+      d.qf_rank[t] = 0;
+      d.qf_tiles[t] = ntile_dense;
+      int same = -1;
+      for (int u = 0; u < t && same < 0; ++u)
+        if (std::memcmp(&rpad[(size_t)u * Sp * Sp], &rpad[(size_t)t * Sp * Sp], sizeof(double) * (size_t)Sp * Sp) == 0) same = u;
+      if (force_dense) { /* keep dense */ }
+      else if (same >= 0) { d.qf_rank[t] = d.qf_rank[same]; d.qf_tiles[t] = d.qf_tiles[same]; Wt[t] = Wt[same]; }
+      else {
+        a.resize((size_t)S * S);
+        bool nonzero = false;
+        for (int i = 0; i < S; ++i)
+          for (int j = 0; j < S; ++j) { a[(size_t)i * S + j] = rpad[((size_t)t * Sp + i) * Sp + j]; nonzero |= a[(size_t)i * S + j] != 0.0; }
+        if (nonzero) {
+          sym_eigh(a, S, w, v);
+          double lmax = 0.0, lmin = 0.0;
+          for (int e = 0; e < S; ++e) { lmax = std::max(lmax, w[e]); lmin = std::min(lmin, w[e]); }
+          const double tol = 1e-12 * lmax;
+          int r = 0;
+          for (int e = 0; e < S; ++e) r += w[e] > tol;
+          const double units_dense = 0.5 * ntile_dense * (ntile_dense + 1);
+          const double units_fac = (r / 64 + (r % 64 ? 0.4 : 0.0)) * ntile_dense;
+          if (lmax > 0.0 && lmin >= -tol && r > 0 && units_fac < 0.9 * units_dense) {
+            d.qf_rank[t] = r;
+            d.qf_tiles[t] = (r + 63) / 64;
+            Wt[t].assign((size_t)r * S, 0.0);
+            std::vector<int> order;
+            for (int e = 0; e < S; ++e) if (w[e] > tol) order.push_back(e);
+            std::sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y] || (w[x] == w[y] && x < y); });
+            for (int row = 0; row < r; ++row) {         // largest eigenvalue first
+              const int e = order[row];
+              const double sc = std::sqrt(w[e]);
+              for (int i = 0; i < S; ++i) Wt[t][(size_t)row * S + i] = sc * v[(size_t)i * S + e];
+            }
+          }
+        }
+      }
+      d.qf_tiles_max = std::max(d.qf_tiles_max, d.qf_tiles[t]);
+      wrows = std::max(wrows, 64 * ((d.qf_rank[t] + 63) / 64));
+    }
+    d.qf_wrows = wrows;
+    wfac.assign((size_t)T * wrows * Sp, 0.0);
+    for (int t = 0; t < T; ++t)
+      for (int e = 0; e < d.qf_rank[t]; ++e)
+        std::memcpy(&wfac[((size_t)t * wrows + e) * Sp], &Wt[t][(size_t)e * S], sizeof(double) * (size_t)S);
+  }
 #define RFINV_TRY(x) do { st = (x); if (st != RFINV_OK) { rfinv_destroy(h); return st; } } while (0)
   RFINV_TRY(upload(flt, &h->d_flt));
   RFINV_TRY(upload(tw, &h->d_tw));
@@ -339,8 +454,9 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   RFINV_TRY(upload(h->h_vp_ref, &h->d_vp_ref));
   RFINV_TRY(upload(h->h_vs_ref, &h->d_vs_ref));
   RFINV_TRY(upload(rpad, &h->d_r_inv));
+  RFINV_TRY(upload(wfac, &h->d_w_fac));
 #undef RFINV_TRY
-  d.flt = h->d_flt; d.tw = h->d_tw; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv;
+  d.flt = h->d_flt; d.tw = h->d_tw; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv; d.w_fac = h->d_w_fac;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { rfinv_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); rfinv_destroy(h); return RFINV_ERR_CUDA; }
   h->own_stream = true;
@@ -354,7 +470,7 @@ void rfinv_destroy(rfinv_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->free_workspace();
   h->free_pt();
-  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv);
+  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);

@@ -5,6 +5,8 @@
 // diagonal of M R^-1 M^T: one fp64 GEMM against the shared, symmetric R^-1 with the row-dot fused into
 // the epilogue.  R^-1 is symmetric, so only tiles on or below the diagonal are visited (off-diagonal
 // tiles count twice); the summation order is fixed (no atomics), results are run-to-run deterministic.
+// Where R^-1 = W W^T with few columns (the truncated pseudo-inverse the reference builds is positive semi-definite of
+// rank ~0.4 S at a = 4), phi = |W^T m|^2: the same GEMM against W^T (2 S r flop) with a sum of squares as epilogue.
 #include "rfinv_common.cuh"
 
 namespace {
@@ -52,7 +54,7 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
   const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile origin: rows wm*32, cols wn*32
   const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
   const int n_rb_grid = ((active ? n_active : C) + TM - 1) / TM;   // row blocks the item index space is built on
-  const int ntile = Sp / TN;
+  const int ntile = cfg.qf_tiles_max;               // column tiles of the trace with the most work items
   const int n_items = ntile * T * n_rb_grid;
   const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
@@ -67,11 +69,13 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
     const int blk = chunk * QF_CHUNK + local % cb;
     const int t = blk / n_rb_grid, rb = blk - t * n_rb_grid;
     const int row0 = rb * TM;
+    const int rank = cfg.qf_rank[t];                // > 0: factor form for this trace
+    const int ntile_t = cfg.qf_tiles[t];
     __syncthreads();                                // previous item is done with s_rows / s_part; s_next is visible
     const int next = s_next;
     int next_raw = 0;
     if (tid == 0) next_raw = atomicAdd(work, 1);    // consumed at the end of the item
-    if (row0 < n_rows) {
+    if (row0 < n_rows && jt < ntile_t) {
       if (tid < TM) {
         int r = row0 + tid;
         r = r < n_rows ? r : n_rows - 1;            // clamp: duplicates are computed but never written
@@ -79,7 +83,10 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
       }
       __syncthreads();
       const double* __restrict__ Mt = misfit + (size_t)t * C * Sp;
-      const double* __restrict__ Rt = cfg.r_inv + (size_t)t * Sp * Sp;
+      const double* __restrict__ Rt = rank > 0 ? cfg.w_fac + (size_t)t * cfg.qf_wrows * Sp : cfg.r_inv + (size_t)t * Sp * Sp;
+      // 8-column fragments of this warp that hold columns of W (all 4 in the dense form)
+      int jw = 4;
+      if (rank > 0) { const int cols = rank - jt * TN - wn * 32; jw = cols <= 0 ? 0 : (cols >= 32 ? 4 : (cols + 7) >> 3); }
       // global -> smem copy assignment: 64 rows x 16 doubles = 512 x 16 B per operand, 4 per thread each
       const double* a_src[4];
       int cp_off[4], cp_row[4];
@@ -96,7 +103,7 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-      const int nk = (jt + 1) * (TN / TK);          // k-slabs up to and including the diagonal tile
+      const int nk = rank > 0 ? Sp / TK : (jt + 1) * (TN / TK);   // dense: k-slabs up to and including the diagonal tile
       const double* b_base = Rt + (size_t)(jt * TN) * Sp;
       // prologue: stage 0
 #pragma unroll
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
           cp_async_wait<0>();
         }
         __syncthreads();
-        if (ks == jt * (TN / TK) && jt > 0) {       // entering the diagonal tile: what came before counts twice
+        if (rank == 0 && ks == jt * (TN / TK) && jt > 0) {   // entering the diagonal tile: what came before counts twice
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -136,9 +143,19 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
 #pragma unroll
           for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDS_STRIDE + kk];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          if (jw == 4) {                            // the hot path stays one straight run of 16 DMMA
 #pragma unroll
-            for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < jw) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+              }
+          }
         }
         __syncthreads();
       }
@@ -147,11 +164,16 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
       for (int i = 0; i < 4; ++i) {
         const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 32 + 2 * fk;
         double v = 0.0;
+        if (rank > 0) {                             // |W^T m|^2: columns beyond the rank hold exact zeros
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
-          v = fma(acc[i][j][0], m.x, v);
-          v = fma(acc[i][j][1], m.y, v);
+          for (int j = 0; j < 4; ++j) { v = fma(acc[i][j][0], acc[i][j][0], v); v = fma(acc[i][j][1], acc[i][j][1], v); }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
+            v = fma(acc[i][j][0], m.x, v);
+            v = fma(acc[i][j][1], m.y, v);
+          }
         }
         // reduce over the 4 lanes sharing a row; the two warps (wn) covering the 64 columns meet in shared memory
         v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -164,14 +186,14 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
       if (tid < TM && row0 + tid < n_rows) part_t[(size_t)jt * jstride + s_rows[tid]] = s_part[0][tid] + s_part[1][tid];
       __threadfence();
       __syncthreads();
-      if (tid == 0) s_last = (atomicAdd(&arrivals[t * n_rb_grid + rb], 1) == ntile - 1);
+      if (tid == 0) s_last = (atomicAdd(&arrivals[t * n_rb_grid + rb], 1) == ntile_t - 1);
       __syncthreads();
       if (s_last) {
         __threadfence();
         if (tid < TM && row0 + tid < n_rows) {
           const int c = s_rows[tid];
           double v = 0.0;
-          for (int j = 0; j < ntile; ++j) v += __ldcg(part_t + (size_t)j * jstride + c);   // fixed order
+          for (int j = 0; j < ntile_t; ++j) v += __ldcg(part_t + (size_t)j * jstride + c);   // fixed order
           phi[(size_t)t * C + c] = v;
         }
         if (tid == 0) arrivals[t * n_rb_grid + rb] = 0;              // ready for the next launch
@@ -206,7 +228,7 @@ int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, dou
                           const int* active, int n_active, const int* n_active_dev, cudaStream_t stream) {
   const int n_rows = active ? n_active : C;
   if (n_rows == 0) return RFINV_OK;
-  const size_t ntile = cfg.nsmp_pad / TN;
+  const size_t ntile = cfg.qf_tiles_max;
   int* work = counters;
   int* arrivals = counters + 4;
   static int per_sm = 0, n_sm = 0;

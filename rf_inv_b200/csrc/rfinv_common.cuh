@@ -29,6 +29,11 @@ struct DevConfig {
   const double* vp_ref;         // [nref]
   const double* vs_ref;         // [nref]
   const double* r_inv;          // [ntrc][nsmp_pad][nsmp_pad] zero padded, symmetric
+  // factor R^-1 = W W^T of the traces whose R^-1 is positive semi-definite of low rank (0 = use the dense form):
+  const double* w_fac;          // [ntrc][qf_wrows][nsmp_pad]: row e = sqrt(lambda_e) * eigenvector e, zero padded
+  int qf_rank[RFINV_MAX_TRC];   // kept eigenpairs per trace, 0 = dense
+  int qf_tiles[RFINV_MAX_TRC];  // 64-column work items per (64 chains, trace): ceil(rank/64), or nsmp_pad/64 when dense
+  int qf_tiles_max, qf_wrows;
 };
 
 // Chain-fastest (structure-of-arrays) model batch in HBM.

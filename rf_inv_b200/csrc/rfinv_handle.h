@@ -20,6 +20,7 @@ struct rfinv_handle {
   double* d_vp_ref = nullptr;
   double* d_vs_ref = nullptr;
   double* d_r_inv = nullptr;
+  double* d_w_fac = nullptr;
   // evaluation workspace (grown on demand)
   int cap = 0;
   int* d_k = nullptr;

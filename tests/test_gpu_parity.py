@@ -235,3 +235,34 @@ np.savez(sys.argv[1], **out)
         err = helpers.rel_err_rft(a, b)
         assert err < 1e-13, (name, err)
         assert not np.array_equal(a, b) or name != "target"   # the switch really changes the computation
+
+
+def test_factored_quadratic_form_matches_dense_form(tmp_path):
+    """quadform_kernel evaluates phi = |W^T m|^2 with R^-1 = W W^T where the factor pays (rank ~0.4 S at a = 4), the
+    dense symmetric form m^T R^-1 m otherwise (RFINV_QF_DENSE=1 forces it).  Both against the LAPACK-route R^-1 the
+    reference would pass; they must agree far inside the 1e-9 bar (the factor drops eigenvalues < 1e-12 lambda_max)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import helpers
+from rf_inv_b200 import workloads
+from rf_inv_b200.evaluator import Evaluator
+cfg = helpers.attach_obs_and_rinv(workloads.make_config("target"), noise=0.01)
+cfg.r_inv = workloads.lapack_r_inv(cfg)
+m = workloads.draw_models(cfg, 200, seed=8, dvs_scale=0.3)
+with Evaluator(cfg) as ev:
+    ll, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+np.savez(sys.argv[1], ll=ll, sig=m["sig"])
+''' % (root, os.path.join(root, "tests"), os.path.join(root, "oracle"))
+    res = {}
+    for tag, val in (("factor", "0"), ("dense", "1")):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=dict(os.environ, RFINV_QF_DENSE=val))
+        res[tag] = np.load(path)
+    cfg = workloads.make_config("target")
+    err = helpers.logl_err(cfg, res["factor"]["ll"], res["dense"]["ll"], res["dense"]["sig"])
+    assert err < 1e-11, err
+    assert not np.array_equal(res["factor"]["ll"], res["dense"]["ll"])   # two different summations

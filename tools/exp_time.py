@@ -8,7 +8,7 @@ so = sys.argv[1]
 capi._lib = capi.load(so)
 from rf_inv_b200.evaluator import Evaluator
 cfg = workloads.make_config("target")
-cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
+cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = workloads.lapack_r_inv(cfg)   # the real R^-1: the quadratic form may use its factor
 nC = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
 m = workloads.draw_models(cfg, nC, seed=100, dvs_scale=0.3)
 with Evaluator(cfg) as ev:
