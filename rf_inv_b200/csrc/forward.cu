@@ -1015,7 +1015,7 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
 int rfinv_forward_bins_per_thread(int nfft) {
   if (nfft <= 64) return 1;
   if (nfft <= 256) return 2;
-  if (nfft <= 1024) return 4;
+  if (nfft <= 2048) return 4;   // 2048: 256 threads x 4 bins (8 bins per thread would need ~250 registers)
   return 8;
 }
 
@@ -1056,11 +1056,11 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
     if (JB <= 2) FWD(2, 128, 6);
     static const int minb3 = getenv("RFINV_FWD_MINB3") ? atoi(getenv("RFINV_FWD_MINB3")) : 4;   // tuning knob
     if (JB <= 3) { if (minb3 == 5) FWD(3, 128, 5); FWD(3, 128, 4); }
-    if (JB <= 4) FWD(4, 128, 4);
-    if (JB <= 6) FWD(6, 128, 2);
-    FWD(8, 128, 2);
+    FWD(4, 128, 4);
   }
+  if (JB <= 3) FWD(3, 256, 2);
   if (JB <= 4) FWD(4, 256, 2);
+  if (JB <= 6) FWD(6, 256, 1);
   FWD(8, 256, 1);
 #undef FWD
 }

@@ -141,7 +141,7 @@ def band_bins(cfg: RFConfig):
     deconvolution keep the full band).  Accounting only -- the library decides for itself."""
     import os
     n, nh = cfg.nfft, cfg.nh
-    jfull = 1 if n <= 64 else (2 if n <= 256 else (4 if n <= 1024 else 8))
+    jfull = 1 if n <= 64 else (2 if n <= 256 else (4 if n <= 2048 else 8))
     nthr = (n // 2) // jfull
     allowed = [1, 2, 3, 4, 6, 8]
     full = os.environ.get("RFINV_FULL_BAND", "0") not in ("", "0") or cfg.deconv_mode == 1
