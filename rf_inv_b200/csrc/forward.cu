@@ -426,6 +426,7 @@ __device__ __forceinline__ void fill_fft_twiddles(double2* s_tw, const double2* 
 // Position of logical element p in the padded FFT buffer: one pad element per 8, so that "8 consecutive
 // elements per thread" (last radix-8 stage) and "consecutive elements across threads" are both conflict free.
 __device__ __forceinline__ int fpad(int p) { return p + (p >> 3); }
+__device__ __forceinline__ unsigned fpad(unsigned p) { return p + (p >> 3); }
 __host__ __device__ inline size_t fft_buf_elems(size_t n) { return n + (n >> 3) + 1; }
 
 // 8-point inverse DFT in registers: v[q] <- sum_r v[r] exp(+2 pi i q r / 8)
@@ -466,43 +467,56 @@ __device__ __forceinline__ void publish_max(double v, double* s_red, int tid) {
   if ((tid & 31) == 0) s_red[tid >> 5] = v;
 }
 
-template <class Sync>
-__device__ double fft_inverse_dif(double2* buf, int n, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
-  double vmax = -INFINITY;
-  int N = n;
-  const double2* stw = twq;
-  for (; N >= 8; N >>= 3) {
-    const int stride = N >> 3;
-    const bool last = (N == 8);
-    for (int j = tid; j < (n >> 3); j += nthr) {
-      const int o = j & (stride - 1), base = ((j - o) << 3) + o;
-      double2 v[8];
+// One radix-8 stage of sub-transform length N (compile time): strides, pad offsets and the twiddle table offset are
+// constants; TW = twiddles follow the butterfly (every stage but N == 8), LAST = collect the maximum imaginary part.
+template <int LOG2N, int N, class Sync>
+__device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restrict__ stw, double& vmax, double* s_red, int tid,
+                                           int nthr, Sync sync) {
+  constexpr unsigned n = 1u << LOG2N, stride = N >> 3;
+  constexpr bool last = (N == 8);
+  for (unsigned j = tid; j < (n >> 3); j += nthr) {
+    const unsigned o = j & (stride - 1), base = ((j - o) << 3) + o;
+    double2 v[8];
+    unsigned pos[8];
+    if (stride % 8 == 0) {        // whole pad groups between the legs: one address, constant offsets
+      const unsigned p0 = base + (base >> 3);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) v[r] = buf[fpad(base + r * stride)];
-      if (!last) {
-        double2 w[7];
+      for (int r = 0; r < 8; ++r) pos[r] = p0 + r * (stride + (stride >> 3));
+    } else {
 #pragma unroll
-        for (int q = 1; q < 8; ++q) w[q - 1] = stw[(q - 1) * stride + o];
-        dft8(v);
-#pragma unroll
-        for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], w[q - 1]);
-      } else {
-        dft8(v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) vmax = fmax(vmax, v[q].y);
-      }
-      buf[fpad(base)] = v[0];              buf[fpad(base + 4 * stride)] = v[1];
-      buf[fpad(base + 2 * stride)] = v[2]; buf[fpad(base + 6 * stride)] = v[3];
-      buf[fpad(base + stride)] = v[4];     buf[fpad(base + 5 * stride)] = v[5];
-      buf[fpad(base + 3 * stride)] = v[6]; buf[fpad(base + 7 * stride)] = v[7];
+      for (int r = 0; r < 8; ++r) pos[r] = (base + r * stride) + ((base + r * stride) >> 3);
     }
-    stw += 7 * stride;
-    if (last) publish_max(vmax, s_red, tid);   // N == 8: no stage follows
-    sync();
+#pragma unroll
+    for (int r = 0; r < 8; ++r) v[r] = buf[pos[r]];
+    if (!last) {
+      double2 w[7];
+#pragma unroll
+      for (int q = 1; q < 8; ++q) w[q - 1] = stw[(q - 1) * stride + o];
+      dft8(v);
+#pragma unroll
+      for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], w[q - 1]);
+    } else {
+      dft8(v);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) vmax = fmax(vmax, v[q].y);
+    }
+    buf[pos[0]] = v[0]; buf[pos[4]] = v[1]; buf[pos[2]] = v[2]; buf[pos[6]] = v[3];
+    buf[pos[1]] = v[4]; buf[pos[5]] = v[5]; buf[pos[3]] = v[6]; buf[pos[7]] = v[7];
   }
-  if (N == 4) {
-    for (int j = tid; j < (n >> 2); j += nthr) {
-      const int base = j << 2;
+  if (last) publish_max(vmax, s_red, tid);   // N == 8: no stage follows
+  sync();
+  if constexpr (N >= 64) fft_stage8<LOG2N, (N >> 3), Sync>(buf, stw + 7 * stride, vmax, s_red, tid, nthr, sync);
+}
+
+template <int LOG2N, class Sync>
+__device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
+  constexpr unsigned n = 1u << LOG2N;
+  constexpr int REM = LOG2N % 3;          // what is left after the radix-8 stages: 1 (N = 1), 2 or 4
+  double vmax = -INFINITY;
+  fft_stage8<LOG2N, (1 << LOG2N), Sync>(buf, twq, vmax, s_red, tid, nthr, sync);
+  if (REM == 2) {
+    for (unsigned j = tid; j < (n >> 2); j += nthr) {
+      const unsigned base = j << 2;
       const double2 v0 = buf[fpad(base)], v1 = buf[fpad(base + 1)], v2 = buf[fpad(base + 2)], v3 = buf[fpad(base + 3)];
       const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
       const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y), a3 = make_double2(-(v1.y - v3.y), v1.x - v3.x);
@@ -513,13 +527,13 @@ __device__ double fft_inverse_dif(double2* buf, int n, const double2* twq, doubl
     }
     publish_max(vmax, s_red, tid);
     sync();
-  } else if (N == 2) {
-    for (int j = tid; j < (n >> 1); j += nthr) {
-      const int base = j << 1;
-      const double2 a = buf[fpad(base)], b = buf[fpad(base + 1)];
+  } else if (REM == 1) {
+    for (unsigned j = tid; j < (n >> 1); j += nthr) {
+      const unsigned base = j << 1, p0 = base + (base >> 3);   // base is even: both elements share a pad group
+      const double2 a = buf[p0], b = buf[p0 + 1];
       const double2 r0 = make_double2(a.x + b.x, a.y + b.y), r1 = make_double2(a.x - b.x, a.y - b.y);
       vmax = fmax(vmax, fmax(r0.y, r1.y));
-      buf[fpad(base)] = r0; buf[fpad(base + 1)] = r1;
+      buf[p0] = r0; buf[p0 + 1] = r1;
     }
     publish_max(vmax, s_red, tid);
     sync();
@@ -528,6 +542,18 @@ __device__ double fft_inverse_dif(double2* buf, int n, const double2* twq, doubl
   double r = s_red[0];
   for (int i = 1; i < nw; ++i) r = fmax(r, s_red[i]);
   return r;
+}
+
+// run-time length -> compile-time instantiation (nfft is a power of two in [64, 4096]); LO..HI = the lengths the caller
+// can see (a kernel variant is tied to a thread count, hence to one or two transform lengths)
+template <int LO, int HI, class Sync>
+__device__ __forceinline__ double fft_inverse_dif(double2* buf, int n, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
+  if constexpr (LO == HI) {
+    return fft_inverse_dif_n<LO>(buf, twq, s_red, tid, nthr, sync);
+  } else {
+    if (n == (1 << LO)) return fft_inverse_dif_n<LO>(buf, twq, s_red, tid, nthr, sync);
+    return fft_inverse_dif<LO + 1, HI>(buf, n, twq, s_red, tid, nthr, sync);
+  }
 }
 
 template <class Sync>
@@ -892,7 +918,10 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
         const int i = tid + q * nthr;
         obs_pre[q] = i < cfg.nsmp ? __ldg(obs_t + i) : 0.0;
       }
-      const double mx = fft_inverse_dif(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
+      // threads per CTA fix the transform length: 32 -> 64/128, 64 -> 256/512, 128 -> 1024, 256 -> 2048/4096
+      constexpr int FLO = BMAX <= 32 ? 6 : (BMAX <= 64 ? 8 : (BMAX <= 128 ? 10 : 11));
+      constexpr int FHI = BMAX <= 32 ? 7 : (BMAX <= 64 ? 9 : (BMAX <= 128 ? 10 : 12));
+      const double mx = fft_inverse_dif<FLO, FHI>(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
       PHASE_MARK(5);
       const double scale = cfg.deconv_mode == 0 ? 1.0 / mx : 1.0;   // src/forward.f90:197-203
       write_outputs(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
@@ -923,7 +952,7 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
   fill_fft_twiddles(s_tw, cfg.tw, n, tid, nthr);
   for (int i = tid; i < n; i += nthr) b0[fpad(i)] = make_double2(x[i], 0.0);
   __syncthreads();
-  fft_inverse_dif(b0, n, s_tw, s_red, tid, nthr, CtaSync());
+  fft_inverse_dif<6, 12>(b0, n, s_tw, s_red, tid, nthr, CtaSync());
   for (int f = tid; f < nh; f += nthr) {
     const double2 v = b0[fpad((int)(__brev((unsigned)f) >> brev_shift))];
     const double w = flt[f];
@@ -936,7 +965,7 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
     }
   }
   __syncthreads();
-  fft_inverse_dif(b1, n, s_tw, s_red, tid, nthr, CtaSync());
+  fft_inverse_dif<6, 12>(b1, n, s_tw, s_red, tid, nthr, CtaSync());
   for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad((int)(__brev((unsigned)i) >> brev_shift))].x;
 }
 
