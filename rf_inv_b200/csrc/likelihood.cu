@@ -198,6 +198,8 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
         }
         if (tid == 0) arrivals[t * n_rb_grid + rb] = 0;              // ready for the next launch
       }
+    } else {
+      __syncthreads();   // skipped item (no such tile / row block): everyone has read s_next before it is rewritten
     }
     if (tid == 0) s_next = (int)gridDim.x + next_raw;
     item = next;
