@@ -208,7 +208,8 @@ def main():
     # pinned host copies for the end-to-end arm
     pin = {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in models.items()}
     pin_np = {k: v.numpy() for k, v in pin.items()}
-    h2d = sum(v.numel() * v.element_size() for v in pin.values())
+    # bytes rfinv_eval_batch copies to the device per call: dVp stays on the host when vp_mode = 0 (format_model ignores it)
+    h2d = sum(v.numel() * v.element_size() for k, v in pin.items() if not (k == "dvp" and cfg.vp_mode == 0))
     d2h = 8 * chains
 
     ev = Evaluator(cfg, device=local_rank)

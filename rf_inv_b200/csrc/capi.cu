@@ -261,6 +261,7 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_k, sizeof(int) * Cz));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_z, sizeof(double) * Cz * (km - 1)));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvp, sizeof(double) * Cz * km));
+  RFINV_CUDA_CHECK(cudaMemset(d_dvp, 0, sizeof(double) * Cz * km));   // stays zero with vp_mode = 0 (never uploaded, never used)
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
@@ -442,6 +443,8 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
       wrows = std::max(wrows, 64 * ((d.qf_rank[t] + 63) / 64));
     }
     d.qf_wrows = wrows;
+    d.qf_full_first = 1;
+    for (int t = 0; t < T; ++t) if (d.qf_rank[t] == 0) d.qf_full_first = 0;
     wfac.assign((size_t)T * wrows * Sp, 0.0);
     for (int t = 0; t < T; ++t)
       for (int e = 0; e < d.qf_rank[t]; ++e)
@@ -528,6 +531,8 @@ static int upload_models(rfinv_handle* h, int C, const int32_t* k, const double*
   struct Item { const double* src; double* dst; int len; } items[4] = {
       {z, h->d_z, km - 1}, {dvp, h->d_dvp, km}, {dvs, h->d_dvs, km}, {sig, h->d_sig, T}};
   for (const Item& it : items) {
+    // vp_mode = 0: format_model never looks at dVp (src/model.f90:214-218, 271-275) -- a third of the upload
+    if (it.src == dvp && h->cfg.vp_mode == 0) continue;
     const size_t nel = (size_t)C * it.len;
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, it.src, sizeof(double) * nel, cudaMemcpyHostToDevice, s));
     to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(h->d_stage, it.dst, C, it.len);
@@ -564,7 +569,7 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
   st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
                       is_valid ? h->d_valid : nullptr, nullptr, 0);
   if (st != RFINV_OK) return st;
-  h->launches += 4;  // the four layout kernels of upload_models
+  h->launches += h->cfg.vp_mode == 0 ? 3 : 4;  // the layout kernels of upload_models
   RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   if (rft)
     RFINV_CUDA_CHECK(cudaMemcpyAsync(rft, h->d_rft_full, sizeof(double) * (size_t)C * h->cfg.ntrc * h->cfg.nfft,

@@ -39,7 +39,7 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 // take items from an atomic counter, largest first.  The CTA that delivers the last of the ntile partials of a
 // (64 chains, trace) block sums them in the fixed order jt = 0..ntile-1 into phi: no floating-point atomics, results
 // are bit-identical from run to run whatever the schedule.
-__global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cfg, int C, const double* __restrict__ misfit,
+__global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig cfg, int C, const double* __restrict__ misfit,
                                                               double* __restrict__ phi, double* __restrict__ partial,
                                                               int* __restrict__ arrivals, int* __restrict__ work,
                                                               const int* __restrict__ active, int n_active,
@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(QF_THREADS) quadform_kernel(const DevConfig cf
     const int nblk = T * n_rb_grid;
     const int chunk = item / (ntile * QF_CHUNK), local = item - chunk * (ntile * QF_CHUNK);
     const int cb = min(QF_CHUNK, nblk - chunk * QF_CHUNK);   // blocks in this chunk (the last one may be short)
-    const int jt = ntile - 1 - local / cb;
+    // dense form: the cost of a tile grows with jt, largest first; factor form: full tiles first, the partial last tile
+    // (rank % 64 columns) fills the tail of the launch
+    const int jt = cfg.qf_full_first ? local / cb : ntile - 1 - local / cb;
     const int blk = chunk * QF_CHUNK + local % cb;
     const int t = blk / n_rb_grid, rb = blk - t * n_rb_grid;
     const int row0 = rb * TM;

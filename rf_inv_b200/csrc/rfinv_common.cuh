@@ -34,6 +34,7 @@ struct DevConfig {
   int qf_rank[RFINV_MAX_TRC];   // kept eigenpairs per trace, 0 = dense
   int qf_tiles[RFINV_MAX_TRC];  // 64-column work items per (64 chains, trace): ceil(rank/64), or nsmp_pad/64 when dense
   int qf_tiles_max, qf_wrows;
+  int qf_full_first;            // every trace uses the factor form: hand out tiles in ascending order (the partial last tile last)
 };
 
 // Chain-fastest (structure-of-arrays) model batch in HBM.
