@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RFINV_ABI_VERSION 1
+#define RFINV_ABI_VERSION 2
 
 /* status codes */
 #define RFINV_OK 0
@@ -86,6 +86,10 @@ typedef struct rfinv_config {
   /* posterior histograms (src/pt_mcmc.f90:396-433) */
   int32_t nbin_z, nbin_vs, nbin_vp, nbin_vpvs, nbin_sig, nbin_amp;
   double amp_min, amp_max;
+  /* Buried station ("BOREHOLE_DEP", the optional second number of the SEA_DEP line; disabled by comment markers in the
+   * reference: src/params.f90:67,203-224, src/forward.f90:289-338,493-516): depth of the receiver below the free surface /
+   * the sea floor in km.  0 = receiver at the surface, which is all the reference can run today.  (ABI version 2.) */
+  double bdep;
 } rfinv_config;
 
 typedef struct rfinv_handle rfinv_handle;

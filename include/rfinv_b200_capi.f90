@@ -26,6 +26,7 @@ module rfinv_b200_capi
      real(c_double)     :: t_high
      integer(c_int32_t) :: nbin_z, nbin_vs, nbin_vp, nbin_vpvs, nbin_sig, nbin_amp
      real(c_double)     :: amp_min, amp_max
+     real(c_double)     :: bdep
   end type rfinv_config
 
   interface

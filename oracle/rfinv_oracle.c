@@ -240,6 +240,7 @@ static void calc_seis(const rfinv_config* c, int nlay, double rayp, int ipha, co
       matmul4(p_mat, p_prod, p_prod); /* forward.f90:262 */
     }
     matmul4(e_inv, p_prod, sl); /* forward.f90:264 */
+    cplx sd4 = c_make(0.0, 0.0);
     if (!sea_flag) {            /* forward.f90:267-275 */
       cplx denom = c_sub(c_mul(sl[2][0], sl[3][1]), c_mul(sl[2][1], sl[3][0]));
       if (ipha >= 0) {
@@ -263,6 +264,38 @@ static void calc_seis(const rfinv_config* c, int nlay, double rayp, int ipha, co
         ur[iomg] = c_div(c_neg(b), d1);
         uz[iomg] = c_div(c_mul(c_neg(lq[0][0]), sl[2][0]), d2);
       }
+      if (c->bdep > 0.0) /* forward.f90:297-306 (commented out): normal stress under the water */
+        sd4 = ipha >= 0 ? c_div(c_mul(lq[1][0], sl[3][0]), d2) : c_div(c_mul(c_neg(lq[1][0]), sl[2][0]), d2);
+    }
+    if (c->bdep > 0.0) {
+      /* Buried station, forward.f90:289-338 -- COMMENTED OUT in the reference.  The displacement-stress vector of the
+       * surface / sea floor is carried down to the station.  Two defects of the commented block are not restated (the
+       * numpy oracle's bdep_literal switch does): the downward loop has no exit after the station's layer, and a station
+       * in the half space is moved by bdep instead of its distance to the last interface. */
+      cplx sd[4] = {ur[iomg], uz[iomg], c_make(0.0, 0.0), sd4}, t4[4];
+      double z_tmp = 0.0;
+      int found = 0;
+      for (int il = ilay0; il < nlay - 1 && !found; ++il) {
+        z_tmp = z_tmp + h[il];
+        double h_use = h[il];
+        if (!(z_tmp < c->bdep)) { h_use = c->bdep + h[il] - z_tmp; found = 1; }
+        layer_matrix_sol(omg, rho[il], alpha[il], beta[il], rayp, h_use, p_mat);
+        for (int i = 0; i < 4; ++i) {
+          t4[i] = c_make(0.0, 0.0);
+          for (int j = 0; j < 4; ++j) t4[i] = c_add(t4[i], c_mul(p_mat[i][j], sd[j]));
+        }
+        memcpy(sd, t4, sizeof(sd));
+      }
+      if (!found) {
+        layer_matrix_sol(omg, rho[nlay - 1], alpha[nlay - 1], beta[nlay - 1], rayp, c->bdep - z_tmp, p_mat);
+        for (int i = 0; i < 4; ++i) {
+          t4[i] = c_make(0.0, 0.0);
+          for (int j = 0; j < 4; ++j) t4[i] = c_add(t4[i], c_mul(p_mat[i][j], sd[j]));
+        }
+        memcpy(sd, t4, sizeof(sd));
+      }
+      ur[iomg] = sd[0];
+      uz[iomg] = sd[1];
     }
   }
 }
@@ -271,7 +304,28 @@ static void calc_seis(const rfinv_config* c, int nlay, double rayp, int ipha, co
 static double direct_arrival(const rfinv_config* c, int nlay, const double* h, const double* v, double rayp) {
   int i0 = c->sdep > 0.0 ? 1 : 0;
   double t = 0.0;
-  for (int i = i0; i < nlay - 1; ++i) t = t + h[i] * sqrt(1.0 / (v[i] * v[i]) - rayp * rayp);
+  if (!(c->bdep > 0.0)) {
+    for (int i = i0; i < nlay - 1; ++i) t = t + h[i] * sqrt(1.0 / (v[i] * v[i]) - rayp * rayp);
+    return t;
+  }
+  /* buried station, forward.f90:493-516 (commented out): delay from the station down to the top of the half space; each
+   * layer with its own velocity (the commented block reads v(i0) for all of them), and a station in the half space
+   * counts its distance to the last interface negatively */
+  double z_sum = 0.0;
+  int i = i0;
+  for (; i < nlay - 1; ++i) {
+    z_sum = z_sum + h[i];
+    if (z_sum > c->bdep) {
+      t = t + (z_sum - c->bdep) * sqrt(1.0 / (v[i] * v[i]) - rayp * rayp);
+      ++i;
+      break;
+    }
+    if (i == nlay - 2) { /* ran out of solid layers */
+      t = t - (c->bdep - z_sum) * sqrt(1.0 / (v[nlay - 1] * v[nlay - 1]) - rayp * rayp);
+      return t;
+    }
+  }
+  for (; i < nlay - 1; ++i) t = t + h[i] * sqrt(1.0 / (v[i] * v[i]) - rayp * rayp);
   return t;
 }
 

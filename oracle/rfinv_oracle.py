@@ -61,6 +61,9 @@ class Config:
     ipha: Sequence[int]
     deconv_mode: int = 0
     sdep: float = 0.0
+    bdep: float = 0.0                          # station depth below the surface / sea floor (BOREHOLE_DEP, commented out
+                                               # in the reference: params.f90:67,203-224); 0 = station at the surface
+    bdep_literal: bool = False                 # transcribe the commented block as it stands (see calc_seis)
     obs: Optional[np.ndarray] = None          # (nsmp, ntrc) float64 (float32 values promoted)
     # reference velocity model
     vp_ref: Optional[np.ndarray] = None
@@ -297,6 +300,34 @@ def calc_seis(cfg: Config, nlay, rayp, ipha, alpha, beta, rho, h):
             else:
                 ur = -b / (a * sl[:, 2, 0] - b * sl[:, 3, 0])
                 uz = -lq[:, 0, 0] * sl[:, 2, 0] / (b * sl[:, 3, 0] - a * sl[:, 2, 0])
+        if cfg.bdep > 0.0:
+            # Buried station ("case of bore hole"), forward.f90:289-338 -- COMMENTED OUT in the reference.  The
+            # displacement-stress vector at the surface / sea floor is carried down to the station depth.
+            sd = np.zeros((nh, 4, 1), dtype=np.complex128)
+            sd[:, 0, 0] = ur
+            sd[:, 1, 0] = uz
+            if sea_flag:                                              # forward.f90:297-306: normal stress under the water
+                den = b * sl[:, 3, 0] - a * sl[:, 2, 0]
+                sd[:, 3, 0] = lq[:, 1, 0] * sl[:, 3, 0] / den if ipha >= 0 else -lq[:, 1, 0] * sl[:, 2, 0] / den
+            z_tmp = 0.0
+            found = False
+            for ilay in range(ilay0, nlay - 1):                       # forward.f90:311-327
+                z_tmp = z_tmp + h[ilay]
+                if z_tmp < cfg.bdep:
+                    sd = np.matmul(layer_matrix_sol(omg, rho[ilay], alpha[ilay], beta[ilay], rayp, h[ilay]), sd)
+                else:
+                    h_tmp = cfg.bdep + h[ilay] - z_tmp
+                    sd = np.matmul(layer_matrix_sol(omg, rho[ilay], alpha[ilay], beta[ilay], rayp, h_tmp), sd)
+                    found = True
+                    if not cfg.bdep_literal:
+                        break      # the commented block has no exit here: it goes on through every deeper layer with the
+                                   # negative thickness bdep + h - z_tmp
+            if not found:                                             # forward.f90:329-334: station in the half space
+                # the commented block propagates by bdep; the distance left below the last interface is bdep - z_tmp
+                d = cfg.bdep if cfg.bdep_literal else cfg.bdep - z_tmp
+                sd = np.matmul(layer_matrix_sol(omg, rho[nlay - 1], alpha[nlay - 1], beta[nlay - 1], rayp, d), sd)
+            ur = sd[:, 0, 0]
+            uz = sd[:, 1, 0]
     return ur, uz
 
 
@@ -308,11 +339,40 @@ def water_level_decon(y, x, pcnt):
 
 
 def direct_arrival(cfg: Config, nlay, h, v, rayp) -> float:
-    """forward.f90:474-491."""
+    """forward.f90:474-491; buried station: the commented variant forward.f90:493-516 (delay from the station, not
+    from the surface, to the top of the half space)."""
     i0 = 1 if cfg.sdep > 0.0 else 0
     t = 0.0
-    for i in range(i0, nlay - 1):
-        t = t + h[i] * math.sqrt(1.0 / (v[i] * v[i]) - rayp * rayp)
+    if cfg.bdep <= 0.0:
+        for i in range(i0, nlay - 1):
+            t = t + h[i] * math.sqrt(1.0 / (v[i] * v[i]) - rayp * rayp)
+        return t
+    z_sum = 0.0
+    if i0 < nlay - 1:                                                 # forward.f90:493-513 (0-based: nlay-1 is the half space)
+        below = 0.0
+        while True:                                                   # layer with the station
+            if i0 == nlay - 1:
+                below = z_sum
+                break
+            z_sum = z_sum + h[i0]
+            if z_sum > cfg.bdep:
+                t = t + (z_sum - cfg.bdep) * math.sqrt(1.0 / (v[i0] * v[i0]) - rayp * rayp)
+                i0 = i0 + 1
+                below = None
+                break
+            i0 = i0 + 1
+        if below is None:
+            vi0 = v[i0] if i0 < nlay else v[nlay - 1]
+            for i in range(i0, nlay - 1):                             # other layers
+                # the commented block takes v(i0) for every one of them (forward.f90:512); the layer's own velocity is meant
+                vv = vi0 if cfg.bdep_literal else v[i]
+                t = t + h[i] * math.sqrt(1.0 / (vv * vv) - rayp * rayp)
+        elif not cfg.bdep_literal:
+            # the loop ran out of layers: the station lies in the half space, bdep - z_sum below its top (the commented
+            # block adds nothing in this case; its `else` branch below only covers models without any solid layer)
+            t = t - (cfg.bdep - below) * math.sqrt(1.0 / (v[nlay - 1] * v[nlay - 1]) - rayp * rayp)
+    else:                                                             # forward.f90:514-516
+        t = t - cfg.bdep * math.sqrt(1.0 / (v[i0] * v[i0]) - rayp * rayp)
     return t
 
 

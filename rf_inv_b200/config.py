@@ -41,6 +41,7 @@ class RfinvConfigC(C.Structure):
         ("nbin_z", C.c_int32), ("nbin_vs", C.c_int32), ("nbin_vp", C.c_int32), ("nbin_vpvs", C.c_int32),
         ("nbin_sig", C.c_int32), ("nbin_amp", C.c_int32),
         ("amp_min", C.c_double), ("amp_max", C.c_double),
+        ("bdep", C.c_double),
     ]
 
 
@@ -69,6 +70,8 @@ class RFConfig:
     ipha: Sequence[int]
     deconv_mode: int = 0
     sdep: float = 0.0
+    bdep: float = 0.0                     # BOREHOLE_DEP: receiver depth below the surface / sea floor (commented out in the
+                                          # reference, src/params.f90:67,203-224); 0 = at the surface
     obs: Optional[np.ndarray] = None      # [ntrc][nsmp]
     r_inv: Optional[np.ndarray] = None    # [ntrc][nsmp][nsmp]; None -> library builds it
     # reference velocity model (src/model.f90:35-36)
@@ -144,6 +147,8 @@ class RFConfig:
             raise ValueError("nfft must be a power of two in [32, 4096]")
         if not (1 <= self.nsmp <= self.nfft):
             raise ValueError("nsmp must be in [1, nfft]")
+        if self.bdep < 0.0:
+            raise ValueError("BOREHOLE_DEP must be positive")          # src/params.f90:214-217 (commented out there)
         if self.deconv_mode not in (0, 1):
             raise ValueError("deconv_mode must be either 0 or 1")  # src/params.f90:195-199
         if self.vp_mode not in (0, 1):
@@ -173,7 +178,7 @@ class RFConfig:
                      "nbin_sig", "nbin_amp"):
             setattr(c, name, int(getattr(self, name)))
         c.iseed = C.c_int32(int(self.iseed) & 0xFFFFFFFF).value
-        for name in ("delta", "t_start", "sdep", "z_ref_min", "dz_ref", "z_min", "z_max", "h_min", "dvs_prior",
+        for name in ("delta", "t_start", "sdep", "bdep", "z_ref_min", "dz_ref", "z_min", "z_max", "h_min", "dvs_prior",
                      "dvp_prior", "vp_min", "vp_max", "vs_min", "vs_max", "vpvs_min", "vpvs_max", "dev_z",
                      "dev_dvs", "dev_dvp", "dev_sig", "t_high", "amp_min", "amp_max"):
             setattr(c, name, float(getattr(self, name)))

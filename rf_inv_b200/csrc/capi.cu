@@ -238,6 +238,7 @@ int check_config(const rfinv_config* c) {
   }
   for (int t = 0; t < c->ntrc; ++t)
     if (c->ipha[t] != 1 && c->ipha[t] != -1) { rfinv_set_error("ipha must be 1 or -1"); return RFINV_ERR_ARG; }
+  if (c->bdep < 0.0) { rfinv_set_error("BOREHOLE_DEP must be positive"); return RFINV_ERR_ARG; }
   if (!(c->delta > 0.0) || !(c->dz_ref > 0.0)) { rfinv_set_error("delta and dz_ref must be positive"); return RFINV_ERR_ARG; }
   return RFINV_OK;
 }
@@ -369,7 +370,7 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   for (int t = 1; t < T; ++t)
     if (cfg->rayps[t] != cfg->rayps[0] || cfg->ipha[t] != cfg->ipha[0]) d.ray_common = 0;
   d.nsmp_pad = ((S + 63) / 64) * 64;
-  d.delta = cfg->delta; d.t_start = cfg->t_start; d.sdep = cfg->sdep; d.z_ref_min = cfg->z_ref_min; d.dz_ref = cfg->dz_ref;
+  d.delta = cfg->delta; d.t_start = cfg->t_start; d.sdep = cfg->sdep; d.bdep = cfg->bdep; d.z_ref_min = cfg->z_ref_min; d.dz_ref = cfg->dz_ref;
   d.z_min = cfg->z_min; d.z_max = cfg->z_max; d.h_min = cfg->h_min;
   d.vp_min = cfg->vp_min; d.vp_max = cfg->vp_max; d.vs_min = cfg->vs_min; d.vs_max = cfg->vs_max;
   d.vpvs_min = cfg->vpvs_min; d.vpvs_max = cfg->vpvs_max;

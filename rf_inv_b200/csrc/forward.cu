@@ -67,8 +67,11 @@ struct RayConst {
   double thw, cbw, sbw;       // water layer: phase per bin, stride rotation
   double tp;                  // direct-arrival delay (src/forward.f90:474-491)
   double2 edge[4];            // fr, fv at the DC pseudo-frequency and at Nyquist
-  int k, valid;
-  int npre, pad_;             // nint((-t_start -/+ tp)/delta): circular shift of the trace (src/forward.f90:177, 186)
+  double sta[4];              // buried station: displacement rows of the scaled basis of the layer above it,
+                              // y1 = sta0 a1 + sta1 b1, y2 = sta2 a2 + sta3 b2 (wave coordinates after that layer's rotation)
+  int k, valid;               // k: solid layers above the bottom boundary condition (model layers + the split at a buried station)
+  int npre, l_sta;            // nint((-t_start -/+ tp)/delta): circular shift of the trace (src/forward.f90:177, 186);
+                              // index of the (sub)layer whose bottom is the buried station, -1 = station at the surface
 };
 constexpr int RC_DOUBLES = sizeof(RayConst) / sizeof(double);
 
@@ -134,6 +137,37 @@ __device__ __forceinline__ void surface_response(const double* h14, const double
   fv = make_double2(-uz.x, uz.y);
 }
 
+// Buried station (src/forward.f90:289-338, commented out in the reference): the surface vector (ur, uz, 0, s4) is the
+// combination alpha * e1 + beta * (0, cw, 0, -rw sw) of the two start vectors, alpha = ur, beta = -i uz / cw, so the
+// displacement at depth is the same combination of the two propagated vectors there.  (ya1, ya2) / (yb1, yb2): their
+// displacement components at the station in the scaled real basis (component 2 carries the factor i of D).
+__device__ __forceinline__ void surface_response_buried(const double* h14, const double* h23, const Wave& wa, const Wave& wb,
+                                                        int ipha, double2 ya, double2 yb, double2& fr, double2& fv) {
+  const double2 A3 = make_double2(fma(h14[0], wa.a1, h14[1] * wa.b1), fma(h23[0], wa.a2, h23[1] * wa.b2));
+  const double2 A4 = make_double2(fma(h14[2], wa.a1, h14[3] * wa.b1), fma(h23[2], wa.a2, h23[3] * wa.b2));
+  const double2 B3 = make_double2(fma(h14[0], wb.a1, h14[1] * wb.b1), fma(h23[0], wb.a2, h23[1] * wb.b2));
+  const double2 B4 = make_double2(fma(h14[2], wb.a1, h14[3] * wb.b1), fma(h23[2], wb.a2, h23[3] * wb.b2));
+  const double2 p = cmul(A3, B4), q = cmul(B3, A4);
+  const double2 dl = make_double2(p.x - q.x, p.y - q.y);
+  const double rn = 1.0 / (dl.x * dl.x + dl.y * dl.y);
+  const double2 inv = make_double2(dl.x * rn, -dl.y * rn);
+  double2 al, be;
+  if (ipha >= 0) {       // ur = B4/Delta, uz = -i cw A4/Delta
+    al = cmul(B4, inv);
+    const double2 w = cmul(A4, inv);
+    be = make_double2(-w.x, -w.y);
+  } else {               // ur = -B3/Delta, uz = +i cw A3/Delta
+    const double2 w0 = cmul(B3, inv);
+    al = make_double2(-w0.x, -w0.y);
+    be = cmul(A3, inv);
+  }
+  const double2 ur = make_double2(fma(al.x, ya.x, be.x * yb.x), fma(al.y, ya.x, be.y * yb.x));
+  const double2 s = make_double2(fma(al.x, ya.y, be.x * yb.y), fma(al.y, ya.y, be.y * yb.y));
+  const double2 uz = make_double2(-s.y, s.x);   // i * s
+  fr = make_double2(ur.x, -ur.y);
+  fv = make_double2(-uz.x, uz.y);
+}
+
 // 2x2 helpers, row-major m[4] = {m11, m12, m21, m22}
 __device__ __forceinline__ void mat2_mul(const double* a, const double* b, double* c) {
   const double c0 = fma(a[0], b[0], a[1] * b[2]), c1 = fma(a[0], b[1], a[1] * b[3]);
@@ -190,6 +224,7 @@ __device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclu
   return x;
 }
 
+template <bool BURIED>
 __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                               double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
                                                               int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
@@ -223,6 +258,30 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   }
   __syncwarp();
 
+  // ---- buried station (src/forward.f90:308-334, commented out in the reference): the layer that holds it is split at the
+  // station depth into two sublayers of the same material, so the station sits on a (transparent) interface of the
+  // propagation; a station below the last interface adds a layer of half-space material on top of the half space.
+  // ls = model layer with the station (k = half space), h_part = its thickness above the station; same running sum
+  // as the reference (z_tmp = z_tmp + h(ilay); z_tmp < bdep continues).
+  constexpr bool buried = BURIED;   // cfg.bdep > 0
+  int ls = -1;
+  double h_part = 0.0;
+  if (buried) {
+    double z_tmp = 0.0;
+    ls = k;
+    for (int l = 0; l < k; ++l) {
+      const double hl = l == 0 ? __dsub_rn(zs[0], cfg.sdep) : __dsub_rn(zs[l], zs[l - 1]);
+      z_tmp = __dadd_rn(z_tmp, hl);
+      if (!(z_tmp < cfg.bdep)) { ls = l; h_part = __dsub_rn(__dadd_rn(cfg.bdep, hl), z_tmp); break; }
+    }
+    if (ls == k) h_part = __dsub_rn(cfg.bdep, z_tmp);
+  }
+  const int ka = buried ? k + 1 : k;    // solid layers of the propagation
+  // Layers above the bottom boundary condition.  A station in the half space does not move it: the incident wave keeps
+  // its phase reference at the last model interface (src/forward.f90:250-264), the extra layer only carries the
+  // vectors on to the station.
+  const int kb = (buried && ls == k) ? k : ka;
+
   // ---- per-layer physics, one layer per lane ----
   const double p2 = __dmul_rn(p, p);
   const double nyq = (double)(cfg.nfft / 2);
@@ -230,7 +289,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   while ((nthr_fwd << nyq_doublings) < cfg.nfft / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d
   bool valid = true;
   double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane k & 31)
-  for (int l = lane; l <= k; l += 32) {
+  for (int la = lane; la <= ka; la += 32) {
+    const int l = (buried && la > ls) ? la - 1 : la;       // model layer behind propagation layer la
     double zc, h, dvs_l, dvp_l;
     if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
     else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
@@ -241,21 +301,27 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
     else if (l < k) ok = ok && !(h < cfg.h_min);           // src/model.f90:257
     valid = valid && ok;
+    double tp_sign = 1.0;                                  // direct-arrival delay counts from the station down
+    if (buried) {
+      if (la == ls) { h = h_part; tp_sign = ls == k ? -1.0 : 0.0; }   // above the station (in the half space: negative)
+      else if (la == ls + 1 && ls < k) h = __dsub_rn(h, h_part);      // rest of the split layer
+      else if (la < ls) tp_sign = 0.0;
+    }
     const double rho = vp_to_rho(a);
     const double beta2 = __dmul_rn(b, b);
     const double bp = 1.0 - 2.0 * beta2 * p2;
     const double eta = sqrt(__dsub_rn(__ddiv_rn(1.0, beta2), p2));              // src/forward.f90:395
     const double xi = sqrt(__dsub_rn(__ddiv_rn(1.0, __dmul_rn(a, a)), p2));    // src/forward.f90:396
-    if (l < k) {
-      PrepLayer& Q = PL[l];
+    if (la < ka) {
+      PrepLayer& Q = PL[la];
       const double g2 = 2.0 * beta2 * p;   // 2 beta^2 p
       const double ieta = 1.0 / eta, irho = 1.0 / rho, ixi = 1.0 / xi;
       Q.v14[0] = p; Q.v14[1] = 1.0; Q.v14[2] = rho * bp; Q.v14[3] = -rho * g2;
       Q.v23[0] = xi; Q.v23[1] = -p * ieta; Q.v23[2] = -rho * g2 * xi; Q.v23[3] = -rho * bp * ieta;
       Q.i14[0] = g2; Q.i14[1] = irho; Q.i14[2] = bp; Q.i14[3] = -p * irho;
       Q.i23[0] = bp * ixi; Q.i23[1] = -p * irho * ixi; Q.i23[2] = -g2 * eta; Q.i23[3] = -eta * irho;
-      Q.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(h, ipha == 1 ? xi : eta) : 0.0;   // src/forward.f90:489-491
-      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + l;
+      Q.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(tp_sign, __dmul_rn(h, ipha == 1 ? xi : eta)) : 0.0;   // src/forward.f90:489-491
+      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + la;
       const double thx = cfg.domg * xi * h, the = cfg.domg * eta * h;
       L->thx = thx; L->the = the;
       double sn, cs;
@@ -280,18 +346,19 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
 
   // ---- interfaces l-1 -> l (l = 1..k-1): tau = V_l^-1 V_{l-1} unscaled, prefix products of its {1,4} diagonal ----
   double carryP = 1.0, carryS = 1.0;      // scale products of the slots already done
-  double sP_last = 1.0, sS_last = 1.0;    // scales of the last solid layer k-1
-  for (int base = 0; base < k; base += 32) {
+  double sP_last = 1.0, sS_last = 1.0;    // scales of the last solid layer above the half space (kb-1)
+  double sP_sta = 1.0, sS_sta = 1.0;      // scales of the layer above a buried station
+  for (int base = 0; base < ka; base += 32) {
     const int l = base + lane;
     double t14[4] = {1.0, 0.0, 0.0, 1.0}, t23[4] = {1.0, 0.0, 0.0, 1.0};
-    if (l >= 1 && l < k) {
+    if (l >= 1 && l < ka) {
       mat2_mul(PL[l].i14, PL[l - 1].v14, t14);
       mat2_mul(PL[l].i23, PL[l - 1].v23, t23);
     }
     const double sP = carryP * warp_scan_mul(t14[0], lane), sS = carryS * warp_scan_mul(t14[3], lane);   // scales of layer l
     double sPp = __shfl_up_sync(0xffffffffu, sP, 1), sSp = __shfl_up_sync(0xffffffffu, sS, 1);           // scales of layer l-1
     if (lane == 0) { sPp = carryP; sSp = carryS; }
-    if (l >= 1 && l < k) {
+    if (l >= 1 && l < ka) {
       double* ic = PL[l - 1].ic;
       const double rP = 1.0 / sP, rS = 1.0 / sS;
       const double pp = sPp * rP, sp = sSp * rP, ps = sPp * rS, ss = sSp * rS;
@@ -300,13 +367,14 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
       LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (l - 1);
       L->t12 = ic[0]; L->t21 = ic[1]; L->u11 = ic[2]; L->u12 = ic[3]; L->u21 = ic[4]; L->u22 = ic[5];
     }
-    const int last_lane = (k - 1 - base) < 31 ? (k - 1 - base) : 31;   // highest lane of this slot holding a solid layer
+    const int last_lane = (ka - 1 - base) < 31 ? (ka - 1 - base) : 31;   // highest lane of this slot holding a solid layer
+    if (buried && ls >= base && ls < base + 32) { sP_sta = __shfl_sync(0xffffffffu, sP, ls - base); sS_sta = __shfl_sync(0xffffffffu, sS, ls - base); }
+    if (kb - 1 >= base && kb - 1 < base + 32) { sP_last = __shfl_sync(0xffffffffu, sP, kb - 1 - base); sS_last = __shfl_sync(0xffffffffu, sS, kb - 1 - base); }
     carryP = __shfl_sync(0xffffffffu, sP, last_lane);
     carryS = __shfl_sync(0xffffffffu, sS, last_lane);
-    sP_last = carryP; sS_last = carryS;
   }
   if (lane == 0) {   // the last solid layer has no in-loop interface: the half space follows
-    LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (k - 1);
+    LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (ka - 1);
     L->t12 = 0.0; L->t21 = 0.0; L->u11 = 1.0; L->u12 = 0.0; L->u21 = 0.0; L->u22 = 1.0;
   }
   __syncwarp();
@@ -328,7 +396,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   {
     // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the scaled basis of
     // the last solid layer
-    const int src_lane = k & 31;
+    const int src_lane = ka & 31;
     const double a = __shfl_sync(0xffffffffu, hs_a, src_lane), b = __shfl_sync(0xffffffffu, hs_b, src_lane);
     const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
     const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
@@ -338,7 +406,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     const double e21 = bp * rho * r2, e22 = b * p, e23 = eta * r2, e24 = p * r2;
     const double r14[4] = {e11, e14, e21, -e24};
     const double r23[4] = {-e12, e13, e22, e23};
-    const PrepLayer& Q = PL[k - 1];
+    const PrepLayer& Q = PL[kb - 1];
     const double v14[4] = {Q.v14[0] * sP_last, Q.v14[1] * sS_last, Q.v14[2] * sP_last, Q.v14[3] * sS_last};
     const double v23[4] = {Q.v23[0] * sP_last, Q.v23[1] * sS_last, Q.v23[2] * sP_last, Q.v23[3] * sS_last};
     mat2_mul(r14, v14, R.h14);
@@ -351,9 +419,18 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     R.q1a = -rw * Q.i14[1]; R.q1b = -rw * Q.i14[3];     // -rw V14^-1 (0, 1)^T
     R.q2a = Q.i23[0]; R.q2b = Q.i23[2];                 // V23^-1 (1, 0)^T
   }
+  R.l_sta = -1;
+  R.sta[0] = R.sta[1] = R.sta[2] = R.sta[3] = 0.0;
+  if (buried) {   // displacement rows of V14 / V23 of the layer above the station, with that layer's scales
+    const PrepLayer& Q = PL[ls];
+    R.l_sta = ls;
+    R.sta[0] = Q.v14[0] * sP_sta; R.sta[1] = Q.v14[1] * sS_sta;
+    R.sta[2] = Q.v23[0] * sP_sta; R.sta[3] = Q.v23[1] * sS_sta;
+  }
 
   // ---- serial part: lanes 0..3 carry (vector a | b) x (DC | Nyquist) down the stack; lane 4 sums the delay ----
   Wave w;
+  double2 y_sta = make_double2(0.0, 0.0);   // displacement components of this lane's vector at a buried station
   {
     const bool is_b = lane & 1, is_nyq = (lane >> 1) & 1;
     const double cw = is_nyq ? cw1 : cw0, sw = is_nyq ? sw1 : sw0;
@@ -362,13 +439,17 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     double tp = 0.0;
     if (lane < 4) {
       const int o = is_nyq ? 4 : 0;
-      for (int l = 0; l < k; ++l) {
+      Wave w_bc = w;
+      for (int l = 0; l < ka; ++l) {
         const PrepLayer& Q = PL[l];
         wave_rotate(w, Q.tr[o], Q.tr[o + 1], Q.tr[o + 2], Q.tr[o + 3]);
-        if (l + 1 < k) wave_interface(w, Q.ic[0], Q.ic[1], Q.ic[2], Q.ic[3], Q.ic[4], Q.ic[5]);
+        if (l == ls) { y_sta.x = fma(R.sta[0], w.a1, R.sta[1] * w.b1); y_sta.y = fma(R.sta[2], w.a2, R.sta[3] * w.b2); }
+        if (l == kb - 1) w_bc = w;   // what the bottom boundary condition sees
+        if (l + 1 < ka) wave_interface(w, Q.ic[0], Q.ic[1], Q.ic[2], Q.ic[3], Q.ic[4], Q.ic[5]);
       }
+      w = w_bc;
     } else if (lane == 4) {
-      for (int l = 0; l < k; ++l) tp = __dadd_rn(tp, PL[l].tpterm);
+      for (int l = 0; l < ka; ++l) tp = __dadd_rn(tp, PL[l].tpterm);
     }
     R.tp = __shfl_sync(0xffffffffu, tp, 4);
   }
@@ -384,18 +465,23 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
       const int e = lane & 1;   // lane parity picks the edge bin: both are finished in one pass
       double2 fr, fv;
       const Wave ea = e ? wv[2] : wv[0], eb = e ? wv[3] : wv[1];
-      surface_response(R.h14, R.h23, ea, eb, e ? cw1 : cw0, ipha, fr, fv);
+      if (!buried) {
+        surface_response(R.h14, R.h23, ea, eb, e ? cw1 : cw0, ipha, fr, fv);
+      } else {
+        const double2 ya = make_double2(__shfl_sync(0xffffffffu, y_sta.x, 2 * e), __shfl_sync(0xffffffffu, y_sta.y, 2 * e));
+        const double2 yb = make_double2(__shfl_sync(0xffffffffu, y_sta.x, 2 * e + 1), __shfl_sync(0xffffffffu, y_sta.y, 2 * e + 1));
+        surface_response_buried(R.h14, R.h23, ea, eb, ipha, ya, yb, fr, fv);
+      }
       R.edge[0].x = __shfl_sync(0xffffffffu, fr.x, 0); R.edge[0].y = __shfl_sync(0xffffffffu, fr.y, 0);
       R.edge[1].x = __shfl_sync(0xffffffffu, fv.x, 0); R.edge[1].y = __shfl_sync(0xffffffffu, fv.y, 0);
       R.edge[2].x = __shfl_sync(0xffffffffu, fr.x, 1); R.edge[2].y = __shfl_sync(0xffffffffu, fr.y, 1);
       R.edge[3].x = __shfl_sync(0xffffffffu, fv.x, 1); R.edge[3].y = __shfl_sync(0xffffffffu, fv.y, 1);
     }
     if (lane == 0) {
-      R.k = k;
+      R.k = kb;
       R.valid = valid;
       R.npre = ipha == 1 ? f_nint((-cfg.t_start - R.tp) / cfg.delta)    // src/forward.f90:177
                          : f_nint((-cfg.t_start + R.tp) / cfg.delta);   // src/forward.f90:186
-      R.pad_ = 0;
       reinterpret_cast<RayConst*>(rc_out)[item] = R;
       if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
     }
@@ -677,7 +763,7 @@ __device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, c
 template <int J, bool STAGE>
 __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha,
                                                  int n, int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                                 double2* s_fr, double2* s_fv) {
+                                                 double2* s_fr, double2* s_fv, bool buried) {
   double h14[4], h23[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
@@ -688,7 +774,8 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
   for (int m = 0; m < J; ++m) {
     const int j = tid + m * nthr;
     double2 fr, fv;
-    surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
+    if (STAGE && buried) surface_response_buried(h14, h23, wa[m], wb[m], ipha, s_fr[j], s_fv[j], fr, fv);   // station pass left them there
+    else surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
     rot(cw, sw, cbw, sbw);
     if (STAGE) {
       if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
@@ -762,8 +849,8 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
 template <int JB, bool STAGE, bool MIXED>
 __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha, int n,
                                                int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                               double2* s_fr, double2* s_fv) {
-#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv)
+                                               double2* s_fr, double2* s_fv, bool buried) {
+#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried)
   if (!MIXED || jm >= JB) { SURF(JB); return; }
   if constexpr (MIXED) {
   if constexpr (JB > 6) if (jm == 6) { SURF(6); return; }
@@ -785,7 +872,7 @@ __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, con
 // in-place FFT buffer; the unfiltered spectra only when they must outlive one FFT (common rays) or feed the
 // water-level deconvolution; two sets of layer / ray constants; quarter-wave twiddles.
 // ------------------------------------------------------------------------------------------------
-template <int J, int BMAX, int MINB, bool MIXED>
+template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
 __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
                                                              const double* __restrict__ lc_in,
                                                              const double* __restrict__ rc_in, int* __restrict__ counter) {
@@ -795,7 +882,8 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * ntr_eff;
-  const bool general = cfg.ray_common || cfg.deconv_mode == 1;   // spectra staged in shared memory
+  constexpr bool buried = BURIED;   // cfg.bdep > 0: a kernel variant of its own, the surface-station variants carry none of it
+  const bool general = cfg.ray_common || cfg.deconv_mode == 1 || buried;   // spectra staged in shared memory
 
   const int n_hi = nthr >> 4;                         // table split: tid = 16*hi + lo
   const int tab_per_layer = 2 * (16 + n_hi);          // double2 entries per layer: (xi | eta) x (lo | hi)
@@ -845,20 +933,35 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     const int k = s_rc->k;
     const int ipha = cfg.ipha[t0];
     PHASE_MARK(0);
-    build_trig_tables(s_tab, s_lc, k, n_hi, tid, nthr);
+    build_trig_tables(s_tab, s_lc, buried ? max(k, s_rc->l_sta + 1) : k, n_hi, tid, nthr);
     __syncthreads();
     PHASE_MARK(1);
 
     const int jm = MIXED ? cfg.jbins[t0] : J;   // bin groups with signal for this trace (<= J; MIXED: it varies by trace)
     Wave wa[J], wb[J];
-    propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
+    // Buried station: a first pass down to the station leaves the displacement components of both vectors there in the
+    // spectrum staging arrays (same thread, same bins as the surface response that combines them); then the full stack.
+    for (int pass = buried ? 0 : 1; pass < 2; ++pass) {
+      propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, pass == 0 ? s_rc->l_sta + 1 : k, n_hi, tid, wa, wb);
+      if (pass == 0) {
+        const double c0 = s_rc->sta[0], c1 = s_rc->sta[1], c2 = s_rc->sta[2], c3 = s_rc->sta[3];
+#pragma unroll
+        for (int m = 0; m < J; ++m) {
+          const int j = tid + m * nthr;
+          if (m < jm) {
+            s_fr[j] = make_double2(fma(c0, wa[m].a1, c1 * wa[m].b1), fma(c2, wa[m].a2, c3 * wa[m].b2));
+            s_fv[j] = make_double2(fma(c0, wb[m].a1, c1 * wb[m].b1), fma(c2, wb[m].a2, c3 * wb[m].b2));
+          }
+        }
+      }
+    }
     PHASE_MARK(2);
     __syncthreads();   // the trigonometric tables are dead: their region becomes the FFT buffer
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
     const int jfull = (n >> 1) / nthr;
-    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv);
-    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv);
+    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried);
+    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -1012,29 +1115,29 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
   const size_t tab_entries = km * 2 * (16 + (nthr >> 4));
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
-  const bool general = cfg.ray_common || cfg.deconv_mode == 1;
+  const bool general = cfg.ray_common || cfg.deconv_mode == 1 || cfg.bdep > 0.0;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
   return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 32 + 2 * sizeof(RayConst) +
          2 * sizeof(LayerConst) * km;
 }
 
-template <int J, int BMAX, int MINB, bool MIXED>
+template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
                      const double* rc, int* counter, int nthr, cudaStream_t stream) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
-  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, per_sm = 0;
   RFINV_CUDA_CHECK(cudaGetDevice(&dev));
   RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED>, nthr, smem));
+  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED, BURIED>, nthr, smem));
   if (per_sm < 1) { rfinv_set_error("forward_kernel does not fit on an SM (%zu bytes of shared memory)", smem); return RFINV_ERR_CUDA; }
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long items = (long long)n_models * ntr_eff;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  forward_kernel<J, BMAX, MINB, MIXED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
+  forward_kernel<J, BMAX, MINB, MIXED, BURIED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -1066,9 +1169,14 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
   int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
   const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
-  RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-  prep_kernel<<<(unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS), 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter,
-                                                                                                         (int)n_items, ntr_eff, nthr);
+  const unsigned prep_grid = (unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS);
+  if (cfg.bdep > 0.0) {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    prep_kernel<true><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
+  } else {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    prep_kernel<false><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
+  }
   RFINV_CUDA_CHECK(cudaGetLastError());
   // kernel variant: <bin groups per thread that are propagated (band limit), upper bound of threads per CTA, CTAs per SM>
   const int JB = cfg.jb_max;
@@ -1076,8 +1184,9 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   for (int t = 0; t < cfg.ntrc; ++t) mixed = mixed || cfg.jbins[t] != JB;
 #define FWD(JJ, BB, MM)                                                                                   \
   do {                                                                                                    \
-    if (mixed || JJ != JB) return launch_forward_t<JJ, BB, MM, true>(cfg, mb, out, lc, rc, counter, nthr, stream); \
-    return launch_forward_t<JJ, BB, MM, false>(cfg, mb, out, lc, rc, counter, nthr, stream);              \
+    if (cfg.bdep > 0.0) return launch_forward_t<JJ, BB, MM, true, true>(cfg, mb, out, lc, rc, counter, nthr, stream); \
+    if (mixed || JJ != JB) return launch_forward_t<JJ, BB, MM, true, false>(cfg, mb, out, lc, rc, counter, nthr, stream); \
+    return launch_forward_t<JJ, BB, MM, false, false>(cfg, mb, out, lc, rc, counter, nthr, stream);       \
   } while (0)
   if (nthr <= 32) { if (JB <= 1) FWD(1, 32, 8); FWD(2, 32, 8); }
   if (nthr <= 64) { if (JB <= 2) FWD(2, 64, 6); FWD(4, 64, 6); }

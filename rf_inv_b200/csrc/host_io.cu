@@ -205,7 +205,12 @@ int32_t rfinv_problem_load(const char* params_path, const char* base_dir, rfinv_
   NUM(2, "T_START T_END") c.t_start = v[0]; p->t_end = v[1];
   NUM(1, "DECONV_MODE") c.deconv_mode = (int)v[0];
   if (c.deconv_mode != 0 && c.deconv_mode != 1) { st = fail(RFINV_ERR_ARG, "ERROR: deconv_mode must be either 0 or 1%s", ""); goto done; }
-  NUM(1, "SEA_DEP") c.sdep = v[0];
+  // SEA_DEP [BOREHOLE_DEP]: the second number is optional (src/params.f90:203-213, commented out in the reference)
+  NEXT("SEA_DEP (BOREHOLE_DEP)")
+  if (parse_numbers(line, 2, v)) { c.sdep = v[0]; c.bdep = v[1]; }
+  else if (parse_numbers(line, 1, v)) { c.sdep = v[0]; c.bdep = 0.0; }
+  else { st = fail(RFINV_ERR_IO, "ERROR: while reading SEA_DEP (BOREHOLE_DEP)%s", ""); goto done; }
+  if (c.bdep < 0.0) { st = fail(RFINV_ERR_ARG, "ERROR: BOREHOLE_DEP must be positive%s", ""); goto done; }
   NEXT("VEL_FILE") p->vel_file = parse_string(line);
   NUM(1, "VP_MODE") c.vp_mode = (int)v[0];
   NUM(2, "K_MIN K_MAX") c.k_min = (int)v[0]; c.k_max = (int)v[1];

@@ -16,6 +16,7 @@ struct DevConfig {
   int ntrc, nfft, nh, nsmp, log2n;
   int deconv_mode, vp_mode, k_min, k_max, prior_mode, nref, ray_common;
   int nsmp_pad;                 // nsmp rounded up to the likelihood tile (64)
+  double bdep;                  // receiver depth below the surface / sea floor (0 = at the surface)
   double delta, t_start, sdep, z_ref_min, dz_ref, z_min, z_max, h_min;
   double vp_min, vp_max, vs_min, vs_max, vpvs_min, vpvs_max;
   double domg;                  // 2 pi / (nfft * delta), src/forward.f90:241

@@ -34,7 +34,7 @@ def load_problem(params_path: str, base_dir: Optional[str] = None) -> RFConfig:
         cfg = RFConfig(
             ntrc=T, nfft=c.nfft, nsmp=S, delta=c.delta, t_start=c.t_start, rayps=list(_arr(c.rayps, T)),
             a_gus=list(_arr(c.a_gus, T)), ipha=[int(x) for x in _arr(c.ipha, T, np.int32)], deconv_mode=c.deconv_mode,
-            sdep=c.sdep, obs=_arr(c.obs, T * S).reshape(T, S), r_inv=None, vp_ref=_arr(c.vp_ref, c.nref),
+            sdep=c.sdep, bdep=c.bdep, obs=_arr(c.obs, T * S).reshape(T, S), r_inv=None, vp_ref=_arr(c.vp_ref, c.nref),
             vs_ref=_arr(c.vs_ref, c.nref), z_ref_min=c.z_ref_min, dz_ref=c.dz_ref, vp_mode=c.vp_mode, k_min=c.k_min,
             k_max=c.k_max, prior_mode=c.prior_mode, z_min=c.z_min, z_max=c.z_max, h_min=c.h_min, dvs_prior=c.dvs_prior,
             dvp_prior=c.dvp_prior, sig_min=list(_arr(c.sig_min, T)), sig_max=list(_arr(c.sig_max, T)), vp_min=c.vp_min,

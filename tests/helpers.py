@@ -17,7 +17,7 @@ def py_config(c: RFConfig) -> pyo.Config:
     """RFConfig -> the numpy oracle's Config (obs is (nsmp, ntrc) there, like the Fortran array)."""
     return pyo.Config(
         ntrc=c.ntrc, nfft=c.nfft, nsmp=c.nsmp, delta=c.delta, t_start=c.t_start, rayps=list(c.rayps),
-        a_gus=list(c.a_gus), ipha=list(c.ipha), deconv_mode=c.deconv_mode, sdep=c.sdep,
+        a_gus=list(c.a_gus), ipha=list(c.ipha), deconv_mode=c.deconv_mode, sdep=c.sdep, bdep=c.bdep,
         obs=None if c.obs is None else np.asarray(c.obs).T.copy(), vp_ref=np.asarray(c.vp_ref),
         vs_ref=np.asarray(c.vs_ref), z_ref_min=c.z_ref_min, dz_ref=c.dz_ref, vp_mode=c.vp_mode, k_min=c.k_min,
         k_max=c.k_max, z_min=c.z_min, z_max=c.z_max, h_min=c.h_min, prior_mode=c.prior_mode, dvs_prior=c.dvs_prior,

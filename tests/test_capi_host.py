@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/rfinv_b200.h but not exported"
         assert s in capi.SIGNATURES, f"{s} has no ctypes signature in rf_inv_b200/capi.py"
-    assert lib.rfinv_abi_version() == 1
+    assert lib.rfinv_abi_version() == 2
 
 
 def test_config_struct_layout_matches_header():

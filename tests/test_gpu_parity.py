@@ -32,6 +32,12 @@ VARIANTS = {
     "n2048_k30": dict(nfft=2048, nsmp=1000, k_max=30, z_max=40.0),
     "n4096": dict(nfft=4096, nsmp=300, k_max=12),
     "nsmp_eq_nfft": dict(nfft=128, nsmp=128),
+    # buried station (BOREHOLE_DEP; commented out in the reference, src/forward.f90:289-338, 493-516)
+    "buried_land": dict(bdep=1.0), "buried_sea": dict(bdep=1.0, sdep=2.0),
+    "buried_S": dict(bdep=7.3, ipha=[-1, -1], rayps=[0.10, 0.12]), "buried_half_space": dict(bdep=25.0),
+    "buried_sea_deconv": dict(bdep=3.0, sdep=1.0, deconv_mode=1), "buried_common": dict(bdep=4.0, rayps=[0.06, 0.06], a_gus=[2.0, 4.0]),
+    "buried_n1024_k20": dict(bdep=2.5, sdep=1.0, nfft=1024, nsmp=512, k_max=20, z_max=40.0),
+    "buried_n2048_k30": dict(bdep=11.0, nfft=2048, nsmp=1000, k_max=30, z_max=40.0),
 }
 
 
@@ -266,3 +272,18 @@ np.savez(sys.argv[1], ll=ll, sig=m["sig"])
     err = helpers.logl_err(cfg, res["factor"]["ll"], res["dense"]["ll"], res["dense"]["sig"])
     assert err < 1e-11, err
     assert not np.array_equal(res["factor"]["ll"], res["dense"]["ll"])   # two different summations
+
+
+def test_buried_station_at_vanishing_depth_reproduces_the_surface_station_on_the_gpu():
+    """The buried-station path (split layer, station pass, combination of the two propagated vectors) against the plain
+    path of the same kernels: a station 1e-9 km deep must give the surface result to ~1e-9."""
+    for kw in (dict(), dict(sdep=2.0)):
+        top = helpers.attach_obs_and_rinv(helpers.small_config(**kw), noise=0.01)
+        m = workloads.draw_models(top, 64, seed=2, dvs_scale=0.3)
+        bur = helpers.small_config(bdep=1e-9, **kw)
+        bur.obs, bur.r_inv = top.obs, top.r_inv
+        with Evaluator(top) as ev:
+            _, rft_top, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+        with Evaluator(bur) as ev:
+            _, rft_bur, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+        assert helpers.rel_err_rft(rft_bur, rft_top) < 1e-8

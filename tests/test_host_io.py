@@ -74,6 +74,17 @@ def test_reader_errors(tmp_path):
     with pytest.raises(capi.RfinvError) as e:
         rio.load_problem(str(tmp_path / "bad.in"))
     assert "deconv_mode must be either 0 or 1" in str(e.value)
+    ok = open(p).read().splitlines()
+    ok[20] = "2.0 1.5"                                              # SEA_DEP BOREHOLE_DEP (src/params.f90:203-213, commented out there)
+    (tmp_path / "bore.in").write_text("\n".join(ok) + "\n")
+    cfg = rio.load_problem(str(tmp_path / "bore.in"))
+    assert cfg.sdep == 2.0 and cfg.bdep == 1.5
+    assert rio.load_problem(p).bdep == 0.0                          # the second number is optional
+    ok[20] = "2.0 -1.0"
+    (tmp_path / "bore_bad.in").write_text("\n".join(ok) + "\n")
+    with pytest.raises(capi.RfinvError) as e:
+        rio.load_problem(str(tmp_path / "bore_bad.in"))
+    assert "BOREHOLE_DEP must be positive" in str(e.value)
     with open(tmp_path / "model" / "sample.velmod", "a") as f:      # non-constant depth increment (src/model.f90:131-138)
         f.write("31.0 5.0 2.89\n")
     with pytest.raises(capi.RfinvError) as e:

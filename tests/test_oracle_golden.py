@@ -176,3 +176,59 @@ def test_pt_mcmc_c_vs_numpy_oracle_identical_sequences():
     assert np.max(np.abs(st["logl"] - logl_py) / np.abs(logl_py)) < 1e-10
     assert np.array_equal(st["temps"], np.concatenate([r.temps for r in ranks]))
     assert np.array_equal(st["k"], np.concatenate([r.k for r in ranks]))
+
+
+# ---- buried station (BOREHOLE_DEP): commented out in the reference (src/forward.f90:289-338, 493-516), no fixture ----
+BURIED = {"land": dict(bdep=1.0), "sea": dict(bdep=1.0, sdep=2.0), "S": dict(bdep=7.3, ipha=[-1, -1], rayps=[0.10, 0.12]),
+          "half_space": dict(bdep=25.0), "sea_deconv": dict(bdep=3.0, sdep=1.0, deconv_mode=1),
+          "common": dict(bdep=4.0, rayps=[0.06, 0.06], a_gus=[2.0, 4.0])}
+
+
+def _py_rft(cfg, m, i, **over):
+    pc = helpers.py_config(cfg)
+    for key, val in over.items():
+        setattr(pc, key, val)
+    nlay, a, b, r, h, _ = pyo.format_model(pc, int(m["k"][i]), m["z"][i], m["dvp"][i], m["dvs"][i])
+    return pyo.calc_rf(pc, pyo.init_filter(pc), nlay, a, b, r, h).T
+
+
+@pytest.mark.parametrize("name", sorted(BURIED))
+def test_buried_station_c_vs_numpy_oracle(name):
+    cfg = helpers.small_config(**BURIED[name])
+    cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
+    m = workloads.draw_models(cfg, 6, seed=3, dvs_scale=0.3)
+    _, rft_c, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    for i in range(6):
+        assert helpers.rel_err_rft(_py_rft(cfg, m, i)[None], rft_c[i][None]) < 1e-12
+
+
+def test_buried_station_at_vanishing_depth_reproduces_the_surface_station():
+    for kw in (dict(), dict(sdep=2.0), dict(ipha=[-1, -1], rayps=[0.10, 0.12])):
+        top = helpers.small_config(**kw)
+        top.obs = np.zeros((top.ntrc, top.nsmp)); top.r_inv = np.zeros((top.ntrc, top.nsmp, top.nsmp))
+        m = workloads.draw_models(top, 8, seed=2, dvs_scale=0.3)
+        _, rft_top, _ = oracle_c.eval_batch(top, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+        bur = helpers.small_config(bdep=1e-9, **kw)
+        bur.obs, bur.r_inv = top.obs, top.r_inv
+        _, rft_bur, _ = oracle_c.eval_batch(bur, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+        assert helpers.rel_err_rft(rft_bur, rft_top) < 1e-8
+
+
+def test_buried_station_restatement_equals_the_commented_block_where_that_block_is_consistent():
+    """The numpy oracle can transcribe the commented block literally (bdep_literal): no exit after the station's layer,
+    bdep instead of the remaining distance in the half space, v(i0) for every layer below the station.  With the station
+    inside the LAST solid layer none of the three matters, and literal == restated to the last bit; with a layer below
+    it they differ visibly (which is why the literal form is not what the CUDA path implements)."""
+    cfg = helpers.small_config(k_max=6)
+    cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
+    km = cfg.k_max
+    m = dict(k=np.array([3, 3], dtype=np.int32), z=np.zeros((2, km - 1)), dvp=np.zeros((2, km)), dvs=np.zeros((2, km)),
+             sig=np.full((2, 2), 0.01))
+    m["z"][:, :3] = [4.0, 9.0, 15.0]
+    m["dvs"][:, :3] = [-0.6, 0.2, 0.5]; m["dvs"][:, km - 1] = 1.2
+    cfg.bdep = 12.0                                  # inside the third (last) solid layer
+    a = _py_rft(cfg, m, 0); b = _py_rft(cfg, m, 0, bdep_literal=True)
+    assert np.array_equal(a, b)
+    cfg.bdep = 6.0                                   # second layer: the literal loop runs on through the third
+    a = _py_rft(cfg, m, 0); b = _py_rft(cfg, m, 0, bdep_literal=True)
+    assert helpers.rel_err_rft(b[None], a[None]) > 1e-3
