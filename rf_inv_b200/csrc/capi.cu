@@ -395,61 +395,147 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   // W = V_r diag(sqrt(lambda_r)) costs 2 S r flop instead of S^2 and sums non-negative terms only.  Eigenvalues below
   // 1e-12 of the largest are rounding residue of the construction (they change phi by < 1e-10 relative) and are
   // dropped; any eigenvalue below -1e-12 lambda_max, or a rank that does not pay, keeps the dense form for that trace.
+  //
+  // Split form.  R_ij = r^((i-j)^2) is a symmetric Toeplitz matrix, so R^-1 commutes with the exchange matrix J
+  // (R^-1[i][j] = R^-1[S-1-i][S-1-j]) and its eigenvectors are symmetric or antisymmetric about the centre of the
+  // window.  In the basis q_i^+- = (e_i +- e_{S-1-i})/sqrt2 (plus the centre sample when S is odd) R^-1 is block
+  // diagonal: phi = s^T M+ s + a^T M- a with s_i = m_i + m_{S-1-i}, a_i = m_i - m_{S-1-i} (the 1/sqrt2 goes into the
+  // factors), two quadratic forms of half the length -- half the flop of the factor form, and two half-size
+  // eigenproblems at create.  Used when R^-1 passes the symmetry test (any R^-1 the reference can build does);
+  // forward_kernel then writes (s | a) instead of m into the misfit rows (DevConfig::qf_split).
   std::vector<double> wfac;
   {
     static const bool force_dense = getenv("RFINV_QF_DENSE") && atoi(getenv("RFINV_QF_DENSE")) != 0;
+    static const bool no_split = getenv("RFINV_QF_NOSPLIT") && atoi(getenv("RFINV_QF_NOSPLIT")) != 0;
     const int ntile_dense = Sp / 64;
-    std::vector<std::vector<double>> Wt(T);      // per trace: [rank][S]
-    std::vector<double> a, w, v;
+    std::vector<std::vector<double>> Wt(T);      // per trace: [wrows_t][Sp], row = one column of W, K contiguous
+    std::vector<int> wrows_t(T, 0);
+    std::vector<double> a, w, v, a2, w2, v2;
     d.qf_tiles_max = 0;
     int wrows = 64;
+    const double rs2 = 0.70710678118654752440;
     for (int t = 0; t < T; ++t) {
-      d.qf_rank[t] = 0;
+      d.qf_rank[t] = 0; d.qf_rank_s[t] = 0; d.qf_split[t] = 0;
       d.qf_tiles[t] = ntile_dense;
+      const double* Rm = &rpad[(size_t)t * Sp * Sp];
+      auto R = [&](int i, int j) { return Rm[(size_t)i * Sp + j]; };
       int same = -1;
       for (int u = 0; u < t && same < 0; ++u)
-        if (std::memcmp(&rpad[(size_t)u * Sp * Sp], &rpad[(size_t)t * Sp * Sp], sizeof(double) * (size_t)Sp * Sp) == 0) same = u;
+        if (std::memcmp(&rpad[(size_t)u * Sp * Sp], Rm, sizeof(double) * (size_t)Sp * Sp) == 0) same = u;
       if (force_dense) { /* keep dense */ }
-      else if (same >= 0) { d.qf_rank[t] = d.qf_rank[same]; d.qf_tiles[t] = d.qf_tiles[same]; Wt[t] = Wt[same]; }
-      else {
-        a.resize((size_t)S * S);
-        bool nonzero = false;
+      else if (same >= 0) {
+        d.qf_rank[t] = d.qf_rank[same]; d.qf_rank_s[t] = d.qf_rank_s[same]; d.qf_split[t] = d.qf_split[same];
+        d.qf_tiles[t] = d.qf_tiles[same]; Wt[t] = Wt[same]; wrows_t[t] = wrows_t[same];
+      } else {
+        double rmax = 0.0, asym = 0.0;
         for (int i = 0; i < S; ++i)
-          for (int j = 0; j < S; ++j) { a[(size_t)i * S + j] = rpad[((size_t)t * Sp + i) * Sp + j]; nonzero |= a[(size_t)i * S + j] != 0.0; }
-        if (nonzero) {
+          for (int j = 0; j < S; ++j) {
+            rmax = std::max(rmax, std::fabs(R(i, j)));
+            asym = std::max(asym, std::fabs(R(i, j) - R(S - 1 - i, S - 1 - j)));
+          }
+        const int ha = S / 2, hs = S - ha;            // antisymmetric / symmetric subspace dimensions
+        const bool split = !no_split && rmax > 0.0 && asym <= 1e-10 * rmax && hs <= Sp / 2;
+        const double units_dense = 0.5 * ntile_dense * (ntile_dense + 1);
+        auto tile_units = [&](int r) { return r / 64 + (r % 64 ? 0.4 : 0.0); };
+        if (split) {
+          // blocks of R^-1 in the orthonormal (+, -) basis; forward_kernel writes the unnormalised sums and differences, so
+          // the 1/sqrt2 of the paired basis vectors goes into the rows of W below
+          a.assign((size_t)hs * hs, 0.0); a2.assign((size_t)ha * ha, 0.0);
+          for (int i = 0; i < ha; ++i)
+            for (int j = 0; j < ha; ++j) {
+              const int ir = S - 1 - i, jr = S - 1 - j;
+              a[(size_t)i * hs + j] = 0.5 * ((R(i, j) + R(ir, jr)) + (R(i, jr) + R(ir, j)));
+              a2[(size_t)i * ha + j] = 0.5 * ((R(i, j) + R(ir, jr)) - (R(i, jr) + R(ir, j)));
+            }
+          if (hs > ha) {                               // centre sample: a basis vector of its own in the + block
+            const int c = ha;
+            a[(size_t)c * hs + c] = R(c, c);
+            for (int i = 0; i < ha; ++i) a[(size_t)i * hs + c] = a[(size_t)c * hs + i] = rs2 * (R(i, c) + R(S - 1 - i, c));
+          }
+          sym_eigh(a, hs, w, v);
+          if (ha > 0) sym_eigh(a2, ha, w2, v2); else { w2.clear(); v2.clear(); }
+          double lmax = 0.0, lmin = 0.0;
+          for (double x : w) { lmax = std::max(lmax, x); lmin = std::min(lmin, x); }
+          for (double x : w2) { lmax = std::max(lmax, x); lmin = std::min(lmin, x); }
+          const double tol = 1e-12 * lmax;
+          std::vector<int> os, oa;
+          for (int e = 0; e < hs; ++e) if (w[e] > tol) os.push_back(e);
+          for (int e = 0; e < ha; ++e) if (w2[e] > tol) oa.push_back(e);
+          std::sort(os.begin(), os.end(), [&](int x, int y) { return w[x] > w[y] || (w[x] == w[y] && x < y); });
+          std::sort(oa.begin(), oa.end(), [&](int x, int y) { return w2[x] > w2[y] || (w2[x] == w2[y] && x < y); });
+          const int rs = (int)os.size(), ra = (int)oa.size(), ts = (rs + 63) / 64, ta = (ra + 63) / 64;
+          const double units_split = 0.5 * (tile_units(rs) + tile_units(ra)) * ntile_dense;
+          if (lmax > 0.0 && lmin >= -tol && rs + ra > 0 && units_split < 0.9 * units_dense) {
+            d.qf_rank[t] = rs + ra; d.qf_rank_s[t] = rs; d.qf_split[t] = 1;
+            d.qf_tiles[t] = ts + ta;
+            wrows_t[t] = 64 * (ts + ta);
+            Wt[t].assign((size_t)wrows_t[t] * Sp, 0.0);
+            for (int row = 0; row < rs; ++row) {        // + block: K range [0, Sp/2)
+              const int e = os[row];
+              const double sc = std::sqrt(w[e]);
+              double* dst = &Wt[t][(size_t)row * Sp];
+              for (int i = 0; i < ha; ++i) dst[i] = sc * rs2 * v[(size_t)i * hs + e];
+              if (hs > ha) dst[ha] = sc * v[(size_t)ha * hs + e];
+            }
+            for (int row = 0; row < ra; ++row) {        // - block: rows from 64 ts on, K range [Sp/2, Sp)
+              const int e = oa[row];
+              const double sc = std::sqrt(w2[e]);
+              double* dst = &Wt[t][(size_t)(64 * ts + row) * Sp + Sp / 2];
+              for (int i = 0; i < ha; ++i) dst[i] = sc * rs2 * v2[(size_t)i * ha + e];
+            }
+          }
+        }
+        if (d.qf_rank[t] == 0 && rmax > 0.0) {          // plain factor form over the whole window
+          a.resize((size_t)S * S);
+          for (int i = 0; i < S; ++i)
+            for (int j = 0; j < S; ++j) a[(size_t)i * S + j] = R(i, j);
           sym_eigh(a, S, w, v);
           double lmax = 0.0, lmin = 0.0;
           for (int e = 0; e < S; ++e) { lmax = std::max(lmax, w[e]); lmin = std::min(lmin, w[e]); }
           const double tol = 1e-12 * lmax;
           int r = 0;
           for (int e = 0; e < S; ++e) r += w[e] > tol;
-          const double units_dense = 0.5 * ntile_dense * (ntile_dense + 1);
-          const double units_fac = (r / 64 + (r % 64 ? 0.4 : 0.0)) * ntile_dense;
-          if (lmax > 0.0 && lmin >= -tol && r > 0 && units_fac < 0.9 * units_dense) {
+          if (lmax > 0.0 && lmin >= -tol && r > 0 && tile_units(r) * ntile_dense < 0.9 * units_dense) {
             d.qf_rank[t] = r;
             d.qf_tiles[t] = (r + 63) / 64;
-            Wt[t].assign((size_t)r * S, 0.0);
+            wrows_t[t] = 64 * d.qf_tiles[t];
+            Wt[t].assign((size_t)wrows_t[t] * Sp, 0.0);
             std::vector<int> order;
             for (int e = 0; e < S; ++e) if (w[e] > tol) order.push_back(e);
             std::sort(order.begin(), order.end(), [&](int x, int y) { return w[x] > w[y] || (w[x] == w[y] && x < y); });
             for (int row = 0; row < r; ++row) {         // largest eigenvalue first
               const int e = order[row];
               const double sc = std::sqrt(w[e]);
-              for (int i = 0; i < S; ++i) Wt[t][(size_t)row * S + i] = sc * v[(size_t)i * S + e];
+              for (int i = 0; i < S; ++i) Wt[t][(size_t)row * Sp + i] = sc * v[(size_t)i * S + e];
             }
           }
         }
       }
       d.qf_tiles_max = std::max(d.qf_tiles_max, d.qf_tiles[t]);
-      wrows = std::max(wrows, 64 * ((d.qf_rank[t] + 63) / 64));
+      wrows = std::max(wrows, wrows_t[t]);
     }
     d.qf_wrows = wrows;
-    d.qf_full_first = 1;
-    for (int t = 0; t < T; ++t) if (d.qf_rank[t] == 0) d.qf_full_first = 0;
     wfac.assign((size_t)T * wrows * Sp, 0.0);
     for (int t = 0; t < T; ++t)
-      for (int e = 0; e < d.qf_rank[t]; ++e)
-        std::memcpy(&wfac[((size_t)t * wrows + e) * Sp], &Wt[t][(size_t)e * S], sizeof(double) * (size_t)S);
+      if (!Wt[t].empty()) std::memcpy(&wfac[(size_t)t * wrows * Sp], Wt[t].data(), sizeof(double) * Wt[t].size());
+    // hand-out order of the column tiles inside a scheduling chunk: most expensive first (dense form: the cost grows
+    // with jt; factor forms: full tiles before partial ones), judged on the trace with the most tiles
+    {
+      int tr = 0;
+      for (int t = 0; t < T; ++t) if (d.qf_tiles[t] > d.qf_tiles[tr]) tr = t;
+      std::vector<std::pair<double, int>> cost;
+      for (int jt = 0; jt < d.qf_tiles_max && jt < RFINV_MAX_QF_TILES; ++jt) {
+        double cst;
+        if (d.qf_rank[tr] == 0) cst = jt + 1;
+        else if (d.qf_split[tr]) {
+          const int rs = d.qf_rank_s[tr], ts = (rs + 63) / 64;
+          cst = std::min(64, jt < ts ? rs - 64 * jt : (d.qf_rank[tr] - rs) - 64 * (jt - ts));
+        } else cst = std::min(64, d.qf_rank[tr] - 64 * jt);
+        cost.push_back({-cst, jt});
+      }
+      std::sort(cost.begin(), cost.end());
+      for (size_t q = 0; q < cost.size(); ++q) d.qf_order[q] = cost[q].second;
+    }
   }
 #define RFINV_TRY(x) do { st = (x); if (st != RFINV_OK) { rfinv_destroy(h); return st; } } while (0)
   RFINV_TRY(upload(flt, &h->d_flt));

@@ -807,16 +807,24 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
 
 // Shift / sign / normalise the transformed trace (src/forward.f90:176-203) and write misfit, cached samples and
 // (optionally) the complete RF.  Element f of the transform sits at bit-reversed position (n is a power of two).
+// Misfit row layout: m_i = rft(i) - obs(i) in [0, nsmp), or with DevConfig::qf_split the sums s_i = m_i + m_{S-1-i} in
+// [0, Sp/2) (the centre sample of an odd window at i = S/2) and the differences a_i = m_i - m_{S-1-i} in [Sp/2, Sp):
+// what the split quadratic form contracts (capi.cu).  The padding of the row is written (zeros) on every call: the
+// rows move when the batch size changes and a stale NaN would survive the multiplication by a zero of R^-1 / W.
 constexpr int OBS_PRE = 4;   // observed samples per thread fetched before the FFT
+// index of the q-th observed sample thread `tid` needs (write_outputs below): the left (q even) or right (q odd) member
+// of its pair p = tid + (q>>1)*nthr of samples (p, S-1-p)
+__device__ __forceinline__ int obs_pre_index(int S, int q, int tid, int nthr) {
+  const int pr = tid + (q >> 1) * nthr;
+  return pr < (S >> 1) ? ((q & 1) ? S - 1 - pr : pr) : S;   // S = nothing to fetch
+}
 __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOutputs& out, const double2* s_buf, int C, int c,
                                               int t, int ipha, int npre, double scale, const double* obs_pre, int tid, int nthr) {
   const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
-  const int nout = out.rft_full ? n : S;
   double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
   double* smp_base = out.rft_smp;
   if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
   double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
-  double* __restrict__ full = out.rft_full ? out.rft_full + ((size_t)c * cfg.ntrc + t) * n : nullptr;
   const double* __restrict__ obs = cfg.obs + (size_t)t * S;
   auto sample = [&](int i) {
     const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
@@ -824,25 +832,36 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
     const double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
     return ipha == 1 ? v : -v;
   };
+  // every thread handles pairs (p, S-1-p) of samples: both layouts come out of the same loop
+  const bool split = cfg.qf_split[t] != 0;
+  const int ha = S >> 1, half = Sp >> 1;
+  auto emit = [&](int pr, double o1, double o2) {
+    const double v1 = sample(pr), v2 = sample(S - 1 - pr);
+    const double d1 = v1 - o1, d2 = v2 - o2;
+    mis[pr] = split ? d1 + d2 : d1;
+    mis[split ? half + pr : S - 1 - pr] = split ? d1 - d2 : d2;
+    if (smp) { smp[pr] = v1; smp[S - 1 - pr] = v2; }
+  };
 #pragma unroll
-  for (int q = 0; q < OBS_PRE; ++q) {
-    const int i = tid + q * nthr;
-    if (i < nout) {
-      const double v = sample(i);
-      if (i < S) {
-        mis[i] = v - obs_pre[q];
-        if (smp) smp[i] = v;
-      }
-      if (full) full[i] = v;
-    }
+  for (int q = 0; q < OBS_PRE / 2; ++q) {
+    const int pr = tid + q * nthr;
+    if (pr < ha) emit(pr, obs_pre[2 * q], obs_pre[2 * q + 1]);
   }
-  for (int i = tid + OBS_PRE * nthr; i < nout; i += nthr) {
-    const double v = sample(i);
-    if (i < S) {
-      mis[i] = v - __ldg(obs + i);
-      if (smp) smp[i] = v;
-    }
-    if (full) full[i] = v;
+  for (int pr = tid + (OBS_PRE / 2) * nthr; pr < ha; pr += nthr) emit(pr, __ldg(obs + pr), __ldg(obs + S - 1 - pr));
+  if ((S & 1) && tid == 0) {                  // centre sample of an odd window: a coordinate of its own in both layouts
+    const double v = sample(ha);
+    mis[ha] = v - __ldg(obs + ha);
+    if (smp) smp[ha] = v;
+  }
+  if (split) {
+    for (int i = S - ha + tid; i < half; i += nthr) mis[i] = 0.0;
+    for (int i = half + ha + tid; i < Sp; i += nthr) mis[i] = 0.0;
+  } else {
+    for (int i = S + tid; i < Sp; i += nthr) mis[i] = 0.0;
+  }
+  if (out.rft_full) {
+    double* __restrict__ full = out.rft_full + ((size_t)c * cfg.ntrc + t) * n;
+    for (int i = tid; i < n; i += nthr) full[i] = sample(i);
   }
 }
 
@@ -1018,7 +1037,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       const double* __restrict__ obs_t = cfg.obs + (size_t)t * cfg.nsmp;
 #pragma unroll
       for (int q = 0; q < OBS_PRE; ++q) {   // observed samples of this thread's outputs: in flight during the FFT
-        const int i = tid + q * nthr;
+        const int i = obs_pre_index(cfg.nsmp, q, tid, nthr);
         obs_pre[q] = i < cfg.nsmp ? __ldg(obs_t + i) : 0.0;
       }
       // threads per CTA fix the transform length: 32 -> 64/128, 64 -> 256/512, 128 -> 1024, 256 -> 2048/4096

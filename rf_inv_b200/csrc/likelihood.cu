@@ -15,7 +15,7 @@ constexpr int TM = 64;    // chains per CTA
 constexpr int TN = 64;    // columns of R^-1 per tile
 constexpr int TK = 16;    // k-slab per pipeline stage
 constexpr int LDS_STRIDE = TK + 4;   // doubles; (row*20 + k) mod 16 distinct over an 8x4 fragment: conflict-free LDS.64
-constexpr int QF_THREADS = 128;      // 4 warps, each owns a 32 x 32 sub-tile
+constexpr int QF_THREADS = 128;      // 4 warps, each owns 32 rows x 4 interleaved 8-column fragments (columns 8 (2j + wn) ..)
 constexpr int QF_CHUNK = 384;        // (trace, row block) pairs per scheduling chunk: 384 x 64 rows x 4 KB = 100 MB of misfits at S = 512
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
   __shared__ int s_next, s_last;
   const int Sp = cfg.nsmp_pad, T = cfg.ntrc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile origin: rows wm*32, cols wn*32
+  const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile: rows wm*32 .., column fragments 2j + wn
   const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
   const int n_rb_grid = ((active ? n_active : C) + TM - 1) / TM;   // row blocks the item index space is built on
   const int ntile = cfg.qf_tiles_max;               // column tiles of the trace with the most work items
@@ -65,9 +65,9 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
     const int nblk = T * n_rb_grid;
     const int chunk = item / (ntile * QF_CHUNK), local = item - chunk * (ntile * QF_CHUNK);
     const int cb = min(QF_CHUNK, nblk - chunk * QF_CHUNK);   // blocks in this chunk (the last one may be short)
-    // dense form: the cost of a tile grows with jt, largest first; factor form: full tiles first, the partial last tile
-    // (rank % 64 columns) fills the tail of the launch
-    const int jt = cfg.qf_full_first ? local / cb : ntile - 1 - local / cb;
+    // most expensive column tiles first (dense form: the cost grows with jt; factor forms: full tiles before partial ones),
+    // so the cheap ones fill the tail of the launch
+    const int jt = cfg.qf_order[local / cb];
     const int blk = chunk * QF_CHUNK + local % cb;
     const int t = blk / n_rb_grid, rb = blk - t * n_rb_grid;
     const int row0 = rb * TM;
@@ -86,9 +86,21 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
       __syncthreads();
       const double* __restrict__ Mt = misfit + (size_t)t * C * Sp;
       const double* __restrict__ Rt = rank > 0 ? cfg.w_fac + (size_t)t * cfg.qf_wrows * Sp : cfg.r_inv + (size_t)t * Sp * Sp;
-      // 8-column fragments of this warp that hold columns of W (all 4 in the dense form)
-      int jw = 4;
-      if (rank > 0) { const int cols = rank - jt * TN - wn * 32; jw = cols <= 0 ? 0 : (cols >= 32 ? 4 : (cols + 7) >> 3); }
+      // 8-column fragments of this warp that hold columns of W (all 4 in the dense form); k range of the item: the whole
+      // misfit row, or in the split form the half that holds s (tiles of the symmetric block) or a (antisymmetric block)
+      int jw = 4, koff = 0, nk = (jt + 1) * (TN / TK);   // dense: k-slabs up to and including the diagonal tile
+      if (rank > 0) {
+        int cols_tile = rank - jt * TN;
+        nk = Sp / TK;
+        if (cfg.qf_split[t]) {
+          const int rs = cfg.qf_rank_s[t], ts = (rs + TN - 1) / TN;
+          cols_tile = jt < ts ? rs - jt * TN : (rank - rs) - (jt - ts) * TN;
+          koff = jt < ts ? 0 : Sp >> 1;
+          nk = (Sp >> 1) / TK;
+        }
+        const int nfrag = cols_tile >= TN ? 8 : (cols_tile <= 0 ? 0 : (cols_tile + 7) >> 3);   // 8-column fragments in use
+        jw = (nfrag + 1 - wn) >> 1;               // fragments 2j + wn of this warp: a partial tile loads both warp columns evenly
+      }
       // global -> smem copy assignment: 64 rows x 16 doubles = 512 x 16 B per operand, 4 per thread each
       const double* a_src[4];
       int cp_off[4], cp_row[4];
@@ -98,15 +110,14 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
         const int row = id >> 3, seg = id & 7;      // 8 segments of 2 doubles per row
         cp_row[q] = row;
         cp_off[q] = row * LDS_STRIDE + seg * 2;
-        a_src[q] = Mt + (size_t)s_rows[row] * Sp + seg * 2;
+        a_src[q] = Mt + (size_t)s_rows[row] * Sp + seg * 2 + koff;
       }
       double acc[4][4][2];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-      const int nk = rank > 0 ? Sp / TK : (jt + 1) * (TN / TK);   // dense: k-slabs up to and including the diagonal tile
-      const double* b_base = Rt + (size_t)(jt * TN) * Sp;
+      const double* b_base = Rt + (size_t)(jt * TN) * Sp + koff;
       // prologue: stage 0
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -136,14 +147,14 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
             for (int j = 0; j < 4; ++j) { acc[i][j][0] *= 2.0; acc[i][j][1] *= 2.0; }
         }
         const double* A = &sA[cur][(wm * 32 + fr) * LDS_STRIDE + fk];
-        const double* B = &sB[cur][(wn * 32 + fr) * LDS_STRIDE + fk];
+        const double* B = &sB[cur][(wn * 8 + fr) * LDS_STRIDE + fk];   // fragment j of this warp = columns 8 (2j + wn) .. + 7
 #pragma unroll
         for (int kk = 0; kk < TK; kk += 4) {
           double a[4], b[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) a[i] = A[i * 8 * LDS_STRIDE + kk];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDS_STRIDE + kk];
+          for (int j = 0; j < 4; ++j) b[j] = B[j * 16 * LDS_STRIDE + kk];
 #pragma unroll
           if (jw == 4) {                            // the hot path stays one straight run of 16 DMMA
 #pragma unroll
@@ -164,7 +175,7 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
       // row-dot with M[:, jt]: lane holds Y[row = 8i + fr][col = 8j + 2*fk + {0,1}] of its warp sub-tile
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 32 + 2 * fk;
+        const double* mrow = Mt + (size_t)s_rows[wm * 32 + 8 * i + fr] * Sp + jt * TN + wn * 8 + 2 * fk;
         double v = 0.0;
         if (rank > 0) {                             // |W^T m|^2: columns beyond the rank hold exact zeros
 #pragma unroll
@@ -172,7 +183,7 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const double2 m = *reinterpret_cast<const double2*>(mrow + 8 * j);
+            const double2 m = *reinterpret_cast<const double2*>(mrow + 16 * j);
             v = fma(acc[i][j][0], m.x, v);
             v = fma(acc[i][j][1], m.y, v);
           }
@@ -223,7 +234,8 @@ __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restri
 
 }  // namespace
 
-size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C) { return (size_t)(cfg.nsmp_pad / TN) * cfg.ntrc * C; }
+// column tiles per (64 chains, trace): nsmp_pad/64 dense, up to 2 ceil(nsmp_pad/128) in the split form
+size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C) { return (size_t)(cfg.nsmp_pad / TN + 1) * cfg.ntrc * C; }
 size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C) { return (size_t)((C + TM - 1) / TM) * cfg.ntrc + 4; }
 
 // partial: rfinv_quadform_partial_doubles(cfg, C) doubles; counters: rfinv_quadform_counter_ints(cfg, capacity) ints, zeroed

@@ -8,6 +8,7 @@
 #define RFINV_MAX_TRC 16     // traces per model (kernel parameter arrays)
 #define RFINV_MAX_K 64       // k_max upper bound: fixed per-chain layer storage
 #define RFINV_MAX_LAY (RFINV_MAX_K + 2)
+#define RFINV_MAX_QF_TILES 64   // nsmp_pad / 64 with nsmp <= nfft <= 4096
 
 #define RFINV_PI 3.1415926535897931  // src/forward.f90:33
 
@@ -33,9 +34,13 @@ struct DevConfig {
   // factor R^-1 = W W^T of the traces whose R^-1 is positive semi-definite of low rank (0 = use the dense form):
   const double* w_fac;          // [ntrc][qf_wrows][nsmp_pad]: row e = sqrt(lambda_e) * eigenvector e, zero padded
   int qf_rank[RFINV_MAX_TRC];   // kept eigenpairs per trace, 0 = dense
-  int qf_tiles[RFINV_MAX_TRC];  // 64-column work items per (64 chains, trace): ceil(rank/64), or nsmp_pad/64 when dense
+  int qf_split[RFINV_MAX_TRC];  // 1: split form -- the misfit row holds (s | a) = (m_i + m_{S-1-i} | m_i - m_{S-1-i}) in its two
+                                // halves [0, nsmp_pad/2) and [nsmp_pad/2, nsmp_pad); factor rows 0.. act on s, rows 64*ceil(rank_s/64).. on a
+  int qf_rank_s[RFINV_MAX_TRC]; // split form: eigenpairs of the symmetric block (the antisymmetric block has qf_rank - qf_rank_s)
+  int qf_tiles[RFINV_MAX_TRC];  // 64-column work items per (64 chains, trace): nsmp_pad/64 when dense, ceil(rank/64), or
+                                // ceil(rank_s/64) + ceil(rank_a/64) in the split form
   int qf_tiles_max, qf_wrows;
-  int qf_full_first;            // every trace uses the factor form: hand out tiles in ascending order (the partial last tile last)
+  int qf_order[RFINV_MAX_QF_TILES];   // hand-out order of the column tiles inside a scheduling chunk (most expensive first)
 };
 
 // Chain-fastest (structure-of-arrays) model batch in HBM.
