@@ -322,6 +322,14 @@ def main():
         capi.check(lib.rfinv_measure_fp64_peak(local_rank, C.byref(dfma), C.byref(dmma)))
         peak = max(dfma.value, dmma.value)
         fl = workloads.flops_per_eval(cfg, k_mean)
+        # the quadratic form as the library evaluates it (chosen at rfinv_create): S^2 + 3S dense, 2 S r + 2 r factor form,
+        # S r + S + 2 r split form (sums / differences of mirrored samples against the two half-length factors)
+        form = ev.quadform_form()
+        S = cfg.nsmp
+        fl["quadform_dense_form"] = fl["quadform"]
+        fl["quadform"] = float(sum((S * r + S + 2 * r) if sp else ((2 * S * r + 2 * r) if r > 0 else (S * S + 3 * S)) for r, rs, sp in form))
+        fl["quadform_form"] = [{"rank": r, "rank_sym": rs, "split": bool(sp)} for r, rs, sp in form]
+        fl["total"] = fl["propagator"] + fl["fft"] + fl["quadform"]
         km = np.mean(np.array(kern_ms), axis=0)
         fwd_flop = (fl["propagator"] + fl["fft"]) * chains
         achieved = fwd_flop / (km[0] * 1e-3) * 1e-12

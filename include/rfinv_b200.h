@@ -148,6 +148,10 @@ int32_t rfinv_set_timing(rfinv_handle* h, int32_t enable);
 /* Device time (ms) of the kernels of the last evaluation: ms[0] forward, ms[1] quadratic form, ms[2] logL.
  * Synchronises the stream.  Requires rfinv_set_timing(h, 1).                                      */
 int32_t rfinv_get_timing(rfinv_handle* h, double* ms);
+/* Form of the quadratic form chosen at rfinv_create, per trace (arrays of ntrc): rank[t] = 0: dense m^T R^-1 m; > 0: factor
+ * form |W^T m|^2 with that many columns; split[t] = 1: the factor acts on sums / differences of mirrored samples (R^-1
+ * commutes with the exchange matrix), rank_s[t] columns on the sums and rank[t] - rank_s[t] on the differences.     */
+int32_t rfinv_get_quadform_form(rfinv_handle* h, int32_t* rank, int32_t* rank_s, int32_t* split);
 /* FP64 roofline denominators measured on `device` right now: dense DFMA and DMMA (mma.sync m8n8k4)
  * loops on all SMs, best of a few repetitions; TFLOP/s.                                           */
 int32_t rfinv_measure_fp64_peak(int32_t device, double* dfma_tflops, double* dmma_tflops);

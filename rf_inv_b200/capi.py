@@ -40,6 +40,7 @@ SIGNATURES = {
     "rfinv_last_launch_count": (C.c_int32, [C.c_void_p]),
     "rfinv_set_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_get_timing": (C.c_int32, [C.c_void_p, dp]),
+    "rfinv_get_quadform_form": (C.c_int32, [C.c_void_p, i32p, i32p, i32p]),
     "rfinv_measure_fp64_peak": (C.c_int32, [C.c_int32, dp, dp]),
     "rfinv_pt_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]),
     "rfinv_pt_draw": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, dp]),

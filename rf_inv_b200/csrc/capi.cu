@@ -592,6 +592,12 @@ int32_t rfinv_set_timing(rfinv_handle* h, int32_t enable) {
   return RFINV_OK;
 }
 
+int32_t rfinv_get_quadform_form(rfinv_handle* h, int32_t* rank, int32_t* rank_s, int32_t* split) {
+  if (!h || !rank || !rank_s || !split) { rfinv_set_error("rfinv_get_quadform_form: NULL argument"); return RFINV_ERR_ARG; }
+  for (int t = 0; t < h->dc.ntrc; ++t) { rank[t] = h->dc.qf_rank[t]; rank_s[t] = h->dc.qf_rank_s[t]; split[t] = h->dc.qf_split[t]; }
+  return RFINV_OK;
+}
+
 int32_t rfinv_get_timing(rfinv_handle* h, double* ms) {
   if (!h || !ms) { rfinv_set_error("NULL argument"); return RFINV_ERR_ARG; }
   if (!h->timing) { rfinv_set_error("rfinv_get_timing: call rfinv_set_timing(h, 1) first"); return RFINV_ERR_STATE; }

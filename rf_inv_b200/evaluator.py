@@ -60,6 +60,13 @@ class Evaluator:
     def synchronize(self) -> None:
         capi.check(self._lib.rfinv_synchronize(self.handle))
 
+    def quadform_form(self):
+        """Per trace: (rank, rank_s, split) of the quadratic form chosen at create (rank 0 = dense m^T R^-1 m)."""
+        T = self.cfg.ntrc
+        r, rs, sp = (C.c_int32 * T)(), (C.c_int32 * T)(), (C.c_int32 * T)()
+        capi.check(self._lib.rfinv_get_quadform_form(self.handle, r, rs, sp))
+        return [(int(r[t]), int(rs[t]), int(sp[t])) for t in range(T)]
+
     @property
     def last_launch_count(self) -> int:
         return int(self._lib.rfinv_last_launch_count(self.handle))
