@@ -55,6 +55,9 @@ def main():
         "land_P": dict(), "sea_P": dict(sdep=2.0), "land_S": dict(ipha=[-1, -1], rayps=[0.10, 0.12]),
         "sea_S_deconv": dict(sdep=1.0, ipha=[-1, -1], deconv_mode=1), "P_deconv": dict(deconv_mode=1),
         "common": dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), "vp1_tstart": dict(vp_mode=1, t_start=-3.0),
+        # buried station (commented out in the reference: no reference output can exist)
+        "buried_sea_P": dict(bdep=1.5, sdep=2.0), "buried_land_S": dict(bdep=6.0, ipha=[-1, -1], rayps=[0.10, 0.12]),
+        "buried_half_space": dict(bdep=25.0),
     }
     for name, kw in cases.items():
         cfg = helpers.attach_obs_and_rinv(helpers.small_config(**kw))

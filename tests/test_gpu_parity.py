@@ -80,9 +80,13 @@ def test_golden_traces_from_reference_fixture():
     assert abs(ll[0] - (-2 * 101 * np.log(0.01))) < 1e-3 * abs(2 * 101 * np.log(0.01))
 
 
-@pytest.mark.parametrize("name", ["land_P", "sea_P", "land_S", "sea_S_deconv", "P_deconv", "common", "vp1_tstart"])
+GOLDEN_KW = dict(VARIANTS, buried_sea_P=dict(bdep=1.5, sdep=2.0), buried_land_S=dict(bdep=6.0, ipha=[-1, -1], rayps=[0.10, 0.12]))
+
+
+@pytest.mark.parametrize("name", ["land_P", "sea_P", "land_S", "sea_S_deconv", "P_deconv", "common", "vp1_tstart", "buried_sea_P",
+                                  "buried_land_S", "buried_half_space"])
 def test_committed_numpy_oracle_vectors(name):
-    cfg = helpers.small_config(**VARIANTS[name])
+    cfg = helpers.small_config(**GOLDEN_KW[name])
     cfg.obs = V[name + "/obs"]
     cfg.r_inv = helpers.scipy_r_inv(cfg)
     m = {k: V[f"{name}/{k}"] for k in ("k", "z", "dvp", "dvs", "sig")}
@@ -287,3 +291,43 @@ def test_buried_station_at_vanishing_depth_reproduces_the_surface_station_on_the
         with Evaluator(bur) as ev:
             _, rft_bur, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
         assert helpers.rel_err_rft(rft_bur, rft_top) < 1e-8
+
+
+def test_split_quadratic_form_matches_the_plain_factor_form(tmp_path):
+    """R^-1 of the reference commutes with the exchange matrix, so quadform_kernel contracts sums / differences of mirrored
+    samples against two half-length factors; RFINV_QF_NOSPLIT=1 keeps the factor over the whole
+    window.  Even and odd window lengths, LAPACK-route R^-1: the two must agree far inside the 1e-9 bar."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = r'''
+import sys, numpy as np
+sys.path[:0] = [%r, %r, %r]
+import helpers
+from rf_inv_b200 import workloads
+from rf_inv_b200.evaluator import Evaluator
+out = {}
+for name, kw in (("even", dict()), ("odd", dict(nsmp=501))):
+    cfg = workloads.make_config("target")
+    for k, v in kw.items(): setattr(cfg, k, v)
+    cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
+    cfg.r_inv = workloads.lapack_r_inv(cfg)
+    m = workloads.draw_models(cfg, 200, seed=8, dvs_scale=0.3)
+    with Evaluator(cfg) as ev:
+        ll, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+        out[name + "_form"] = np.array(ev.quadform_form())
+    out[name] = ll; out[name + "_sig"] = m["sig"]
+np.savez(sys.argv[1], **out)
+''' % (root, os.path.join(root, "tests"), os.path.join(root, "oracle"))
+    res = {}
+    for tag, val in (("split", "0"), ("plain", "1")):
+        path = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", script, path], check=True, env=dict(os.environ, RFINV_QF_NOSPLIT=val))
+        res[tag] = np.load(path)
+    for name, S in (("even", 512), ("odd", 501)):
+        cfg = workloads.make_config("target"); cfg.nsmp = S
+        assert res["split"][name + "_form"][:, 2].all() and not res["plain"][name + "_form"][:, 2].any()
+        assert (res["split"][name + "_form"][:, 0] == res["plain"][name + "_form"][:, 0]).all()      # same total rank
+        err = helpers.logl_err(cfg, res["split"][name], res["plain"][name], res["plain"][name + "_sig"])
+        assert err < 1e-11, (name, err)
+        assert not np.array_equal(res["split"][name], res["plain"][name])   # two different summations

@@ -87,10 +87,13 @@ def test_deviates_c_vs_numpy_oracle(kind):
     assert abs(np.mean(a)) < 0.2 and 0.7 < np.std(a) < (1.7 if kind == "laplace" else 1.2)
 
 
-CASES = ["land_P", "sea_P", "land_S", "sea_S_deconv", "P_deconv", "common", "vp1_tstart"]
+CASES = ["land_P", "sea_P", "land_S", "sea_S_deconv", "P_deconv", "common", "vp1_tstart", "buried_sea_P", "buried_land_S",
+         "buried_half_space"]
 KW = {"land_P": dict(), "sea_P": dict(sdep=2.0), "land_S": dict(ipha=[-1, -1], rayps=[0.10, 0.12]),
       "sea_S_deconv": dict(sdep=1.0, ipha=[-1, -1], deconv_mode=1), "P_deconv": dict(deconv_mode=1),
-      "common": dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), "vp1_tstart": dict(vp_mode=1, t_start=-3.0)}
+      "common": dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), "vp1_tstart": dict(vp_mode=1, t_start=-3.0),
+      "buried_sea_P": dict(bdep=1.5, sdep=2.0), "buried_land_S": dict(bdep=6.0, ipha=[-1, -1], rayps=[0.10, 0.12]),
+      "buried_half_space": dict(bdep=25.0)}
 
 
 def case_cfg(name):
