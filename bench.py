@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- forward+likelihood evaluations per second on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c3|c4|c5|sample] [--chains C]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload target|c2|c3|c3_buried|c4|c5|sample] [--chains C]
     python bench.py --impl reference ...      # the CPU restatement of the reference algorithm on the host cores
 
 A step = one pass of the hot path (format_model -> propagator -> filter/FFT -> misfit -> correlated-noise
@@ -28,7 +28,7 @@ from rf_inv_b200 import workloads  # noqa: E402
 
 METRIC = "forward+likelihood evals/sec"
 UNIT = "evals/s"
-DEFAULT_CHAINS = {"target": 16384, "c2": 4096, "c3": 8192, "c4": 8192, "c5": 4096, "sample": 4096}
+DEFAULT_CHAINS = {"target": 16384, "c2": 4096, "c3": 8192, "c3_buried": 8192, "c4": 8192, "c5": 4096, "sample": 4096}
 
 
 def parse():

@@ -11,7 +11,7 @@ from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 
 out = {"tolerance": 1e-9, "configs": {}}
-for name, n in [("sample", 1024), ("c2", 1024), ("c3", 1024), ("c4", 1024), ("c4_laplace", 1024), ("c5", 1024), ("target", 1024)]:
+for name, n in [("sample", 1024), ("c2", 1024), ("c3", 1024), ("c3_buried", 1024), ("c4", 1024), ("c4_laplace", 1024), ("c5", 1024), ("target", 1024)]:
     cfg = helpers.attach_obs_and_rinv(workloads.make_config(name), noise=0.01)
     m = workloads.draw_models(cfg, n, seed=2024, dvs_scale=0.5)
     t0 = time.time()
@@ -35,4 +35,15 @@ out["pt_fixed_seed_C1"] = {"iterations": n_iter, "chains": nproc * cfg.nchains,
                            "nprop_oracle": ocnt["nprop"].tolist(), "naccept_oracle": ocnt["naccept"].tolist(),
                            "logl_max_rel_err": helpers.logl_err(cfg, st["logl"], ost["logl"], ost["sig"]),
                            "first_divergence_iteration": int(np.argmax((fl != ofl).any(axis=1))) if (fl != ofl).any() else None}
+# the same identity with a buried station (sample configuration, receiver 0.5 km below the sea floor)
+cfg = workloads.make_config("sample"); cfg.bdep = 0.5
+cfg = helpers.attach_obs_and_rinv(cfg, noise=0.01)
+n_iter = 200
+pt = ParallelTempering(cfg, nproc); pt.set_logging(n_iter); pt.run(n_iter)
+fl, ty, sw = pt.log(n_iter); st = pt.state(); pt.close()
+orc = oracle_c.OraclePT(cfg, nproc); ofl, oty, osw = orc.run(n_iter); ost = orc.state()
+out["pt_fixed_seed_C1_buried"] = {"iterations": n_iter, "chains": nproc * cfg.nchains, "bdep": cfg.bdep,
+                                  "accept_flags_identical": bool(np.array_equal(fl, ofl)),
+                                  "proposal_types_identical": bool(np.array_equal(ty, oty)), "swaps_identical": bool(np.array_equal(sw, osw)),
+                                  "logl_max_rel_err": helpers.logl_err(cfg, st["logl"], ost["logl"], ost["sig"])}
 print(json.dumps(out, indent=1))
