@@ -184,7 +184,7 @@ def test_device_resident_entry_and_determinism():
     assert valid.cpu().numpy().all()
 
 
-@pytest.mark.parametrize("workload,n_models", [("c2", 4096), ("target", 2048), ("c5", 512)])
+@pytest.mark.parametrize("workload,n_models", [("c2", 4096), ("target", 2048), ("c3_buried", 1024), ("c5", 512)])
 def test_full_size_properties(workload, n_models):
     """BASELINE.json sizes: the oracle checks a seeded subsample; size-independent properties cover the rest:
     permutation equivariance, sigma scaling of logL (phi is sigma independent), time-shift property of t_start."""
