@@ -243,12 +243,16 @@ int check_config(const rfinv_config* c) {
   return RFINV_OK;
 }
 
-// chain-major host layout -> chain-fastest device layout: out[i*C + c] = in[c*len + i]
-__global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int C, int len) {
+// chain-major host layout -> chain-fastest device layout for the n models from c0 on: out[i*C + c0 + c] = in[c*len + i]
+__global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int C, int c0, int n, int len) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)C * len) return;
-  const int c = (int)(idx % C), i = (int)(idx / C);
-  out[idx] = in[(size_t)c * len + i];
+  if (idx >= (long long)n * len) return;
+  const int c = (int)(idx % n), i = (int)(idx / n);
+  out[(size_t)i * C + c0 + c] = in[(size_t)c * len + i];
+}
+__global__ void iota_kernel(int* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = i;
 }
 
 }  // namespace
@@ -266,6 +270,9 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_iota, sizeof(int) * Cz));
+  iota_kernel<<<(unsigned)((Cz + 255) / 256), 256, 0, stream>>>(d_iota, C);
+  RFINV_CUDA_CHECK(cudaGetLastError());
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_misfit, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMemset(d_misfit, 0, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_phi, sizeof(double) * Cz * T));
@@ -280,7 +287,8 @@ int rfinv_handle::ensure_capacity(int C) {
 }
 
 void rfinv_handle::free_workspace() {
-  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage);
+  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage); cudaFree(d_iota);
+  d_iota = nullptr;
   cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch); cudaFree(d_qpart); cudaFree(d_qcnt);
   d_qpart = nullptr; d_qcnt = nullptr;
   d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = d_scratch = nullptr;
@@ -562,6 +570,11 @@ void rfinv_destroy(rfinv_handle* h) {
   h->free_pt();
   cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  if (h->stream_copy) {
+    cudaStreamSynchronize(h->stream_copy);
+    cudaStreamDestroy(h->stream_copy);
+    for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_copy[i]);
+  }
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -616,19 +629,20 @@ int32_t rfinv_get_r_inv(rfinv_handle* h, double* r_inv) {
   return RFINV_OK;
 }
 
+// models [c0, c0 + n) of a batch of C: host (chain-major) -> device (chain-fastest), asynchronous on stream s
 static int upload_models(rfinv_handle* h, int C, const int32_t* k, const double* z, const double* dvp, const double* dvs,
-                         const double* sig) {
+                         const double* sig, cudaStream_t s, int c0 = 0, int n = -1) {
   const int km = h->cfg.k_max, T = h->cfg.ntrc;
-  cudaStream_t s = h->stream;
-  RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k, k, sizeof(int) * (size_t)C, cudaMemcpyHostToDevice, s));
+  if (n < 0) n = C;
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k + c0, k + c0, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s));
   struct Item { const double* src; double* dst; int len; } items[4] = {
       {z, h->d_z, km - 1}, {dvp, h->d_dvp, km}, {dvs, h->d_dvs, km}, {sig, h->d_sig, T}};
   for (const Item& it : items) {
     // vp_mode = 0: format_model never looks at dVp (src/model.f90:214-218, 271-275) -- a third of the upload
     if (it.src == dvp && h->cfg.vp_mode == 0) continue;
-    const size_t nel = (size_t)C * it.len;
-    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, it.src, sizeof(double) * nel, cudaMemcpyHostToDevice, s));
-    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(h->d_stage, it.dst, C, it.len);
+    const size_t nel = (size_t)n * it.len;
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, it.src + (size_t)c0 * it.len, sizeof(double) * nel, cudaMemcpyHostToDevice, s));
+    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, s>>>(h->d_stage, it.dst, C, c0, n, it.len);
     RFINV_CUDA_CHECK(cudaGetLastError());
   }
   return RFINV_OK;
@@ -658,11 +672,41 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
       h->cap_rft_full = need;
     }
   }
-  if ((st = upload_models(h, C, k, z, dvp, dvs, sig)) != RFINV_OK) return st;
-  st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
-                      is_valid ? h->d_valid : nullptr, nullptr, 0);
-  if (st != RFINV_OK) return st;
-  h->launches += h->cfg.vp_mode == 0 ? 3 : 4;  // the layout kernels of upload_models
+  // Large batches: the upload runs on a second stream in two pieces, a small head (1/8 of the models) and the rest, and
+  // the evaluation of the head hides the transfer of the rest (RFINV_UPLOAD_OVERLAP=0: one piece on the handle's stream).
+  static const bool overlap_ok = !(getenv("RFINV_UPLOAD_OVERLAP") && atoi(getenv("RFINV_UPLOAD_OVERLAP")) == 0);
+  const int n_layout = h->cfg.vp_mode == 0 ? 3 : 4;   // layout kernels per upload_models call
+  if (overlap_ok && C >= 8192) {
+    if (!h->stream_copy) {
+      RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
+      for (int i = 0; i < 3; ++i) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+    }
+    static const int head_16ths = getenv("RFINV_UPLOAD_HEAD_16THS") ? std::max(1, std::min(15, atoi(getenv("RFINV_UPLOAD_HEAD_16THS")))) : 2;
+    const int head = (int)((((long long)C * head_16ths / 16 + 63) / 64) * 64);
+    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[0], h->stream));                 // earlier work on the handle's stream reads these buffers
+    RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream_copy, h->ev_copy[0], 0));
+    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream_copy, 0, head)) != RFINV_OK) return st;
+    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[1], h->stream_copy));
+    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream_copy, head, C - head)) != RFINV_OK) return st;
+    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[2], h->stream_copy));
+    int launched = 0;
+    for (int piece = 0; piece < 2; ++piece) {
+      RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[1 + piece], 0));
+      const int c0 = piece ? head : 0, n = piece ? C - head : head;
+      st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, nullptr, nullptr, rft ? h->d_rft_full : nullptr,
+                          is_valid ? h->d_valid : nullptr, h->d_iota + c0, n);
+      if (st != RFINV_OK) return st;
+      launched += h->launches;
+    }
+    if ((st = rfinv_launch_loglik(h->dc, C, h->d_phi, h->d_sig, h->d_logl, h->stream)) != RFINV_OK) return st;
+    h->launches = launched + 1 + 2 * n_layout;
+  } else {
+    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream)) != RFINV_OK) return st;
+    st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
+                        is_valid ? h->d_valid : nullptr, nullptr, 0);
+    if (st != RFINV_OK) return st;
+    h->launches += n_layout;  // the layout kernels of upload_models
+  }
   RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   if (rft)
     RFINV_CUDA_CHECK(cudaMemcpyAsync(rft, h->d_rft_full, sizeof(double) * (size_t)C * h->cfg.ntrc * h->cfg.nfft,
@@ -734,7 +778,7 @@ int32_t rfinv_format_model_batch(rfinv_handle* h, int32_t C, const int32_t* k, c
   int st = h->ensure_capacity(C);
   if (st != RFINV_OK) return st;
   std::vector<double> sig((size_t)C * h->cfg.ntrc, 1.0);
-  if ((st = upload_models(h, C, k, z, dvp, dvs, sig.data())) != RFINV_OK) return st;
+  if ((st = upload_models(h, C, k, z, dvp, dvs, sig.data(), h->stream)) != RFINV_OK) return st;
   const int stride = h->cfg.k_max + 1;
   int* d_nlay = nullptr;
   double* d_out = nullptr;

@@ -29,6 +29,9 @@ struct rfinv_handle {
   uint8_t* d_valid = nullptr;
   double* d_qpart = nullptr;    // quadform_kernel partial sums
   int* d_qcnt = nullptr;        // quadform_kernel work / arrival counters
+  int* d_iota = nullptr;        // 0, 1, 2, ...: `active` list of a contiguous piece of the batch (rfinv_eval_batch)
+  cudaStream_t stream_copy = nullptr;   // rfinv_eval_batch: upload of the tail of a large batch while its head is evaluated
+  cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
   size_t cap_rft_full = 0;
   int launches = 0;
   bool timing = false;

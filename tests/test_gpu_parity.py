@@ -331,3 +331,34 @@ np.savez(sys.argv[1], **out)
         err = helpers.logl_err(cfg, res["split"][name], res["plain"][name], res["plain"][name + "_sig"])
         assert err < 1e-11, (name, err)
         assert not np.array_equal(res["split"][name], res["plain"][name])   # two different summations
+
+
+def test_large_host_batch_with_overlapped_upload_equals_the_device_resident_entry():
+    """rfinv_eval_batch uploads batches of >= 8192 models in two pieces on a second stream and evaluates the head while
+    the tail is in flight (contiguous `active` lists).  Same kernels, same arithmetic: logL, validity flags and traces
+    must equal the single-piece device-resident evaluation to the last bit; ragged size, invalid models included."""
+    import torch
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(sdep=2.0), noise=0.01)
+    n = 8192 + 77
+    m = workloads.draw_models(cfg, n, seed=17, dvs_scale=0.3)
+    m["z"][5000:5040] *= 0.05                       # some invalid models in the tail piece
+    soa = workloads.to_soa(m)
+    dev = torch.device("cuda:0")
+    d = {k: torch.from_numpy(v).to(dev) for k, v in soa.items()}
+    logl = torch.empty(n, dtype=torch.float64, device=dev)
+    valid = torch.empty(n, dtype=torch.uint8, device=dev)
+    with Evaluator(cfg) as ev:
+        ll_h, rft_h, val_h = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True, want_valid=True)
+        n_launch = ev.last_launch_count
+        ev.set_stream(torch.cuda.current_stream().cuda_stream)
+        ev.calc_likelihood_device(n, d["k"].data_ptr(), d["z"].data_ptr(), d["dvp"].data_ptr(), d["dvs"].data_ptr(),
+                                  d["sig"].data_ptr(), logl.data_ptr(), 0, valid.data_ptr())
+        torch.cuda.synchronize()
+        ll_h2, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])      # again, other stream, warm buffers
+    assert n_launch == 2 * 3 + 1 + 2 * 3            # two pieces: (prep, forward, quadform) each, logL, 2 x 3 layout kernels
+    assert np.array_equal(ll_h, logl.cpu().numpy(), equal_nan=True) and np.array_equal(ll_h, ll_h2, equal_nan=True)
+    assert np.array_equal(val_h, valid.cpu().numpy().astype(bool)) and not val_h[5000:5040].all()
+    sub = np.arange(0, n, 97)
+    _, rft_o, _ = oracle_c.eval_batch(cfg, m["k"][sub], m["z"][sub], m["dvp"][sub], m["dvs"][sub], m["sig"][sub])
+    ok = val_h[sub]
+    assert helpers.rel_err_rft(rft_h[sub][ok], rft_o[ok]) < RTOL
