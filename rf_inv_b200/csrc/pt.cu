@@ -346,28 +346,36 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
 }
 
 // ordered compaction of the chains that need a forward evaluation (single CTA, deterministic)
-__global__ void pt_compact_kernel(const PtDev p) {
-  __shared__ int s_cnt[1024];
+__global__ void __launch_bounds__(1024) pt_compact_kernel(const PtDev p) {
+  // ordered list of the chains whose proposal needs a forward evaluation: one CTA, per round 1024 chains -- warp
+  // ballots, then a scan of the 32 warp counts by the first warp (two barriers per round)
+  __shared__ int s_warp[32];
   __shared__ int s_base;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_base = 0;
   __syncthreads();
   for (int start = 0; start < p.Cl; start += nthr) {
     const int c = start + tid;
-    const int f = (c < p.Cl && p.pflag[c] == 1) ? 1 : 0;
-    s_cnt[tid] = f;
+    const bool f = c < p.Cl && p.pflag[c] == 1;
+    const unsigned b = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) s_warp[warp] = __popc(b);
     __syncthreads();
-    for (int o = 1; o < nthr; o <<= 1) {  // inclusive scan
-      const int v = tid >= o ? s_cnt[tid - o] : 0;
-      __syncthreads();
-      s_cnt[tid] += v;
-      __syncthreads();
+    const int base = s_base;
+    if (warp == 0) {
+      int v = lane < (nthr >> 5) ? s_warp[lane] : 0;
+      for (int o = 1; o < 32; o <<= 1) {   // inclusive scan of the warp counts
+        const int u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+      }
+      s_warp[lane] = v;
     }
-    if (f) p.active[s_base + s_cnt[tid] - 1] = c;
     __syncthreads();
-    if (tid == nthr - 1) s_base += s_cnt[tid];
+    if (f) p.active[base + (warp ? s_warp[warp - 1] : 0) + __popc(b & ((1u << lane) - 1u))] = c;
+    const int total = s_warp[(nthr >> 5) - 1];
     __syncthreads();
+    if (tid == 0) s_base = base + total;
   }
+  __syncthreads();
   if (tid == 0) { *p.n_active = s_base; *p.n_eval += (unsigned long long)s_base; }
 }
 
