@@ -362,3 +362,31 @@ def test_large_host_batch_with_overlapped_upload_equals_the_device_resident_entr
     _, rft_o, _ = oracle_c.eval_batch(cfg, m["k"][sub], m["z"][sub], m["dvp"][sub], m["dvs"][sub], m["sig"][sub])
     ok = val_h[sub]
     assert helpers.rel_err_rft(rft_h[sub][ok], rft_o[ok]) < RTOL
+
+
+@pytest.mark.parametrize("kind,expect", [("low_rank", "factor"), ("full_rank", "dense"), ("toeplitz", "split")])
+def test_quadratic_form_picks_a_form_that_fits_the_matrix_it_is_given(kind, expect):
+    """The caller may pass any R^-1 (src/likelihood.f90 only ever builds the Toeplitz one).  A positive semi-definite matrix
+    without the mirror symmetry gets the plain factor form when its rank is low and the dense form otherwise; the split
+    form is only taken when R^-1 commutes with the exchange matrix.  All three against the oracle's dense m^T R^-1 m."""
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(nfft=512, nsmp=200), noise=0.01)
+    rng = np.random.default_rng(4)
+    S = cfg.nsmp
+    if kind != "toeplitz":
+        r = 40 if kind == "low_rank" else S
+        mats = []
+        for t in range(cfg.ntrc):
+            a = rng.normal(size=(S, r)) / np.sqrt(S)
+            mats.append(a @ a.T * 50.0)
+        cfg.r_inv = np.stack(mats)
+    m = workloads.draw_models(cfg, 128, seed=9, dvs_scale=0.3)
+    ll_o, _, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    with Evaluator(cfg) as ev:
+        form = ev.quadform_form()
+        ll_g, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    for rank, rank_s, split in form:
+        got = "split" if split else ("factor" if rank > 0 else "dense")
+        assert got == expect, form
+    if kind == "low_rank":
+        assert all(rank == 40 for rank, _, _ in form)
+    assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < RTOL
