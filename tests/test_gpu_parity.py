@@ -390,3 +390,20 @@ def test_quadratic_form_picks_a_form_that_fits_the_matrix_it_is_given(kind, expe
     if kind == "low_rank":
         assert all(rank == 40 for rank, _, _ in form)
     assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < RTOL
+
+
+def test_forward_test_geometry_of_the_reference_with_borehole_depth():
+    """src/forward_test.f90's model (20 km layer alpha 5 / beta 2.5 over a half space alpha 8 / beta 4, p = 0.06, S phase,
+    a = 8, t_start = -3, nfft = 1024, borehole depth 3 km) through the model interface (densities from vp_to_rho: the
+    boundary has no density input), surface and buried station, against the oracle."""
+    from test_oracle_golden import forward_test_config
+    for bdep in (0.0, 3.0):
+        cfg = forward_test_config(bdep)
+        km = cfg.k_max
+        m = dict(k=np.array([1], dtype=np.int32), z=np.zeros((1, km - 1)), dvp=np.zeros((1, km)), dvs=np.zeros((1, km)),
+                 sig=np.full((1, 1), 0.01))
+        m["z"][0, 0] = 20.0
+        m["dvp"][0, km - 1] = 3.0; m["dvs"][0, km - 1] = 1.5
+        (ll_g, rft_g, val_g), (ll_o, rft_o, val_o) = gpu_vs_oracle(cfg, m)
+        assert val_g[0] and val_o[0]
+        assert helpers.rel_err_rft(rft_g, rft_o) < RTOL

@@ -235,3 +235,31 @@ def test_buried_station_restatement_equals_the_commented_block_where_that_block_
     cfg.bdep = 6.0                                   # second layer: the literal loop runs on through the third
     a = _py_rft(cfg, m, 0); b = _py_rft(cfg, m, 0, bdep_literal=True)
     assert helpers.rel_err_rft(b[None], a[None]) > 1e-3
+
+
+def forward_test_config(bdep):
+    """src/forward_test.f90:36-58: one S receiver function, a = 8, delta = 0.05, t_start = -3, nfft = 1024, borehole 3 km."""
+    vp_ref, vs_ref = workloads.reference_velmod(60.0, vp=5.0, vs=2.5)
+    from rf_inv_b200.config import RFConfig
+    cfg = RFConfig(ntrc=1, nfft=1024, nsmp=512, delta=0.05, t_start=-3.0, rayps=[0.06], a_gus=[8.0], ipha=[-1], deconv_mode=0,
+                   sdep=0.0, bdep=bdep, vp_ref=vp_ref, vs_ref=vs_ref, vp_mode=1, k_min=1, k_max=4, z_max=40.0, vp_max=8.6,
+                   vs_max=5.0, sig_min=[0.01], sig_max=[0.01])
+    cfg.obs = np.zeros((1, 512)); cfg.r_inv = np.zeros((1, 512, 512))
+    return cfg
+
+
+def test_forward_test_program_of_the_reference_with_its_borehole_depth():
+    """The reference's own (stale, F5) smoke program: 2 layers alpha = [5, 8], beta = [2.5, 4], rho = [3.0, 3.3],
+    h = [20, -10], p = 0.06, S phase, bdep = 3.  No output of it exists (it does not compile against params.f90 any
+    more); the two restatements must agree on exactly its inputs, with and without the borehole depth, and the station
+    3 km down must see the direct S earlier than the surface station."""
+    alpha, beta, rho, h = [5.0, 8.0], [2.5, 4.0], [3.0, 3.3], [20.0, -10.0]
+    out = {}
+    for bdep in (0.0, 3.0):
+        cfg = forward_test_config(bdep)
+        rc = oracle_c.calc_rf_layers(cfg, alpha, beta, rho, h)
+        pc = helpers.py_config(cfg)
+        rp = pyo.calc_rf(pc, pyo.init_filter(pc), 2, np.array(alpha), np.array(beta), np.array(rho), np.array(h)).T
+        assert np.isfinite(rc).all() and helpers.rel_err_rft(rp[None], rc[None]) < 1e-12
+        out[bdep] = rc
+    assert helpers.rel_err_rft(out[3.0][None], out[0.0][None]) > 1e-2      # the borehole depth matters
