@@ -9,7 +9,8 @@ from rf_inv_b200 import workloads
 from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 for kw in (dict(sdep=2.0, ntrc=2), dict(nfft=1024, nsmp=300, k_max=12, ntrc=2, rayps=[0.05, 0.07], a_gus=[2.0, 4.0], sig_min=[0.01, 0.01], sig_max=[0.02, 0.01]),
-           dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), dict(deconv_mode=1)):
+           dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), dict(deconv_mode=1), dict(bdep=1.0, sdep=2.0), dict(bdep=25.0),
+           dict(bdep=6.0, rayps=[0.06, 0.06], nsmp=100)):
     cfg = helpers.attach_obs_and_rinv(helpers.small_config(**kw), noise=0.01)
     m = workloads.draw_models(cfg, 40, seed=3, dvs_scale=0.3)
     with Evaluator(cfg) as ev:
@@ -18,6 +19,12 @@ for kw in (dict(sdep=2.0, ntrc=2), dict(nfft=1024, nsmp=300, k_max=12, ntrc=2, r
 cfg = helpers.attach_obs_and_rinv(helpers.small_config(nchains=4, ncool=1, sig_min=[0.005, 0.01], sig_max=[0.05, 0.01], nburn=2, niter=6, ncorr=2,
                                                        nbin_z=20, nbin_vs=20, nbin_vp=20, nbin_vpvs=20, nbin_sig=10, nbin_amp=20, amp_min=-1.0, amp_max=1.0), noise=0.01)
 pt = ParallelTempering(cfg, 6); pt.run(8); print("pt ok", pt.counters()["nprop"].sum()); pt.close()
+cfg.nchains = 16; cfg.bdep = 0.7
+pt = ParallelTempering(cfg, 70); pt.run(3); print("pt 1120 chains ok", pt.counters()["nprop"].sum()); pt.close()   # two rounds of pt_compact_kernel
+m = workloads.draw_models(cfg, 8192 + 5, seed=4, dvs_scale=0.3)
+with Evaluator(cfg) as ev:      # two-piece upload on the second stream
+    ll, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+assert np.isfinite(ll).all()
 print("case ok")
 PY
 for tool in memcheck racecheck synccheck; do
