@@ -48,6 +48,8 @@ def lib():
         L.orc_init_filter.argtypes = [cfgp, dp]
         L.orc_eval_batch.restype = C.c_int32
         L.orc_eval_batch.argtypes = [cfgp, C.c_int32, i32p, dp, dp, dp, dp, dp, dp, u8p, C.c_int32]
+        L.orc_eval_batch_cond.restype = C.c_int32
+        L.orc_eval_batch_cond.argtypes = [cfgp, C.c_int32, i32p, dp, dp, dp, dp, dp, dp, u8p, C.c_int32, dp]
         L.orc_calc_rf_layers.restype = C.c_int32
         L.orc_calc_rf_layers.argtypes = [cfgp, C.c_int32, dp, dp, dp, dp, dp]
         L.orc_mt_sequence.argtypes = [C.c_uint32, C.c_int32, dp]
@@ -120,9 +122,10 @@ def calc_rf_layers(cfg: RFConfig, alpha, beta, rho, h) -> np.ndarray:
     return rft
 
 
-def eval_batch(cfg: RFConfig, k, z, dvp, dvs, sig, want_rft: bool = True, nthreads: int = 0):
+def eval_batch(cfg: RFConfig, k, z, dvp, dvs, sig, want_rft: bool = True, nthreads: int = 0, want_cond: bool = False):
     """calc_likelihood over C models.  Layouts: z[C][k_max-1], dvp/dvs[C][k_max], sig[C][ntrc].
-    Returns (logl[C], rft[C][ntrc][nfft] or None, is_valid[C])."""
+    Returns (logl[C], rft[C][ntrc][nfft] or None, is_valid[C]) -- and with want_cond the condition number
+    max|rx| / maxval(rx) of the reference's normalisation per (model, trace) as a fourth item."""
     c = cfg.to_c()
     k = np.ascontiguousarray(k, dtype=np.int32)
     nC = k.shape[0]
@@ -132,6 +135,13 @@ def eval_batch(cfg: RFConfig, k, z, dvp, dvs, sig, want_rft: bool = True, nthrea
     logl = np.empty(nC)
     rft = np.empty((nC, cfg.ntrc, cfg.nfft)) if want_rft else None
     valid = np.empty(nC, dtype=np.uint8)
+    if want_cond:
+        cond = np.ones((nC, cfg.ntrc))
+        st = lib().orc_eval_batch_cond(C.byref(c), nC, _p(k, i32p), _p(z, dp), _p(dvp, dp), _p(dvs, dp), _p(sig, dp),
+                                       _p(logl, dp), _p(rft, dp), _p(valid, u8p), int(nthreads), _p(cond, dp))
+        if st != 0:
+            raise RuntimeError("orc_eval_batch: obs / r_inv missing in config")
+        return logl, rft, valid.astype(bool), cond
     st = lib().orc_eval_batch(C.byref(c), nC, _p(k, i32p), _p(z, dp), _p(dvp, dp), _p(dvs, dp), _p(sig, dp),
                               _p(logl, dp), _p(rft, dp), _p(valid, u8p), int(nthreads))
     if st != 0:

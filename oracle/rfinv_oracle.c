@@ -396,6 +396,7 @@ static void c2r(const fft_plan* p, const cplx* half, double* out, cplx* work) {
 typedef struct {
   cplx *ur, *uz, *fr, *fv, *rff, *cx, *work;
   double *rx, *amp;
+  double norm_cond[64]; /* per trace: max|rx| / maxval(rx) of the normalising vertical trace (diagnostics, see orc_eval_batch_cond) */
 } rf_ws;
 static rf_ws* ws_create(int n) {
   rf_ws* w = (rf_ws*)malloc(sizeof(rf_ws));
@@ -467,11 +468,16 @@ static void calc_rf(const rfinv_config* c, const fft_plan* plan, const double* f
     if (c->deconv_mode == 0) { /* forward.f90:197-203 */
       for (int i = 0; i < nh; ++i) w->cx[i] = c_scale(w->fv[i], f[i]);
       c2r(plan, w->cx, w->rx, w->work);
-      double fac = w->rx[0];
-      for (int i = 1; i < n; ++i)
+      double fac = w->rx[0], amax = fabs(w->rx[0]);
+      for (int i = 1; i < n; ++i) {
         if (w->rx[i] > fac) fac = w->rx[i];
+        if (fabs(w->rx[i]) > amax) amax = fabs(w->rx[i]);
+      }
       if (fac != fac) fac = NAN;
       for (int i = 0; i < n; ++i) out[i] = out[i] / fac;
+      if (t < 64) w->norm_cond[t] = amax / fabs(fac);
+    } else if (t < 64) {
+      w->norm_cond[t] = 1.0;
     }
   }
 }
@@ -498,6 +504,24 @@ static double loglik_from_rft(const rfinv_config* c, const double* rft, const do
 
 /* calc_likelihood (likelihood.f90:56-101) over C models; OpenMP over models.
  * Layouts as rfinv_eval_batch (include/rfinv_b200.h).  Returns 0, or 1 when r_inv/obs missing. */
+/* Condition number of the normalisation of every (model, trace): the reference divides by maxval(rx) of the filtered
+ * vertical trace (forward.f90:197-203) -- the largest POSITIVE sample, not the largest magnitude.  Where the main pulse
+ * of that trace is negative (S incidence on a nearly transparent model) the divisor is a small ripple and every
+ * rounding error of the trace is amplified by max|rx| / maxval(rx): two correct fp64 evaluations of the reference's own
+ * formulas then agree to eps * cond only.  cond[C][ntrc]; 1 with deconv_mode 1. */
+static double* g_cond_out = NULL;
+int32_t orc_eval_batch(const rfinv_config* c, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                       const double* dvs, const double* sig, double* logl, double* rft_out, uint8_t* is_valid,
+                       int32_t nthreads);
+int32_t orc_eval_batch_cond(const rfinv_config* c, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                            const double* dvs, const double* sig, double* logl, double* rft_out, uint8_t* is_valid,
+                            int32_t nthreads, double* cond) {
+  g_cond_out = cond;
+  int32_t st = orc_eval_batch(c, C, k, z, dvp, dvs, sig, logl, rft_out, is_valid, nthreads);
+  g_cond_out = NULL;
+  return st;
+}
+
 int32_t orc_eval_batch(const rfinv_config* c, int32_t C, const int32_t* k, const double* z, const double* dvp,
                        const double* dvs, const double* sig, double* logl, double* rft_out, uint8_t* is_valid,
                        int32_t nthreads) {
@@ -526,6 +550,8 @@ int32_t orc_eval_batch(const rfinv_config* c, int32_t C, const int32_t* k, const
       logl[ic] = loglik_from_rft(c, rft, sig + (size_t)ic * T, mis);
       if (rft_out) memcpy(rft_out + (size_t)ic * n * T, rft, sizeof(double) * (size_t)n * T);
       if (is_valid) is_valid[ic] = (uint8_t)ok;
+      if (g_cond_out)
+        for (int t = 0; t < T && t < 64; ++t) g_cond_out[(size_t)ic * T + t] = w->norm_cond[t];
     }
     free(rft); free(mis); ws_destroy(w);
   }

@@ -11,11 +11,11 @@ from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 
 out = {"tolerance": 1e-9, "configs": {}}
-for name, n in [("sample", 1024), ("c2", 1024), ("c3", 1024), ("c3_buried", 1024), ("c4", 1024), ("c4_laplace", 1024), ("c5", 1024), ("target", 1024)]:
+for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192), ("c4", 8192), ("c4_laplace", 4096), ("c5", 4096), ("target", 8192)]:
     cfg = helpers.attach_obs_and_rinv(workloads.make_config(name), noise=0.01)
     m = workloads.draw_models(cfg, n, seed=2024, dvs_scale=0.5)
     t0 = time.time()
-    ll_o, rft_o, val_o = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    ll_o, rft_o, val_o, cond = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_cond=True)
     t_cpu = time.time() - t0
     with Evaluator(cfg) as ev:
         ll_g, rft_g, val_g = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True, want_valid=True)
@@ -24,6 +24,16 @@ for name, n in [("sample", 1024), ("c2", 1024), ("c3", 1024), ("c3_buried", 1024
                             "logl_max_rel_err": helpers.logl_err(cfg, ll_g, ll_o, m["sig"]),
                             "valid_flags_equal": bool(np.array_equal(val_g, val_o)), "nan_logl": int(np.isnan(ll_g).sum()),
                             "oracle_seconds": round(t_cpu, 2)}
+    # Conditioning of the reference's normalisation (rft = rx / maxval(rx_vertical), src/forward.f90:197-203): where the main
+    # pulse of the vertical trace is negative, maxval() is a small ripple and any two fp64 evaluations of the reference's own
+    # formulas only agree to eps * cond, cond = max|rx| / maxval(rx) (oracle/rfinv_oracle.c orc_eval_batch_cond).
+    e_mt = np.max(np.abs(rft_g - rft_o), axis=-1) / np.max(np.abs(rft_o), axis=-1)          # [model][trace]
+    well = cond <= 1.0e3
+    out["configs"][name].update({
+        "norm_condition_max": float(np.max(cond)), "traces_with_norm_condition_above_1e3": int((~well).sum()),
+        "rft_max_rel_err_where_condition_le_1e3": float(np.max(e_mt[well])),
+        "rft_max_rel_err_over_condition": float(np.max(e_mt / cond)),
+        "logl_max_rel_err_where_condition_le_1e3": helpers.logl_err(cfg, ll_g[well.all(axis=1)], ll_o[well.all(axis=1)], m["sig"][well.all(axis=1)])})
 cfg = helpers.attach_obs_and_rinv(workloads.make_config("sample"), noise=0.01)
 n_iter, nproc = 500, 20
 pt = ParallelTempering(cfg, nproc); pt.set_logging(n_iter); pt.run(n_iter)
