@@ -263,3 +263,24 @@ def test_forward_test_program_of_the_reference_with_its_borehole_depth():
         assert np.isfinite(rc).all() and helpers.rel_err_rft(rp[None], rc[None]) < 1e-12
         out[bdep] = rc
     assert helpers.rel_err_rft(out[3.0][None], out[0.0][None]) > 1e-2      # the borehole depth matters
+
+
+def test_maxval_normalisation_condition_number_explains_oracle_vs_oracle_differences():
+    """src/forward.f90:197-203 divides by maxval(rx) (largest POSITIVE sample).  On nearly transparent models under S
+    incidence that is a ripple; the two restatements of the same dense algorithm then differ by eps * cond.  Pins the
+    diagnostic (orc_eval_batch_cond) on two such models of the c4 sample and on ordinary ones."""
+    cfg = helpers.attach_obs_and_rinv(workloads.make_config("c4"), noise=0.01)
+    m = workloads.draw_models(cfg, 8192, seed=2024, dvs_scale=0.5)
+    idx = np.array([7734, 4056, 100, 101])
+    sub = {k: v[idx] for k, v in m.items()}
+    _, rft_c, _, cond = oracle_c.eval_batch(cfg, sub["k"], sub["z"], sub["dvp"], sub["dvs"], sub["sig"], want_cond=True)
+    assert cond[0, 2] > 1e6 and cond[1, 2] > 1e6 and np.all(cond[:, :2] == 1.0) and np.all(cond[2:] < 10.0)
+    pc = helpers.py_config(cfg)
+    flt = pyo.init_filter(pc)
+    for j in range(4):
+        nlay, a, b, r, h, _ = pyo.format_model(pc, int(sub["k"][j]), sub["z"][j], sub["dvp"][j], sub["dvs"][j])
+        rp = pyo.calc_rf(pc, flt, nlay, a, b, r, h).T
+        err = np.max(np.abs(rp - rft_c[j]), axis=-1) / np.max(np.abs(rft_c[j]), axis=-1)
+        assert np.all(err < 1e-12 * cond[j])
+        if j < 2:
+            assert err[2] > 1e-12            # far above rounding level: the amplification is real
