@@ -65,7 +65,7 @@ struct Mt {
     y ^= (y << 7) & 0x9d2c5680u;
     y ^= (y << 15) & 0xefc60000u;
     y ^= y >> 18;
-    return (double)y / 4294967296.0;  // src/mt19937.f90:125-129: [0,1)
+    return (double)y * 2.3283064365386963e-10;  // y / 2^32 (src/mt19937.f90:125-129: [0,1)); a power of two: the product is the exact quotient
   }
   __device__ double grnd() {
     if (mti >= 624) reload();
@@ -396,18 +396,13 @@ __global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p, int log_slo
     }
     const double del_s = __dadd_rn(__ddiv_rn(__dsub_rn(ll, p.logl[c]), temp), p.log_prior12[c]);  // src/pt_mcmc.f90:608
     yn = p.log_r[c] <= del_s;
-    if (yn) {
+    if (yn) {   // the model arrays follow in pt_adopt_kernel (one thread per array element instead of a loop per chain)
       p.logl[c] = ll;
       p.k[c] = p.pk[c];
-      for (int i = 0; i < km - 1; ++i) p.z[(size_t)i * Cl + c] = p.pz[(size_t)i * Cl + c];
-      for (int i = 0; i < km; ++i) { p.dvp[(size_t)i * Cl + c] = p.pdvp[(size_t)i * Cl + c]; p.dvs[(size_t)i * Cl + c] = p.pdvs[(size_t)i * Cl + c]; }
-      for (int t = 0; t < T; ++t) p.sig[(size_t)t * Cl + c] = p.psig[(size_t)t * Cl + c];
-      if (flag == 1) {
-        for (int t = 0; t < T; ++t) p.phi[(size_t)t * Cl + c] = p.pphi[(size_t)t * Cl + c];
-        p.slot[c] ^= 1;  // the proposal's RF samples were written to the other slot
-      }
+      if (flag == 1) p.slot[c] ^= 1;  // the proposal's RF samples were written to the other slot
     }
   }
+  p.pflag[c] = (int8_t)(yn ? (flag == 1 ? 3 : 4) : 0);   // for pt_adopt_kernel: 3 = adopt model and phi, 4 = model only
   if (temp <= 1.0 + (double)1.0e-6f) {  // src/pt_mcmc.f90:196-201
     atomicAdd(&p.nprop[p.itype[c] - 1], 1ULL);
     if (yn) atomicAdd(&p.naccept[p.itype[c] - 1], 1ULL);
@@ -416,6 +411,25 @@ __global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p, int log_slo
     p.log_flags[(size_t)log_slot * Cl + c] = (int8_t)(flag == -1 ? -1 : yn);
     p.log_itypes[(size_t)log_slot * Cl + c] = p.itype[c];
   }
+}
+
+// accepted proposals become the current state (src/pt_mcmc.f90:186-194): rows z | dvp | dvs | sig | phi, chain fastest
+__global__ void pt_adopt_kernel(const DevConfig cfg, const PtDev p) {
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  const int rows = 3 * km - 1 + 2 * T;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)rows * Cl) return;
+  int row = (int)(idx / Cl);
+  const int c = (int)(idx - (long long)row * Cl);
+  const int code = p.pflag[c];
+  if (code < 3) return;
+  const double* src; double* dst;
+  if (row < km - 1) { src = p.pz; dst = p.z; }
+  else if ((row -= km - 1) < km) { src = p.pdvp; dst = p.dvp; }
+  else if ((row -= km) < km) { src = p.pdvs; dst = p.dvs; }
+  else if ((row -= km) < T) { src = p.psig; dst = p.sig; }
+  else { if (code != 3) return; row -= T; src = p.pphi; dst = p.phi; }
+  dst[(size_t)row * Cl + c] = src[(size_t)row * Cl + c];
 }
 
 // likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200); fixed-order tree sum
@@ -816,6 +830,10 @@ int32_t rfinv_pt_local_step(rfinv_handle* h) {
   RFINV_CUDA_CHECK(cudaGetLastError());
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
   pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d, log_slot);
+  {
+    const long long n_el = (long long)(3 * h->dc.k_max - 1 + 2 * h->dc.ntrc) * d.Cl;
+    pt_adopt_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, q>>>(h->dc, d);
+  }
   pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist + s->it_done);
   {
     const int it = s->it_done + 1;  // 1-based iteration number (src/pt_mcmc.f90:204-205)
