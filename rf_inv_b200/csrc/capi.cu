@@ -308,8 +308,9 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   int st;
   launches = 0;
   if (timing) cudaEventRecord(ev[0], stream);
-  if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream)) != RFINV_OK) return st;
-  launches += 2;
+  int n_fwd = 0;
+  if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream, &n_fwd)) != RFINV_OK) return st;
+  launches += n_fwd;
   if (timing) cudaEventRecord(ev[1], stream);
   if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, d_qpart, d_qcnt, active, n_active, nullptr, stream)) != RFINV_OK) return st;
   ++launches;

@@ -59,6 +59,17 @@ struct LayerConst {
 };
 constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 12
 
+// The rays one forward_kernel launch works on: every ray of the configuration, or -- when the traces have different
+// band limits -- the traces of one band-limit group, so that each group runs the kernel variant built for its width.
+// (trace indices packed four bits each: a kernel parameter array indexed at run time would be copied to local memory)
+struct TraceSel {
+  int n;
+  unsigned long long packed;
+  __host__ __device__ int t(int i) const { return (int)((packed >> (4 * i)) & 15ULL); }
+  __host__ void push(int trace) { packed |= (unsigned long long)trace << (4 * n); ++n; }
+};
+static_assert(RFINV_MAX_TRC <= 16, "TraceSel packs trace indices in four bits");
+
 // Per (model, ray) constants written by prep_kernel.
 struct RayConst {
   double h14[4], h23[4];      // rows 3,4 of E^-1 (1/w factors removed) times the last solid layer's basis, per block
@@ -231,7 +242,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   extern __shared__ __align__(16) double prep_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int item = blockIdx.x * PREP_WARPS + warp;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0;   // work counter of the forward_kernel launch that follows on the same stream
+  if (blockIdx.x == 0 && threadIdx.x < RFINV_MAX_TRC) counter[threadIdx.x] = 0;   // work counters of the forward_kernel launches that follow on the same stream
   if (item >= n_items) return;
   if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
@@ -894,13 +905,15 @@ __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, con
 template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
 __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
                                                              const double* __restrict__ lc_in,
-                                                             const double* __restrict__ rc_in, int* __restrict__ counter) {
+                                                             const double* __restrict__ rc_in, int* __restrict__ counter,
+                                                             const TraceSel sel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
-  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * ntr_eff;
+  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;   // rays per model in the scratch arrays prep_kernel filled
+  // items of this launch: (model, ray) for the rays in `sel` (all of them, or the traces of one band-limit group)
+  const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   constexpr bool buried = BURIED;   // cfg.bdep > 0: a kernel variant of its own, the surface-station variants carry none of it
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || buried;   // spectra staged in shared memory
 
@@ -917,7 +930,9 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 32);     // [2]
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
 
-  auto prefetch = [&](int item, int slot) {
+  auto prefetch = [&](int item_sel, int slot) {
+    const int ci_ = item_sel / sel.n;
+    const size_t item = (size_t)ci_ * ntr_eff + sel.t(item_sel - ci_ * sel.n);   // index into prep_kernel's arrays
     const double2* src = reinterpret_cast<const double2*>(rc_in + (size_t)item * RC_DOUBLES);
     double2* dst = reinterpret_cast<double2*>(s_rc2 + slot);
     for (int i = tid; i < RC_DOUBLES / 2; i += nthr) cp_async16(dst + i, src + i);
@@ -947,7 +962,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     if (tid == 0) next2 = atomicAdd(counter, 1);   // consumed at the end of the iteration: nobody waits for the round trip
     const RayConst* s_rc = s_rc2 + slot;
     const LayerConst* s_lc = s_lc2 + (size_t)slot * km;
-    const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
+    const int ci = item / sel.n, t0 = sel.t(item - ci * sel.n);
     const int c = mb.active ? mb.active[ci] : ci;
     const int k = s_rc->k;
     const int ipha = cfg.ipha[t0];
@@ -1142,7 +1157,7 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
 
 template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
-                     const double* rc, int* counter, int nthr, cudaStream_t stream) {
+                     const double* rc, int* counter, int nthr, cudaStream_t stream, const TraceSel& sel) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
   RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1152,60 +1167,23 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
   RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED, BURIED>, nthr, smem));
   if (per_sm < 1) { rfinv_set_error("forward_kernel does not fit on an SM (%zu bytes of shared memory)", smem); return RFINV_ERR_CUDA; }
   const int n_models = mb.active ? mb.n_active : mb.C;
-  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  const long long items = (long long)n_models * ntr_eff;
+  const long long items = (long long)n_models * sel.n;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  forward_kernel<J, BMAX, MINB, MIXED, BURIED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter);
+  forward_kernel<J, BMAX, MINB, MIXED, BURIED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter, sel);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
 
-}  // namespace
-
-int rfinv_forward_bins_per_thread(int nfft) {
-  if (nfft <= 64) return 1;
-  if (nfft <= 256) return 2;
-  if (nfft <= 2048) return 4;   // 2048: 256 threads x 4 bins (8 bins per thread would need ~250 registers)
-  return 8;
-}
-
-size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
-  const long long ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES) + 2;   // + the work counter
-}
-
-// scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
-int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
-                         cudaStream_t stream) {
-  const int J = rfinv_forward_bins_per_thread(cfg.nfft);
-  const int nthr = (cfg.nfft / 2) / J;
-  const int n_models = mb.active ? mb.n_active : mb.C;
-  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
-  const long long n_items = (long long)n_models * ntr_eff;
-  if (n_items == 0) return RFINV_OK;
-  double* lc = scratch;
-  double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
-  int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
-  const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
-  const unsigned prep_grid = (unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS);
-  if (cfg.bdep > 0.0) {
-    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    prep_kernel<true><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
-  } else {
-    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    prep_kernel<false><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
-  }
-  RFINV_CUDA_CHECK(cudaGetLastError());
-  // kernel variant: <bin groups per thread that are propagated (band limit), upper bound of threads per CTA, CTAs per SM>
-  const int JB = cfg.jb_max;
-  bool mixed = false;   // traces with different band limits: the kernel picks the loop length per item
-  for (int t = 0; t < cfg.ntrc; ++t) mixed = mixed || cfg.jbins[t] != JB;
+// kernel variant for a group of traces that keep JB bin groups: <bin groups per thread that are propagated (band limit),
+// upper bound of threads per CTA, CTAs per SM, MIXED = the variant is wider than the group>
+int launch_forward_group(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc, const double* rc,
+                         int* counter, int nthr, cudaStream_t stream, const TraceSel& sel, int JB) {
 #define FWD(JJ, BB, MM)                                                                                   \
   do {                                                                                                    \
-    if (cfg.bdep > 0.0) return launch_forward_t<JJ, BB, MM, true, true>(cfg, mb, out, lc, rc, counter, nthr, stream); \
-    if (mixed || JJ != JB) return launch_forward_t<JJ, BB, MM, true, false>(cfg, mb, out, lc, rc, counter, nthr, stream); \
-    return launch_forward_t<JJ, BB, MM, false, false>(cfg, mb, out, lc, rc, counter, nthr, stream);       \
+    if (cfg.bdep > 0.0) return launch_forward_t<JJ, BB, MM, true, true>(cfg, mb, out, lc, rc, counter, nthr, stream, sel); \
+    if (JJ != JB) return launch_forward_t<JJ, BB, MM, true, false>(cfg, mb, out, lc, rc, counter, nthr, stream, sel); \
+    return launch_forward_t<JJ, BB, MM, false, false>(cfg, mb, out, lc, rc, counter, nthr, stream, sel);  \
   } while (0)
   if (nthr <= 32) { if (JB <= 1) FWD(1, 32, 8); FWD(2, 32, 8); }
   if (nthr <= 64) { if (JB <= 2) FWD(2, 64, 6); FWD(4, 64, 6); }
@@ -1220,6 +1198,60 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   if (JB <= 6) FWD(6, 256, 1);
   FWD(8, 256, 1);
 #undef FWD
+}
+
+}  // namespace
+
+int rfinv_forward_bins_per_thread(int nfft) {
+  if (nfft <= 64) return 1;
+  if (nfft <= 256) return 2;
+  if (nfft <= 2048) return 4;   // 2048: 256 threads x 4 bins (8 bins per thread would need ~250 registers)
+  return 8;
+}
+
+size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
+  const long long ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
+  return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES) + RFINV_MAX_TRC / 2;   // + the work counters
+}
+
+// scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
+int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
+                         cudaStream_t stream, int* n_kernels) {
+  const int J = rfinv_forward_bins_per_thread(cfg.nfft);
+  const int nthr = (cfg.nfft / 2) / J;
+  const int n_models = mb.active ? mb.n_active : mb.C;
+  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
+  const long long n_items = (long long)n_models * ntr_eff;
+  if (n_items == 0) { if (n_kernels) *n_kernels = 0; return RFINV_OK; }
+  double* lc = scratch;
+  double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
+  int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
+  const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
+  const unsigned prep_grid = (unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS);
+  if (cfg.bdep > 0.0) {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    prep_kernel<true><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
+  } else {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    prep_kernel<false><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
+  }
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  // One launch per band-limit group: traces whose Gaussian filters keep the same number of bin groups share a launch of
+  // the kernel variant built for exactly that many (different widths in one launch would have to run the widest
+  // variant for every item: more registers, spills in the layer loop).  Common rays: one launch, one ray.
+  int n_launch = 0;
+  for (int g = 8; g >= 1; --g) {           // widest group first
+    TraceSel sel;
+    sel.n = 0; sel.packed = 0ULL;
+    if (cfg.ray_common) { if (g == cfg.jb_max) sel.push(0); }
+    else for (int t = 0; t < cfg.ntrc; ++t) if (cfg.jbins[t] == g) sel.push(t);
+    if (sel.n == 0) continue;
+    const int st = launch_forward_group(cfg, mb, out, lc, rc, counter + n_launch, nthr, stream, sel, g);
+    if (st != RFINV_OK) return st;
+    ++n_launch;
+  }
+  if (n_kernels) *n_kernels = 1 + n_launch;   // prep_kernel + one forward_kernel per band-limit group
+  return RFINV_OK;
 }
 
 // in / out: [n_series][nfft] in HBM, trace_of[n_series]: which trace's filter shapes the series

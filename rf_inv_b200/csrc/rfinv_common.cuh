@@ -111,7 +111,7 @@ struct EvalOutputs {
 // prep_kernel + forward_kernel.  scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles in HBM
 size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models);
 int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
-                         cudaStream_t stream);
+                         cudaStream_t stream, int* n_kernels = nullptr);   // n_kernels: kernels launched (optional)
 // bins per thread of forward_kernel for the full band (threads per CTA = nfft/2 / this)
 int rfinv_forward_bins_per_thread(int nfft);
 // phi[ntrc][C] = m^T R^-1 m per trace and model.  partial / counters: scratch sized by the two functions below, the
