@@ -700,16 +700,48 @@ __device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerCon
   }
 }
 
+// Water layer: cos / sin of (tid * thw) -- the phase of the thread's first bin -- from a two-level table like the layers'
+// (s_tabw: lo[16] | hi[n_hi], built once per item by two otherwise idle threads) instead of a sincos per thread.
+__device__ __forceinline__ void build_water_table(double2* s_tabw, double thw, int n_hi, int tid, int nthr) {
+  const int level = nthr - 1 - tid;          // the last thread builds the lo level, the one before it the hi level
+  if (level > 1 || thw == 0.0) return;
+  const int cnt = level ? n_hi : 16;
+  double2 e[16];
+  e[0] = make_double2(1.0, 0.0);
+  sincos(thw * (level ? 16.0 : 1.0), &e[1].y, &e[1].x);
+#pragma unroll
+  for (int len = 2; len < 16; len <<= 1) {
+    e[len] = e[len >> 1];
+    rot(e[len].x, e[len].y, e[len >> 1].x, e[len >> 1].y);
+#pragma unroll
+    for (int j = 1; j < len; ++j) {
+      e[len + j] = e[j];
+      rot(e[len + j].x, e[len + j].y, e[len].x, e[len].y);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i)
+    if (i < cnt) s_tabw[level * 16 + i] = e[i];
+}
+__device__ __forceinline__ void water_phase(const double2* s_tabw, double thw, int tid, double& cw, double& sw) {
+  cw = 1.0; sw = 0.0;
+  if (thw != 0.0) {
+    const double2 a = s_tabw[tid & 15], b = s_tabw[16 + (tid >> 4)];
+    cw = a.x; sw = a.y;
+    rot(cw, sw, b.x, b.y);
+  }
+}
+
 // Propagator product over the k solid layers, top down, in wave coordinates, for the J bins tid + m*nthr of this thread.
 template <int J>
-__device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, int k, int n_hi,
-                                          int tid, Wave* wa, Wave* wb) {
+__device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, const double2* s_tabw,
+                                          int k, int n_hi, int tid, Wave* wa, Wave* wb) {
   const int tab_per_layer = 2 * (16 + n_hi);
   {
     const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
     const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
-    double cw = 1.0, sw = 0.0;
-    if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
+    double cw, sw;
+    water_phase(s_tabw, thw, tid, cw, sw);
 #pragma unroll
     for (int m = 0; m < J; ++m) {
       wa[m].a1 = a1; wa[m].a2 = 0.0; wa[m].b1 = b1; wa[m].b2 = 0.0;
@@ -756,15 +788,15 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
 
 // Runs the layer loop for the first jm (<= JB) bin groups of the thread; jm takes the values band_limits() hands out.
 template <int JB, bool MIXED>
-__device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, int k,
-                                                 int n_hi, int tid, Wave* wa, Wave* wb) {
-  if (!MIXED || jm >= JB) { propagate<JB>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
+__device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab,
+                                                 const double2* s_tabw, int k, int n_hi, int tid, Wave* wa, Wave* wb) {
+  if (!MIXED || jm >= JB) { propagate<JB>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
   if constexpr (MIXED) {
-  if constexpr (JB > 6) if (jm == 6) { propagate<6>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 4) if (jm == 4) { propagate<4>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 3) if (jm == 3) { propagate<3>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 2) if (jm == 2) { propagate<2>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 1) propagate<1>(s_rc, s_lc, s_tab, k, n_hi, tid, wa, wb);
+  if constexpr (JB > 6) if (jm == 6) { propagate<6>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 4) if (jm == 4) { propagate<4>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 3) if (jm == 3) { propagate<3>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 2) if (jm == 2) { propagate<2>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
+  if constexpr (JB > 1) propagate<1>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb);
   }
 }
 
@@ -774,13 +806,13 @@ __device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, c
 template <int J, bool STAGE>
 __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha,
                                                  int n, int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                                 double2* s_fr, double2* s_fv, bool buried) {
+                                                 double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw) {
   double h14[4], h23[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
   const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
-  double cw = 1.0, sw = 0.0;
-  if (thw != 0.0) sincos((double)tid * thw, &sw, &cw);
+  double cw, sw;
+  water_phase(s_tabw, thw, tid, cw, sw);
 #pragma unroll
   for (int m = 0; m < J; ++m) {
     const int j = tid + m * nthr;
@@ -879,8 +911,8 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
 template <int JB, bool STAGE, bool MIXED>
 __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha, int n,
                                                int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                               double2* s_fr, double2* s_fv, bool buried) {
-#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried)
+                                               double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw) {
+#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried, s_tabw)
   if (!MIXED || jm >= JB) { SURF(JB); return; }
   if constexpr (MIXED) {
   if constexpr (JB > 6) if (jm == 6) { SURF(6); return; }
@@ -929,6 +961,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   double* s_red = reinterpret_cast<double*>(s_twq + fft_twiddle_entries(n));   // [32]
   RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 32);     // [2]
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
+  double2* s_tabw = reinterpret_cast<double2*>(s_lc2 + 2 * (size_t)km);   // [16 + n_hi] water-layer phase table (not aliased)
 
   auto prefetch = [&](int item_sel, int slot) {
     const int ci_ = item_sel / sel.n;
@@ -968,6 +1001,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     const int ipha = cfg.ipha[t0];
     PHASE_MARK(0);
     build_trig_tables(s_tab, s_lc, buried ? max(k, s_rc->l_sta + 1) : k, n_hi, tid, nthr);
+    build_water_table(s_tabw, s_rc->thw, n_hi, tid, nthr);
     __syncthreads();
     PHASE_MARK(1);
 
@@ -976,7 +1010,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     // Buried station: a first pass down to the station leaves the displacement components of both vectors there in the
     // spectrum staging arrays (same thread, same bins as the surface response that combines them); then the full stack.
     for (int pass = buried ? 0 : 1; pass < 2; ++pass) {
-      propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, pass == 0 ? s_rc->l_sta + 1 : k, n_hi, tid, wa, wb);
+      propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, s_tabw, pass == 0 ? s_rc->l_sta + 1 : k, n_hi, tid, wa, wb);
       if (pass == 0) {
         const double c0 = s_rc->sta[0], c1 = s_rc->sta[1], c2 = s_rc->sta[2], c3 = s_rc->sta[3];
 #pragma unroll
@@ -994,8 +1028,8 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
     const int jfull = (n >> 1) / nthr;
-    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried);
-    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false);
+    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw);
+    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -1152,7 +1186,7 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || cfg.bdep > 0.0;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
   return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 32 + 2 * sizeof(RayConst) +
-         2 * sizeof(LayerConst) * km;
+         2 * sizeof(LayerConst) * km + sizeof(double2) * (16 + (nthr >> 4));
 }
 
 template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
