@@ -35,7 +35,7 @@ def _base(**kw) -> RFConfig:
 
 
 def make_config(name: str) -> RFConfig:
-    """Workload names: sample (C1), c2, c3, c3_buried, c4, c4_laplace, c5, target."""
+    """Workload names: sample (C1), c2, c3, c3_buried, c3_deconv, c3_common, c4, c4_laplace, c5, target."""
     if name == "sample":  # sample_syn/params.in as shipped (incl. SEA_DEP 2.0), 20 ranks x 5 chains
         vp_ref, vs_ref = reference_velmod(30.0)
         return _base(ntrc=2, nfft=256, nsmp=101, rayps=[0.06, 0.08], a_gus=[4.0, 4.0], ipha=[1, 1], sdep=2.0,
@@ -49,6 +49,14 @@ def make_config(name: str) -> RFConfig:
     if name == "c3_buried":  # BASELINE.json config 3 as worded: sea-water top layer AND buried receiver (1 km below the sea floor)
         cfg = make_config("c3")
         cfg.bdep = 1.0
+        return cfg
+    if name == "c3_deconv":  # c3 with water-level deconvolution (DECONV_MODE 1)
+        cfg = make_config("c3")
+        cfg.deconv_mode = 1
+        return cfg
+    if name == "c3_common":  # c3 with one ray for all traces: one propagator pass per model (check_ray, src/forward.f90:59-76)
+        cfg = make_config("c3")
+        cfg.rayps = [0.06, 0.06, 0.06]
         return cfg
     if name in ("c4", "c4_laplace"):  # joint P and S with velocity-perturbation prior
         return _base(ntrc=4, nfft=1024, nsmp=512, rayps=[0.05, 0.07, 0.10, 0.12], a_gus=[4.0, 4.0, 4.0, 4.0],

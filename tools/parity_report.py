@@ -11,7 +11,7 @@ from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 
 out = {"tolerance": 1e-9, "configs": {}}
-for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192), ("c4", 8192), ("c4_laplace", 4096), ("c5", 4096), ("target", 8192)]:
+for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192), ("c3_deconv", 8192), ("c3_common", 8192), ("c4", 8192), ("c4_laplace", 4096), ("c5", 4096), ("target", 8192)]:
     cfg = helpers.attach_obs_and_rinv(workloads.make_config(name), noise=0.01)
     m = workloads.draw_models(cfg, n, seed=2024, dvs_scale=0.5)
     t0 = time.time()
