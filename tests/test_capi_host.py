@@ -131,3 +131,22 @@ def test_models_valid_agrees_with_oracle_format_model():
     ok = workloads.models_valid(cfg, m["k"], m["z"], m["dvp"], m["dvs"])
     for i in range(40):
         assert ok[i] == oracle_c.format_model(cfg, int(m["k"][i]), m["z"][i], m["dvp"][i], m["dvs"][i])[5]
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """bench.py --impl reference (the CPU restatement timed on the host cores) is run by the driver next to the CUDA arm:
+    exactly one JSON line on stdout, with the same metric / unit / config keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--cpu-sample", "48"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["metric"] == "forward+likelihood evals/sec" and j["unit"] == "evals/s"
+    assert j["higher_is_better"] is True and j["value"] > 0 and j["config"]["workload"] == "target"
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
