@@ -43,9 +43,21 @@ extern "C" int rfinv_debug_get_phases(unsigned long long* out) {
   cudaMemcpyToSymbol(g_phase, zero, sizeof(zero));
   return e == cudaSuccess ? 0 : 2;
 }
+// prep_kernel phases (lane 0 of every warp), slots 8..14
+#define PREP_MARK(i)                                                             \
+  do {                                                                           \
+    if (lane == 0) {                                                             \
+      const long long now__ = clock64();                                         \
+      atomicAdd(&g_phase[8 + (i)], (unsigned long long)(now__ - tp_phase__));    \
+      tp_phase__ = now__;                                                        \
+    }                                                                            \
+  } while (0)
+#define PREP_INIT() long long tp_phase__ = clock64()
 #else
 #define PHASE_MARK(i) do { } while (0)
 #define PHASE_INIT() do { } while (0)
+#define PREP_MARK(i) do { } while (0)
+#define PREP_INIT() do { } while (0)
 #endif
 
 namespace {
@@ -256,6 +268,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   double *du = zu + km, *su = du + km, *zs = su + km, *dps = zs + km, *dss = dps + km;
   PrepLayer* PL = reinterpret_cast<PrepLayer*>(dss + km);
 
+  PREP_INIT();
   // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
   for (int i = lane; i < k; i += 32) {
     zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
@@ -293,6 +306,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   // vectors on to the station.
   const int kb = (buried && ls == k) ? k : ka;
 
+  PREP_MARK(0);
   // ---- per-layer physics, one layer per lane ----
   const double p2 = __dmul_rn(p, p);
   const double nyq = (double)(cfg.nfft / 2);
@@ -355,6 +369,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   valid = __all_sync(0xffffffffu, valid);
   __syncwarp();
 
+  PREP_MARK(1);
   // ---- interfaces l-1 -> l (l = 1..k-1): tau = V_l^-1 V_{l-1} unscaled, prefix products of its {1,4} diagonal ----
   double carryP = 1.0, carryS = 1.0;      // scale products of the slots already done
   double sP_last = 1.0, sS_last = 1.0;    // scales of the last solid layer above the half space (kb-1)
@@ -390,6 +405,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   }
   __syncwarp();
 
+  PREP_MARK(2);
   // ---- ray constants: half space, water layer, start vectors ----
   RayConst R;
   double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
@@ -439,6 +455,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     R.sta[2] = Q.v23[0] * sP_sta; R.sta[3] = Q.v23[1] * sS_sta;
   }
 
+  PREP_MARK(3);
   // ---- serial part: lanes 0..3 carry (vector a | b) x (DC | Nyquist) down the stack; lane 4 sums the delay ----
   Wave w;
   double2 y_sta = make_double2(0.0, 0.0);   // displacement components of this lane's vector at a buried station
@@ -465,6 +482,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     R.tp = __shfl_sync(0xffffffffu, tp, 4);
   }
   {
+    PREP_MARK(4);
     // gather the four vectors on every lane; lane 0 finishes the two edge bins
     Wave wv[4];
 #pragma unroll
@@ -497,6 +515,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
       if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
     }
   }
+  PREP_MARK(5);
 }
 
 // Twiddles of the radix-8 DIF stages, one table per stage laid out [q-1][o] (q = 1..7 output index of the butterfly,
