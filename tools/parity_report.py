@@ -35,7 +35,7 @@ for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192
         "rft_max_rel_err_over_condition": float(np.max(e_mt / cond)),
         "logl_max_rel_err_where_condition_le_1e3": helpers.logl_err(cfg, ll_g[well.all(axis=1)], ll_o[well.all(axis=1)], m["sig"][well.all(axis=1)])})
 cfg = helpers.attach_obs_and_rinv(workloads.make_config("sample"), noise=0.01)
-n_iter, nproc = 500, 20
+n_iter, nproc = 3000, 20
 pt = ParallelTempering(cfg, nproc); pt.set_logging(n_iter); pt.run(n_iter)
 fl, ty, sw = pt.log(n_iter); cnt = pt.counters(); st = pt.state(); pt.close()
 orc = oracle_c.OraclePT(cfg, nproc); ofl, oty, osw = orc.run(n_iter); ocnt = orc.counters(n_iter); ost = orc.state()
