@@ -185,3 +185,23 @@ def test_run_driver_writes_reference_output_set(tmp_path):
     syn = np.loadtxt(out / "syn_trace.ppd")
     assert syn.shape == (2 * 101 * 100, 4) and abs(syn[:100, 2].sum() - 1.0) < 1e-3
     assert os.path.getsize(out / "sigma.ppd") == 0                    # sigma fixed for both traces: nothing written
+
+
+def test_full_length_sample_run_recovers_the_data_generating_structure():
+    """The sample configuration at the reference's own run length (sample_syn/params.in: N_BURN 3000 + N_ITER 8000, 20
+    ranks x 5 chains = 1.1 M chain steps, a few seconds here) on synthetic data of true.velmod's structure (fast layer over
+    a slow layer over a fast half space below a 2 km sea): the posterior-mean Vs profile (vs_z.mean = vs_mean / nmod)
+    must show that structure.  Fixed seed and deterministic kernels: the numbers are reproducible."""
+    cfg = helpers.attach_obs_and_rinv(workloads.make_config("sample"), noise=0.01)
+    pt = ParallelTempering(cfg, 20)
+    pt.run(cfg.nburn + cfg.niter)
+    h = pt.hist(); cnt = pt.counters(); pt.close()
+    assert h["nmod"] == (cfg.niter // cfg.ncorr) * 20 * cfg.ncool
+    assert cnt["nprop"].sum() == (cfg.nburn + cfg.niter) * 20 * cfg.ncool
+    dz = cfg.z_max / cfg.nbin_z
+    mean = lambda z: h["vs_mean"][int(z / dz)] / h["nmod"]
+    tm = workloads.true_model(cfg)
+    top, mid, bot = 2.89 + tm["dvs"][0, 0], 2.89 + tm["dvs"][0, 1], 2.89 + tm["dvs"][0, -1]      # 4.76, 3.54, 4.68 km/s
+    v_top, v_mid, v_bot = mean(2.5), mean(7.0), mean(14.0)
+    assert v_top - v_mid > 0.4 and v_bot - v_mid > 0.4                     # high - low - high
+    assert abs(v_top - top) < 0.5 and abs(v_mid - mid) < 0.5 and abs(v_bot - bot) < 0.5
