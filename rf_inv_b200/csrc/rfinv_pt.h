@@ -9,7 +9,7 @@ struct PtDev {
   int isig_trc[RFINV_MAX_TRC], sig_mode[RFINV_MAX_TRC];
   double sig_min[RFINV_MAX_TRC], sig_max[RFINV_MAX_TRC];
   double t_high, dev_z, dev_dvs, dev_dvp, dev_sig, dvs_prior, dvp_prior;
-  // mt19937 streams, one per virtual rank: mt[i*G + r]
+  // mt19937 streams, one per virtual rank: word i of stream r at mt[r*624 + i]
   uint32_t* mt;
   int* mti;
   // current state
