@@ -1002,11 +1002,12 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   prefetch(item, 0);
   asm volatile("cp.async.commit_group;\n" ::);
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(counter, 1);
+  asm volatile("cp.async.wait_all;\n" ::);
+  __syncthreads();   // constants of the first item and the twiddles have landed; s_next is visible
 
   while (item < n_items) {
     PHASE_INIT();
-    asm volatile("cp.async.wait_all;\n" ::);
-    __syncthreads();   // constants of `item` (and, the first time, the twiddles) have landed; s_next is visible
+    // the constants of `item` and s_next were published by the barrier that closed the previous iteration
     const int next = s_next;
     if (next < n_items) prefetch(next, slot ^ 1);
     asm volatile("cp.async.commit_group;\n" ::);
@@ -1116,7 +1117,8 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       const double scale = cfg.deconv_mode == 0 ? 1.0 / mx : 1.0;   // src/forward.f90:197-203
       write_outputs(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
       if (tid == 0 && t + 1 == t_end) s_next = (int)gridDim.x + next2;
-      __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables
+      asm volatile("cp.async.wait_all;\n" ::);   // the next item's constants, in flight since the top of this iteration
+      __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables; constants and s_next published
       PHASE_MARK(6);
     }
     item = next;
