@@ -250,10 +250,7 @@ __global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict_
   const int c = (int)(idx % n), i = (int)(idx / n);
   out[(size_t)i * C + c0 + c] = in[(size_t)c * len + i];
 }
-__global__ void iota_kernel(int* out, int n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = i;
-}
+constexpr int UPLOAD_PIECE = 2048;   // models per piece of a large upload (rfinv_eval_batch)
 
 }  // namespace
 
@@ -270,9 +267,13 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
-  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_iota, sizeof(int) * Cz));
-  iota_kernel<<<(unsigned)((Cz + 255) / 256), 256, 0, stream>>>(d_iota, C);
-  RFINV_CUDA_CHECK(cudaGetLastError());
+  ready_cap = (C + UPLOAD_PIECE - 1) / UPLOAD_PIECE;
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_ready, sizeof(int) * (size_t)(ready_cap + 1)));
+  RFINV_CUDA_CHECK(cudaMemset(d_ready, 0, sizeof(int) * (size_t)(ready_cap + 1)));
+  if (!h_ready) {
+    RFINV_CUDA_CHECK(cudaHostAlloc((void**)&h_ready, sizeof(int) * 2, cudaHostAllocDefault));
+    h_ready[0] = h_ready[1] = 0;
+  }
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_misfit, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMemset(d_misfit, 0, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_phi, sizeof(double) * Cz * T));
@@ -287,8 +288,8 @@ int rfinv_handle::ensure_capacity(int C) {
 }
 
 void rfinv_handle::free_workspace() {
-  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage); cudaFree(d_iota);
-  d_iota = nullptr;
+  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage); cudaFree(d_ready);
+  d_ready = nullptr; ready_cap = 0;
   cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch); cudaFree(d_qpart); cudaFree(d_qcnt);
   d_qpart = nullptr; d_qcnt = nullptr;
   d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = d_scratch = nullptr;
@@ -298,9 +299,10 @@ void rfinv_handle::free_workspace() {
 
 int rfinv_handle::eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs,
                               const double* sig, double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid,
-                              const int* active, int n_active) {
+                              const int* active, int n_active, const ModelBatch* layout) {
   // misfit scratch is sized by capacity; its [t][c] stride uses the C of this call
   ModelBatch mb;
+  if (layout) mb = *layout;
   mb.C = C; mb.k = k; mb.z = z; mb.dvp = dvp; mb.dvs = dvs; mb.sig = sig; mb.active = active; mb.n_active = n_active; mb.n_active_dev = nullptr;
   EvalOutputs out;
   out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_smp_alt = nullptr; out.slot = nullptr; out.slot_invert = 0;
@@ -574,8 +576,9 @@ void rfinv_destroy(rfinv_handle* h) {
   if (h->stream_copy) {
     cudaStreamSynchronize(h->stream_copy);
     cudaStreamDestroy(h->stream_copy);
-    for (int i = 0; i < 3; ++i) cudaEventDestroy(h->ev_copy[i]);
+    for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
   }
+  if (h->h_ready) cudaFreeHost(h->h_ready);
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -673,47 +676,66 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
       h->cap_rft_full = need;
     }
   }
-  // Large batches: the upload runs on a second stream in two pieces, a small head (1/8 of the models) and the rest, and
-  // the evaluation of the head hides the transfer of the rest (RFINV_UPLOAD_OVERLAP=0: one piece on the handle's stream).
+  // Upload.  z / dvp / dvs go up exactly as the caller holds them (chain slowest): prep_kernel reads that layout
+  // directly, one warp per model reading consecutive words, so no layout kernels run (only sig, which loglik_kernel wants
+  // chain fastest, is transposed).  dVp stays on the host at vp_mode 0: format_model never looks at it
+  // (src/model.f90:214-218, 271-275).  Large batches go up in pieces of UPLOAD_PIECE models on a second stream, each
+  // followed by a 4-byte copy of this call's epoch into the piece's `ready` word; prep_kernel starts at once and waits
+  // per model for its piece, so only the first piece's transfer is exposed (RFINV_UPLOAD_OVERLAP=0: plain copies on the
+  // handle's stream).  Only copy-engine work is queued behind the waiting kernel: it cannot starve what it waits for.
   static const bool overlap_ok = !(getenv("RFINV_UPLOAD_OVERLAP") && atoi(getenv("RFINV_UPLOAD_OVERLAP")) == 0);
-  const int n_layout = h->cfg.vp_mode == 0 ? 3 : 4;   // layout kernels per upload_models call
-  if (overlap_ok && C >= 8192) {
+  const int km = h->cfg.k_max, T = h->cfg.ntrc;
+  const bool pieces = overlap_ok && C >= 4 * UPLOAD_PIECE;
+  ModelBatch layout;
+  layout.chain_major = 1;
+  cudaStream_t up = h->stream;
+  if (pieces) {
     if (!h->stream_copy) {
       RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
-      for (int i = 0; i < 3; ++i) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+      for (int i = 0; i < 2; ++i) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
     }
-    static const int head_16ths = getenv("RFINV_UPLOAD_HEAD_16THS") ? std::max(1, std::min(15, atoi(getenv("RFINV_UPLOAD_HEAD_16THS")))) : 2;
-    const int head = (int)((((long long)C * head_16ths / 16 + 63) / 64) * 64);
+    up = h->stream_copy;
+    h->h_ready[0] = ++h->ready_epoch;
+    layout.ready = h->d_ready; layout.ready_chunk = UPLOAD_PIECE; layout.ready_epoch = h->ready_epoch;
+    layout.ready_timeout = h->d_ready + h->ready_cap;
     RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[0], h->stream));                 // earlier work on the handle's stream reads these buffers
-    RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream_copy, h->ev_copy[0], 0));
-    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream_copy, 0, head)) != RFINV_OK) return st;
-    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[1], h->stream_copy));
-    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream_copy, head, C - head)) != RFINV_OK) return st;
-    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[2], h->stream_copy));
-    int launched = 0;
-    for (int piece = 0; piece < 2; ++piece) {
-      RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[1 + piece], 0));
-      const int c0 = piece ? head : 0, n = piece ? C - head : head;
-      st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, nullptr, nullptr, rft ? h->d_rft_full : nullptr,
-                          is_valid ? h->d_valid : nullptr, h->d_iota + c0, n);
-      if (st != RFINV_OK) return st;
-      launched += h->launches;
-    }
-    if ((st = rfinv_launch_loglik(h->dc, C, h->d_phi, h->d_sig, h->d_logl, h->stream)) != RFINV_OK) return st;
-    h->launches = launched + 1 + 2 * n_layout;
-  } else {
-    if ((st = upload_models(h, C, k, z, dvp, dvs, sig, h->stream)) != RFINV_OK) return st;
-    st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
-                        is_valid ? h->d_valid : nullptr, nullptr, 0);
-    if (st != RFINV_OK) return st;
-    h->launches += n_layout;  // the layout kernels of upload_models
+    RFINV_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_copy[0], 0));
   }
+  for (int c0 = 0; c0 < C; c0 += pieces ? UPLOAD_PIECE : C) {
+    const size_t n = (size_t)std::min(pieces ? UPLOAD_PIECE : C, C - c0);
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k + c0, k + c0, sizeof(int) * n, cudaMemcpyHostToDevice, up));
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_z + (size_t)c0 * (km - 1), z + (size_t)c0 * (km - 1), sizeof(double) * n * (km - 1), cudaMemcpyHostToDevice, up));
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvs + (size_t)c0 * km, dvs + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
+    if (h->cfg.vp_mode == 1)
+      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvp + (size_t)c0 * km, dvp + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
+    if (pieces)
+      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_ready + c0 / UPLOAD_PIECE, h->h_ready, sizeof(int), cudaMemcpyHostToDevice, up));
+  }
+  {  // sig: only the likelihood reads it, after everything else
+    const size_t nel = (size_t)C * T;
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * nel, cudaMemcpyHostToDevice, up));
+    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, up>>>(h->d_stage, h->d_sig, C, 0, C, T);
+    RFINV_CUDA_CHECK(cudaGetLastError());
+    if (pieces) RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[1], up));
+  }
+  st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, nullptr, nullptr, rft ? h->d_rft_full : nullptr,
+                      is_valid ? h->d_valid : nullptr, nullptr, 0, &layout);
+  if (st != RFINV_OK) return st;
+  if (pieces) RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[1], 0));
+  if ((st = rfinv_launch_loglik(h->dc, C, h->d_phi, h->d_sig, h->d_logl, h->stream)) != RFINV_OK) return st;
+  h->launches += 2;   // sig layout kernel, logL
+  if (pieces) RFINV_CUDA_CHECK(cudaMemcpyAsync(h->h_ready + 1, h->d_ready + h->ready_cap, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   if (rft)
     RFINV_CUDA_CHECK(cudaMemcpyAsync(rft, h->d_rft_full, sizeof(double) * (size_t)C * h->cfg.ntrc * h->cfg.nfft,
                                      cudaMemcpyDeviceToHost, h->stream));
   if (is_valid) RFINV_CUDA_CHECK(cudaMemcpyAsync(is_valid, h->d_valid, (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (pieces && h->h_ready[1] != 0) {
+    cudaMemsetAsync(h->d_ready + h->ready_cap, 0, sizeof(int), h->stream);
+    rfinv_set_error("rfinv_eval_batch: a piece of the upload never arrived on the device");
+    return RFINV_ERR_CUDA;
+  }
   return RFINV_OK;
 }
 

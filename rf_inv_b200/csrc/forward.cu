@@ -260,6 +260,20 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
   const int km = cfg.k_max, C = mb.C;
+  if (mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
+    if (lane == 0) {
+      const int* flag = mb.ready + c / mb.ready_chunk;
+      const long long t_wait = clock64();
+      int seen;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if (seen == mb.ready_epoch) break;
+        if (clock64() - t_wait > 4000000000LL) { *mb.ready_timeout = 1; break; }   // ~2 s: the copy never arrived
+        __nanosleep(200);
+      }
+    }
+    __syncwarp();
+  }
   int k = mb.k[c];
   k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
   const double p = cfg.rayp[t0];
@@ -271,7 +285,12 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   PREP_INIT();
   // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
   for (int i = lane; i < k; i += 32) {
-    zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
+    if (mb.chain_major) {
+      zu[i] = mb.z[(size_t)c * (km - 1) + i]; su[i] = mb.dvs[(size_t)c * km + i];
+      du[i] = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + i] : 0.0;   // not uploaded at vp_mode 0 (format_model never reads it)
+    } else {
+      zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
+    }
   }
   __syncwarp();
   for (int i = lane; i < k; i += 32) {
@@ -320,7 +339,8 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
     else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
     else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
-           dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; }
+           if (mb.chain_major) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
+           else { dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; } }
     double a, b;
     bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
     if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229

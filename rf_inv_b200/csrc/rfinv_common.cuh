@@ -54,6 +54,14 @@ struct ModelBatch {
   const int* active;            // optional list of model indices to evaluate (nullptr = all)
   int n_active;                 // length of `active` (upper bound when n_active_dev is set)
   const int* n_active_dev;      // optional: actual length of `active`, resident on device (grids are sized by n_active)
+  // Host-layout batch (rfinv_eval_batch): z / dvp / dvs as the caller holds them, chain slowest -- z[c*(k_max-1) + i],
+  // dvp / dvs[c*k_max + i] -- so the upload is a plain copy.  (sig stays chain-fastest: only loglik_kernel reads it.)
+  int chain_major = 0;
+  // Upload in flight (optional): piece c / ready_chunk of the batch has landed when ready[c / ready_chunk] == ready_epoch
+  // (a 4-byte copy queued behind the piece's data on the copy stream); prep_kernel waits per model.
+  const int* ready = nullptr;
+  int ready_chunk = 1, ready_epoch = 0;
+  int* ready_timeout = nullptr; // set when a wait gives up (~2 s): the evaluation is then reported as failed
 };
 
 // Fortran NINT (round half away from zero)

@@ -29,9 +29,13 @@ struct rfinv_handle {
   uint8_t* d_valid = nullptr;
   double* d_qpart = nullptr;    // quadform_kernel partial sums
   int* d_qcnt = nullptr;        // quadform_kernel work / arrival counters
-  int* d_iota = nullptr;        // 0, 1, 2, ...: `active` list of a contiguous piece of the batch (rfinv_eval_batch)
-  cudaStream_t stream_copy = nullptr;   // rfinv_eval_batch: upload of the tail of a large batch while its head is evaluated
-  cudaEvent_t ev_copy[3] = {nullptr, nullptr, nullptr};
+  // rfinv_eval_batch: the models go up as the caller holds them (chain slowest, no layout kernels); large batches in
+  // pieces on a second stream while prep_kernel already works on the pieces that have landed
+  cudaStream_t stream_copy = nullptr;
+  cudaEvent_t ev_copy[2] = {nullptr, nullptr};
+  int* d_ready = nullptr;       // [pieces] + 1: epoch of the last upload that filled the piece | time-out flag
+  int* h_ready = nullptr;       // pinned: [0] the epoch being written, [1] time-out flag read back
+  int ready_cap = 0, ready_epoch = 0;
   size_t cap_rft_full = 0;
   int launches = 0;
   bool timing = false;
@@ -44,5 +48,6 @@ struct rfinv_handle {
   void free_pt();
   // forward + quadratic form (+ logL) for device-resident chain-fastest arrays
   int eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs, const double* sig,
-                  double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid, const int* active, int n_active);
+                  double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid, const int* active, int n_active,
+                  const ModelBatch* layout = nullptr);   // layout: chain_major / ready* fields to take over (host path)
 };
