@@ -247,7 +247,9 @@ __device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclu
   return x;
 }
 
-template <bool BURIED>
+// HOSTLAYOUT: the batch of rfinv_eval_batch (chain-slowest arrays, possibly still arriving piece by piece); the
+// device-resident variants carry none of that
+template <bool BURIED, bool HOSTLAYOUT>
 __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                               double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
                                                               int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
@@ -260,7 +262,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
   const int c = mb.active ? mb.active[ci] : ci;
   const int km = cfg.k_max, C = mb.C;
-  if (mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
+  if (HOSTLAYOUT && mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
     if (lane == 0) {
       const int* flag = mb.ready + c / mb.ready_chunk;
       const long long t_wait = clock64();
@@ -285,7 +287,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
   PREP_INIT();
   // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
   for (int i = lane; i < k; i += 32) {
-    if (mb.chain_major) {
+    if (HOSTLAYOUT) {
       zu[i] = mb.z[(size_t)c * (km - 1) + i]; su[i] = mb.dvs[(size_t)c * km + i];
       du[i] = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + i] : 0.0;   // not uploaded at vp_mode 0 (format_model never reads it)
     } else {
@@ -339,7 +341,7 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
     else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
     else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
-           if (mb.chain_major) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
+           if (HOSTLAYOUT) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
            else { dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; } }
     double a, b;
     bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
@@ -1303,13 +1305,14 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
   const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
   const unsigned prep_grid = (unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS);
-  if (cfg.bdep > 0.0) {
-    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    prep_kernel<true><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
-  } else {
-    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
-    prep_kernel<false><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr);
-  }
+#define PREP(BUR, HOST)                                                                                                    \
+  do {                                                                                                                     \
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<BUR, HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem)); \
+    prep_kernel<BUR, HOST><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr); \
+  } while (0)
+  if (cfg.bdep > 0.0) { if (mb.chain_major) PREP(true, true); else PREP(true, false); }
+  else { if (mb.chain_major) PREP(false, true); else PREP(false, false); }
+#undef PREP
   RFINV_CUDA_CHECK(cudaGetLastError());
   // One launch per band-limit group: traces whose Gaussian filters keep the same number of bin groups share a launch of
   // the kernel variant built for exactly that many (different widths in one launch would have to run the widest
