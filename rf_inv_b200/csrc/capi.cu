@@ -250,7 +250,15 @@ __global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict_
   const int c = (int)(idx % n), i = (int)(idx / n);
   out[(size_t)i * C + c0 + c] = in[(size_t)c * len + i];
 }
-constexpr int UPLOAD_PIECE = 2048;   // models per piece of a large upload (rfinv_eval_batch)
+// Large uploads (rfinv_eval_batch) go up in four pieces of at least UPLOAD_PIECE_MIN models: measured at 16 384 models,
+// pieces of 1024 / 2048 / 4096 / 8192 give 9.3 / 9.9 / 10.2 / 9.8 M evals/s end to end (every copy costs a few
+// microseconds of set-up; the first piece is exposed).  RFINV_UPLOAD_PIECE overrides the piece size (tuning).
+constexpr int UPLOAD_PIECE_MIN = 2048;
+static int upload_piece(int C) {
+  static const int forced = getenv("RFINV_UPLOAD_PIECE") ? std::max(UPLOAD_PIECE_MIN, atoi(getenv("RFINV_UPLOAD_PIECE"))) : 0;
+  if (forced) return forced;
+  return std::max(UPLOAD_PIECE_MIN, ((C / 4 + 255) / 256) * 256);
+}
 
 }  // namespace
 
@@ -267,7 +275,7 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
-  ready_cap = (C + UPLOAD_PIECE - 1) / UPLOAD_PIECE;
+  ready_cap = (C + UPLOAD_PIECE_MIN - 1) / UPLOAD_PIECE_MIN;
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_ready, sizeof(int) * (size_t)(ready_cap + 1)));
   RFINV_CUDA_CHECK(cudaMemset(d_ready, 0, sizeof(int) * (size_t)(ready_cap + 1)));
   if (!h_ready) {
@@ -679,13 +687,14 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
   // Upload.  z / dvp / dvs go up exactly as the caller holds them (chain slowest): prep_kernel reads that layout
   // directly, one warp per model reading consecutive words, so no layout kernels run (only sig, which loglik_kernel wants
   // chain fastest, is transposed).  dVp stays on the host at vp_mode 0: format_model never looks at it
-  // (src/model.f90:214-218, 271-275).  Large batches go up in pieces of UPLOAD_PIECE models on a second stream, each
+  // (src/model.f90:214-218, 271-275).  Large batches go up in pieces (upload_piece()) on a second stream, each
   // followed by a 4-byte copy of this call's epoch into the piece's `ready` word; prep_kernel starts at once and waits
   // per model for its piece, so only the first piece's transfer is exposed (RFINV_UPLOAD_OVERLAP=0: plain copies on the
   // handle's stream).  Only copy-engine work is queued behind the waiting kernel: it cannot starve what it waits for.
   static const bool overlap_ok = !(getenv("RFINV_UPLOAD_OVERLAP") && atoi(getenv("RFINV_UPLOAD_OVERLAP")) == 0);
   const int km = h->cfg.k_max, T = h->cfg.ntrc;
-  const bool pieces = overlap_ok && C >= 4 * UPLOAD_PIECE;
+  const bool pieces = overlap_ok && C >= 4 * UPLOAD_PIECE_MIN;
+  const int piece = pieces ? upload_piece(C) : C;
   ModelBatch layout;
   layout.chain_major = 1;
   cudaStream_t up = h->stream;
@@ -696,20 +705,20 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
     }
     up = h->stream_copy;
     h->h_ready[0] = ++h->ready_epoch;
-    layout.ready = h->d_ready; layout.ready_chunk = UPLOAD_PIECE; layout.ready_epoch = h->ready_epoch;
+    layout.ready = h->d_ready; layout.ready_chunk = piece; layout.ready_epoch = h->ready_epoch;
     layout.ready_timeout = h->d_ready + h->ready_cap;
     RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[0], h->stream));                 // earlier work on the handle's stream reads these buffers
     RFINV_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_copy[0], 0));
   }
-  for (int c0 = 0; c0 < C; c0 += pieces ? UPLOAD_PIECE : C) {
-    const size_t n = (size_t)std::min(pieces ? UPLOAD_PIECE : C, C - c0);
+  for (int c0 = 0; c0 < C; c0 += piece) {
+    const size_t n = (size_t)std::min(piece, C - c0);
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k + c0, k + c0, sizeof(int) * n, cudaMemcpyHostToDevice, up));
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_z + (size_t)c0 * (km - 1), z + (size_t)c0 * (km - 1), sizeof(double) * n * (km - 1), cudaMemcpyHostToDevice, up));
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvs + (size_t)c0 * km, dvs + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
     if (h->cfg.vp_mode == 1)
       RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvp + (size_t)c0 * km, dvp + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
     if (pieces)
-      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_ready + c0 / UPLOAD_PIECE, h->h_ready, sizeof(int), cudaMemcpyHostToDevice, up));
+      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_ready + c0 / piece, h->h_ready, sizeof(int), cudaMemcpyHostToDevice, up));
   }
   {  // sig: only the likelihood reads it, after everything else
     const size_t nel = (size_t)C * T;
