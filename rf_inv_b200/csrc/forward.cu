@@ -68,8 +68,10 @@ struct LayerConst {
   double cbx, sbx, cbe, sbe;  // rotation by B*thx, B*the (B = threads per CTA = frequency stride of a thread)
   double t12, t21;            // interface to the next layer, {1,4} block [[1, t12], [t21, 1]] on (P, S) coordinates
   double u11, u12, u21, u22;  // interface to the next layer, {2,3} block
+  double cb2x, cb2e;          // 2 cbx, 2 cbe: third and later bins of a thread by cos((m+1)b + t) = 2 cos b cos(mb + t) - cos((m-1)b + t)
 };
-constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 12
+constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 14
+static_assert(LC_DOUBLES % 2 == 0, "LayerConst is moved in 16-byte pieces");
 
 // The rays one forward_kernel launch works on: every ray of the configuration, or -- when the traces have different
 // band limits -- the traces of one band-limit group, so that each group runs the kernel variant built for its width.
@@ -199,10 +201,10 @@ __device__ __forceinline__ void mat2_mul(const double* a, const double* b, doubl
 }
 
 // ------------------------------------------------------------------------------------------------
-// prep_kernel: one WARP per (model, ray), lane <-> layer.  format_model (src/model.f90:175-290), the per-layer
-// constants of the wave-coordinate propagator for this ray (rotation angles, interface blocks), half-space /
-// water-layer constants, the direct-arrival delay, and the two bins that do not fit the regular frequency grid
-// of forward_kernel: the DC pseudo-frequency omega = 1.0e-5 (src/forward.f90:246-248) and the Nyquist bin.
+// prep_kernel: one CTA per MODEL, one warp per ray, lane <-> layer.  format_model (src/model.f90:175-290) once per
+// model, then per ray the per-layer constants of the wave-coordinate propagator (rotation angles, interface blocks),
+// half-space / water-layer constants, the direct-arrival delay, and the two bins that do not fit the regular
+// frequency grid of forward_kernel: the DC pseudo-frequency omega = 1.0e-5 (src/forward.f90:246-248) and Nyquist.
 //
 // Basis of a solid layer (columns = standing P wave, standing S wave; rows = components {1,4} / {2,3}):
 //   V14 = [[p, 1], [rho bp, -2 rho beta^2 p]],          V14^-1 = [[2 beta^2 p, 1/rho], [bp, -p/rho]]
@@ -212,20 +214,33 @@ __device__ __forceinline__ void mat2_mul(const double* a, const double* b, doubl
 // unit diagonal: with tau = (unscaled V_l^-1)(unscaled V_{l-1}), sP_l = prod tau14[0][0], sS_l = prod tau14[1][1]
 // (warp prefix products), and the interface constants only need the ratio r = sS/sP of the layer above.
 //
-// Phases (warp-synchronous, staged through shared memory): rank sort of the interfaces; per-layer physics, all
-// transcendental functions included, one layer per lane; prefix products and interface constants; then the only
-// serial part: lanes 0-3 carry the four edge-bin vectors down the stack while lane 4 sums the delay in the
-// reference's order.
+// Phases: (A) warp 0: rank sort of the interfaces, then everything of a layer that does not depend on the ray --
+// reference-velocity lookup, validity, density, 1/alpha^2, 1/beta^2 -- one layer per lane, left in shared memory for
+// the other warps; (B) every warp, for its ray: per-layer physics with all transcendental functions, prefix products
+// and interface constants, ray constants; (C) the only serial part, once per model: the four edge-bin vectors
+// (a | b) x (DC | Nyquist) of EVERY ray go down the stack side by side, four lanes per ray, next to the lanes that sum
+// the delays in the reference's order; (D) the finished RayConst records leave through one coalesced copy.
 // ------------------------------------------------------------------------------------------------
-struct PrepLayer {
+struct PrepBasis {   // per (ray, layer), shared memory
   double v14[4], v23[4];   // unscaled basis blocks of this layer
   double i14[4], i23[4];   // their inverses (closed form)
+};
+struct PrepSerial {  // per (ray, layer): what the serial pass reads
   double tr[8];            // cos, sin of (w xi h), (w eta h) at the DC pseudo-frequency, then at Nyquist
   double ic[6];            // t12, t21, u11, u12, u21, u22 of the interface below this layer
   double tpterm, pad;
 };
-constexpr int PREP_WARPS = 4;
-__host__ __device__ inline size_t prep_smem_doubles_per_warp(int km) { return (size_t)6 * km + (size_t)(km + 1) * (sizeof(PrepLayer) / sizeof(double)); }
+struct PrepShared {  // per layer of the propagation: independent of the ray
+  double h, rho, irho, beta2, inv_b2, inv_a2, a, b;
+};
+constexpr int PB_DOUBLES = sizeof(PrepBasis) / sizeof(double), PS_DOUBLES = sizeof(PrepSerial) / sizeof(double);
+constexpr int PSH_DOUBLES = sizeof(PrepShared) / sizeof(double);
+constexpr int PREP_RAYS_PER_PASS = 6;   // rays of one serial pass: 4 vector lanes + 1 delay lane each
+constexpr int PREP_MISC_DOUBLES = 8;    // k, ls, valid (ints) and h_part
+// shared memory of a prep_kernel CTA, in doubles: [model part | per-ray part x rays]
+__host__ __device__ inline size_t prep_sorted_doubles(int km) { return ((size_t)3 * km + 1) & ~(size_t)1; }   // zs | dps | dss, 16-byte granular
+__host__ __device__ inline size_t prep_smem_model_doubles(int km) { return prep_sorted_doubles(km) + (size_t)(km + 2) * PSH_DOUBLES + PREP_MISC_DOUBLES; }
+__host__ __device__ inline size_t prep_smem_ray_doubles(int km) { return (size_t)(km + 1) * PB_DOUBLES + (size_t)km * PS_DOUBLES + RC_DOUBLES + 4; }
 
 // sin, cos of a small argument (|x| < 0.01: Taylor remainder < 3e-21); falls back to sincos otherwise
 __device__ __forceinline__ void small_sincos(double x, double* sn, double* cs) {
@@ -250,148 +265,193 @@ __device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclu
 // HOSTLAYOUT: the batch of rfinv_eval_batch (chain-slowest arrays, possibly still arriving piece by piece); the
 // device-resident variants carry none of that
 template <bool BURIED, bool HOSTLAYOUT>
-__global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
-                                                              double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
-                                                              int* __restrict__ counter, int n_items, int ntr_eff, int nthr_fwd) {
+__global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
+                                                                 double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
+                                                                 int* __restrict__ counter, int n_models, int ntr_eff, int nthr_fwd,
+                                                                 int rays_per_cta) {
   extern __shared__ __align__(16) double prep_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int item = blockIdx.x * PREP_WARPS + warp;
+  // a model with many rays is spread over several CTAs (shared memory): group g works on rays [t_first, t_first + nr_cta)
+  const int n_groups = (ntr_eff + rays_per_cta - 1) / rays_per_cta;
+  const int ci = blockIdx.x / n_groups, t_first = (blockIdx.x - ci * n_groups) * rays_per_cta;
+  const int nr_cta = min(rays_per_cta, ntr_eff - t_first);
   if (blockIdx.x == 0 && threadIdx.x < RFINV_MAX_TRC) counter[threadIdx.x] = 0;   // work counters of the forward_kernel launches that follow on the same stream
-  if (item >= n_items) return;
-  if (mb.n_active_dev && item >= *mb.n_active_dev * ntr_eff) return;
-  const int ci = item / ntr_eff, t0 = item - ci * ntr_eff;
+  if (ci >= n_models) return;
+  if (mb.n_active_dev && ci >= *mb.n_active_dev) return;
   const int c = mb.active ? mb.active[ci] : ci;
   const int km = cfg.k_max, C = mb.C;
-  if (HOSTLAYOUT && mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
-    if (lane == 0) {
-      const int* flag = mb.ready + c / mb.ready_chunk;
-      const long long t_wait = clock64();
-      int seen;
-      for (;;) {
-        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-        if (seen == mb.ready_epoch) break;
-        if (clock64() - t_wait > 4000000000LL) { *mb.ready_timeout = 1; break; }   // ~2 s: the copy never arrived
-        __nanosleep(200);
+  const bool has_ray = warp < nr_cta;          // (a short last group leaves warps without a ray: they only keep the barriers)
+  const int t0 = t_first + (has_ray ? warp : 0);   // the ray of this warp
+  const size_t item = (size_t)ci * ntr_eff + t0;
+  // ---- shared memory ----
+  double* zs = prep_smem;                      // sorted interfaces and their perturbations
+  double *dps = zs + km, *dss = dps + km;
+  PrepShared* LA = reinterpret_cast<PrepShared*>(zs + prep_sorted_doubles(km));   // [km + 2]
+  double* s_misc = reinterpret_cast<double*>(LA + km + 2);
+  int* s_int = reinterpret_cast<int*>(s_misc + 1);                               // k, ls, valid
+  double* ray0 = s_misc + PREP_MISC_DOUBLES;
+  const size_t ray_stride = prep_smem_ray_doubles(km);
+  auto ray_basis = [&](int t) { return reinterpret_cast<PrepBasis*>(ray0 + (size_t)t * ray_stride); };                  // [km + 1]
+  auto ray_serial = [&](int t) { return reinterpret_cast<PrepSerial*>(ray0 + (size_t)t * ray_stride + (size_t)(km + 1) * PB_DOUBLES); };   // [km]
+  auto ray_const = [&](int t) { return reinterpret_cast<RayConst*>(ray0 + (size_t)t * ray_stride + (size_t)(km + 1) * PB_DOUBLES + (size_t)km * PS_DOUBLES); };
+  auto ray_water = [&](int t) { return reinterpret_cast<double*>(ray_const(t)) + RC_DOUBLES; };   // cw0, sw0, cw1, sw1
+  constexpr bool buried = BURIED;   // cfg.bdep > 0
+
+  PREP_INIT();
+  if (warp == 0) {
+    if (HOSTLAYOUT && mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
+      if (lane == 0) {
+        const int* flag = mb.ready + c / mb.ready_chunk;
+        const long long t_wait = clock64();
+        int seen;
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+          if (seen == mb.ready_epoch) break;
+          if (clock64() - t_wait > 4000000000LL) { *mb.ready_timeout = 1; break; }   // ~2 s: the copy never arrived
+          __nanosleep(200);
+        }
+      }
+      __syncwarp();
+    }
+    int k = mb.k[c];
+    k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
+    // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
+    double* zu = reinterpret_cast<double*>(ray_basis(0));   // unsorted z, dvp, dvs: the region is rewritten in phase B
+    double *du = zu + km, *su = du + km;
+    for (int i = lane; i < k; i += 32) {
+      if (HOSTLAYOUT) {
+        zu[i] = mb.z[(size_t)c * (km - 1) + i]; su[i] = mb.dvs[(size_t)c * km + i];
+        du[i] = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + i] : 0.0;   // not uploaded at vp_mode 0 (format_model never reads it)
+      } else {
+        zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
       }
     }
     __syncwarp();
-  }
-  int k = mb.k[c];
-  k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
-  const double p = cfg.rayp[t0];
-  const int ipha = cfg.ipha[t0];
-  double* zu = prep_smem + (size_t)warp * prep_smem_doubles_per_warp(km);   // unsorted z, dvp, dvs, then sorted
-  double *du = zu + km, *su = du + km, *zs = su + km, *dps = zs + km, *dss = dps + km;
-  PrepLayer* PL = reinterpret_cast<PrepLayer*>(dss + km);
-
-  PREP_INIT();
-  // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
-  for (int i = lane; i < k; i += 32) {
-    if (HOSTLAYOUT) {
-      zu[i] = mb.z[(size_t)c * (km - 1) + i]; su[i] = mb.dvs[(size_t)c * km + i];
-      du[i] = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + i] : 0.0;   // not uploaded at vp_mode 0 (format_model never reads it)
-    } else {
-      zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
+    for (int i = lane; i < k; i += 32) {
+      const double zi = zu[i];
+      int rank = 0;
+      for (int j = 0; j < k; ++j) { const double zj = zu[j]; rank += (zj < zi || (zj == zi && j < i)) ? 1 : 0; }
+      zs[rank] = zi; dps[rank] = du[i]; dss[rank] = su[i];
     }
-  }
-  __syncwarp();
-  for (int i = lane; i < k; i += 32) {
-    const double zi = zu[i];
-    int rank = 0;
-    for (int j = 0; j < k; ++j) { const double zj = zu[j]; rank += (zj < zi || (zj == zi && j < i)) ? 1 : 0; }
-    zs[rank] = zi; dps[rank] = du[i]; dss[rank] = su[i];
-  }
-  __syncwarp();
+    __syncwarp();
 
-  // ---- buried station (src/forward.f90:308-334, commented out in the reference): the layer that holds it is split at the
-  // station depth into two sublayers of the same material, so the station sits on a (transparent) interface of the
-  // propagation; a station below the last interface adds a layer of half-space material on top of the half space.
-  // ls = model layer with the station (k = half space), h_part = its thickness above the station; same running sum
-  // as the reference (z_tmp = z_tmp + h(ilay); z_tmp < bdep continues).
-  constexpr bool buried = BURIED;   // cfg.bdep > 0
-  int ls = -1;
-  double h_part = 0.0;
-  if (buried) {
-    double z_tmp = 0.0;
-    ls = k;
-    for (int l = 0; l < k; ++l) {
-      const double hl = l == 0 ? __dsub_rn(zs[0], cfg.sdep) : __dsub_rn(zs[l], zs[l - 1]);
-      z_tmp = __dadd_rn(z_tmp, hl);
-      if (!(z_tmp < cfg.bdep)) { ls = l; h_part = __dsub_rn(__dadd_rn(cfg.bdep, hl), z_tmp); break; }
+    // ---- buried station (src/forward.f90:308-334, commented out in the reference): the layer that holds it is split at the
+    // station depth into two sublayers of the same material, so the station sits on a (transparent) interface of the
+    // propagation; a station below the last interface adds a layer of half-space material on top of the half space.
+    // ls = model layer with the station (k = half space), h_part = its thickness above the station; same running sum
+    // as the reference (z_tmp = z_tmp + h(ilay); z_tmp < bdep continues).
+    int ls = -1;
+    double h_part = 0.0;
+    if (buried) {
+      double z_tmp = 0.0;
+      ls = k;
+      for (int l = 0; l < k; ++l) {
+        const double hl = l == 0 ? __dsub_rn(zs[0], cfg.sdep) : __dsub_rn(zs[l], zs[l - 1]);
+        z_tmp = __dadd_rn(z_tmp, hl);
+        if (!(z_tmp < cfg.bdep)) { ls = l; h_part = __dsub_rn(__dadd_rn(cfg.bdep, hl), z_tmp); break; }
+      }
+      if (ls == k) h_part = __dsub_rn(cfg.bdep, z_tmp);
     }
-    if (ls == k) h_part = __dsub_rn(cfg.bdep, z_tmp);
+    const int ka = buried ? k + 1 : k;    // solid layers of the propagation
+    PREP_MARK(0);
+    // ---- what a layer has that does not depend on the ray, one layer per lane ----
+    bool valid = true;
+    for (int la = lane; la <= ka; la += 32) {
+      const int l = (buried && la > ls) ? la - 1 : la;       // model layer behind propagation layer la
+      double zc, h, dvs_l, dvp_l;
+      if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
+      else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
+      else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
+             if (HOSTLAYOUT) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
+             else { dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; } }
+      double a, b;
+      bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
+      if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
+      else if (l < k) ok = ok && !(h < cfg.h_min);           // src/model.f90:257
+      valid = valid && ok;
+      if (buried) {
+        if (la == ls) h = h_part;                                        // above the station
+        else if (la == ls + 1 && ls < k) h = __dsub_rn(h, h_part);       // rest of the split layer
+      }
+      PrepShared S;
+      S.h = h; S.a = a; S.b = b;
+      S.rho = vp_to_rho(a);
+      S.irho = 1.0 / S.rho;
+      S.beta2 = __dmul_rn(b, b);
+      S.inv_b2 = __ddiv_rn(1.0, S.beta2);                     // src/forward.f90:395
+      S.inv_a2 = __ddiv_rn(1.0, __dmul_rn(a, a));             // src/forward.f90:396
+      LA[la] = S;
+    }
+    valid = __all_sync(0xffffffffu, valid);
+    if (lane == 0) { s_int[0] = k; s_int[1] = ls; s_int[2] = valid ? 1 : 0; s_misc[0] = h_part; }
+    PREP_MARK(1);
   }
-  const int ka = buried ? k + 1 : k;    // solid layers of the propagation
+  __syncthreads();
+
+  const int k = s_int[0], ls = s_int[1];
+  const bool valid = s_int[2] != 0;
+  const int ka = buried ? k + 1 : k;
   // Layers above the bottom boundary condition.  A station in the half space does not move it: the incident wave keeps
   // its phase reference at the last model interface (src/forward.f90:250-264), the extra layer only carries the
   // vectors on to the station.
   const int kb = (buried && ls == k) ? k : ka;
+  PrepBasis* PB = ray_basis(warp);
+  PrepSerial* PS = ray_serial(warp);
+  if (has_ray) {
 
-  PREP_MARK(0);
-  // ---- per-layer physics, one layer per lane ----
+  // ---- (B) per-layer physics of this ray, one layer per lane ----
+  const double p = cfg.rayp[t0];
+  const int ipha = cfg.ipha[t0];
   const double p2 = __dmul_rn(p, p);
   const double nyq = (double)(cfg.nfft / 2);
   int nyq_doublings = 0;
   while ((nthr_fwd << nyq_doublings) < cfg.nfft / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d
-  bool valid = true;
-  double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane k & 31)
+  double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane ka & 31)
   for (int la = lane; la <= ka; la += 32) {
-    const int l = (buried && la > ls) ? la - 1 : la;       // model layer behind propagation layer la
-    double zc, h, dvs_l, dvp_l;
-    if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
-    else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
-    else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
-           if (HOSTLAYOUT) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
-           else { dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; } }
-    double a, b;
-    bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
-    if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
-    else if (l < k) ok = ok && !(h < cfg.h_min);           // src/model.f90:257
-    valid = valid && ok;
+    const PrepShared S = LA[la];
+    const double h = S.h, rho = S.rho, beta2 = S.beta2;
     double tp_sign = 1.0;                                  // direct-arrival delay counts from the station down
     if (buried) {
-      if (la == ls) { h = h_part; tp_sign = ls == k ? -1.0 : 0.0; }   // above the station (in the half space: negative)
-      else if (la == ls + 1 && ls < k) h = __dsub_rn(h, h_part);      // rest of the split layer
+      if (la == ls) tp_sign = ls == k ? -1.0 : 0.0;        // above the station (in the half space: negative)
       else if (la < ls) tp_sign = 0.0;
     }
-    const double rho = vp_to_rho(a);
-    const double beta2 = __dmul_rn(b, b);
     const double bp = 1.0 - 2.0 * beta2 * p2;
-    const double eta = sqrt(__dsub_rn(__ddiv_rn(1.0, beta2), p2));              // src/forward.f90:395
-    const double xi = sqrt(__dsub_rn(__ddiv_rn(1.0, __dmul_rn(a, a)), p2));    // src/forward.f90:396
+    const double eta = sqrt(__dsub_rn(S.inv_b2, p2));      // src/forward.f90:395
+    const double xi = sqrt(__dsub_rn(S.inv_a2, p2));       // src/forward.f90:396
     if (la < ka) {
-      PrepLayer& Q = PL[la];
+      PrepBasis& Q = PB[la];
+      PrepSerial& Z = PS[la];
       const double g2 = 2.0 * beta2 * p;   // 2 beta^2 p
-      const double ieta = 1.0 / eta, irho = 1.0 / rho, ixi = 1.0 / xi;
+      const double ieta = 1.0 / eta, irho = S.irho, ixi = 1.0 / xi;
       Q.v14[0] = p; Q.v14[1] = 1.0; Q.v14[2] = rho * bp; Q.v14[3] = -rho * g2;
       Q.v23[0] = xi; Q.v23[1] = -p * ieta; Q.v23[2] = -rho * g2 * xi; Q.v23[3] = -rho * bp * ieta;
       Q.i14[0] = g2; Q.i14[1] = irho; Q.i14[2] = bp; Q.i14[3] = -p * irho;
       Q.i23[0] = bp * ixi; Q.i23[1] = -p * irho * ixi; Q.i23[2] = -g2 * eta; Q.i23[3] = -eta * irho;
-      Q.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(tp_sign, __dmul_rn(h, ipha == 1 ? xi : eta)) : 0.0;   // src/forward.f90:489-491
-      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + la;
+      Z.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(tp_sign, __dmul_rn(h, ipha == 1 ? xi : eta)) : 0.0;   // src/forward.f90:489-491
+      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + item * km + la;
       const double thx = cfg.domg * xi * h, the = cfg.domg * eta * h;
       L->thx = thx; L->the = the;
-      double sn, cs;
-      sincos((double)nthr_fwd * thx, &sn, &cs); L->cbx = cs; L->sbx = sn;
-      sincos((double)nthr_fwd * the, &sn, &cs); L->cbe = cs; L->sbe = sn;
-      small_sincos((double)1.0e-5f * xi * h, &Q.tr[1], &Q.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
-      small_sincos((double)1.0e-5f * eta * h, &Q.tr[3], &Q.tr[2]);
+      double snx, csx, sne, cse;
+      sincos((double)nthr_fwd * thx, &snx, &csx); L->cbx = csx; L->sbx = snx;
+      sincos((double)nthr_fwd * the, &sne, &cse); L->cbe = cse; L->sbe = sne;
+      L->cb2x = csx + csx; L->cb2e = cse + cse;
+      small_sincos((double)1.0e-5f * xi * h, &Z.tr[1], &Z.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
+      small_sincos((double)1.0e-5f * eta * h, &Z.tr[3], &Z.tr[2]);
       // Nyquist = (nfft/2) bins = nyq_doublings doublings of the stride rotation; its bin carries the smallest
       // filter weight of the whole spectrum, so the doubled rounding error is immaterial
-      double cn = L->cbx, sn2 = L->sbx, ce = L->cbe, se = L->sbe;
+      double cn = csx, sn2 = snx, ce = cse, se = sne;
       for (int d = 0; d < nyq_doublings; ++d) {
         const double c2 = fma(cn, cn, -sn2 * sn2), s2 = 2.0 * cn * sn2; cn = c2; sn2 = s2;
         const double c3 = fma(ce, ce, -se * se), s3 = 2.0 * ce * se; ce = c3; se = s3;
       }
-      Q.tr[4] = cn; Q.tr[5] = sn2; Q.tr[6] = ce; Q.tr[7] = se;
+      Z.tr[4] = cn; Z.tr[5] = sn2; Z.tr[6] = ce; Z.tr[7] = se;
     } else {
-      hs_a = a; hs_b = b; hs_rho = rho; hs_xi = xi; hs_eta = eta; hs_bp = bp; hs_beta2 = beta2;
+      hs_a = S.a; hs_b = S.b; hs_rho = rho; hs_xi = xi; hs_eta = eta; hs_bp = bp; hs_beta2 = beta2;
     }
   }
-  valid = __all_sync(0xffffffffu, valid);
   __syncwarp();
 
-  PREP_MARK(1);
+  PREP_MARK(2);
   // ---- interfaces l-1 -> l (l = 1..k-1): tau = V_l^-1 V_{l-1} unscaled, prefix products of its {1,4} diagonal ----
   double carryP = 1.0, carryS = 1.0;      // scale products of the slots already done
   double sP_last = 1.0, sS_last = 1.0;    // scales of the last solid layer above the half space (kb-1)
@@ -400,19 +460,19 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     const int l = base + lane;
     double t14[4] = {1.0, 0.0, 0.0, 1.0}, t23[4] = {1.0, 0.0, 0.0, 1.0};
     if (l >= 1 && l < ka) {
-      mat2_mul(PL[l].i14, PL[l - 1].v14, t14);
-      mat2_mul(PL[l].i23, PL[l - 1].v23, t23);
+      mat2_mul(PB[l].i14, PB[l - 1].v14, t14);
+      mat2_mul(PB[l].i23, PB[l - 1].v23, t23);
     }
     const double sP = carryP * warp_scan_mul(t14[0], lane), sS = carryS * warp_scan_mul(t14[3], lane);   // scales of layer l
     double sPp = __shfl_up_sync(0xffffffffu, sP, 1), sSp = __shfl_up_sync(0xffffffffu, sS, 1);           // scales of layer l-1
     if (lane == 0) { sPp = carryP; sSp = carryS; }
     if (l >= 1 && l < ka) {
-      double* ic = PL[l - 1].ic;
+      double* ic = PS[l - 1].ic;
       const double rP = 1.0 / sP, rS = 1.0 / sS;
       const double pp = sPp * rP, sp = sSp * rP, ps = sPp * rS, ss = sSp * rS;
       ic[0] = t14[1] * sp; ic[1] = t14[2] * ps;
       ic[2] = t23[0] * pp; ic[3] = t23[1] * sp; ic[4] = t23[2] * ps; ic[5] = t23[3] * ss;
-      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (l - 1);
+      LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + item * km + (l - 1);
       L->t12 = ic[0]; L->t21 = ic[1]; L->u11 = ic[2]; L->u12 = ic[3]; L->u21 = ic[4]; L->u22 = ic[5];
     }
     const int last_lane = (ka - 1 - base) < 31 ? (ka - 1 - base) : 31;   // highest lane of this slot holding a solid layer
@@ -422,122 +482,153 @@ __global__ void __launch_bounds__(32 * PREP_WARPS) prep_kernel(const DevConfig c
     carryS = __shfl_sync(0xffffffffu, sS, last_lane);
   }
   if (lane == 0) {   // the last solid layer has no in-loop interface: the half space follows
-    LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + (size_t)item * km + (ka - 1);
+    LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + item * km + (ka - 1);
     L->t12 = 0.0; L->t21 = 0.0; L->u11 = 1.0; L->u12 = 0.0; L->u21 = 0.0; L->u22 = 1.0;
+    double* ic = PS[ka - 1].ic;
+    ic[0] = 0.0; ic[1] = 0.0; ic[2] = 1.0; ic[3] = 0.0; ic[4] = 0.0; ic[5] = 1.0;
   }
   __syncwarp();
 
-  PREP_MARK(2);
-  // ---- ray constants: half space, water layer, start vectors ----
-  RayConst R;
-  double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
-  if (cfg.sdep > 0.0) {   // water layer (src/model.f90:201-207, src/forward.f90:424-442)
-    const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
-    const double xiw = sqrt(1.0 / (aw * aw) - p * p);
-    R.thw = cfg.domg * xiw * hw;
-    sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
-    rw = rhow / xiw;
-    small_sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
-    sincos(nyq * R.thw, &sw1, &cw1);
-  } else {
-    R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
-  }
-  {
-    // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the scaled basis of
-    // the last solid layer
-    const int src_lane = ka & 31;
-    const double a = __shfl_sync(0xffffffffu, hs_a, src_lane), b = __shfl_sync(0xffffffffu, hs_b, src_lane);
-    const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
-    const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
-    const double beta2 = __shfl_sync(0xffffffffu, hs_beta2, src_lane);
-    const double r1 = 1.0 / (2.0 * rho * a * xi), r2 = 1.0 / (2.0 * rho * b * eta);
-    const double e11 = beta2 * p * (2.0 * rho * xi) * r1, e12 = bp * rho * r1, e13 = p * r1, e14 = xi * r1;
-    const double e21 = bp * rho * r2, e22 = b * p, e23 = eta * r2, e24 = p * r2;
-    const double r14[4] = {e11, e14, e21, -e24};
-    const double r23[4] = {-e12, e13, e22, e23};
-    const PrepLayer& Q = PL[kb - 1];
-    const double v14[4] = {Q.v14[0] * sP_last, Q.v14[1] * sS_last, Q.v14[2] * sP_last, Q.v14[3] * sS_last};
-    const double v23[4] = {Q.v23[0] * sP_last, Q.v23[1] * sS_last, Q.v23[2] * sP_last, Q.v23[3] * sS_last};
-    mat2_mul(r14, v14, R.h14);
-    mat2_mul(r23, v23, R.h23);
-  }
-  {
-    // start vectors in layer 0's coordinates (scale 1): e1, and (0, cw, 0, -rw sw) for a free / water-loaded surface
-    const PrepLayer& Q = PL[0];
-    R.a1 = Q.i14[0]; R.b1 = Q.i14[2];                   // V14^-1 (1, 0)^T
-    R.q1a = -rw * Q.i14[1]; R.q1b = -rw * Q.i14[3];     // -rw V14^-1 (0, 1)^T
-    R.q2a = Q.i23[0]; R.q2b = Q.i23[2];                 // V23^-1 (1, 0)^T
-  }
-  R.l_sta = -1;
-  R.sta[0] = R.sta[1] = R.sta[2] = R.sta[3] = 0.0;
-  if (buried) {   // displacement rows of V14 / V23 of the layer above the station, with that layer's scales
-    const PrepLayer& Q = PL[ls];
-    R.l_sta = ls;
-    R.sta[0] = Q.v14[0] * sP_sta; R.sta[1] = Q.v14[1] * sS_sta;
-    R.sta[2] = Q.v23[0] * sP_sta; R.sta[3] = Q.v23[1] * sS_sta;
-  }
-
   PREP_MARK(3);
-  // ---- serial part: lanes 0..3 carry (vector a | b) x (DC | Nyquist) down the stack; lane 4 sums the delay ----
-  Wave w;
-  double2 y_sta = make_double2(0.0, 0.0);   // displacement components of this lane's vector at a buried station
+  // ---- ray constants: half space, water layer, start vectors ----
   {
+    RayConst R;
+    double cw0 = 1.0, sw0 = 0.0, cw1 = 1.0, sw1 = 0.0, rw = 0.0;
+    if (cfg.sdep > 0.0) {   // water layer (src/model.f90:201-207, src/forward.f90:424-442)
+      const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
+      const double xiw = sqrt(1.0 / (aw * aw) - p * p);
+      R.thw = cfg.domg * xiw * hw;
+      sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
+      rw = rhow / xiw;
+      small_sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
+      sincos(nyq * R.thw, &sw1, &cw1);
+    } else {
+      R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
+    }
+    {
+      // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the scaled basis of
+      // the last solid layer
+      const int src_lane = ka & 31;
+      const double a = __shfl_sync(0xffffffffu, hs_a, src_lane), b = __shfl_sync(0xffffffffu, hs_b, src_lane);
+      const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
+      const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
+      const double beta2 = __shfl_sync(0xffffffffu, hs_beta2, src_lane);
+      const double r1 = 1.0 / (2.0 * rho * a * xi), r2 = 1.0 / (2.0 * rho * b * eta);
+      const double e11 = beta2 * p * (2.0 * rho * xi) * r1, e12 = bp * rho * r1, e13 = p * r1, e14 = xi * r1;
+      const double e21 = bp * rho * r2, e22 = b * p, e23 = eta * r2, e24 = p * r2;
+      const double r14[4] = {e11, e14, e21, -e24};
+      const double r23[4] = {-e12, e13, e22, e23};
+      const PrepBasis& Q = PB[kb - 1];
+      const double v14[4] = {Q.v14[0] * sP_last, Q.v14[1] * sS_last, Q.v14[2] * sP_last, Q.v14[3] * sS_last};
+      const double v23[4] = {Q.v23[0] * sP_last, Q.v23[1] * sS_last, Q.v23[2] * sP_last, Q.v23[3] * sS_last};
+      mat2_mul(r14, v14, R.h14);
+      mat2_mul(r23, v23, R.h23);
+    }
+    {
+      // start vectors in layer 0's coordinates (scale 1): e1, and (0, cw, 0, -rw sw) for a free / water-loaded surface
+      const PrepBasis& Q = PB[0];
+      R.a1 = Q.i14[0]; R.b1 = Q.i14[2];                   // V14^-1 (1, 0)^T
+      R.q1a = -rw * Q.i14[1]; R.q1b = -rw * Q.i14[3];     // -rw V14^-1 (0, 1)^T
+      R.q2a = Q.i23[0]; R.q2b = Q.i23[2];                 // V23^-1 (1, 0)^T
+    }
+    R.l_sta = -1;
+    R.sta[0] = R.sta[1] = R.sta[2] = R.sta[3] = 0.0;
+    if (buried) {   // displacement rows of V14 / V23 of the layer above the station, with that layer's scales
+      const PrepBasis& Q = PB[ls];
+      R.l_sta = ls;
+      R.sta[0] = Q.v14[0] * sP_sta; R.sta[1] = Q.v14[1] * sS_sta;
+      R.sta[2] = Q.v23[0] * sP_sta; R.sta[3] = Q.v23[1] * sS_sta;
+    }
+    R.k = kb;
+    R.valid = valid;
+    R.tp = 0.0; R.npre = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) R.edge[i] = make_double2(0.0, 0.0);
+    if (lane == 0) {   // staged in shared memory; the serial pass completes it
+      *ray_const(warp) = R;
+      double* W = ray_water(warp);
+      W[0] = cw0; W[1] = sw0; W[2] = cw1; W[3] = sw1;
+    }
+  }
+  PREP_MARK(4);
+  }   // has_ray
+  __syncthreads();
+
+  // ---- (C) serial part, once per model: four lanes per ray carry (vector a | b) x (DC | Nyquist) down the stack; one more
+  // lane per ray sums the delay in the reference's order.  Up to PREP_RAYS_PER_PASS rays per warp. ----
+  for (int r0 = warp * PREP_RAYS_PER_PASS; r0 < nr_cta; r0 += (int)(blockDim.x >> 5) * PREP_RAYS_PER_PASS) {   // r0: ray index inside the CTA
+    const int nr = min(PREP_RAYS_PER_PASS, nr_cta - r0);
+    const bool vec_lane = lane < 4 * nr, tp_lane = lane >= 4 * nr && lane < 5 * nr;
+    const int tr_ray = r0 + (vec_lane ? (lane >> 2) : (tp_lane ? lane - 4 * nr : 0));   // the ray this lane works for
+    const RayConst* Rr = ray_const(tr_ray);
+    const double* Wr = ray_water(tr_ray);
+    const PrepSerial* Zr = ray_serial(tr_ray);
     const bool is_b = lane & 1, is_nyq = (lane >> 1) & 1;
-    const double cw = is_nyq ? cw1 : cw0, sw = is_nyq ? sw1 : sw0;
-    if (!is_b) { w.a1 = R.a1; w.b1 = R.b1; w.a2 = 0.0; w.b2 = 0.0; }
-    else { w.a1 = sw * R.q1a; w.b1 = sw * R.q1b; w.a2 = cw * R.q2a; w.b2 = cw * R.q2b; }
+    Wave w;
+    double2 y_sta = make_double2(0.0, 0.0);   // displacement components of this lane's vector at a buried station
     double tp = 0.0;
-    if (lane < 4) {
+    {
+      const double cw = is_nyq ? Wr[2] : Wr[0], sw = is_nyq ? Wr[3] : Wr[1];
+      if (!is_b) { w.a1 = Rr->a1; w.b1 = Rr->b1; w.a2 = 0.0; w.b2 = 0.0; }
+      else { w.a1 = sw * Rr->q1a; w.b1 = sw * Rr->q1b; w.a2 = cw * Rr->q2a; w.b2 = cw * Rr->q2b; }
+    }
+    if (vec_lane) {
       const int o = is_nyq ? 4 : 0;
+      const double st0 = Rr->sta[0], st1 = Rr->sta[1], st2 = Rr->sta[2], st3 = Rr->sta[3];
       Wave w_bc = w;
       for (int l = 0; l < ka; ++l) {
-        const PrepLayer& Q = PL[l];
+        const PrepSerial& Q = Zr[l];
         wave_rotate(w, Q.tr[o], Q.tr[o + 1], Q.tr[o + 2], Q.tr[o + 3]);
-        if (l == ls) { y_sta.x = fma(R.sta[0], w.a1, R.sta[1] * w.b1); y_sta.y = fma(R.sta[2], w.a2, R.sta[3] * w.b2); }
+        if (buried && l == ls) { y_sta.x = fma(st0, w.a1, st1 * w.b1); y_sta.y = fma(st2, w.a2, st3 * w.b2); }
         if (l == kb - 1) w_bc = w;   // what the bottom boundary condition sees
         if (l + 1 < ka) wave_interface(w, Q.ic[0], Q.ic[1], Q.ic[2], Q.ic[3], Q.ic[4], Q.ic[5]);
       }
       w = w_bc;
-    } else if (lane == 4) {
-      for (int l = 0; l < ka; ++l) tp = __dadd_rn(tp, PL[l].tpterm);
+    } else if (tp_lane) {
+      for (int l = 0; l < ka; ++l) tp = __dadd_rn(tp, Zr[l].tpterm);
+      RayConst* Rw = ray_const(tr_ray);
+      const int iph = cfg.ipha[t_first + tr_ray];
+      Rw->tp = tp;
+      Rw->npre = iph == 1 ? f_nint((-cfg.t_start - tp) / cfg.delta)    // src/forward.f90:177
+                          : f_nint((-cfg.t_start + tp) / cfg.delta);   // src/forward.f90:186
     }
-    R.tp = __shfl_sync(0xffffffffu, tp, 4);
-  }
-  {
-    PREP_MARK(4);
-    // gather the four vectors on every lane; lane 0 finishes the two edge bins
-    Wave wv[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      wv[i].a1 = __shfl_sync(0xffffffffu, w.a1, i); wv[i].a2 = __shfl_sync(0xffffffffu, w.a2, i);
-      wv[i].b1 = __shfl_sync(0xffffffffu, w.b1, i); wv[i].b2 = __shfl_sync(0xffffffffu, w.b2, i);
-    }
+    PREP_MARK(5);
+    // lanes 2r + e finish edge bin e (0 = DC, 1 = Nyquist) of ray r: vectors a, b of that bin sit in lanes 4r + 2e, 4r + 2e + 1
     {
-      const int e = lane & 1;   // lane parity picks the edge bin: both are finished in one pass
-      double2 fr, fv;
-      const Wave ea = e ? wv[2] : wv[0], eb = e ? wv[3] : wv[1];
-      if (!buried) {
-        surface_response(R.h14, R.h23, ea, eb, e ? cw1 : cw0, ipha, fr, fv);
-      } else {
-        const double2 ya = make_double2(__shfl_sync(0xffffffffu, y_sta.x, 2 * e), __shfl_sync(0xffffffffu, y_sta.y, 2 * e));
-        const double2 yb = make_double2(__shfl_sync(0xffffffffu, y_sta.x, 2 * e + 1), __shfl_sync(0xffffffffu, y_sta.y, 2 * e + 1));
-        surface_response_buried(R.h14, R.h23, ea, eb, ipha, ya, yb, fr, fv);
+      const int rr = lane >> 1, e = lane & 1;
+      const bool fin = lane < 2 * nr;
+      const int src_a = fin ? 4 * rr + 2 * e : 0, src_b = src_a + 1;
+      Wave ea, eb;
+      ea.a1 = __shfl_sync(0xffffffffu, w.a1, src_a); ea.a2 = __shfl_sync(0xffffffffu, w.a2, src_a);
+      ea.b1 = __shfl_sync(0xffffffffu, w.b1, src_a); ea.b2 = __shfl_sync(0xffffffffu, w.b2, src_a);
+      eb.a1 = __shfl_sync(0xffffffffu, w.a1, src_b); eb.a2 = __shfl_sync(0xffffffffu, w.a2, src_b);
+      eb.b1 = __shfl_sync(0xffffffffu, w.b1, src_b); eb.b2 = __shfl_sync(0xffffffffu, w.b2, src_b);
+      const double2 ya = make_double2(__shfl_sync(0xffffffffu, y_sta.x, src_a), __shfl_sync(0xffffffffu, y_sta.y, src_a));
+      const double2 yb = make_double2(__shfl_sync(0xffffffffu, y_sta.x, src_b), __shfl_sync(0xffffffffu, y_sta.y, src_b));
+      if (fin) {
+        RayConst* Rf = ray_const(r0 + rr);
+        const double* Wf = ray_water(r0 + rr);
+        double h14[4], h23[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { h14[i] = Rf->h14[i]; h23[i] = Rf->h23[i]; }
+        double2 fr, fv;
+        if (!buried) surface_response(h14, h23, ea, eb, e ? Wf[2] : Wf[0], cfg.ipha[t_first + r0 + rr], fr, fv);
+        else surface_response_buried(h14, h23, ea, eb, cfg.ipha[t_first + r0 + rr], ya, yb, fr, fv);
+        Rf->edge[2 * e] = fr; Rf->edge[2 * e + 1] = fv;
       }
-      R.edge[0].x = __shfl_sync(0xffffffffu, fr.x, 0); R.edge[0].y = __shfl_sync(0xffffffffu, fr.y, 0);
-      R.edge[1].x = __shfl_sync(0xffffffffu, fv.x, 0); R.edge[1].y = __shfl_sync(0xffffffffu, fv.y, 0);
-      R.edge[2].x = __shfl_sync(0xffffffffu, fr.x, 1); R.edge[2].y = __shfl_sync(0xffffffffu, fr.y, 1);
-      R.edge[3].x = __shfl_sync(0xffffffffu, fv.x, 1); R.edge[3].y = __shfl_sync(0xffffffffu, fv.y, 1);
-    }
-    if (lane == 0) {
-      R.k = kb;
-      R.valid = valid;
-      R.npre = ipha == 1 ? f_nint((-cfg.t_start - R.tp) / cfg.delta)    // src/forward.f90:177
-                         : f_nint((-cfg.t_start + R.tp) / cfg.delta);   // src/forward.f90:186
-      reinterpret_cast<RayConst*>(rc_out)[item] = R;
-      if (is_valid && t0 == 0) is_valid[c] = (uint8_t)valid;
     }
   }
-  PREP_MARK(5);
+  __syncthreads();
+  // ---- (D) the RayConst records of this model: one contiguous, coalesced copy ----
+  {
+    double2* dst = reinterpret_cast<double2*>(rc_out + ((size_t)ci * ntr_eff + t_first) * RC_DOUBLES);
+    for (int i = threadIdx.x; i < nr_cta * (RC_DOUBLES / 2); i += blockDim.x) {
+      const int t = i / (RC_DOUBLES / 2), j = i - t * (RC_DOUBLES / 2);
+      dst[i] = reinterpret_cast<const double2*>(ray_const(t))[j];
+    }
+    if (is_valid && threadIdx.x == 0 && t_first == 0) is_valid[c] = (uint8_t)valid;
+  }
+  PREP_MARK(6);
 }
 
 // Twiddles of the radix-8 DIF stages, one table per stage laid out [q-1][o] (q = 1..7 output index of the butterfly,
@@ -561,11 +652,15 @@ __device__ __forceinline__ void fill_fft_twiddles(double2* s_tw, const double2* 
   }
 }
 
-// Position of logical element p in the padded FFT buffer: one pad element per 8, so that "8 consecutive
-// elements per thread" (last radix-8 stage) and "consecutive elements across threads" are both conflict free.
-__device__ __forceinline__ int fpad(int p) { return p + (p >> 3); }
-__device__ __forceinline__ unsigned fpad(unsigned p) { return p + (p >> 3); }
-__host__ __device__ inline size_t fft_buf_elems(size_t n) { return n + (n >> 3) + 1; }
+// Position of logical element p in the padded FFT buffer: one pad element per 8 -- "8 consecutive elements per thread"
+// (last radix-8 stage) and "consecutive elements across threads" are both conflict free -- plus, for n >= 512, one per
+// n/8: the transform leaves element f at bit-reversed position, so the consecutive samples the output phase reads differ
+// in the TOP bits of the position, which this term folds into the bank index (28 -> 5 wavefronts per warp-wide read at
+// n = 1024; sh = log2(n) - 3, or 31 = no second term for the short transforms run by 32 / 64 threads).
+__host__ __device__ __forceinline__ int fft_pad_shift(int log2n) { return log2n >= 9 ? log2n - 3 : 31; }
+__device__ __forceinline__ int fpad(int p, int sh) { return p + (p >> 3) + (p >> sh); }
+__device__ __forceinline__ unsigned fpad(unsigned p, int sh) { return p + (p >> 3) + (p >> sh); }
+__host__ __device__ inline size_t fft_buf_elems(size_t n) { return n + (n >> 3) + 9; }
 
 // 8-point inverse DFT in registers: v[q] <- sum_r v[r] exp(+2 pi i q r / 8)
 __device__ __forceinline__ void dft8(double2* v) {
@@ -611,18 +706,23 @@ template <int LOG2N, int N, class Sync>
 __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restrict__ stw, double& vmax, double* s_red, int tid,
                                            int nthr, Sync sync) {
   constexpr unsigned n = 1u << LOG2N, stride = N >> 3;
+  constexpr int PSH = LOG2N >= 9 ? LOG2N - 3 : 31;
   constexpr bool last = (N == 8);
   for (unsigned j = tid; j < (n >> 3); j += nthr) {
     const unsigned o = j & (stride - 1), base = ((j - o) << 3) + o;
     double2 v[8];
     unsigned pos[8];
-    if (stride % 8 == 0) {        // whole pad groups between the legs: one address, constant offsets
-      const unsigned p0 = base + (base >> 3);
+    // base + r * stride never carries into bit PSH (a butterfly stays inside one block of n/8 elements, or, in the first
+    // stage, moves by whole blocks): with whole groups of 8 between the legs the padded positions are one address plus
+    // constant offsets
+    if (stride % 8 == 0) {
+      const unsigned p0 = fpad(base, PSH);
+      constexpr unsigned step = stride + (stride >> 3) + (PSH < 31 ? (stride >> PSH) : 0u);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) pos[r] = p0 + r * (stride + (stride >> 3));
+      for (int r = 0; r < 8; ++r) pos[r] = p0 + r * step;
     } else {
 #pragma unroll
-      for (int r = 0; r < 8; ++r) pos[r] = (base + r * stride) + ((base + r * stride) >> 3);
+      for (int r = 0; r < 8; ++r) pos[r] = fpad(base + r * stride, PSH);
     }
 #pragma unroll
     for (int r = 0; r < 8; ++r) v[r] = buf[pos[r]];
@@ -649,25 +749,26 @@ __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restri
 template <int LOG2N, class Sync>
 __device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
   constexpr unsigned n = 1u << LOG2N;
+  constexpr int PSH = LOG2N >= 9 ? LOG2N - 3 : 31;
   constexpr int REM = LOG2N % 3;          // what is left after the radix-8 stages: 1 (N = 1), 2 or 4
   double vmax = -INFINITY;
   fft_stage8<LOG2N, (1 << LOG2N), Sync>(buf, twq, vmax, s_red, tid, nthr, sync);
   if (REM == 2) {
     for (unsigned j = tid; j < (n >> 2); j += nthr) {
-      const unsigned base = j << 2;
-      const double2 v0 = buf[fpad(base)], v1 = buf[fpad(base + 1)], v2 = buf[fpad(base + 2)], v3 = buf[fpad(base + 3)];
+      const unsigned p0 = fpad(j << 2, PSH);     // the four elements share a pad group
+      const double2 v0 = buf[p0], v1 = buf[p0 + 1], v2 = buf[p0 + 2], v3 = buf[p0 + 3];
       const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
       const double2 a2 = make_double2(v1.x + v3.x, v1.y + v3.y), a3 = make_double2(-(v1.y - v3.y), v1.x - v3.x);
       const double2 r0 = make_double2(a0.x + a2.x, a0.y + a2.y), r1 = make_double2(a1.x + a3.x, a1.y + a3.y);
       const double2 r2 = make_double2(a0.x - a2.x, a0.y - a2.y), r3 = make_double2(a1.x - a3.x, a1.y - a3.y);
       vmax = fmax(fmax(vmax, r0.y), fmax(fmax(r1.y, r2.y), r3.y));
-      buf[fpad(base)] = r0; buf[fpad(base + 2)] = r1; buf[fpad(base + 1)] = r2; buf[fpad(base + 3)] = r3;
+      buf[p0] = r0; buf[p0 + 2] = r1; buf[p0 + 1] = r2; buf[p0 + 3] = r3;
     }
     publish_max(vmax, s_red, tid);
     sync();
   } else if (REM == 1) {
     for (unsigned j = tid; j < (n >> 1); j += nthr) {
-      const unsigned base = j << 1, p0 = base + (base >> 3);   // base is even: both elements share a pad group
+      const unsigned p0 = fpad(j << 1, PSH);     // both elements share a pad group
       const double2 a = buf[p0], b = buf[p0 + 1];
       const double2 r0 = make_double2(a.x + b.x, a.y + b.y), r1 = make_double2(a.x - b.x, a.y - b.y);
       vmax = fmax(vmax, fmax(r0.y, r1.y));
@@ -712,16 +813,23 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // Two-level rotation tables of one item: cos/sin(t*theta) = rot(lo[t & 15], hi[t >> 4]) for t < 16*n_hi.
-// Per layer: [xi lo 0..15 | xi hi 0..n_hi-1 | eta lo 0..15 | eta hi 0..n_hi-1], entries (cos, sin).
+// Layout [row][column]: rows 0..15 = lo level (multiples 0..15 of theta), rows 16..16+n_hi-1 = hi level (multiples of
+// 16 theta); column 2l + which (which = 0: xi, 1: eta) for layer l; row stride 2 k_max + 1 entries.  Consecutive tasks of
+// a level write consecutive columns of a row and the 16 rows a warp reads in the layer loop start in different banks
+// (odd stride): no bank conflicts on either side (the layer-major layout of the first version cost 24 wavefronts per
+// store instead of 3).
 // One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
 // independent rotations inside a level (error ~1e-16 * log2(16)).
-__device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerConst* s_lc, int k, int n_hi, int tid, int nthr) {
-  const int tab_per_layer = 2 * (16 + n_hi);
-  for (int task = tid; task < 4 * k; task += nthr) {
-    const int l = task >> 2, which = (task >> 1) & 1, level = task & 1;
+__host__ __device__ inline size_t trig_table_entries(size_t km, size_t nthr) { return (16 + (nthr >> 4)) * (2 * km + 1); }
+template <int NT>
+__device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerConst* s_lc, int k, int km, int tid) {
+  constexpr int n_hi = NT >> 4;
+  const int ts = 2 * km + 1;
+  for (int task = tid; task < 4 * k; task += NT) {
+    const int level = task >= 2 * k ? 1 : 0, idx = task - level * 2 * k;
+    const int l = idx >> 1, which = idx & 1;
     const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
-    const int cnt = level ? n_hi : 16;
-    double2* dst = s_tab + l * tab_per_layer + which * (16 + n_hi) + level * 16;
+    double2* dst = s_tab + (level ? 16 * ts : 0) + idx;
     double2 e[16];
     e[0] = make_double2(1.0, 0.0);
     sincos(th, &e[1].y, &e[1].x);
@@ -737,7 +845,7 @@ __device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerCon
     }
 #pragma unroll
     for (int i = 0; i < 16; ++i)
-      if (i < cnt) dst[i] = e[i];
+      if (i < n_hi || !level) dst[i * ts] = e[i];
   }
 }
 
@@ -773,11 +881,12 @@ __device__ __forceinline__ void water_phase(const double2* s_tabw, double thw, i
   }
 }
 
-// Propagator product over the k solid layers, top down, in wave coordinates, for the J bins tid + m*nthr of this thread.
-template <int J>
+// Propagator product over the k solid layers, top down, in wave coordinates, for the J bins tid + m*NT of this thread.
+// The (cos, sin) pairs of the thread's first bin come from the two-level tables, those of its second bin by the stride
+// rotation, from the third on by the three-term recurrence with 2 cos(stride) (one FMA per value instead of two instructions).
+template <int J, int NT>
 __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab, const double2* s_tabw,
-                                          int k, int n_hi, int tid, Wave* wa, Wave* wb) {
-  const int tab_per_layer = 2 * (16 + n_hi);
+                                          int k, int km, int tid, Wave* wa, Wave* wb) {
   {
     const double thw = s_rc->thw, cbw = s_rc->cbw, sbw = s_rc->sbw;
     const double a1 = s_rc->a1, b1 = s_rc->b1, q1a = s_rc->q1a, q1b = s_rc->q1b, q2a = s_rc->q2a, q2b = s_rc->q2b;
@@ -790,16 +899,30 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
       rot(cw, sw, cbw, sbw);
     }
   }
-  const int t_lo = tid & 15, t_hi = 16 + (tid >> 4);
+  const int ts = 2 * km + 1;
+  const double2* p_lo = s_tab + (tid & 15) * ts;            // rows of this thread in the two table levels
+  const double2* p_hi = s_tab + (16 + (tid >> 4)) * ts;
   for (int l = 0; l < k; ++l) {
     const LayerConst& L = s_lc[l];
-    const double2* tab = s_tab + l * tab_per_layer;
     double c1, s1, c2, s2;
     {
-      const double2 a = tab[t_lo], b = tab[t_hi], cc = tab[16 + n_hi + t_lo], d = tab[16 + n_hi + t_hi];
+      const double2 a = p_lo[2 * l], cc = p_lo[2 * l + 1], b = p_hi[2 * l], d = p_hi[2 * l + 1];
       c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
       c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
     }
+    double pc1 = 0.0, ps1 = 0.0, pc2 = 0.0, ps2 = 0.0;   // the pairs of the previous bin (recurrence)
+    auto advance = [&](int m) {
+      if (m == 0) {
+        pc1 = c1; ps1 = s1; pc2 = c2; ps2 = s2;
+        rot(c1, s1, L.cbx, L.sbx);
+        rot(c2, s2, L.cbe, L.sbe);
+      } else {
+        const double cb2x = L.cb2x, cb2e = L.cb2e;
+        const double n1 = fma(cb2x, c1, -pc1), m1 = fma(cb2x, s1, -ps1), n2 = fma(cb2e, c2, -pc2), m2 = fma(cb2e, s2, -ps2);
+        pc1 = c1; ps1 = s1; pc2 = c2; ps2 = s2;
+        c1 = n1; s1 = m1; c2 = n2; s2 = m2;
+      }
+    };
     if (l + 1 < k) {
       const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
 #pragma unroll
@@ -808,36 +931,30 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
         wave_rotate(wb[m], c1, s1, c2, s2);
         wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
         wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
-        if (m + 1 < J) {
-          rot(c1, s1, L.cbx, L.sbx);
-          rot(c2, s2, L.cbe, L.sbe);
-        }
+        if (m + 1 < J) advance(m);
       }
     } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
 #pragma unroll
       for (int m = 0; m < J; ++m) {
         wave_rotate(wa[m], c1, s1, c2, s2);
         wave_rotate(wb[m], c1, s1, c2, s2);
-        if (m + 1 < J) {
-          rot(c1, s1, L.cbx, L.sbx);
-          rot(c2, s2, L.cbe, L.sbe);
-        }
+        if (m + 1 < J) advance(m);
       }
     }
   }
 }
 
 // Runs the layer loop for the first jm (<= JB) bin groups of the thread; jm takes the values band_limits() hands out.
-template <int JB, bool MIXED>
+template <int JB, int NT, bool MIXED>
 __device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, const LayerConst* s_lc, const double2* s_tab,
-                                                 const double2* s_tabw, int k, int n_hi, int tid, Wave* wa, Wave* wb) {
-  if (!MIXED || jm >= JB) { propagate<JB>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
+                                                 const double2* s_tabw, int k, int km, int tid, Wave* wa, Wave* wb) {
+  if (!MIXED || jm >= JB) { propagate<JB, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb); return; }
   if constexpr (MIXED) {
-  if constexpr (JB > 6) if (jm == 6) { propagate<6>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 4) if (jm == 4) { propagate<4>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 3) if (jm == 3) { propagate<3>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 2) if (jm == 2) { propagate<2>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb); return; }
-  if constexpr (JB > 1) propagate<1>(s_rc, s_lc, s_tab, s_tabw, k, n_hi, tid, wa, wb);
+  if constexpr (JB > 6) if (jm == 6) { propagate<6, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb); return; }
+  if constexpr (JB > 4) if (jm == 4) { propagate<4, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb); return; }
+  if constexpr (JB > 3) if (jm == 3) { propagate<3, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb); return; }
+  if constexpr (JB > 2) if (jm == 2) { propagate<2, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb); return; }
+  if constexpr (JB > 1) propagate<1, NT>(s_rc, s_lc, s_tab, s_tabw, k, km, tid, wa, wb);
   }
 }
 
@@ -847,7 +964,7 @@ __device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, c
 template <int J, bool STAGE>
 __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha,
                                                  int n, int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                                 double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw) {
+                                                 double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh) {
   double h14[4], h23[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
@@ -867,14 +984,14 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
       const double f = flt[j];
       const double2 xv = make_double2(fv.x * f, fv.y * f);
       const double2 xr = ipha == 1 ? make_double2(fr.x * f, fr.y * f) : xv;
-      s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
-      s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
+      s_buf[fpad(j, psh)] = make_double2(xr.x - xv.y, xr.y + xv.x);
+      s_buf[fpad(n - j, psh)] = make_double2(xr.x + xv.y, xv.x - xr.y);
     }
   }
   for (int m = J; m < jfull; ++m) {    // bins above the band limit of this trace (band_limits(), capi.cu)
     const int j = tid + m * nthr;
     if (STAGE) { s_fr[j] = make_double2(0.0, 0.0); s_fv[j] = make_double2(0.0, 0.0); }
-    else { s_buf[fpad(j)] = make_double2(0.0, 0.0); s_buf[fpad(n - j)] = make_double2(0.0, 0.0); }
+    else { s_buf[fpad(j, psh)] = make_double2(0.0, 0.0); s_buf[fpad(n - j, psh)] = make_double2(0.0, 0.0); }
   }
   if (tid == 0) {  // the two bins off the regular grid
     if (STAGE) {
@@ -883,8 +1000,8 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
     } else {       // c2r ignores the imaginary parts of DC and Nyquist
       const double f0 = flt[0], f1 = flt[nh - 1];
       const double2 r0 = ipha == 1 ? s_rc->edge[0] : s_rc->edge[1], r1 = ipha == 1 ? s_rc->edge[2] : s_rc->edge[3];
-      s_buf[fpad(0)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
-      s_buf[fpad(nh - 1)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
+      s_buf[fpad(0, psh)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
+      s_buf[fpad(nh - 1, psh)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
     }
   }
 }
@@ -904,7 +1021,7 @@ __device__ __forceinline__ int obs_pre_index(int S, int q, int tid, int nthr) {
 }
 __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOutputs& out, const double2* s_buf, int C, int c,
                                               int t, int ipha, int npre, double scale, const double* obs_pre, int tid, int nthr) {
-  const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n;
+  const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n, psh = fft_pad_shift(cfg.log2n);
   double* __restrict__ mis = out.misfit + ((size_t)t * C + c) * Sp;
   double* smp_base = out.rft_smp;
   if (out.slot && ((out.slot[c] ^ out.slot_invert) & 1)) smp_base = out.rft_smp_alt;
@@ -913,7 +1030,7 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
   auto sample = [&](int i) {
     const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
                             : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
-    const double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift))].x * scale;
+    const double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift), psh)].x * scale;
     return ipha == 1 ? v : -v;
   };
   // every thread handles pairs (p, S-1-p) of samples: both layouts come out of the same loop
@@ -952,8 +1069,8 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
 template <int JB, bool STAGE, bool MIXED>
 __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha, int n,
                                                int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                               double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw) {
-#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried, s_tabw)
+                                               double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh) {
+#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried, s_tabw, psh)
   if (!MIXED || jm >= JB) { SURF(JB); return; }
   if constexpr (MIXED) {
   if constexpr (JB > 6) if (jm == 6) { SURF(6); return; }
@@ -982,17 +1099,17 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
                                                              const TraceSel sel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ int s_next;
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C;
+  const int tid = threadIdx.x;
+  constexpr int nthr = BMAX;       // threads per CTA (launch_forward_t launches exactly BMAX): addressing and loop bounds fold
+  const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C, psh = fft_pad_shift(cfg.log2n);
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;   // rays per model in the scratch arrays prep_kernel filled
   // items of this launch: (model, ray) for the rays in `sel` (all of them, or the traces of one band-limit group)
   const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   constexpr bool buried = BURIED;   // cfg.bdep > 0: a kernel variant of its own, the surface-station variants carry none of it
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || buried;   // spectra staged in shared memory
 
-  const int n_hi = nthr >> 4;                         // table split: tid = 16*hi + lo
-  const int tab_per_layer = 2 * (16 + n_hi);          // double2 entries per layer: (xi | eta) x (lo | hi)
-  const size_t tab_entries = (size_t)km * tab_per_layer;
+  constexpr int n_hi = nthr >> 4;                     // table split: tid = 16*hi + lo
+  const size_t tab_entries = trig_table_entries(km, nthr);
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
   double2* s_buf = reinterpret_cast<double2*>(smem_raw);
   double2* s_tab = s_buf;                             // dead before the FFT buffer is first written
@@ -1042,7 +1159,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     const int k = s_rc->k;
     const int ipha = cfg.ipha[t0];
     PHASE_MARK(0);
-    build_trig_tables(s_tab, s_lc, buried ? max(k, s_rc->l_sta + 1) : k, n_hi, tid, nthr);
+    build_trig_tables<nthr>(s_tab, s_lc, buried ? max(k, s_rc->l_sta + 1) : k, km, tid);
     build_water_table(s_tabw, s_rc->thw, n_hi, tid, nthr);
     __syncthreads();
     PHASE_MARK(1);
@@ -1052,7 +1169,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     // Buried station: a first pass down to the station leaves the displacement components of both vectors there in the
     // spectrum staging arrays (same thread, same bins as the surface response that combines them); then the full stack.
     for (int pass = buried ? 0 : 1; pass < 2; ++pass) {
-      propagate_groups<J, MIXED>(jm, s_rc, s_lc, s_tab, s_tabw, pass == 0 ? s_rc->l_sta + 1 : k, n_hi, tid, wa, wb);
+      propagate_groups<J, nthr, MIXED>(jm, s_rc, s_lc, s_tab, s_tabw, pass == 0 ? s_rc->l_sta + 1 : k, km, tid, wa, wb);
       if (pass == 0) {
         const double c0 = s_rc->sta[0], c1 = s_rc->sta[1], c2 = s_rc->sta[2], c3 = s_rc->sta[3];
 #pragma unroll
@@ -1070,8 +1187,8 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
     const int jfull = (n >> 1) / nthr;
-    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw);
-    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw);
+    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw, psh);
+    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw, psh);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -1115,10 +1232,10 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
           double2 xv = make_double2(0.0, 0.0);
           if (cfg.deconv_mode == 0) xv = make_double2(s_fv[j].x * f, s_fv[j].y * f);
           if (j == 0 || j == nh - 1) {
-            s_buf[fpad(j)] = make_double2(xr.x, xv.x);
+            s_buf[fpad(j, psh)] = make_double2(xr.x, xv.x);
           } else {
-            s_buf[fpad(j)] = make_double2(xr.x - xv.y, xr.y + xv.x);
-            s_buf[fpad(n - j)] = make_double2(xr.x + xv.y, xv.x - xr.y);
+            s_buf[fpad(j, psh)] = make_double2(xr.x - xv.y, xr.y + xv.x);
+            s_buf[fpad(n - j, psh)] = make_double2(xr.x + xv.y, xv.x - xr.y);
           }
         }
         __syncthreads();
@@ -1156,7 +1273,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg, const double* __restrict__ in,
                                                            const int* __restrict__ trace_of, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, nthr = blockDim.x, n = cfg.nfft, nh = cfg.nh, brev_shift = 32 - cfg.log2n;
+  const int tid = threadIdx.x, nthr = blockDim.x, n = cfg.nfft, nh = cfg.nh, brev_shift = 32 - cfg.log2n, psh = fft_pad_shift(cfg.log2n);
   double2* b0 = reinterpret_cast<double2*>(smem_raw);
   double2* b1 = b0 + fft_buf_elems(n);
   double2* s_tw = b1 + fft_buf_elems(n);
@@ -1164,23 +1281,23 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
   const double* x = in + (size_t)blockIdx.x * n;
   const double* __restrict__ flt = cfg.flt + (size_t)trace_of[blockIdx.x] * nh;
   fill_fft_twiddles(s_tw, cfg.tw, n, tid, nthr);
-  for (int i = tid; i < n; i += nthr) b0[fpad(i)] = make_double2(x[i], 0.0);
+  for (int i = tid; i < n; i += nthr) b0[fpad(i, psh)] = make_double2(x[i], 0.0);
   __syncthreads();
   fft_inverse_dif<6, 12>(b0, n, s_tw, s_red, tid, nthr, CtaSync());
   for (int f = tid; f < nh; f += nthr) {
-    const double2 v = b0[fpad((int)(__brev((unsigned)f) >> brev_shift))];
+    const double2 v = b0[fpad((int)(__brev((unsigned)f) >> brev_shift), psh)];
     const double w = flt[f];
     const double2 y = make_double2(v.x * w, -v.y * w);          // r2c bin f (conjugate), filtered
     if (f == 0 || f == nh - 1) {
-      b1[fpad(f)] = make_double2(y.x, 0.0);                     // c2r ignores these imaginary parts
+      b1[fpad(f, psh)] = make_double2(y.x, 0.0);                     // c2r ignores these imaginary parts
     } else {
-      b1[fpad(f)] = y;
-      b1[fpad(n - f)] = make_double2(y.x, -y.y);
+      b1[fpad(f, psh)] = y;
+      b1[fpad(n - f, psh)] = make_double2(y.x, -y.y);
     }
   }
   __syncthreads();
   fft_inverse_dif<6, 12>(b1, n, s_tw, s_red, tid, nthr, CtaSync());
-  for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad((int)(__brev((unsigned)i) >> brev_shift))].x;
+  for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad((int)(__brev((unsigned)i) >> brev_shift), psh)].x;
 }
 
 __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, int* nlay_out, double* alpha,
@@ -1224,7 +1341,7 @@ __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, in
 
 size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
-  const size_t tab_entries = km * 2 * (16 + (nthr >> 4));
+  const size_t tab_entries = trig_table_entries(km, nthr);
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || cfg.bdep > 0.0;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
@@ -1237,6 +1354,7 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
                      const double* rc, int* counter, int nthr, cudaStream_t stream, const TraceSel& sel) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
+  if (nthr != BMAX) { rfinv_set_error("forward_kernel<%d,%d>: launched with %d threads", J, BMAX, nthr); return RFINV_ERR_ARG; }
   RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, per_sm = 0;
   RFINV_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1303,12 +1421,18 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   double* lc = scratch;
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
   int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
-  const size_t prep_smem = sizeof(double) * PREP_WARPS * prep_smem_doubles_per_warp(cfg.k_max);
-  const unsigned prep_grid = (unsigned)((n_items + PREP_WARPS - 1) / PREP_WARPS);
+  // prep_kernel: one CTA per model, one warp per ray
+  // (rays per CTA: all of them while the shared memory stays below ~96 KB, else the model is spread over several CTAs)
+  int n_groups = 1;
+  while (sizeof(double) * (prep_smem_model_doubles(cfg.k_max) + (size_t)((ntr_eff + n_groups - 1) / n_groups) * prep_smem_ray_doubles(cfg.k_max)) > 96 * 1024 &&
+         n_groups < ntr_eff) ++n_groups;
+  const int rays_per_cta = (ntr_eff + n_groups - 1) / n_groups;
+  n_groups = (ntr_eff + rays_per_cta - 1) / rays_per_cta;
+  const size_t prep_smem = sizeof(double) * (prep_smem_model_doubles(cfg.k_max) + (size_t)rays_per_cta * prep_smem_ray_doubles(cfg.k_max));
 #define PREP(BUR, HOST)                                                                                                    \
   do {                                                                                                                     \
     RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<BUR, HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem)); \
-    prep_kernel<BUR, HOST><<<prep_grid, 32 * PREP_WARPS, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, (int)n_items, ntr_eff, nthr); \
+    prep_kernel<BUR, HOST><<<(unsigned)n_models * n_groups, 32 * rays_per_cta, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, n_models, ntr_eff, nthr, rays_per_cta); \
   } while (0)
   if (cfg.bdep > 0.0) { if (mb.chain_major) PREP(true, true); else PREP(true, false); }
   else { if (mb.chain_major) PREP(false, true); else PREP(false, false); }
