@@ -322,14 +322,10 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream, &n_fwd)) != RFINV_OK) return st;
   launches += n_fwd;
   if (timing) cudaEventRecord(ev[1], stream);
-  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, d_qpart, d_qcnt, active, n_active, nullptr, stream)) != RFINV_OK) return st;
+  // logL leaves the same kernel (its last CTA per block of 64 chains sums the traces): no separate loglik_kernel launch
+  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, d_qpart, d_qcnt, active, n_active, nullptr, stream, logl ? sig : nullptr, logl)) != RFINV_OK) return st;
   ++launches;
-  if (timing) cudaEventRecord(ev[2], stream);
-  if (logl) {
-    if ((st = rfinv_launch_loglik(dc, C, d_phi, sig, logl, stream)) != RFINV_OK) return st;
-    ++launches;
-  }
-  if (timing) cudaEventRecord(ev[3], stream);
+  if (timing) { cudaEventRecord(ev[2], stream); cudaEventRecord(ev[3], stream); }
   return RFINV_OK;
 }
 

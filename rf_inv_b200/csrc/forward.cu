@@ -64,13 +64,14 @@ namespace {
 
 // Per (model, ray, solid layer) constants, written by prep_kernel.
 struct LayerConst {
-  double thx, the;            // domg*xi*h, domg*eta*h : phase advance per frequency bin
+  double c1x, s1x, c1e, s1e;      // cos, sin of thx = domg*xi*h and the = domg*eta*h: the phase advance per frequency bin
+  double c16x, s16x, c16e, s16e;  // cos, sin of 16 thx, 16 the (seeds of the two table levels of forward_kernel)
   double cbx, sbx, cbe, sbe;  // rotation by B*thx, B*the (B = threads per CTA = frequency stride of a thread)
   double t12, t21;            // interface to the next layer, {1,4} block [[1, t12], [t21, 1]] on (P, S) coordinates
   double u11, u12, u21, u22;  // interface to the next layer, {2,3} block
   double cb2x, cb2e;          // 2 cbx, 2 cbe: third and later bins of a thread by cos((m+1)b + t) = 2 cos b cos(mb + t) - cos((m-1)b + t)
 };
-constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 14
+constexpr int LC_DOUBLES = sizeof(LayerConst) / sizeof(double);  // 20
 static_assert(LC_DOUBLES % 2 == 0, "LayerConst is moved in 16-byte pieces");
 
 // The rays one forward_kernel launch works on: every ray of the configuration, or -- when the traces have different
@@ -90,6 +91,7 @@ struct RayConst {
   double a1, b1;              // start vector e1 in the wave coordinates of the top solid layer
   double q1a, q1b, q2a, q2b;  // start vector (0, cw, 0, -rw sw): (a1,b1) = sw*(q1a,q1b), (a2,b2) = cw*(q2a,q2b)
   double thw, cbw, sbw;       // water layer: phase per bin, stride rotation
+  double wseed[4];            // cos, sin of thw and of 16 thw: seeds of the water-layer phase table
   double tp;                  // direct-arrival delay (src/forward.f90:474-491)
   double2 edge[4];            // fr, fv at the DC pseudo-frequency and at Nyquist
   double sta[4];              // buried station: displacement rows of the scaled basis of the layer above it,
@@ -99,6 +101,7 @@ struct RayConst {
                               // index of the (sub)layer whose bottom is the buried station, -1 = station at the surface
 };
 constexpr int RC_DOUBLES = sizeof(RayConst) / sizeof(double);
+static_assert(sizeof(RayConst) % 16 == 0, "RayConst is moved in 16-byte pieces");
 
 __device__ __forceinline__ void rot(double& c, double& s, double cb, double sb) {
   double c2 = c * cb - s * sb;
@@ -240,7 +243,7 @@ constexpr int PREP_MISC_DOUBLES = 8;    // k, ls, valid (ints) and h_part
 // shared memory of a prep_kernel CTA, in doubles: [model part | per-ray part x rays]
 __host__ __device__ inline size_t prep_sorted_doubles(int km) { return ((size_t)3 * km + 1) & ~(size_t)1; }   // zs | dps | dss, 16-byte granular
 __host__ __device__ inline size_t prep_smem_model_doubles(int km) { return prep_sorted_doubles(km) + (size_t)(km + 2) * PSH_DOUBLES + PREP_MISC_DOUBLES; }
-__host__ __device__ inline size_t prep_smem_ray_doubles(int km) { return (size_t)(km + 1) * PB_DOUBLES + (size_t)km * PS_DOUBLES + RC_DOUBLES + 4; }
+__host__ __device__ inline size_t prep_smem_ray_doubles(int km) { return (size_t)(km + 1) * PB_DOUBLES + (size_t)km * PS_DOUBLES + RC_DOUBLES + 8; }
 
 // sin, cos of a small argument (|x| < 0.01: Taylor remainder < 3e-21); falls back to sincos otherwise
 __device__ __forceinline__ void small_sincos(double x, double* sn, double* cs) {
@@ -265,7 +268,7 @@ __device__ __forceinline__ double warp_scan_mul(double x, int lane) {   // inclu
 // HOSTLAYOUT: the batch of rfinv_eval_batch (chain-slowest arrays, possibly still arriving piece by piece); the
 // device-resident variants carry none of that
 template <bool BURIED, bool HOSTLAYOUT>
-__global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
+__global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                                  double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
                                                                  int* __restrict__ counter, int n_models, int ntr_eff, int nthr_fwd,
                                                                  int rays_per_cta) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
   auto ray_basis = [&](int t) { return reinterpret_cast<PrepBasis*>(ray0 + (size_t)t * ray_stride); };                  // [km + 1]
   auto ray_serial = [&](int t) { return reinterpret_cast<PrepSerial*>(ray0 + (size_t)t * ray_stride + (size_t)(km + 1) * PB_DOUBLES); };   // [km]
   auto ray_const = [&](int t) { return reinterpret_cast<RayConst*>(ray0 + (size_t)t * ray_stride + (size_t)(km + 1) * PB_DOUBLES + (size_t)km * PS_DOUBLES); };
-  auto ray_water = [&](int t) { return reinterpret_cast<double*>(ray_const(t)) + RC_DOUBLES; };   // cw0, sw0, cw1, sw1
+  auto ray_water = [&](int t) { return reinterpret_cast<double*>(ray_const(t)) + RC_DOUBLES; };   // cw0, sw0, cw1, sw1 | xi, eta, bp of the half space
   constexpr bool buried = BURIED;   // cfg.bdep > 0
 
   PREP_INIT();
@@ -313,18 +316,34 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
       }
       __syncwarp();
     }
+    // The layer count and the model arrays are requested together (one memory latency instead of two): every lane loads
+    // its elements whether or not they lie below k -- the arrays are k_max long -- and drops the rest.
     int k = mb.k[c];
+    double zr[2] = {0.0, 0.0}, dr[2] = {0.0, 0.0}, sr[2] = {0.0, 0.0};
+    static_assert(RFINV_MAX_K <= 64, "two elements per lane");
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      if (i < km - 1) {
+        if (HOSTLAYOUT) {
+          zr[q] = mb.z[(size_t)c * (km - 1) + i]; sr[q] = mb.dvs[(size_t)c * km + i];
+          if (cfg.vp_mode == 1) dr[q] = mb.dvp[(size_t)c * km + i];   // not uploaded at vp_mode 0 (format_model never reads it)
+        } else {
+          zr[q] = mb.z[(size_t)i * C + c]; dr[q] = mb.dvp[(size_t)i * C + c]; sr[q] = mb.dvs[(size_t)i * C + c];
+        }
+      }
+    }
+    double dvs_half, dvp_half = 0.0;              // perturbations of the half space: element k_max of the arrays
+    if (HOSTLAYOUT) { dvs_half = mb.dvs[(size_t)c * km + km - 1]; if (cfg.vp_mode == 1) dvp_half = mb.dvp[(size_t)c * km + km - 1]; }
+    else { dvs_half = mb.dvs[(size_t)(km - 1) * C + c]; dvp_half = mb.dvp[(size_t)(km - 1) * C + c]; }
     k = k < 1 ? 1 : (k > km - 1 ? km - 1 : k);
     // ---- sort the k interfaces by depth with their perturbations (src/sort.f90:34-68; ties keep their order) ----
     double* zu = reinterpret_cast<double*>(ray_basis(0));   // unsorted z, dvp, dvs: the region is rewritten in phase B
     double *du = zu + km, *su = du + km;
-    for (int i = lane; i < k; i += 32) {
-      if (HOSTLAYOUT) {
-        zu[i] = mb.z[(size_t)c * (km - 1) + i]; su[i] = mb.dvs[(size_t)c * km + i];
-        du[i] = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + i] : 0.0;   // not uploaded at vp_mode 0 (format_model never reads it)
-      } else {
-        zu[i] = mb.z[(size_t)i * C + c]; du[i] = mb.dvp[(size_t)i * C + c]; su[i] = mb.dvs[(size_t)i * C + c];
-      }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int i = lane + 32 * q;
+      if (i < k) { zu[i] = zr[q]; du[i] = dr[q]; su[i] = sr[q]; }
     }
     __syncwarp();
     for (int i = lane; i < k; i += 32) {
@@ -361,9 +380,7 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
       double zc, h, dvs_l, dvp_l;
       if (l == 0) { zc = __dmul_rn(0.5, __dadd_rn(cfg.sdep, zs[0])); h = __dsub_rn(zs[0], cfg.sdep); dvs_l = dss[0]; dvp_l = dps[0]; }
       else if (l < k) { zc = __dmul_rn(0.5, __dadd_rn(zs[l], zs[l - 1])); h = __dsub_rn(zs[l], zs[l - 1]); dvs_l = dss[l]; dvp_l = dps[l]; }
-      else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0;
-             if (HOSTLAYOUT) { dvs_l = mb.dvs[(size_t)c * km + km - 1]; dvp_l = cfg.vp_mode == 1 ? mb.dvp[(size_t)c * km + km - 1] : 0.0; }
-             else { dvs_l = mb.dvs[(size_t)(km - 1) * C + c]; dvp_l = mb.dvp[(size_t)(km - 1) * C + c]; } }
+      else { zc = __dmul_rn(0.5, __dadd_rn(cfg.z_max, zs[k - 1])); h = 999.0; dvs_l = dvs_half; dvp_l = dvp_half; }
       double a, b;
       bool ok = layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
       if (l == 0) ok = ok && !(h < __dmul_rn(0.125, a));     // src/model.f90:229
@@ -406,7 +423,6 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
   const double nyq = (double)(cfg.nfft / 2);
   int nyq_doublings = 0;
   while ((nthr_fwd << nyq_doublings) < cfg.nfft / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d
-  double hs_a = 0.0, hs_b = 0.0, hs_rho = 0.0, hs_xi = 0.0, hs_eta = 0.0, hs_bp = 0.0, hs_beta2 = 0.0;   // half space (lane ka & 31)
   for (int la = lane; la <= ka; la += 32) {
     const PrepShared S = LA[la];
     const double h = S.h, rho = S.rho, beta2 = S.beta2;
@@ -429,11 +445,24 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
       Q.i23[0] = bp * ixi; Q.i23[1] = -p * irho * ixi; Q.i23[2] = -g2 * eta; Q.i23[3] = -eta * irho;
       Z.tpterm = cfg.deconv_mode == 0 ? __dmul_rn(tp_sign, __dmul_rn(h, ipha == 1 ? xi : eta)) : 0.0;   // src/forward.f90:489-491
       LayerConst* L = reinterpret_cast<LayerConst*>(lc_out) + item * km + la;
+      // All transcendental functions of the layer: the phase advance per bin; 16 times it (forward_kernel builds its
+      // two-level rotation tables from these two seeds by angle addition alone) and the stride rotation B = 16 * 2^d follow
+      // by angle doubling (4 + d <= 8 doublings: a phase error of at most 2^8 ulp = 3e-14, against a tolerance of 1e-9).
       const double thx = cfg.domg * xi * h, the = cfg.domg * eta * h;
-      L->thx = thx; L->the = the;
       double snx, csx, sne, cse;
-      sincos((double)nthr_fwd * thx, &snx, &csx); L->cbx = csx; L->sbx = snx;
-      sincos((double)nthr_fwd * the, &sne, &cse); L->cbe = cse; L->sbe = sne;
+      sincos(thx, &snx, &csx); L->c1x = csx; L->s1x = snx;
+      sincos(the, &sne, &cse); L->c1e = cse; L->s1e = sne;
+#pragma unroll
+      for (int d = 0; d < 4; ++d) {
+        const double c2 = fma(csx, csx, -snx * snx), s2 = 2.0 * csx * snx; csx = c2; snx = s2;
+        const double c3 = fma(cse, cse, -sne * sne), s3 = 2.0 * cse * sne; cse = c3; sne = s3;
+      }
+      L->c16x = csx; L->s16x = snx; L->c16e = cse; L->s16e = sne;
+      for (int b = 16; b < nthr_fwd; b <<= 1) {
+        const double c2 = fma(csx, csx, -snx * snx), s2 = 2.0 * csx * snx; csx = c2; snx = s2;
+        const double c3 = fma(cse, cse, -sne * sne), s3 = 2.0 * cse * sne; cse = c3; sne = s3;
+      }
+      L->cbx = csx; L->sbx = snx; L->cbe = cse; L->sbe = sne;
       L->cb2x = csx + csx; L->cb2e = cse + cse;
       small_sincos((double)1.0e-5f * xi * h, &Z.tr[1], &Z.tr[0]);   // (omega*xi)*z with omega = 1.0e-5 (single precision literal)
       small_sincos((double)1.0e-5f * eta * h, &Z.tr[3], &Z.tr[2]);
@@ -445,8 +474,9 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
         const double c3 = fma(ce, ce, -se * se), s3 = 2.0 * ce * se; ce = c3; se = s3;
       }
       Z.tr[4] = cn; Z.tr[5] = sn2; Z.tr[6] = ce; Z.tr[7] = se;
-    } else {
-      hs_a = S.a; hs_b = S.b; hs_rho = rho; hs_xi = xi; hs_eta = eta; hs_bp = bp; hs_beta2 = beta2;
+    } else {   // half space: its ray-dependent quantities go to the ray constants through shared memory
+      double* W = ray_water(warp);
+      W[4] = xi; W[5] = eta; W[6] = bp;
     }
   }
   __syncwarp();
@@ -498,21 +528,25 @@ __global__ void __launch_bounds__(32 * RFINV_MAX_TRC) prep_kernel(const DevConfi
       const double aw = 1.5, rhow = 1.0, hw = cfg.sdep;
       const double xiw = sqrt(1.0 / (aw * aw) - p * p);
       R.thw = cfg.domg * xiw * hw;
-      sincos((double)nthr_fwd * R.thw, &R.sbw, &R.cbw);
+      sincos(R.thw, &R.wseed[1], &R.wseed[0]);
+      R.cbw = R.wseed[0]; R.sbw = R.wseed[1];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) { const double c2 = fma(R.cbw, R.cbw, -R.sbw * R.sbw), s2 = 2.0 * R.cbw * R.sbw; R.cbw = c2; R.sbw = s2; }
+      R.wseed[2] = R.cbw; R.wseed[3] = R.sbw;
+      for (int b = 16; b < nthr_fwd; b <<= 1) { const double c2 = fma(R.cbw, R.cbw, -R.sbw * R.sbw), s2 = 2.0 * R.cbw * R.sbw; R.cbw = c2; R.sbw = s2; }
       rw = rhow / xiw;
       small_sincos((double)1.0e-5f * xiw * hw, &sw0, &cw0);
       sincos(nyq * R.thw, &sw1, &cw1);
     } else {
       R.thw = 0.0; R.cbw = 1.0; R.sbw = 0.0;
+      R.wseed[0] = R.wseed[2] = 1.0; R.wseed[1] = R.wseed[3] = 0.0;
     }
     {
       // half space: rows 3,4 of E^-1 (src/forward.f90:350-380) without their 1/omega factors, times the scaled basis of
       // the last solid layer
-      const int src_lane = ka & 31;
-      const double a = __shfl_sync(0xffffffffu, hs_a, src_lane), b = __shfl_sync(0xffffffffu, hs_b, src_lane);
-      const double rho = __shfl_sync(0xffffffffu, hs_rho, src_lane), xi = __shfl_sync(0xffffffffu, hs_xi, src_lane);
-      const double eta = __shfl_sync(0xffffffffu, hs_eta, src_lane), bp = __shfl_sync(0xffffffffu, hs_bp, src_lane);
-      const double beta2 = __shfl_sync(0xffffffffu, hs_beta2, src_lane);
+      const PrepShared& H = LA[ka];
+      const double* W = ray_water(warp);
+      const double a = H.a, b = H.b, rho = H.rho, beta2 = H.beta2, xi = W[4], eta = W[5], bp = W[6];
       const double r1 = 1.0 / (2.0 * rho * a * xi), r2 = 1.0 / (2.0 * rho * b * eta);
       const double e11 = beta2 * p * (2.0 * rho * xi) * r1, e12 = bp * rho * r1, e13 = p * r1, e14 = xi * r1;
       const double e21 = bp * rho * r2, e22 = b * p, e23 = eta * r2, e24 = p * r2;
@@ -818,8 +852,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // a level write consecutive columns of a row and the 16 rows a warp reads in the layer loop start in different banks
 // (odd stride): no bank conflicts on either side (the layer-major layout of the first version cost 24 wavefronts per
 // store instead of 3).
-// One thread per (layer, angle, level): one sincos, then angle doubling e[len+j] = rot(e[j], e[len]) -- log depth,
-// independent rotations inside a level (error ~1e-16 * log2(16)).
+// One thread per (layer, angle, level): the seed (cos, sin)(theta) or (cos, sin)(16 theta) comes from prep_kernel, then angle
+// doubling e[len+j] = rot(e[j], e[len]) -- log depth, independent rotations inside a level (error ~1e-16 * log2(16)).
 __host__ __device__ inline size_t trig_table_entries(size_t km, size_t nthr) { return (16 + (nthr >> 4)) * (2 * km + 1); }
 template <int NT>
 __device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerConst* s_lc, int k, int km, int tid) {
@@ -828,11 +862,10 @@ __device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerCon
   for (int task = tid; task < 4 * k; task += NT) {
     const int level = task >= 2 * k ? 1 : 0, idx = task - level * 2 * k;
     const int l = idx >> 1, which = idx & 1;
-    const double th = (which ? s_lc[l].the : s_lc[l].thx) * (level ? 16.0 : 1.0);
     double2* dst = s_tab + (level ? 16 * ts : 0) + idx;
     double2 e[16];
     e[0] = make_double2(1.0, 0.0);
-    sincos(th, &e[1].y, &e[1].x);
+    e[1] = reinterpret_cast<const double2*>(&s_lc[l].c1x)[2 * level + which];   // (c1x,s1x) (c1e,s1e) (c16x,s16x) (c16e,s16e)
 #pragma unroll
     for (int len = 2; len < 16; len <<= 1) {
       e[len] = e[len >> 1];
@@ -850,14 +883,14 @@ __device__ __forceinline__ void build_trig_tables(double2* s_tab, const LayerCon
 }
 
 // Water layer: cos / sin of (tid * thw) -- the phase of the thread's first bin -- from a two-level table like the layers'
-// (s_tabw: lo[16] | hi[n_hi], built once per item by two otherwise idle threads) instead of a sincos per thread.
-__device__ __forceinline__ void build_water_table(double2* s_tabw, double thw, int n_hi, int tid, int nthr) {
+// (s_tabw: lo[16] | hi[n_hi], built once per item by two otherwise idle threads from prep_kernel's seeds).
+__device__ __forceinline__ void build_water_table(double2* s_tabw, const RayConst* s_rc, int n_hi, int tid, int nthr) {
   const int level = nthr - 1 - tid;          // the last thread builds the lo level, the one before it the hi level
-  if (level > 1 || thw == 0.0) return;
+  if (level > 1 || s_rc->thw == 0.0) return;
   const int cnt = level ? n_hi : 16;
   double2 e[16];
   e[0] = make_double2(1.0, 0.0);
-  sincos(thw * (level ? 16.0 : 1.0), &e[1].y, &e[1].x);
+  e[1] = make_double2(s_rc->wseed[2 * level], s_rc->wseed[2 * level + 1]);
 #pragma unroll
   for (int len = 2; len < 16; len <<= 1) {
     e[len] = e[len >> 1];
@@ -902,14 +935,17 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
   const int ts = 2 * km + 1;
   const double2* p_lo = s_tab + (tid & 15) * ts;            // rows of this thread in the two table levels
   const double2* p_hi = s_tab + (16 + (tid >> 4)) * ts;
+  double c1, s1, c2, s2;                                    // the pairs of the thread's first bin in the current layer
+  {
+    const double2 a = p_lo[0], cc = p_lo[1], b = p_hi[0], d = p_hi[1];
+    c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
+    c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
+  }
   for (int l = 0; l < k; ++l) {
     const LayerConst& L = s_lc[l];
-    double c1, s1, c2, s2;
-    {
-      const double2 a = p_lo[2 * l], cc = p_lo[2 * l + 1], b = p_hi[2 * l], d = p_hi[2 * l + 1];
-      c1 = a.x; s1 = a.y; rot(c1, s1, b.x, b.y);
-      c2 = cc.x; s2 = cc.y; rot(c2, s2, d.x, d.y);
-    }
+    const int ln = l + 1 < k ? l + 1 : l;
+    double2 na, ncc, nb, nd;                             // table entries of the next layer: fetched while the last bin of
+                                                         // this one is computed, so no warp waits for them at the layer top
     double pc1 = 0.0, ps1 = 0.0, pc2 = 0.0, ps2 = 0.0;   // the pairs of the previous bin (recurrence)
     auto advance = [&](int m) {
       if (m == 0) {
@@ -927,12 +963,20 @@ __device__ __forceinline__ void propagate(const RayConst* s_rc, const LayerConst
       const double t12 = L.t12, t21 = L.t21, u11 = L.u11, u12 = L.u12, u21 = L.u21, u22 = L.u22;
 #pragma unroll
       for (int m = 0; m < J; ++m) {
+#ifndef RFINV_NO_TABPREFETCH
+        if (m == J - 1) { na = p_lo[2 * ln]; ncc = p_lo[2 * ln + 1]; nb = p_hi[2 * ln]; nd = p_hi[2 * ln + 1]; }
+#endif
         wave_rotate(wa[m], c1, s1, c2, s2);
         wave_rotate(wb[m], c1, s1, c2, s2);
         wave_interface(wa[m], t12, t21, u11, u12, u21, u22);
         wave_interface(wb[m], t12, t21, u11, u12, u21, u22);
         if (m + 1 < J) advance(m);
       }
+#ifdef RFINV_NO_TABPREFETCH
+      na = p_lo[2 * ln]; ncc = p_lo[2 * ln + 1]; nb = p_hi[2 * ln]; nd = p_hi[2 * ln + 1];
+#endif
+      c1 = na.x; s1 = na.y; rot(c1, s1, nb.x, nb.y);
+      c2 = ncc.x; s2 = ncc.y; rot(c2, s2, nd.x, nd.y);
     } else {   // last solid layer: the half space follows (rows 3,4 of E^-1 are applied by surface_response)
 #pragma unroll
       for (int m = 0; m < J; ++m) {
@@ -1121,8 +1165,11 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
   double2* s_tabw = reinterpret_cast<double2*>(s_lc2 + 2 * (size_t)km);   // [16 + n_hi] water-layer phase table (not aliased)
 
+  // item / sel.n without an integer division per item: multiply-high by ceil(2^32 / n), exact for item < 2^32 / n
+  const unsigned sel_magic = sel.n > 1 ? (unsigned)((0x100000000ULL + (unsigned)sel.n - 1u) / (unsigned)sel.n) : 0u;
+  auto div_sel = [&](int x) { return sel.n > 1 ? (int)__umulhi((unsigned)x, sel_magic) : x; };
   auto prefetch = [&](int item_sel, int slot) {
-    const int ci_ = item_sel / sel.n;
+    const int ci_ = div_sel(item_sel);
     const size_t item = (size_t)ci_ * ntr_eff + sel.t(item_sel - ci_ * sel.n);   // index into prep_kernel's arrays
     const double2* src = reinterpret_cast<const double2*>(rc_in + (size_t)item * RC_DOUBLES);
     double2* dst = reinterpret_cast<double2*>(s_rc2 + slot);
@@ -1154,13 +1201,13 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     if (tid == 0) next2 = atomicAdd(counter, 1);   // consumed at the end of the iteration: nobody waits for the round trip
     const RayConst* s_rc = s_rc2 + slot;
     const LayerConst* s_lc = s_lc2 + (size_t)slot * km;
-    const int ci = item / sel.n, t0 = sel.t(item - ci * sel.n);
+    const int ci = div_sel(item), t0 = sel.t(item - ci * sel.n);
     const int c = mb.active ? mb.active[ci] : ci;
     const int k = s_rc->k;
     const int ipha = cfg.ipha[t0];
     PHASE_MARK(0);
     build_trig_tables<nthr>(s_tab, s_lc, buried ? max(k, s_rc->l_sta + 1) : k, km, tid);
-    build_water_table(s_tabw, s_rc->thw, n_hi, tid, nthr);
+    build_water_table(s_tabw, s_rc, n_hi, tid, nthr);
     __syncthreads();
     PHASE_MARK(1);
 

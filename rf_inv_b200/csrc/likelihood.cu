@@ -43,7 +43,8 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
                                                               double* __restrict__ phi, double* __restrict__ partial,
                                                               int* __restrict__ arrivals, int* __restrict__ work,
                                                               const int* __restrict__ active, int n_active,
-                                                              const int* __restrict__ n_active_dev) {
+                                                              const int* __restrict__ n_active_dev, const double* __restrict__ sig,
+                                                              double* __restrict__ logl) {
   __shared__ __align__(16) double sA[2][TM * LDS_STRIDE];
   __shared__ __align__(16) double sB[2][TN * LDS_STRIDE];
   __shared__ int s_rows[TM];
@@ -210,6 +211,28 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
           phi[(size_t)t * C + c] = v;
         }
         if (tid == 0) arrivals[t * n_rb_grid + rb] = 0;              // ready for the next launch
+        // logL of the block's chains (src/likelihood.f90:94-96, same operation order) by the CTA that completes the last
+        // trace of the block: one kernel less per evaluation
+        if (logl) {
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) s_last = (atomicAdd(&arrivals[T * n_rb_grid + rb], 1) == T - 1);
+          __syncthreads();
+          if (s_last) {
+            __threadfence();
+            if (tid < TM && row0 + tid < n_rows) {
+              const int c = s_rows[tid];
+              double ll = 0.0;
+              for (int tt = 0; tt < T; ++tt) {
+                const double sg = sig[(size_t)tt * C + c];
+                const double ph = __ldcg(phi + (size_t)tt * C + c);
+                ll = __dsub_rn(__dsub_rn(ll, __ddiv_rn(__dmul_rn(0.5, ph), __dmul_rn(sg, sg))), __dmul_rn((double)cfg.nsmp, log(sg)));
+              }
+              logl[c] = ll;
+            }
+            if (tid == 0) arrivals[T * n_rb_grid + rb] = 0;
+          }
+        }
       }
     } else {
       __syncthreads();   // skipped item (no such tile / row block): everyone has read s_next before it is rewritten
@@ -236,30 +259,35 @@ __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restri
 
 // column tiles per (64 chains, trace): nsmp_pad/64 dense, up to 2 ceil(nsmp_pad/128) in the split form
 size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C) { return (size_t)(cfg.nsmp_pad / TN + 1) * cfg.ntrc * C; }
-size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C) { return (size_t)((C + TM - 1) / TM) * cfg.ntrc + 4; }
+size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C) { return (size_t)((C + TM - 1) / TM) * (cfg.ntrc + 1) + 4; }
 
 // partial: rfinv_quadform_partial_doubles(cfg, C) doubles; counters: rfinv_quadform_counter_ints(cfg, capacity) ints, zeroed
 // once at allocation (the arrival counters reset themselves; the work counter is cleared here before every launch)
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, double* partial, int* counters,
-                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream) {
+                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream, const double* sig,
+                          double* logl) {
   const int n_rows = active ? n_active : C;
   if (n_rows == 0) return RFINV_OK;
   const size_t ntile = cfg.qf_tiles_max;
   int* work = counters;
   int* arrivals = counters + 4;
-  static int per_sm = 0, n_sm = 0;
-  if (per_sm == 0) {
-    int dev = 0;
-    RFINV_CUDA_CHECK(cudaGetDevice(&dev));
+  // resident CTAs of the current device, cached per device id (handles may live on different devices; concurrent first
+  // calls compute and store the same value)
+  static int resident_of_device[64] = {0};
+  int dev = 0;
+  RFINV_CUDA_CHECK(cudaGetDevice(&dev));
+  long long resident = (dev >= 0 && dev < 64) ? resident_of_device[dev] : 0;
+  if (resident == 0) {
+    int per_sm = 0, n_sm = 0;
     RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, quadform_kernel, QF_THREADS, 0));
-    if (per_sm < 1) per_sm = 1;
+    resident = (long long)n_sm * (per_sm < 1 ? 1 : per_sm);
+    if (dev >= 0 && dev < 64) resident_of_device[dev] = (int)resident;
   }
   const long long items = (long long)ntile * cfg.ntrc * ((n_rows + TM - 1) / TM);
-  const long long resident = (long long)n_sm * per_sm;
   RFINV_CUDA_CHECK(cudaMemsetAsync(work, 0, sizeof(int), stream));
   quadform_kernel<<<(unsigned)(items < resident ? items : resident), QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, partial, arrivals, work,
-                                                                                              active, n_active, n_active_dev);
+                                                                                              active, n_active, n_active_dev, sig, logl);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }

@@ -126,8 +126,10 @@ int rfinv_forward_bins_per_thread(int nfft);
 // counters zeroed at allocation
 size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C);
 size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C);
+// sig / logl (optional, chain fastest): logl[c] = sum_t -0.5 phi/sig^2 - nsmp log(sig) is written by the same kernel
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, double* partial, int* counters,
-                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream);
+                          const int* active, int n_active, const int* n_active_dev, cudaStream_t stream,
+                          const double* sig = nullptr, double* logl = nullptr);
 // logl[c] = sum_t -0.5 phi/sig^2 - nsmp log(sig)   (src/likelihood.f90:94-96)
 int rfinv_launch_loglik(const DevConfig& cfg, int C, const double* phi, const double* sig, double* logl,
                         cudaStream_t stream);

@@ -32,8 +32,8 @@ tot = sum(out[i] for i in range(7))
 print(f"CTAs {n}, mean cycles per CTA {tot / n:.0f}, k_mean {m['k'].mean():.2f}")
 for i, nm in enumerate(names):
     print(f"  {nm:20s} {out[i] / n:9.0f} cycles  {100.0 * out[i] / tot:5.1f}%")
-pnames = ["load + sort", "layer physics", "interfaces + scans", "ray constants", "edge bins (serial)", "surface + store"]
-ptot = sum(out[8 + i] for i in range(6))
-print(f"prep_kernel, mean cycles per warp (= item) {ptot / n:.0f}")
+pnames = ["load + sort (warp 0)", "shared layer physics (warp 0)", "barrier + per-ray physics", "interfaces + scans", "ray constants", "edge bins (serial, warp 0)", "edge surface + store"]
+ptot = sum(out[8 + i] for i in range(7))
+print(f"prep_kernel, warp-cycles per model {ptot / len(m['k']):.0f} (summed over the warps of a CTA)")
 for i, nm in enumerate(pnames):
-    print(f"  {nm:20s} {out[8 + i] / n:9.0f} cycles  {100.0 * out[8 + i] / ptot:5.1f}%")
+    print(f"  {nm:32s} {out[8 + i] / len(m['k']):9.0f} cycles  {100.0 * out[8 + i] / ptot:5.1f}%")
