@@ -696,19 +696,36 @@ __device__ __forceinline__ int fpad(int p, int sh) { return p + (p >> 3) + (p >>
 __device__ __forceinline__ unsigned fpad(unsigned p, int sh) { return p + (p >> 3) + (p >> sh); }
 __host__ __device__ inline size_t fft_buf_elems(size_t n) { return n + (n >> 3) + 9; }
 
-// 8-point inverse DFT in registers: v[q] <- sum_r v[r] exp(+2 pi i q r / 8)
+// 8-point inverse DFT in registers: v[q] <- sum_r v[r] exp(+2 pi i q r / 8).  Z = bit mask of inputs known to be zero (legs of
+// the first FFT stage that lie above the band limit): their additions are dropped, not executed with a zero operand.
+template <bool ZA, bool ZB>
+__device__ __forceinline__ double2 zadd(double2 a, double2 b) {
+  if constexpr (ZA && ZB) return make_double2(0.0, 0.0);
+  else if constexpr (ZB) return a;
+  else if constexpr (ZA) return b;
+  else return make_double2(a.x + b.x, a.y + b.y);
+}
+template <bool ZA, bool ZB>
+__device__ __forceinline__ double2 zsub(double2 a, double2 b) {
+  if constexpr (ZA && ZB) return make_double2(0.0, 0.0);
+  else if constexpr (ZB) return a;
+  else if constexpr (ZA) return make_double2(-b.x, -b.y);
+  else return make_double2(a.x - b.x, a.y - b.y);
+}
+template <unsigned Z = 0u>
 __device__ __forceinline__ void dft8(double2* v) {
   const double hs = 0.70710678118654752440;
+  constexpr bool z0 = Z & 1u, z1 = Z & 2u, z2 = Z & 4u, z3 = Z & 8u, z4 = Z & 16u, z5 = Z & 32u, z6 = Z & 64u, z7 = Z & 128u;
   double2 e0, e1, e2, e3, o0, o1, o2, o3;
   {
-    const double2 a = make_double2(v[0].x + v[4].x, v[0].y + v[4].y), b = make_double2(v[0].x - v[4].x, v[0].y - v[4].y);
-    const double2 c = make_double2(v[2].x + v[6].x, v[2].y + v[6].y), d = make_double2(-(v[2].y - v[6].y), v[2].x - v[6].x);
+    const double2 a = zadd<z0, z4>(v[0], v[4]), b = zsub<z0, z4>(v[0], v[4]);
+    const double2 c = zadd<z2, z6>(v[2], v[6]), dd = zsub<z2, z6>(v[2], v[6]), d = make_double2(-dd.y, dd.x);
     e0 = make_double2(a.x + c.x, a.y + c.y); e1 = make_double2(b.x + d.x, b.y + d.y);
     e2 = make_double2(a.x - c.x, a.y - c.y); e3 = make_double2(b.x - d.x, b.y - d.y);
   }
   {
-    const double2 a = make_double2(v[1].x + v[5].x, v[1].y + v[5].y), b = make_double2(v[1].x - v[5].x, v[1].y - v[5].y);
-    const double2 c = make_double2(v[3].x + v[7].x, v[3].y + v[7].y), d = make_double2(-(v[3].y - v[7].y), v[3].x - v[7].x);
+    const double2 a = zadd<z1, z5>(v[1], v[5]), b = zsub<z1, z5>(v[1], v[5]);
+    const double2 c = zadd<z3, z7>(v[3], v[7]), dd = zsub<z3, z7>(v[3], v[7]), d = make_double2(-dd.y, dd.x);
     o0 = make_double2(a.x + c.x, a.y + c.y);
     const double2 t1 = make_double2(b.x + d.x, b.y + d.y), t2 = make_double2(a.x - c.x, a.y - c.y);
     const double2 t3 = make_double2(b.x - d.x, b.y - d.y);
@@ -736,10 +753,15 @@ __device__ __forceinline__ void publish_max(double v, double* s_red, int tid) {
 
 // One radix-8 stage of sub-transform length N (compile time): strides, pad offsets and the twiddle table offset are
 // constants; TW = twiddles follow the butterfly (every stage but N == 8), LAST = collect the maximum imaginary part.
-template <int LOG2N, int N, class Sync>
+// PLO..PHI (first stage only; empty when PLO > PHI): legs of every butterfly that hold zeros because their bins lie above the
+// band limit of the trace (bins [J NT, n - J NT] except Nyquist): not loaded, not added.  The one exception is the
+// butterfly with offset 0 (thread 0), whose leg 4 is the Nyquist bin: its contribution (+-X on the 8 outputs) is added back.
+template <int LOG2N, int N, class Sync, int PLO = 8, int PHI = -1>
 __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restrict__ stw, double& vmax, double* s_red, int tid,
                                            int nthr, Sync sync) {
   constexpr unsigned n = 1u << LOG2N, stride = N >> 3;
+  constexpr bool prune = PLO <= PHI;
+  constexpr unsigned zmask = prune ? (((1u << (PHI + 1)) - 1u) & ~((1u << PLO) - 1u)) : 0u;
   constexpr int PSH = LOG2N >= 9 ? LOG2N - 3 : 31;
   constexpr bool last = (N == 8);
   for (unsigned j = tid; j < (n >> 3); j += nthr) {
@@ -759,12 +781,17 @@ __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restri
       for (int r = 0; r < 8; ++r) pos[r] = fpad(base + r * stride, PSH);
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) v[r] = buf[pos[r]];
+    for (int r = 0; r < 8; ++r) if (!((zmask >> r) & 1u)) v[r] = buf[pos[r]];
     if (!last) {
       double2 w[7];
 #pragma unroll
       for (int q = 1; q < 8; ++q) w[q - 1] = stw[(q - 1) * stride + o];
-      dft8(v);
+      dft8<zmask>(v);
+      if (prune && o == 0) {     // leg 4 of this butterfly is the Nyquist bin
+        const double2 x = buf[pos[4]];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = (q & 1) ? make_double2(v[q].x - x.x, v[q].y - x.y) : make_double2(v[q].x + x.x, v[q].y + x.y);
+      }
 #pragma unroll
       for (int q = 1; q < 8; ++q) v[q] = cmul(v[q], w[q - 1]);
     } else {
@@ -780,13 +807,20 @@ __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restri
   if constexpr (N >= 64) fft_stage8<LOG2N, (N >> 3), Sync>(buf, stw + 7 * stride, vmax, s_red, tid, nthr, sync);
 }
 
-template <int LOG2N, class Sync>
+// JP, NT (optional): the spectrum is zero in bins [JP NT, n - JP NT] except Nyquist (band limit of forward_kernel)
+template <int LOG2N, class Sync, int JP = 0, int NT = 1>
 __device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
   constexpr unsigned n = 1u << LOG2N;
+#ifdef RFINV_NO_FFT_PRUNE
+  constexpr int PLO = 8, PHI = -1;
+#else
+  constexpr int jfull = (1 << (LOG2N - 1)) / NT;                          // bin groups of the full band
+  constexpr int PLO = (JP > 0 && LOG2N >= 6) ? (4 * JP + jfull - 1) / jfull : 8, PHI = 7 - PLO;   // leg r covers bins [r n/8, (r+1) n/8)
+#endif
   constexpr int PSH = LOG2N >= 9 ? LOG2N - 3 : 31;
   constexpr int REM = LOG2N % 3;          // what is left after the radix-8 stages: 1 (N = 1), 2 or 4
   double vmax = -INFINITY;
-  fft_stage8<LOG2N, (1 << LOG2N), Sync>(buf, twq, vmax, s_red, tid, nthr, sync);
+  fft_stage8<LOG2N, (1 << LOG2N), Sync, PLO, PHI>(buf, twq, vmax, s_red, tid, nthr, sync);
   if (REM == 2) {
     for (unsigned j = tid; j < (n >> 2); j += nthr) {
       const unsigned p0 = fpad(j << 2, PSH);     // the four elements share a pad group
@@ -819,13 +853,13 @@ __device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2*
 
 // run-time length -> compile-time instantiation (nfft is a power of two in [64, 4096]); LO..HI = the lengths the caller
 // can see (a kernel variant is tied to a thread count, hence to one or two transform lengths)
-template <int LO, int HI, class Sync>
+template <int LO, int HI, class Sync, int JP = 0, int NT = 1>
 __device__ __forceinline__ double fft_inverse_dif(double2* buf, int n, const double2* twq, double* s_red, int tid, int nthr, Sync sync) {
   if constexpr (LO == HI) {
-    return fft_inverse_dif_n<LO>(buf, twq, s_red, tid, nthr, sync);
+    return fft_inverse_dif_n<LO, Sync, JP, NT>(buf, twq, s_red, tid, nthr, sync);
   } else {
-    if (n == (1 << LO)) return fft_inverse_dif_n<LO>(buf, twq, s_red, tid, nthr, sync);
-    return fft_inverse_dif<LO + 1, HI>(buf, n, twq, s_red, tid, nthr, sync);
+    if (n == (1 << LO)) return fft_inverse_dif_n<LO, Sync, JP, NT>(buf, twq, s_red, tid, nthr, sync);
+    return fft_inverse_dif<LO + 1, HI, Sync, JP, NT>(buf, n, twq, s_red, tid, nthr, sync);
   }
 }
 
@@ -1037,6 +1071,12 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
     if (STAGE) { s_fr[j] = make_double2(0.0, 0.0); s_fv[j] = make_double2(0.0, 0.0); }
     else { s_buf[fpad(j, psh)] = make_double2(0.0, 0.0); s_buf[fpad(n - j, psh)] = make_double2(0.0, 0.0); }
   }
+  if (!STAGE && tid == 0 && 2 * jfull * nthr < n) {
+    // pruned first FFT stage (jfull = the kernel variant's bin groups): the butterfly with offset 0 still reads its leg
+    // n - jfull*nthr, the mirror of the first bin above the band limit
+    s_buf[fpad(jfull * nthr, psh)] = make_double2(0.0, 0.0);
+    s_buf[fpad(n - jfull * nthr, psh)] = make_double2(0.0, 0.0);
+  }
   if (tid == 0) {  // the two bins off the regular grid
     if (STAGE) {
       s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
@@ -1234,8 +1274,13 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
     const int jfull = (n >> 1) / nthr;
+#ifdef RFINV_NO_FFT_PRUNE
+    constexpr bool kPruned = false;
+#else
+    constexpr bool kPruned = true;   // the first FFT stage skips the bin groups from J on: nobody has to zero them
+#endif
     if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw, psh);
-    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw, psh);
+    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, kPruned ? J : jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw, psh);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -1298,7 +1343,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       // threads per CTA fix the transform length: 32 -> 64/128, 64 -> 256/512, 128 -> 1024, 256 -> 2048/4096
       constexpr int FLO = BMAX <= 32 ? 6 : (BMAX <= 64 ? 8 : (BMAX <= 128 ? 10 : 11));
       constexpr int FHI = BMAX <= 32 ? 7 : (BMAX <= 64 ? 9 : (BMAX <= 128 ? 10 : 12));
-      const double mx = fft_inverse_dif<FLO, FHI>(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
+      const double mx = fft_inverse_dif<FLO, FHI, CtaSync, J, nthr>(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
       PHASE_MARK(5);
       const double scale = cfg.deconv_mode == 0 ? 1.0 / mx : 1.0;   // src/forward.f90:197-203
       write_outputs(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
