@@ -12,6 +12,13 @@
 
 static thread_local char g_err[1024] = "";
 
+bool rfinv_pdl_enabled() {
+  // measured on B200 (target shape, 16 384 chains, interleaved A/B): 1.3087 ms per step with programmatic launches against
+  // 1.2954 ms without -- the early forward_kernel CTAs get in the way of prep_kernel's last wave.  Off unless RFINV_PDL=1.
+  static const bool on = getenv("RFINV_PDL") && atoi(getenv("RFINV_PDL")) != 0;
+  return on;
+}
+
 void rfinv_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);

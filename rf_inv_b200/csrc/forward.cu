@@ -140,15 +140,16 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // Boundary conditions (src/forward.f90:267-287) in the scaled real basis, then the sign conventions of
 // calc_rf (src/forward.f90:145-146): fr = conj(ur), fv = -conj(uz).  (A3, A4) / (B3, B4) are rows 3,4 of
 // E^-1 prod(P) applied to the two propagated vectors: real parts from the {1,4} block, imaginary parts from {2,3}.
+// `gain` multiplies both results (the Gaussian filter weight of the bin: folded into the reciprocal of the determinant).
 __device__ __forceinline__ void surface_response(const double* h14, const double* h23, const Wave& wa, const Wave& wb,
-                                                 double cw, int ipha, double2& fr, double2& fv) {
+                                                 double cw, int ipha, double2& fr, double2& fv, double gain = 1.0) {
   const double2 A3 = make_double2(fma(h14[0], wa.a1, h14[1] * wa.b1), fma(h23[0], wa.a2, h23[1] * wa.b2));
   const double2 A4 = make_double2(fma(h14[2], wa.a1, h14[3] * wa.b1), fma(h23[2], wa.a2, h23[3] * wa.b2));
   const double2 B3 = make_double2(fma(h14[0], wb.a1, h14[1] * wb.b1), fma(h23[0], wb.a2, h23[1] * wb.b2));
   const double2 B4 = make_double2(fma(h14[2], wb.a1, h14[3] * wb.b1), fma(h23[2], wb.a2, h23[3] * wb.b2));
   const double2 p = cmul(A3, B4), q = cmul(B3, A4);
   const double2 dl = make_double2(p.x - q.x, p.y - q.y);
-  const double rn = 1.0 / (dl.x * dl.x + dl.y * dl.y);
+  const double rn = gain / (dl.x * dl.x + dl.y * dl.y);
   const double2 inv = make_double2(dl.x * rn, -dl.y * rn);
   double2 ur, uz;
   if (ipha >= 0) {
@@ -278,6 +279,7 @@ __global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatc
   const int n_groups = (ntr_eff + rays_per_cta - 1) / rays_per_cta;
   const int ci = blockIdx.x / n_groups, t_first = (blockIdx.x - ci * n_groups) * rays_per_cta;
   const int nr_cta = min(rays_per_cta, ntr_eff - t_first);
+  pdl_trigger();   // forward_kernel may take the SM slots this kernel's last wave frees (it waits for our results: pdl_wait)
   if (blockIdx.x == 0 && threadIdx.x < RFINV_MAX_TRC) counter[threadIdx.x] = 0;   // work counters of the forward_kernel launches that follow on the same stream
   if (ci >= n_models) return;
   if (mb.n_active_dev && ci >= *mb.n_active_dev) return;
@@ -1054,14 +1056,13 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
     const int j = tid + m * nthr;
     double2 fr, fv;
     if (STAGE && buried) surface_response_buried(h14, h23, wa[m], wb[m], ipha, s_fr[j], s_fv[j], fr, fv);   // station pass left them there
-    else surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv);
+    else surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv, STAGE ? 1.0 : flt[j]);   // filtered on the way out
     rot(cw, sw, cbw, sbw);
     if (STAGE) {
       if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
     } else if (j > 0) {
-      const double f = flt[j];
-      const double2 xv = make_double2(fv.x * f, fv.y * f);
-      const double2 xr = ipha == 1 ? make_double2(fr.x * f, fr.y * f) : xv;
+      const double2 xv = fv;
+      const double2 xr = ipha == 1 ? fr : xv;
       s_buf[fpad(j, psh)] = make_double2(xr.x - xv.y, xr.y + xv.x);
       s_buf[fpad(n - j, psh)] = make_double2(xr.x + xv.y, xv.x - xr.y);
     }
@@ -1188,7 +1189,6 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   const int n = cfg.nfft, nh = cfg.nh, km = cfg.k_max, C = mb.C, psh = fft_pad_shift(cfg.log2n);
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;   // rays per model in the scratch arrays prep_kernel filled
   // items of this launch: (model, ray) for the rays in `sel` (all of them, or the traces of one band-limit group)
-  const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   constexpr bool buried = BURIED;   // cfg.bdep > 0: a kernel variant of its own, the surface-station variants carry none of it
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || buried;   // spectra staged in shared memory
 
@@ -1223,8 +1223,11 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   // after that is on its way back from the atomic counter (thread 0 holds it in a register until the end of the
   // iteration, so nobody waits for the round trip).
   int item = blockIdx.x, slot = 0;
+  pdl_trigger();                               // quadform_kernel may queue up behind this grid
+  fill_fft_twiddles(s_twq, cfg.tw, n, tid, nthr);   // (nothing of prep_kernel is touched before pdl_wait)
+  pdl_wait();                                  // prep_kernel (and everything before it on the stream) is complete
+  const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   if (item >= n_items) return;
-  fill_fft_twiddles(s_twq, cfg.tw, n, tid, nthr);
   prefetch(item, 0);
   asm volatile("cp.async.commit_group;\n" ::);
   if (tid == 0) s_next = (int)gridDim.x + atomicAdd(counter, 1);
@@ -1457,8 +1460,7 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
   const long long items = (long long)n_models * sel.n;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  forward_kernel<J, BMAX, MINB, MIXED, BURIED><<<grid, nthr, smem, stream>>>(cfg, mb, out, lc, rc, counter, sel);
-  RFINV_CUDA_CHECK(cudaGetLastError());
+  RFINV_CUDA_CHECK(rfinv_launch_pdl(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, dim3(grid), dim3(nthr), smem, stream, cfg, mb, out, lc, rc, counter, sel));
   return RFINV_OK;
 }
 

@@ -53,12 +53,13 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
   const int Sp = cfg.nsmp_pad, T = cfg.ntrc;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp >> 1, wn = warp & 1;          // warp sub-tile: rows wm*32 .., column fragments 2j + wn
-  const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
   const int n_rb_grid = ((active ? n_active : C) + TM - 1) / TM;   // row blocks the item index space is built on
   const int ntile = cfg.qf_tiles_max;               // column tiles of the trace with the most work items
   const int n_items = ntile * T * n_rb_grid;
   const int fr = lane >> 2, fk = lane & 3;          // fragment coordinates
-  if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);
+  if (tid == 0) s_next = (int)gridDim.x + atomicAdd(work, 1);   // (the counter was left at zero by the previous launch)
+  pdl_wait();                                       // forward_kernel has delivered the misfit rows
+  const int n_rows = active ? (n_active_dev ? *n_active_dev : n_active) : C;
   int item = blockIdx.x;
   while (item < n_items) {
     // item order: (trace, row block) pairs in chunks of QF_CHUNK (their misfit rows, 64 x Sp doubles each, stay in L2
@@ -240,6 +241,11 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
     if (tid == 0) s_next = (int)gridDim.x + next_raw;
     item = next;
   }
+  // the last CTA to leave resets the work counter for the next launch (no memset between the kernels of an evaluation)
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; }
+  }
 }
 
 __global__ void loglik_kernel(const DevConfig cfg, int C, const double* __restrict__ phi, const double* __restrict__ sig,
@@ -262,7 +268,7 @@ size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C) { return (siz
 size_t rfinv_quadform_counter_ints(const DevConfig& cfg, int C) { return (size_t)((C + TM - 1) / TM) * (cfg.ntrc + 1) + 4; }
 
 // partial: rfinv_quadform_partial_doubles(cfg, C) doubles; counters: rfinv_quadform_counter_ints(cfg, capacity) ints, zeroed
-// once at allocation (the arrival counters reset themselves; the work counter is cleared here before every launch)
+// once at allocation (the arrival counters and the work counter reset themselves at the end of every launch)
 int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, double* phi, double* partial, int* counters,
                           const int* active, int n_active, const int* n_active_dev, cudaStream_t stream, const double* sig,
                           double* logl) {
@@ -285,10 +291,8 @@ int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, dou
     if (dev >= 0 && dev < 64) resident_of_device[dev] = (int)resident;
   }
   const long long items = (long long)ntile * cfg.ntrc * ((n_rows + TM - 1) / TM);
-  RFINV_CUDA_CHECK(cudaMemsetAsync(work, 0, sizeof(int), stream));
-  quadform_kernel<<<(unsigned)(items < resident ? items : resident), QF_THREADS, 0, stream>>>(cfg, C, misfit, phi, partial, arrivals, work,
-                                                                                              active, n_active, n_active_dev, sig, logl);
-  RFINV_CUDA_CHECK(cudaGetLastError());
+  RFINV_CUDA_CHECK(rfinv_launch_pdl(quadform_kernel, dim3((unsigned)(items < resident ? items : resident)), dim3(QF_THREADS), 0, stream, cfg, C,
+                                    misfit, phi, partial, arrivals, work, active, n_active, n_active_dev, sig, logl));
   return RFINV_OK;
 }
 

@@ -106,6 +106,24 @@ __device__ __forceinline__ bool layer_velocity(const DevConfig& cfg, double zc, 
 
 void rfinv_set_error(const char* fmt, ...);
 
+// Programmatic dependent launch (sm_90+): a kernel launched with rfinv_launch_pdl may start while the kernel before it on the
+// stream is still draining -- its CTAs take the SM slots the predecessor's last CTAs free, run their prologue, and block in
+// pdl_wait() until the predecessor has completed and its writes are visible.  The predecessor calls pdl_trigger() early
+// (a kernel that never does releases its dependents when it exits).  Opt-in (RFINV_PDL=1): measured slower, see capi.cu.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool rfinv_pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t rfinv_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = rfinv_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // kernel launchers (forward.cu, likelihood.cu); all asynchronous on `stream`
 struct EvalOutputs {
   double* misfit;     // [ntrc][C][nsmp_pad]  rft(1:nsmp) - obs, zero padded          (required)
