@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define RFINV_ABI_VERSION 2
+#define RFINV_ABI_VERSION 3
 
 /* status codes */
 #define RFINV_OK 0
@@ -117,6 +117,16 @@ int32_t rfinv_set_stream(rfinv_handle* h, uint64_t cuda_stream);
 int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
                          const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid);
 
+/* Asynchronous form of rfinv_eval_batch for hosts that keep two (or more) groups of chains in flight, e.g. the two halves of
+ * the chains of one MPI rank of the reference (src/pt_mcmc.f90:77-201 proposes and judges every chain independently):
+ * _begin queues upload, evaluation and the read-back of logl (and is_valid, may be NULL) of one batch on the stream and
+ * workspace of `slot` (0 or 1) and returns at once; _end waits until logl[] is filled.  With two slots in flight the
+ * transfers of one batch hide behind the kernels of the other.  The host arrays must stay untouched until _end returns
+ * (page-locked memory for real overlap; pageable memory works, synchronously).  The complete RF (rft) is not returned. */
+int32_t rfinv_eval_batch_begin(rfinv_handle* h, int32_t slot, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                               const double* dvs, const double* sig, double* logl, uint8_t* is_valid);
+int32_t rfinv_eval_batch_end(rfinv_handle* h, int32_t slot);
+
 /* Same evaluation with DEVICE pointers in the library's chain-fastest layout:
  *   k[C], z[k_max-1][C], dvp[k_max][C], dvs[k_max][C], sig[ntrc][C], logl[C],
  *   rft_smp[ntrc][C][nsmp] (first nsmp samples only; may be 0), is_valid[C] (may be 0).
@@ -174,6 +184,29 @@ int32_t rfinv_pt_ntype(rfinv_handle* h);
 int32_t rfinv_pt_set_logging(rfinv_handle* h, int32_t cap_iters);
 /* pt_control (src/pt_mcmc.f90:468-576) for n_iter iterations when this handle owns ALL ranks. */
 int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter);
+/* ---- one process per GPU: the collectives of the path, inside the library (NCCL over NVLink) ---------------------
+ * Replaces the reference's MPI traffic on this path: pt_control's swap exchange (src/pt_mcmc.f90:518-571: mpi_bcast of the
+ * pair, mpi_send / mpi_recv of temperature and likelihood) becomes ONE ncclAllGather of the swap tables per iteration on the
+ * handle's stream; output_results' 14 mpi_reduce and 2 mpi_gather (src/mcmc_out.f90:52-93) become rfinv_pt_reduce_outputs.
+ * NCCL is bound at run time (libnccl.so.2, or the file named by RFINV_NCCL_LIB).  The host only carries the communicator id
+ * from one process to the others (MPI_Bcast of rfinv_comm_id_bytes() bytes in the Fortran host).                          */
+int32_t rfinv_comm_id_bytes(void);
+/* On ONE process: a fresh communicator id (ncclUniqueId), id_out[rfinv_comm_id_bytes()]. */
+int32_t rfinv_comm_create_id(void* id_out);
+/* On EVERY process (collective): joins the communicator of `world` processes as process `rank`. */
+int32_t rfinv_comm_init(rfinv_handle* h, const void* id, int32_t world, int32_t rank);
+int32_t rfinv_comm_destroy(rfinv_handle* h);
+/* world / rank of the handle's communicator (1 / 0 without one) and the version of the NCCL library bound (0: none). */
+int32_t rfinv_comm_info(rfinv_handle* h, int32_t* world, int32_t* rank, int32_t* nccl_version);
+/* pt_control (src/pt_mcmc.f90:468-576) for n_iter iterations over the processes of the communicator; process q must have
+ * called rfinv_pt_init(h, nproc_total, q * G, G).  Bit-identical to the single-process run of the same nproc_total.
+ * Like rfinv_pt_run, the launch sequence of an iteration is captured once in a CUDA graph and replayed. */
+int32_t rfinv_pt_run_distributed(rfinv_handle* h, int32_t n_iter);
+/* Collective, once, after the last iteration: process 0 then holds the job-wide sums of the bookkeeping arrays, counters and
+ * likelihood history and the recorded models of every process in process order -- what mpi_reduce / mpi_gather deliver on
+ * rank 0 -- and returns them through rfinv_pt_get_hist / _get_counters / _get_models. */
+int32_t rfinv_pt_reduce_outputs(rfinv_handle* h);
+
 /* Multi-process iteration, step 1: every chain proposes, is evaluated and accepted/rejected; fills this
  * process's swap table [temps(Cl) | logL(Cl) | next uniform of each local stream (G) | itarget1, itarget2]. */
 int32_t rfinv_pt_local_step(rfinv_handle* h);

@@ -32,6 +32,8 @@ SIGNATURES = {
     "rfinv_destroy": (None, [C.c_void_p]),
     "rfinv_set_stream": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "rfinv_eval_batch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp, dp, dp, dp, dp, u8p]),
+    "rfinv_eval_batch_begin": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, i32p, dp, dp, dp, dp, dp, u8p]),
+    "rfinv_eval_batch_end": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_eval_batch_device": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_uint64] * 8),
     "rfinv_format_model_batch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp, dp, i32p, dp, dp, dp, dp, u8p]),
     "rfinv_filter_traces": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp]),
@@ -47,6 +49,13 @@ SIGNATURES = {
     "rfinv_pt_ntype": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_set_logging": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_pt_run": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rfinv_comm_id_bytes": (C.c_int32, []),
+    "rfinv_comm_create_id": (C.c_int32, [C.c_void_p]),
+    "rfinv_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "rfinv_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "rfinv_comm_info": (C.c_int32, [C.c_void_p, i32p, i32p, i32p]),
+    "rfinv_pt_run_distributed": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "rfinv_pt_reduce_outputs": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_local_step": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_swap_table": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64), i32p]),
     "rfinv_pt_apply_swap": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_int32]),

@@ -257,21 +257,17 @@ __global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict_
   const int c = (int)(idx % n), i = (int)(idx / n);
   out[(size_t)i * C + c0 + c] = in[(size_t)c * len + i];
 }
-// Large uploads (rfinv_eval_batch) go up in four pieces of at least UPLOAD_PIECE_MIN models: measured at 16 384 models,
-// pieces of 1024 / 2048 / 4096 / 8192 give 9.3 / 9.9 / 10.2 / 9.8 M evals/s end to end (every copy costs a few
-// microseconds of set-up; the first piece is exposed).  RFINV_UPLOAD_PIECE overrides the piece size (tuning).
+// Large uploads (rfinv_eval_batch) go up in RFINV_UPLOAD_PIECES pieces of at least UPLOAD_PIECE_MIN models: measured at
+// 16 384 models, pieces of 1024 / 2048 / 4096 / 8192 give 9.3 / 9.9 / 10.2 / 9.8 M evals/s end to end (every copy costs a few
+// microseconds of set-up; the first piece is exposed).
 constexpr int UPLOAD_PIECE_MIN = 2048;
-static int upload_piece(int C) {
-  static const int forced = getenv("RFINV_UPLOAD_PIECE") ? std::max(UPLOAD_PIECE_MIN, atoi(getenv("RFINV_UPLOAD_PIECE"))) : 0;
-  if (forced) return forced;
-  return std::max(UPLOAD_PIECE_MIN, ((C / 4 + 255) / 256) * 256);
-}
+static int upload_piece(int C) { return std::max(UPLOAD_PIECE_MIN, ((C / RFINV_UPLOAD_PIECES + 255) / 256) * 256); }
 
 }  // namespace
 
-int rfinv_handle::ensure_capacity(int C) {
+int EvalWorkspace::grow(const DevConfig& dc, const rfinv_config& cfg, int device, int C) {
   if (C <= cap) return RFINV_OK;
-  free_workspace();
+  release();
   const int km = cfg.k_max, T = cfg.ntrc;
   const size_t Cz = (size_t)C;
   RFINV_CUDA_CHECK(cudaSetDevice(device));
@@ -282,13 +278,6 @@ int rfinv_handle::ensure_capacity(int C) {
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_dvs, sizeof(double) * Cz * km));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_sig, sizeof(double) * Cz * T));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_stage, sizeof(double) * Cz * (size_t)std::max(km, T)));
-  ready_cap = (C + UPLOAD_PIECE_MIN - 1) / UPLOAD_PIECE_MIN;
-  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_ready, sizeof(int) * (size_t)(ready_cap + 1)));
-  RFINV_CUDA_CHECK(cudaMemset(d_ready, 0, sizeof(int) * (size_t)(ready_cap + 1)));
-  if (!h_ready) {
-    RFINV_CUDA_CHECK(cudaHostAlloc((void**)&h_ready, sizeof(int) * 2, cudaHostAllocDefault));
-    h_ready[0] = h_ready[1] = 0;
-  }
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_misfit, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMemset(d_misfit, 0, sizeof(double) * Cz * T * dc.nsmp_pad));
   RFINV_CUDA_CHECK(cudaMalloc((void**)&d_phi, sizeof(double) * Cz * T));
@@ -302,9 +291,8 @@ int rfinv_handle::ensure_capacity(int C) {
   return RFINV_OK;
 }
 
-void rfinv_handle::free_workspace() {
-  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage); cudaFree(d_ready);
-  d_ready = nullptr; ready_cap = 0;
+void EvalWorkspace::release() {
+  cudaFree(d_k); cudaFree(d_z); cudaFree(d_dvp); cudaFree(d_dvs); cudaFree(d_sig); cudaFree(d_stage);
   cudaFree(d_misfit); cudaFree(d_phi); cudaFree(d_logl); cudaFree(d_valid); cudaFree(d_rft_full); cudaFree(d_scratch); cudaFree(d_qpart); cudaFree(d_qcnt);
   d_qpart = nullptr; d_qcnt = nullptr;
   d_k = nullptr; d_z = d_dvp = d_dvs = d_sig = d_stage = d_misfit = d_phi = d_logl = d_rft_full = d_scratch = nullptr;
@@ -314,25 +302,29 @@ void rfinv_handle::free_workspace() {
 
 int rfinv_handle::eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs,
                               const double* sig, double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid,
-                              const int* active, int n_active, const ModelBatch* layout) {
+                              const int* active, int n_active, const ModelBatch* layout, EvalWorkspace* w, cudaStream_t s,
+                              bool prep_done) {
+  if (!w) w = this;
+  if (!s) s = stream;
   // misfit scratch is sized by capacity; its [t][c] stride uses the C of this call
   ModelBatch mb;
   if (layout) mb = *layout;
   mb.C = C; mb.k = k; mb.z = z; mb.dvp = dvp; mb.dvs = dvs; mb.sig = sig; mb.active = active; mb.n_active = n_active; mb.n_active_dev = nullptr;
   EvalOutputs out;
-  out.misfit = d_misfit; out.rft_smp = rft_smp; out.rft_smp_alt = nullptr; out.slot = nullptr; out.slot_invert = 0;
+  out.misfit = w->d_misfit; out.rft_smp = rft_smp; out.rft_smp_alt = nullptr; out.slot = nullptr; out.slot_invert = 0;
   out.rft_full = rft_full; out.is_valid = is_valid;
   int st;
   launches = 0;
-  if (timing) cudaEventRecord(ev[0], stream);
+  const bool timed = timing && w == this;
+  if (timed) cudaEventRecord(ev[0], s);
   int n_fwd = 0;
-  if ((st = rfinv_launch_forward(dc, mb, out, d_scratch, stream, &n_fwd)) != RFINV_OK) return st;
+  if ((st = rfinv_launch_forward(dc, mb, out, w->d_scratch, s, &n_fwd, prep_done)) != RFINV_OK) return st;
   launches += n_fwd;
-  if (timing) cudaEventRecord(ev[1], stream);
+  if (timed) cudaEventRecord(ev[1], s);
   // logL leaves the same kernel (its last CTA per block of 64 chains sums the traces): no separate loglik_kernel launch
-  if ((st = rfinv_launch_quadform(dc, C, d_misfit, d_phi, d_qpart, d_qcnt, active, n_active, nullptr, stream, logl ? sig : nullptr, logl)) != RFINV_OK) return st;
+  if ((st = rfinv_launch_quadform(dc, C, w->d_misfit, w->d_phi, w->d_qpart, w->d_qcnt, active, n_active, nullptr, s, logl ? sig : nullptr, logl)) != RFINV_OK) return st;
   ++launches;
-  if (timing) { cudaEventRecord(ev[2], stream); cudaEventRecord(ev[3], stream); }
+  if (timed) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); }
   return RFINV_OK;
 }
 
@@ -580,16 +572,20 @@ void rfinv_destroy(rfinv_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  h->free_pt();              // first: the captured iteration graphs hold references on the communicator (ncclCommDestroy waits for them)
+  rfinv_comm_destroy(h);
   h->free_workspace();
-  h->free_pt();
   cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_copy) {
     cudaStreamSynchronize(h->stream_copy);
     cudaStreamDestroy(h->stream_copy);
-    for (int i = 0; i < 2; ++i) cudaEventDestroy(h->ev_copy[i]);
+    for (cudaEvent_t e : h->ev_copy) if (e) cudaEventDestroy(e);
   }
-  if (h->h_ready) cudaFreeHost(h->h_ready);
+  for (int i = 0; i < RFINV_ASYNC_SLOTS; ++i) {
+    if (h->async_stream[i]) { cudaStreamSynchronize(h->async_stream[i]); cudaStreamDestroy(h->async_stream[i]); }
+    if (h->async_ws[i]) { h->async_ws[i]->release(); delete h->async_ws[i]; }
+  }
   for (int i = 0; i < 4; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -663,21 +659,27 @@ static int upload_models(rfinv_handle* h, int C, const int32_t* k, const double*
   return RFINV_OK;
 }
 
-int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
-                         const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid) {
+static int check_models(const rfinv_handle* h, const char* who, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                        const double* dvs, const double* sig, const double* logl) {
   if (!h || C < 0 || (C > 0 && (!k || !z || !dvp || !dvs || !sig || !logl))) {
-    rfinv_set_error("rfinv_eval_batch: NULL argument");
+    rfinv_set_error("%s: NULL argument", who);
     return RFINV_ERR_ARG;
   }
-  if (C == 0) return RFINV_OK;
   for (int c = 0; c < C; ++c)
     if (k[c] < 1 || k[c] > h->cfg.k_max - 1) {
-      rfinv_set_error("rfinv_eval_batch: k[%d]=%d outside [1,k_max-1]", c, k[c]);
+      rfinv_set_error("%s: k[%d]=%d outside [1,k_max-1]", who, c, k[c]);
       return RFINV_ERR_ARG;
     }
-  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
-  int st = h->ensure_capacity(C);
+  return RFINV_OK;
+}
+
+int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                         const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid) {
+  int st = check_models(h, "rfinv_eval_batch", C, k, z, dvp, dvs, sig, logl);
   if (st != RFINV_OK) return st;
+  if (C == 0) return RFINV_OK;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if ((st = h->ensure_capacity(C)) != RFINV_OK) return st;
   if (rft) {
     const size_t need = (size_t)C * h->cfg.ntrc * h->cfg.nfft;
     if (need > h->cap_rft_full) {
@@ -688,66 +690,112 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
     }
   }
   // Upload.  z / dvp / dvs go up exactly as the caller holds them (chain slowest): prep_kernel reads that layout
-  // directly, one warp per model reading consecutive words, so no layout kernels run (only sig, which loglik_kernel wants
+  // directly, one warp per model reading consecutive words, so no layout kernels run (only sig, which the likelihood wants
   // chain fastest, is transposed).  dVp stays on the host at vp_mode 0: format_model never looks at it
-  // (src/model.f90:214-218, 271-275).  Large batches go up in pieces (upload_piece()) on a second stream, each
-  // followed by a 4-byte copy of this call's epoch into the piece's `ready` word; prep_kernel starts at once and waits
-  // per model for its piece, so only the first piece's transfer is exposed (RFINV_UPLOAD_OVERLAP=0: plain copies on the
-  // handle's stream).  Only copy-engine work is queued behind the waiting kernel: it cannot starve what it waits for.
+  // (src/model.f90:214-218, 271-275).  Large batches go up in pieces (upload_piece()) on a second stream; prep_kernel is
+  // launched per piece on the handle's stream behind the event that marks the piece's arrival, so only the first piece's
+  // transfer is exposed and nothing ever polls (RFINV_UPLOAD_OVERLAP=0: plain copies on the handle's stream).
   static const bool overlap_ok = !(getenv("RFINV_UPLOAD_OVERLAP") && atoi(getenv("RFINV_UPLOAD_OVERLAP")) == 0);
   const int km = h->cfg.k_max, T = h->cfg.ntrc;
-  const bool pieces = overlap_ok && C >= 4 * UPLOAD_PIECE_MIN;
+  const bool pieces = overlap_ok && C >= RFINV_UPLOAD_PIECES * UPLOAD_PIECE_MIN;
   const int piece = pieces ? upload_piece(C) : C;
-  ModelBatch layout;
-  layout.chain_major = 1;
+  ModelBatch mb;
+  mb.chain_major = 1;
+  mb.C = C; mb.k = h->d_k; mb.z = h->d_z; mb.dvp = h->d_dvp; mb.dvs = h->d_dvs; mb.sig = h->d_sig;
+  mb.active = nullptr; mb.n_active = 0; mb.n_active_dev = nullptr;
   cudaStream_t up = h->stream;
   if (pieces) {
     if (!h->stream_copy) {
       RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&h->stream_copy, cudaStreamNonBlocking));
-      for (int i = 0; i < 2; ++i) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_copy[i], cudaEventDisableTiming));
+      for (cudaEvent_t& e : h->ev_copy) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
     up = h->stream_copy;
-    h->h_ready[0] = ++h->ready_epoch;
-    layout.ready = h->d_ready; layout.ready_chunk = piece; layout.ready_epoch = h->ready_epoch;
-    layout.ready_timeout = h->d_ready + h->ready_cap;
-    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[0], h->stream));                 // earlier work on the handle's stream reads these buffers
-    RFINV_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_copy[0], 0));
+    RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[RFINV_UPLOAD_PIECES], h->stream));   // earlier work on the handle's stream reads these buffers
+    RFINV_CUDA_CHECK(cudaStreamWaitEvent(up, h->ev_copy[RFINV_UPLOAD_PIECES], 0));
   }
-  for (int c0 = 0; c0 < C; c0 += piece) {
+  if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+  int ip = 0;
+  for (int c0 = 0; c0 < C; c0 += piece, ++ip) {
     const size_t n = (size_t)std::min(piece, C - c0);
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_k + c0, k + c0, sizeof(int) * n, cudaMemcpyHostToDevice, up));
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_z + (size_t)c0 * (km - 1), z + (size_t)c0 * (km - 1), sizeof(double) * n * (km - 1), cudaMemcpyHostToDevice, up));
     RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvs + (size_t)c0 * km, dvs + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
     if (h->cfg.vp_mode == 1)
       RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_dvp + (size_t)c0 * km, dvp + (size_t)c0 * km, sizeof(double) * n * km, cudaMemcpyHostToDevice, up));
-    if (pieces)
-      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_ready + c0 / piece, h->h_ready, sizeof(int), cudaMemcpyHostToDevice, up));
+    if (pieces) {
+      RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[ip], up));
+      RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[ip], 0));
+    }
+    if ((st = rfinv_launch_prep(h->dc, mb, is_valid ? h->d_valid : nullptr, h->d_scratch, h->stream, c0, (int)n)) != RFINV_OK) return st;
+    if (ip == 0) {  // sig (only the likelihood reads it) travels behind the first piece: it has landed long before forward_kernel ends
+      const size_t nel = (size_t)C * T;
+      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * nel, cudaMemcpyHostToDevice, up));
+      to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, up>>>(h->d_stage, h->d_sig, C, 0, C, T);
+      RFINV_CUDA_CHECK(cudaGetLastError());
+      if (pieces) RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[RFINV_UPLOAD_PIECES + 1], up));
+    }
   }
-  {  // sig: only the likelihood reads it, after everything else
-    const size_t nel = (size_t)C * T;
-    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * nel, cudaMemcpyHostToDevice, up));
-    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, up>>>(h->d_stage, h->d_sig, C, 0, C, T);
-    RFINV_CUDA_CHECK(cudaGetLastError());
-    if (pieces) RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[1], up));
-  }
-  st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, nullptr, nullptr, rft ? h->d_rft_full : nullptr,
-                      is_valid ? h->d_valid : nullptr, nullptr, 0, &layout);
+  if (pieces) RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[RFINV_UPLOAD_PIECES + 1], 0));
+  const bool timing_saved = h->timing;
+  h->timing = false;   // ev[0] is already on the stream (before the first piece of prep_kernel)
+  st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
+                      is_valid ? h->d_valid : nullptr, nullptr, 0, &mb, nullptr, nullptr, /*prep_done=*/true);
+  h->timing = timing_saved;
   if (st != RFINV_OK) return st;
-  if (pieces) RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[1], 0));
-  if ((st = rfinv_launch_loglik(h->dc, C, h->d_phi, h->d_sig, h->d_logl, h->stream)) != RFINV_OK) return st;
-  h->launches += 2;   // sig layout kernel, logL
-  if (pieces) RFINV_CUDA_CHECK(cudaMemcpyAsync(h->h_ready + 1, h->d_ready + h->ready_cap, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  h->launches += ip + 1;   // prep_kernel per piece, sig layout kernel
+  if (h->timing) { cudaEventRecord(h->ev[1], h->stream); cudaEventRecord(h->ev[2], h->stream); cudaEventRecord(h->ev[3], h->stream); }
   RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   if (rft)
     RFINV_CUDA_CHECK(cudaMemcpyAsync(rft, h->d_rft_full, sizeof(double) * (size_t)C * h->cfg.ntrc * h->cfg.nfft,
                                      cudaMemcpyDeviceToHost, h->stream));
   if (is_valid) RFINV_CUDA_CHECK(cudaMemcpyAsync(is_valid, h->d_valid, (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  if (pieces && h->h_ready[1] != 0) {
-    cudaMemsetAsync(h->d_ready + h->ready_cap, 0, sizeof(int), h->stream);
-    rfinv_set_error("rfinv_eval_batch: a piece of the upload never arrived on the device");
-    return RFINV_ERR_CUDA;
+  return RFINV_OK;
+}
+
+// Asynchronous form of rfinv_eval_batch: everything of one batch -- upload, kernels, read-back of logL -- is queued on the
+// slot's own stream and workspace; with two slots in flight the transfers of one batch hide behind the kernels of the other.
+int32_t rfinv_eval_batch_begin(rfinv_handle* h, int32_t slot, int32_t C, const int32_t* k, const double* z, const double* dvp,
+                               const double* dvs, const double* sig, double* logl, uint8_t* is_valid) {
+  int st = check_models(h, "rfinv_eval_batch_begin", C, k, z, dvp, dvs, sig, logl);
+  if (st != RFINV_OK) return st;
+  if (slot < 0 || slot >= RFINV_ASYNC_SLOTS) { rfinv_set_error("rfinv_eval_batch_begin: slot must be in [0,%d)", RFINV_ASYNC_SLOTS); return RFINV_ERR_ARG; }
+  if (h->async_pending[slot]) { rfinv_set_error("rfinv_eval_batch_begin: slot %d is in flight; call rfinv_eval_batch_end first", slot); return RFINV_ERR_STATE; }
+  if (C == 0) return RFINV_OK;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->async_ws[slot]) {
+    h->async_ws[slot] = new EvalWorkspace();
+    RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&h->async_stream[slot], cudaStreamNonBlocking));
   }
+  EvalWorkspace* w = h->async_ws[slot];
+  cudaStream_t s = h->async_stream[slot];
+  if ((st = w->grow(h->dc, h->cfg, h->device, C)) != RFINV_OK) return st;
+  const int km = h->cfg.k_max, T = h->cfg.ntrc;
+  const size_t n = (size_t)C;
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(w->d_k, k, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(w->d_z, z, sizeof(double) * n * (km - 1), cudaMemcpyHostToDevice, s));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(w->d_dvs, dvs, sizeof(double) * n * km, cudaMemcpyHostToDevice, s));
+  if (h->cfg.vp_mode == 1) RFINV_CUDA_CHECK(cudaMemcpyAsync(w->d_dvp, dvp, sizeof(double) * n * km, cudaMemcpyHostToDevice, s));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(w->d_stage, sig, sizeof(double) * n * T, cudaMemcpyHostToDevice, s));
+  to_soa_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, s>>>(w->d_stage, w->d_sig, C, 0, C, T);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  ModelBatch layout;
+  layout.chain_major = 1;
+  st = h->eval_device(C, w->d_k, w->d_z, w->d_dvp, w->d_dvs, w->d_sig, w->d_logl, nullptr, nullptr, is_valid ? w->d_valid : nullptr,
+                      nullptr, 0, &layout, w, s);
+  if (st != RFINV_OK) return st;
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(logl, w->d_logl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  if (is_valid) RFINV_CUDA_CHECK(cudaMemcpyAsync(is_valid, w->d_valid, n, cudaMemcpyDeviceToHost, s));
+  h->async_pending[slot] = true;
+  return RFINV_OK;
+}
+
+int32_t rfinv_eval_batch_end(rfinv_handle* h, int32_t slot) {
+  if (!h || slot < 0 || slot >= RFINV_ASYNC_SLOTS) { rfinv_set_error("rfinv_eval_batch_end: bad handle or slot"); return RFINV_ERR_ARG; }
+  if (!h->async_pending[slot]) return RFINV_OK;
+  h->async_pending[slot] = false;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->async_stream[slot]));
   return RFINV_OK;
 }
 

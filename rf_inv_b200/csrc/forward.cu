@@ -272,15 +272,16 @@ template <bool BURIED, bool HOSTLAYOUT>
 __global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatch mb, double* __restrict__ lc_out,
                                                                  double* __restrict__ rc_out, uint8_t* __restrict__ is_valid,
                                                                  int* __restrict__ counter, int n_models, int ntr_eff, int nthr_fwd,
-                                                                 int rays_per_cta) {
+                                                                 int rays_per_cta, int m_begin) {
   extern __shared__ __align__(16) double prep_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // a model with many rays is spread over several CTAs (shared memory): group g works on rays [t_first, t_first + nr_cta)
   const int n_groups = (ntr_eff + rays_per_cta - 1) / rays_per_cta;
-  const int ci = blockIdx.x / n_groups, t_first = (blockIdx.x - ci * n_groups) * rays_per_cta;
+  const int bm = blockIdx.x / n_groups, t_first = (blockIdx.x - bm * n_groups) * rays_per_cta;
+  const int ci = m_begin + bm;                 // this launch covers the models [m_begin, n_models) of the batch (host path: one piece)
   const int nr_cta = min(rays_per_cta, ntr_eff - t_first);
   pdl_trigger();   // forward_kernel may take the SM slots this kernel's last wave frees (it waits for our results: pdl_wait)
-  if (blockIdx.x == 0 && threadIdx.x < RFINV_MAX_TRC) counter[threadIdx.x] = 0;   // work counters of the forward_kernel launches that follow on the same stream
+  if (blockIdx.x == 0 && m_begin == 0 && threadIdx.x < RFINV_MAX_TRC) counter[threadIdx.x] = 0;   // work counters of the forward_kernel launches that follow on the same stream
   if (ci >= n_models) return;
   if (mb.n_active_dev && ci >= *mb.n_active_dev) return;
   const int c = mb.active ? mb.active[ci] : ci;
@@ -304,20 +305,6 @@ __global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatc
 
   PREP_INIT();
   if (warp == 0) {
-    if (HOSTLAYOUT && mb.ready) {   // the model may still be on its way from the host (rfinv_eval_batch uploads in pieces)
-      if (lane == 0) {
-        const int* flag = mb.ready + c / mb.ready_chunk;
-        const long long t_wait = clock64();
-        int seen;
-        for (;;) {
-          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-          if (seen == mb.ready_epoch) break;
-          if (clock64() - t_wait > 4000000000LL) { *mb.ready_timeout = 1; break; }   // ~2 s: the copy never arrived
-          __nanosleep(200);
-        }
-      }
-      __syncwarp();
-    }
     // The layer count and the model arrays are requested together (one memory latency instead of two): every lane loads
     // its elements whether or not they lie below k -- the arrays are k_max long -- and drops the rest.
     int k = mb.k[c];
@@ -1503,20 +1490,20 @@ size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
   return (size_t)(n_models * ntr_eff) * ((size_t)cfg.k_max * LC_DOUBLES + RC_DOUBLES) + RFINV_MAX_TRC / 2;   // + the work counters
 }
 
-// scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
-int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
-                         cudaStream_t stream, int* n_kernels) {
+// prep_kernel for the models [m_begin, m_begin + m_count) of the batch; scratch as in rfinv_launch_forward
+int rfinv_launch_prep(const DevConfig& cfg, const ModelBatch& mb, uint8_t* is_valid, double* scratch, cudaStream_t stream,
+                      int m_begin, int m_count) {
   const int J = rfinv_forward_bins_per_thread(cfg.nfft);
   const int nthr = (cfg.nfft / 2) / J;
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long n_items = (long long)n_models * ntr_eff;
-  if (n_items == 0) { if (n_kernels) *n_kernels = 0; return RFINV_OK; }
+  if (m_count <= 0) return RFINV_OK;
   double* lc = scratch;
   double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
   int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
-  // prep_kernel: one CTA per model, one warp per ray
-  // (rays per CTA: all of them while the shared memory stays below ~96 KB, else the model is spread over several CTAs)
+  // one CTA per model, one warp per ray (rays per CTA: all of them while the shared memory stays below ~96 KB, else the
+  // model is spread over several CTAs)
   int n_groups = 1;
   while (sizeof(double) * (prep_smem_model_doubles(cfg.k_max) + (size_t)((ntr_eff + n_groups - 1) / n_groups) * prep_smem_ray_doubles(cfg.k_max)) > 96 * 1024 &&
          n_groups < ntr_eff) ++n_groups;
@@ -1526,12 +1513,31 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
 #define PREP(BUR, HOST)                                                                                                    \
   do {                                                                                                                     \
     RFINV_CUDA_CHECK(cudaFuncSetAttribute(prep_kernel<BUR, HOST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem)); \
-    prep_kernel<BUR, HOST><<<(unsigned)n_models * n_groups, 32 * rays_per_cta, prep_smem, stream>>>(cfg, mb, lc, rc, out.is_valid, counter, n_models, ntr_eff, nthr, rays_per_cta); \
+    prep_kernel<BUR, HOST><<<(unsigned)m_count * n_groups, 32 * rays_per_cta, prep_smem, stream>>>(cfg, mb, lc, rc, is_valid, counter, m_begin + m_count, ntr_eff, nthr, rays_per_cta, m_begin); \
   } while (0)
   if (cfg.bdep > 0.0) { if (mb.chain_major) PREP(true, true); else PREP(true, false); }
   else { if (mb.chain_major) PREP(false, true); else PREP(false, false); }
 #undef PREP
   RFINV_CUDA_CHECK(cudaGetLastError());
+  return RFINV_OK;
+}
+
+// scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
+int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
+                         cudaStream_t stream, int* n_kernels, bool prep_done) {
+  const int J = rfinv_forward_bins_per_thread(cfg.nfft);
+  const int nthr = (cfg.nfft / 2) / J;
+  const int n_models = mb.active ? mb.n_active : mb.C;
+  const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
+  const long long n_items = (long long)n_models * ntr_eff;
+  if (n_items == 0) { if (n_kernels) *n_kernels = 0; return RFINV_OK; }
+  double* lc = scratch;
+  double* rc = scratch + (size_t)n_items * cfg.k_max * LC_DOUBLES;
+  int* counter = reinterpret_cast<int*>(rc + (size_t)n_items * RC_DOUBLES);
+  if (!prep_done) {
+    const int st = rfinv_launch_prep(cfg, mb, out.is_valid, scratch, stream, 0, n_models);
+    if (st != RFINV_OK) return st;
+  }
   // One launch per band-limit group: traces whose Gaussian filters keep the same number of bin groups share a launch of
   // the kernel variant built for exactly that many (different widths in one launch would have to run the widest
   // variant for every item: more registers, spills in the layer loop).  Common rays: one launch, one ray.
@@ -1546,7 +1552,7 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
     if (st != RFINV_OK) return st;
     ++n_launch;
   }
-  if (n_kernels) *n_kernels = 1 + n_launch;   // prep_kernel + one forward_kernel per band-limit group
+  if (n_kernels) *n_kernels = (prep_done ? 0 : 1) + n_launch;   // prep_kernel + one forward_kernel per band-limit group
   return RFINV_OK;
 }
 

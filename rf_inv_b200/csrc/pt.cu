@@ -380,7 +380,14 @@ __global__ void __launch_bounds__(1024) pt_compact_kernel(const PtDev p) {
 }
 
 // ---------------- acceptance: src/pt_mcmc.f90:178-201, one thread per chain ----------------
-__global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p, int log_slot) {
+// slot of the current iteration in the optional logs, or -1
+__device__ __forceinline__ int pt_log_slot(const PtDev& p) {
+  if (!p.log_flags) return -1;
+  const int s = *p.it_dev - p.log_base;
+  return (s >= 0 && s < p.log_cap) ? s : -1;
+}
+
+__global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.Cl) return;
   const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
@@ -407,7 +414,8 @@ __global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p, int log_slo
     atomicAdd(&p.nprop[p.itype[c] - 1], 1ULL);
     if (yn) atomicAdd(&p.naccept[p.itype[c] - 1], 1ULL);
   }
-  if (p.log_flags && log_slot >= 0) {
+  const int log_slot = pt_log_slot(p);
+  if (log_slot >= 0) {
     p.log_flags[(size_t)log_slot * Cl + c] = (int8_t)(flag == -1 ? -1 : yn);
     p.log_itypes[(size_t)log_slot * Cl + c] = p.itype[c];
   }
@@ -433,7 +441,8 @@ __global__ void pt_adopt_kernel(const DevConfig cfg, const PtDev p) {
 }
 
 // likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200); fixed-order tree sum
-__global__ void pt_lhist_kernel(const PtDev p, double* out) {
+__global__ void pt_lhist_kernel(const PtDev p, double* lhist) {   // lhist[iteration]
+  double* out = lhist + *p.it_dev;
   __shared__ double s[1024];
   const int tid = threadIdx.x;
   double acc = 0.0;
@@ -481,8 +490,10 @@ __global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* ta
 }
 
 // judge_pt (src/pt_mcmc.f90:580-595) evaluated identically by every process from the gathered tables.
-__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len, int log_slot) {
+__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int log_slot = pt_log_slot(p);
+  *p.it_dev += 1;                    // the iteration is complete: the last kernel of its launch sequence
   if (p.nchains < 2) return;
   const int G = p.G, Cl = p.Cl;
   const double* t0 = gathered;  // process 0 owns virtual rank 0
@@ -501,7 +512,7 @@ __global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world,
     if (yn) p.temps[l1] = temp2;
   }
   if (me == own2 && yn) p.temps[l2] = temp1;
-  if (p.log_swaps && log_slot >= 0) {
+  if (log_slot >= 0) {
     p.log_swaps[3 * log_slot] = i1; p.log_swaps[3 * log_slot + 1] = i2; p.log_swaps[3 * log_slot + 2] = yn;
   }
 }
@@ -618,6 +629,7 @@ __global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
     } else {  // src/pt_mcmc.f90:260-263: assignment, not accumulation (ocean layer)
       p.vpvs_mean[iz - 1] = cfg.vpvs_min;
       p.vs_mean[iz - 1] = cfg.vs_min;
+      p.ocean_bin[iz - 1] = 1;
       vs_rec = cfg.vs_min;
     }
     if (p.vp_model && imod < p.cap_models) {
@@ -635,6 +647,13 @@ __global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
   }
 }
 __global__ void pt_record_finish_kernel(const PtDev p) { *p.nmod += (unsigned long long)*p.cold_count; }
+// After the job-wide sum over processes (rfinv_pt_reduce_outputs): the bins the reference ASSIGNS instead of accumulating hold
+// (processes that recorded) x the assigned value; they are set back to the value itself, so that the job-wide result does not
+// depend on how many processes the virtual ranks were spread over (in the reference it does: DESIGN.md section 8).
+__global__ void pt_fix_ocean_kernel(const DevConfig cfg, const PtDev p) {
+  const int iz = blockIdx.x * blockDim.x + threadIdx.x;
+  if (iz < p.nbin_z && p.ocean_bin[iz]) { p.vs_mean[iz] = cfg.vs_min; p.vpvs_mean[iz] = cfg.vpvs_min; }
+}
 
 template <typename T>
 int dalloc(T** p, size_t n) {
@@ -644,6 +663,18 @@ int dalloc(T** p, size_t n) {
 }
 
 }  // namespace
+
+int rfinv_pt_fix_assigned_bins(rfinv_handle* h) {
+  PtDev& d = h->pt->dev;
+  pt_fix_ocean_kernel<<<(d.nbin_z + 127) / 128, 128, 0, h->stream>>>(h->dc, d);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  return RFINV_OK;
+}
+
+void rfinv_handle::invalidate_pt_graphs() {
+  if (!pt) return;
+  for (cudaGraphExec_t& g : pt->graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+}
 
 void rfinv_handle::free_pt() {
   if (!pt) return;
@@ -655,8 +686,9 @@ void rfinv_handle::free_pt() {
   cudaFree(d.nprop); cudaFree(d.naccept); cudaFree(d.n_eval);
   cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
   cudaFree(d.nk); cudaFree(d.nz); cudaFree(d.nsig); cudaFree(d.namp); cudaFree(d.nvpz); cudaFree(d.nvsz); cudaFree(d.nvpvsz); cudaFree(d.nmod);
-  cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count);
-  cudaFree(pt->d_lhist); cudaFree(pt->d_table);
+  cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count); cudaFree(d.ocean_bin);
+  cudaFree(pt->d_lhist); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
+  for (cudaGraphExec_t g : pt->graph) if (g) cudaGraphExecDestroy(g);
   delete pt;
   pt = nullptr;
 }
@@ -731,7 +763,7 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   A(dalloc(&d.pk, Cl)); A(dalloc(&d.pz, Cl * (km - 1))); A(dalloc(&d.pdvp, Cl * km)); A(dalloc(&d.pdvs, Cl * km));
   A(dalloc(&d.psig, Cl * T)); A(dalloc(&d.pphi, Cl * T)); A(dalloc(&d.log_r, Cl)); A(dalloc(&d.log_prior12, Cl));
   A(dalloc(&d.itype, Cl)); A(dalloc(&d.pflag, Cl)); A(dalloc(&d.active, Cl)); A(dalloc(&d.n_active, 1));
-  A(dalloc(&d.nprop, 8)); A(dalloc(&d.naccept, 8)); A(dalloc(&d.n_eval, 1));
+  A(dalloc(&d.nprop, 8)); A(dalloc(&d.naccept, 8)); A(dalloc(&d.n_eval, 1)); A(dalloc(&d.it_dev, 1));
   d.nburn = c.nburn; d.ncorr = c.ncorr > 0 ? c.ncorr : 1;
   d.nbin_z = c.nbin_z; d.nbin_vs = c.nbin_vs; d.nbin_vp = c.nbin_vp; d.nbin_vpvs = c.nbin_vpvs; d.nbin_sig = c.nbin_sig;
   d.nbin_amp = c.nbin_amp; d.amp_min = c.amp_min; d.amp_max = c.amp_max;
@@ -741,7 +773,7 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
     A(dalloc(&d.namp, (size_t)c.nbin_amp * S * T)); A(dalloc(&d.nvpz, (size_t)c.nbin_z * c.nbin_vp));
     A(dalloc(&d.nvsz, (size_t)c.nbin_z * c.nbin_vs)); A(dalloc(&d.nvpvsz, (size_t)c.nbin_z * c.nbin_vpvs)); A(dalloc(&d.nmod, 1));
     A(dalloc(&d.vp_mean, (size_t)c.nbin_z)); A(dalloc(&d.vs_mean, (size_t)c.nbin_z)); A(dalloc(&d.vpvs_mean, (size_t)c.nbin_z));
-    A(dalloc(&d.cold_ordinal, Cl)); A(dalloc(&d.cold_count, 1));
+    A(dalloc(&d.cold_ordinal, Cl)); A(dalloc(&d.cold_count, 1)); A(dalloc(&d.ocean_bin, (size_t)c.nbin_z));
     // all_models: the reference allocates nbin_z x (nchains*niter/ncorr) per rank (src/pt_mcmc.f90:405-406)
     const long long want = (long long)(c.niter / d.ncorr) * (long long)Cl;
     if (want > 0 && (double)want * c.nbin_z * 16.0 <= 8.0e9) {
@@ -756,11 +788,17 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   A(h->ensure_capacity(d.Cl));
 #undef A
   pt_init_kernel<<<(d.G + 63) / 64, 64, 0, h->stream>>>(h->dc, d);
-  RFINV_CUDA_CHECK(cudaGetLastError());
   // init_rft, src/likelihood.f90:143-163: forward + likelihood of every initial model
-  if ((st = pt_eval(h, /*proposal=*/false, /*all=*/true)) != RFINV_OK) return st;
-  if ((st = rfinv_launch_loglik(h->dc, d.Cl, d.phi, d.sig, d.logl, h->stream)) != RFINV_OK) return st;
-  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  st = cudaGetLastError() == cudaSuccess ? RFINV_OK : RFINV_ERR_CUDA;
+  if (st == RFINV_OK) st = pt_eval(h, /*proposal=*/false, /*all=*/true);
+  if (st == RFINV_OK) st = rfinv_launch_loglik(h->dc, d.Cl, d.phi, d.sig, d.logl, h->stream);
+  if (st == RFINV_OK) {
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { rfinv_set_error("rfinv_pt_init: %s", cudaGetErrorString(e)); st = RFINV_ERR_CUDA; }
+  } else if (st == RFINV_ERR_CUDA && !*rfinv_last_error()) {
+    rfinv_set_error("rfinv_pt_init: kernel launch failed");
+  }
+  if (st != RFINV_OK) { h->free_pt(); return st; }
   s->it_done = 0;
   s->n_eval = d.Cl;
   return RFINV_OK;
@@ -789,67 +827,89 @@ int32_t rfinv_pt_draw(rfinv_handle* h, int32_t local_rank, int32_t kind, int32_t
 
 int32_t rfinv_pt_ntype(rfinv_handle* h) { return (h && h->pt) ? h->pt->dev.ntype : -1; }
 
+static void pt_drop_graphs(PtState* s) {
+  for (cudaGraphExec_t& g : s->graph) { if (g) cudaGraphExecDestroy(g); g = nullptr; }
+}
+
 int32_t rfinv_pt_set_logging(rfinv_handle* h, int32_t cap_iters) {
   int st = pt_require(h, "rfinv_pt_set_logging");
   if (st != RFINV_OK) return st;
   PtState* s = h->pt;
   PtDev& d = s->dev;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  pt_drop_graphs(s);   // the log pointers are baked into the captured launches
   cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
   d.log_flags = nullptr; d.log_itypes = nullptr; d.log_swaps = nullptr;
-  s->log_cap = 0; s->log_used = 0;
+  s->log_cap = 0; s->log_base = s->it_done;
   if (cap_iters > 0) {
     if ((st = dalloc(&d.log_flags, (size_t)cap_iters * d.Cl)) != RFINV_OK) return st;
     if ((st = dalloc(&d.log_itypes, (size_t)cap_iters * d.Cl)) != RFINV_OK) return st;
     if ((st = dalloc(&d.log_swaps, (size_t)cap_iters * 3)) != RFINV_OK) return st;
     s->log_cap = cap_iters;
   }
+  d.log_cap = s->log_cap; d.log_base = s->log_base;
   return RFINV_OK;
 }
 
-// Everything of one iteration except the swap decision: proposal pass, batched evaluation, acceptance,
-// likelihood history, and this process's swap table.
-int32_t rfinv_pt_local_step(rfinv_handle* h) {
-  int st = pt_require(h, "rfinv_pt_local_step");
-  if (st != RFINV_OK) return st;
+// room in the likelihood history for iterations [0, upto); never called while a launch sequence is being captured
+static int pt_reserve_lhist(rfinv_handle* h, int upto) {
+  PtState* s = h->pt;
+  if (upto <= s->cap_lhist) return RFINV_OK;
+  int ncap = s->cap_lhist;
+  while (ncap < upto) ncap *= 2;
+  double* nl = nullptr;
+  int st;
+  if ((st = dalloc(&nl, (size_t)ncap)) != RFINV_OK) return st;
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  RFINV_CUDA_CHECK(cudaMemcpy(nl, s->d_lhist, sizeof(double) * s->cap_lhist, cudaMemcpyDeviceToDevice));
+  cudaFree(s->d_lhist);
+  s->d_lhist = nl; s->cap_lhist = ncap;
+  pt_drop_graphs(s);   // the history pointer is baked into the captured launches
+  return RFINV_OK;
+}
+
+// The launches of one iteration except the swap decision: proposal pass, batched evaluation, acceptance, likelihood
+// history, (posterior bookkeeping,) and this process's swap table.  Nothing here depends on the host's iteration counter.
+static int pt_enqueue_local(rfinv_handle* h, bool record) {
   PtState* s = h->pt;
   PtDev& d = s->dev;
-  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
   cudaStream_t q = h->stream;
-  if (s->it_done >= s->cap_lhist) {  // grow the likelihood history
-    double* nl = nullptr;
-    const int ncap = s->cap_lhist * 2;
-    if ((st = dalloc(&nl, (size_t)ncap)) != RFINV_OK) return st;
-    RFINV_CUDA_CHECK(cudaMemcpyAsync(nl, s->d_lhist, sizeof(double) * s->cap_lhist, cudaMemcpyDeviceToDevice, q));
-    RFINV_CUDA_CHECK(cudaStreamSynchronize(q));
-    cudaFree(s->d_lhist);
-    s->d_lhist = nl; s->cap_lhist = ncap;
-  }
-  const int log_slot = (s->log_cap > 0 && s->log_used < s->log_cap) ? s->log_used : -1;
+  int st;
   pt_propose_kernel<<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d);
   pt_compact_kernel<<<1, 1024, 0, q>>>(d);
   RFINV_CUDA_CHECK(cudaGetLastError());
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
-  pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d, log_slot);
+  pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d);
   {
     const long long n_el = (long long)(3 * h->dc.k_max - 1 + 2 * h->dc.ntrc) * d.Cl;
     pt_adopt_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, q>>>(h->dc, d);
   }
-  pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist + s->it_done);
-  {
-    const int it = s->it_done + 1;  // 1-based iteration number (src/pt_mcmc.f90:204-205)
-    if (s->record && it > d.nburn && it % d.ncorr == 0) {
-      pt_coldscan_kernel<<<1, 1024, 0, q>>>(d);
-      pt_record_kernel<<<d.Cl, 128, 0, q>>>(h->dc, d);
-      pt_record_finish_kernel<<<1, 1, 0, q>>>(d);
-    }
+  pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist);
+  if (record) {
+    pt_coldscan_kernel<<<1, 1024, 0, q>>>(d);
+    pt_record_kernel<<<d.Cl, 128, 0, q>>>(h->dc, d);
+    pt_record_finish_kernel<<<1, 1, 0, q>>>(d);
   }
   {
     const int nb_rank = (d.G * 32 + 127) / 128, nb_copy = (d.Cl + 127) / 128;
     pt_table_kernel<<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table);
   }
   RFINV_CUDA_CHECK(cudaGetLastError());
-  s->pending_log_slot = log_slot;
   return RFINV_OK;
+}
+
+// does iteration number it_done + 1 record the posterior bookkeeping?  (src/pt_mcmc.f90:204-205)
+static bool pt_records(const PtState* s) {
+  const int it = s->it_done + 1;
+  return s->record && it > s->dev.nburn && it % s->dev.ncorr == 0;
+}
+
+int32_t rfinv_pt_local_step(rfinv_handle* h) {
+  int st = pt_require(h, "rfinv_pt_local_step");
+  if (st != RFINV_OK) return st;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if ((st = pt_reserve_lhist(h, h->pt->it_done + 1)) != RFINV_OK) return st;
+  return pt_enqueue_local(h, pt_records(h->pt));
 }
 
 int32_t rfinv_pt_swap_table(rfinv_handle* h, uint64_t* dev_ptr, int32_t* n_doubles) {
@@ -869,30 +929,96 @@ int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t 
     rfinv_set_error("rfinv_pt_apply_swap: world=%d inconsistent with nproc_total=%d, rank_count=%d", world, s->dev.nproc_total, s->dev.G);
     return RFINV_ERR_ARG;
   }
-  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len,
-                                          s->pending_log_slot);
+  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len);
   RFINV_CUDA_CHECK(cudaGetLastError());
-  if (s->pending_log_slot >= 0) s->log_used++;
   s->it_done++;
   return RFINV_OK;
 }
 
-// single-process run: pt_control's loop (src/pt_mcmc.f90:488-572)
+// One whole iteration on the handle's stream: local step, (all-gather of the swap tables over the handle's communicator,)
+// swap decision.  world == 1: the own table is the gathered table.
+static int pt_enqueue_iteration(rfinv_handle* h, int world, bool record) {
+  PtState* s = h->pt;
+  int st;
+  if ((st = pt_enqueue_local(h, record)) != RFINV_OK) return st;
+  const double* gathered = s->d_table;
+  if (world > 1) {
+    if ((st = rfinv_comm_allgather(h, s->d_table, s->d_gather, (size_t)s->table_len, h->stream)) != RFINV_OK) return st;
+    gathered = s->d_gather;
+  }
+  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, gathered, world, s->table_len);
+  RFINV_CUDA_CHECK(cudaGetLastError());
+  return RFINV_OK;
+}
+
+// pt_control's loop (src/pt_mcmc.f90:488-572) for n_iter iterations over `world` processes.  The launch sequence of an
+// iteration -- a dozen kernels and, with several processes, one ncclAllGather -- is captured once per variant (with /
+// without the bookkeeping kernels) in a CUDA graph and replayed: one launch per iteration instead of twelve
+// (RFINV_PT_GRAPH=0: plain launches).
+static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
+  PtState* s = h->pt;
+  int st;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if ((st = pt_reserve_lhist(h, s->it_done + n_iter)) != RFINV_OK) return st;
+  if (world > 1 && s->cap_gather < world * s->table_len) {
+    cudaFree(s->d_gather); s->d_gather = nullptr; s->cap_gather = 0;
+    if ((st = dalloc(&s->d_gather, (size_t)world * s->table_len)) != RFINV_OK) return st;
+    s->cap_gather = world * s->table_len;
+    pt_drop_graphs(s);
+  }
+  static const bool use_graph = !(getenv("RFINV_PT_GRAPH") && atoi(getenv("RFINV_PT_GRAPH")) == 0);
+  if (s->graph_world != world) { pt_drop_graphs(s); s->graph_world = world; }
+  for (int it = 0; it < n_iter; ++it) {
+    const bool record = pt_records(s);
+    if (use_graph) {
+      cudaGraphExec_t& g = s->graph[record ? 1 : 0];
+      if (!g) {
+        cudaGraph_t graph = nullptr;
+        RFINV_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        st = pt_enqueue_iteration(h, world, record);
+        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        if (st != RFINV_OK) { if (graph) cudaGraphDestroy(graph); return st; }
+        if (e != cudaSuccess) { rfinv_set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
+        e = cudaGraphInstantiate(&g, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { g = nullptr; rfinv_set_error("cudaGraphInstantiate: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
+      }
+      RFINV_CUDA_CHECK(cudaGraphLaunch(g, h->stream));
+    } else if ((st = pt_enqueue_iteration(h, world, record)) != RFINV_OK) {
+      return st;
+    }
+    s->it_done++;
+  }
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return RFINV_OK;
+}
+
+// single-process run
 int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter) {
   int st = pt_require(h, "rfinv_pt_run");
   if (st != RFINV_OK) return st;
   PtState* s = h->pt;
   if (s->dev.G != s->dev.nproc_total) {
-    rfinv_set_error("rfinv_pt_run: this handle holds %d of %d ranks; drive rfinv_pt_local_step/apply_swap instead", s->dev.G,
-                    s->dev.nproc_total);
+    rfinv_set_error("rfinv_pt_run: this handle holds %d of %d ranks; use rfinv_pt_run_distributed (or rfinv_pt_local_step / apply_swap)",
+                    s->dev.G, s->dev.nproc_total);
     return RFINV_ERR_STATE;
   }
-  for (int it = 0; it < n_iter; ++it) {
-    if ((st = rfinv_pt_local_step(h)) != RFINV_OK) return st;
-    if ((st = rfinv_pt_apply_swap(h, reinterpret_cast<uint64_t>(s->d_table), 1)) != RFINV_OK) return st;
+  return pt_iterate(h, n_iter, 1);
+}
+
+// one process per GPU: the handle's communicator (rfinv_comm_init) carries the per-iteration all-gather
+int32_t rfinv_pt_run_distributed(rfinv_handle* h, int32_t n_iter) {
+  int st = pt_require(h, "rfinv_pt_run_distributed");
+  if (st != RFINV_OK) return st;
+  PtState* s = h->pt;
+  const int world = h->comm ? h->comm_world : 1;
+  if (world * s->dev.G != s->dev.nproc_total || s->dev.rank_begin != (h->comm ? h->comm_rank : 0) * s->dev.G) {
+    rfinv_set_error("rfinv_pt_run_distributed: process %d of %d must own the virtual ranks [%d, %d) of %d (rfinv_pt_init), it owns [%d, %d)",
+                    h->comm ? h->comm_rank : 0, world, (h->comm ? h->comm_rank : 0) * s->dev.G, ((h->comm ? h->comm_rank : 0) + 1) * s->dev.G,
+                    s->dev.nproc_total, s->dev.rank_begin, s->dev.rank_begin + s->dev.G);
+    return RFINV_ERR_STATE;
   }
-  RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  return RFINV_OK;
+  return pt_iterate(h, n_iter, world);
 }
 
 int32_t rfinv_pt_get_state(rfinv_handle* h, int32_t* k, double* z, double* dvp, double* dvs, double* sig, double* logl,
@@ -987,11 +1113,13 @@ int32_t rfinv_pt_get_log(rfinv_handle* h, int8_t* flags, int8_t* itypes, int32_t
   if (st != RFINV_OK) return st;
   PtState* s = h->pt;
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
-  const size_t n = (size_t)s->log_used * s->dev.Cl;
+  int log_used = s->it_done - s->log_base;
+  log_used = log_used < 0 ? 0 : (log_used > s->log_cap ? s->log_cap : log_used);
+  const size_t n = (size_t)log_used * s->dev.Cl;
   if (flags && n) RFINV_CUDA_CHECK(cudaMemcpy(flags, s->dev.log_flags, n, cudaMemcpyDeviceToHost));
   if (itypes && n) RFINV_CUDA_CHECK(cudaMemcpy(itypes, s->dev.log_itypes, n, cudaMemcpyDeviceToHost));
-  if (swaps && s->log_used) RFINV_CUDA_CHECK(cudaMemcpy(swaps, s->dev.log_swaps, sizeof(int32_t) * 3 * s->log_used, cudaMemcpyDeviceToHost));
-  if (n_logged) *n_logged = s->log_used;
+  if (swaps && log_used) RFINV_CUDA_CHECK(cudaMemcpy(swaps, s->dev.log_swaps, sizeof(int32_t) * 3 * log_used, cudaMemcpyDeviceToHost));
+  if (n_logged) *n_logged = log_used;
   return RFINV_OK;
 }
 

@@ -57,11 +57,6 @@ struct ModelBatch {
   // Host-layout batch (rfinv_eval_batch): z / dvp / dvs as the caller holds them, chain slowest -- z[c*(k_max-1) + i],
   // dvp / dvs[c*k_max + i] -- so the upload is a plain copy.  (sig stays chain-fastest: only loglik_kernel reads it.)
   int chain_major = 0;
-  // Upload in flight (optional): piece c / ready_chunk of the batch has landed when ready[c / ready_chunk] == ready_epoch
-  // (a 4-byte copy queued behind the piece's data on the copy stream); prep_kernel waits per model.
-  const int* ready = nullptr;
-  int ready_chunk = 1, ready_epoch = 0;
-  int* ready_timeout = nullptr; // set when a wait gives up (~2 s): the evaluation is then reported as failed
 };
 
 // Fortran NINT (round half away from zero)
@@ -137,7 +132,12 @@ struct EvalOutputs {
 // prep_kernel + forward_kernel.  scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles in HBM
 size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models);
 int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
-                         cudaStream_t stream, int* n_kernels = nullptr);   // n_kernels: kernels launched (optional)
+                         cudaStream_t stream, int* n_kernels = nullptr,    // n_kernels: kernels launched (optional)
+                         bool prep_done = false);                          // prep_done: rfinv_launch_prep already covered the batch
+// prep_kernel alone for the models [m_begin, m_begin + m_count) of the batch (index into `active` when that is set): the
+// host path launches it piece by piece behind the pieces of the upload
+int rfinv_launch_prep(const DevConfig& cfg, const ModelBatch& mb, uint8_t* is_valid, double* scratch, cudaStream_t stream,
+                      int m_begin, int m_count);
 // bins per thread of forward_kernel for the full band (threads per CTA = nfft/2 / this)
 int rfinv_forward_bins_per_thread(int nfft);
 // phi[ntrc][C] = m^T R^-1 m per trace and model.  partial / counters: scratch sized by the two functions below, the

@@ -29,22 +29,37 @@ struct PtDev {
   double amp_min, amp_max;
   unsigned long long *nk, *nz, *nsig, *namp, *nvpz, *nvsz, *nvpvsz, *nmod;
   double *vp_mean, *vs_mean, *vpvs_mean;
+  uint8_t* ocean_bin;                                 // [nbin_z] depth bins inside the sea layer: their vs / vpvs means are ASSIGNED (src/pt_mcmc.f90:260-263)
   double *vp_model, *vs_model;                        // [cap_models][nbin_z] (all_models), may be null
   long long cap_models;
   int *cold_ordinal, *cold_count;                     // ordered numbering of the chains recorded this iteration
-  // optional per-iteration logs (tests)
+  // optional per-iteration logs (tests): iteration `it` (0-based, read from *it_dev) goes to slot it - log_base if that is
+  // inside [0, log_cap)
   int8_t *log_flags, *log_itypes;
   int32_t* log_swaps;
+  int log_base, log_cap;
+  // iterations completed, on the device: advanced by pt_swap_kernel, read by the kernels that index by iteration
+  // (likelihood history, logs) -- nothing of an iteration's launch sequence depends on the host's counter, so the sequence
+  // can be captured once in a CUDA graph and replayed
+  int* it_dev;
 };
+
+struct ncclComm;   // NCCL communicator (comm.cu)
 
 struct PtState {
   PtDev dev;
   int it_done = 0;
+  // one iteration as a CUDA graph: [0] plain, [1] with the posterior bookkeeping kernels (every ncorr-th iteration after
+  // the burn-in); invalidated when something that is baked into the launches changes (logging, capacity)
+  cudaGraphExec_t graph[2] = {nullptr, nullptr};
+  int graph_world = 0;
+  double* d_gather = nullptr;  // swap tables of all processes (distributed run)
+  int cap_gather = 0;
   int cap_lhist = 0;
   double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
   double* d_table = nullptr;   // swap table of this process
   int table_len = 0;
-  int log_cap = 0, log_used = 0, pending_log_slot = -1;
+  int log_cap = 0, log_base = 0;
   long long n_eval = 0;
   bool record = false;
 };

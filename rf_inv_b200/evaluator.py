@@ -100,6 +100,21 @@ class Evaluator:
                                               _p(valid, capi.u8p)))
         return logl, rft, (valid.astype(bool) if valid is not None else None)
 
+    def calc_likelihood_begin(self, slot: int, k, z, dvp, dvs, sig, logl: np.ndarray, valid: Optional[np.ndarray] = None):
+        """Asynchronous calc_likelihood of one group of chains in `slot` (0 or 1): returns at once, `logl` (and `valid`) are
+        filled when calc_likelihood_end(slot) returns.  The arrays are used in place (no copies: pass C-contiguous arrays of the
+        right dtype, page-locked for real overlap) and must stay alive and untouched until then."""
+        n = k.shape[0]
+        for a, dt, shape in ((k, np.int32, (n,)), (z, np.float64, (n, self.cfg.k_max - 1)), (dvp, np.float64, (n, self.cfg.k_max)),
+                             (dvs, np.float64, (n, self.cfg.k_max)), (sig, np.float64, (n, self.cfg.ntrc)), (logl, np.float64, (n,))):
+            if a.dtype != dt or a.shape != shape or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("calc_likelihood_begin needs C-contiguous arrays of the boundary's dtypes and shapes")
+        capi.check(self._lib.rfinv_eval_batch_begin(self.handle, int(slot), n, _p(k, capi.i32p), _p(z, capi.dp), _p(dvp, capi.dp),
+                                                    _p(dvs, capi.dp), _p(sig, capi.dp), _p(logl, capi.dp), _p(valid, capi.u8p)))
+
+    def calc_likelihood_end(self, slot: int) -> None:
+        capi.check(self._lib.rfinv_eval_batch_end(self.handle, int(slot)))
+
     def calc_likelihood_device(self, C_models: int, d_k: int, d_z: int, d_dvp: int, d_dvs: int, d_sig: int, d_logl: int,
                                d_rft_smp: int = 0, d_is_valid: int = 0) -> None:
         """Same evaluation on device-resident chain-fastest arrays (raw device pointers); asynchronous."""

@@ -38,6 +38,7 @@ class ParallelTempering:
         self.n_local = self.rank_count * cfg.nchains
         self.ntype = int(self._lib.rfinv_pt_ntype(self.ev.handle))
         self._gather_buf = None
+        self._comm = False
 
     def close(self):
         self.ev.close()
@@ -54,19 +55,49 @@ class ParallelTempering:
         capi.check(self._lib.rfinv_pt_swap_table(self.ev.handle, C.byref(ptr), C.byref(n)))
         return ptr.value, n.value
 
-    def run_distributed(self, n_iter: int, dist, torch) -> None:
-        """pt_control with the per-iteration exchange done by torch.distributed (NCCL all-gather)."""
+    def init_comm(self, dist=None, torch=None, id_bytes: Optional[bytes] = None) -> None:
+        """Joins the library's own NCCL communicator (rfinv_comm_init).  The communicator id is created on process 0 and
+        carried to the others by the host -- here through torch.distributed (any backend), or pass `id_bytes`."""
+        if self.world == 1 or self._comm:
+            return
+        n = int(self._lib.rfinv_comm_id_bytes())
+        if id_bytes is None:
+            buf = (C.c_ubyte * n)()
+            if self.rank == 0:
+                capi.check(self._lib.rfinv_comm_create_id(buf))
+            box = [bytes(buf)]
+            dist.broadcast_object_list(box, src=0)
+            id_bytes = box[0]
+        raw = (C.c_ubyte * n).from_buffer_copy(id_bytes)
+        capi.check(self._lib.rfinv_comm_init(self.ev.handle, raw, self.world, self.rank))
+        self._comm = True
+
+    def run_distributed(self, n_iter: int, dist=None, torch=None) -> None:
+        """pt_control over all processes: local step, ncclAllGather of the swap tables and swap decision, all queued by the
+        library on the handle's stream (one CUDA graph launch per iteration).  dist / torch are only needed once, to carry
+        the communicator id (init_comm)."""
+        self.init_comm(dist, torch)
+        capi.check(self._lib.rfinv_pt_run_distributed(self.ev.handle, int(n_iter)))
+
+    def run_distributed_torch(self, n_iter: int, dist, torch) -> None:
+        """The same loop with the exchange done by torch.distributed (kept for comparison with the in-library collective).
+        The handle must share torch's current stream (set_stream), or the all-gather races with the library's kernels."""
+        self.ev.set_stream(torch.cuda.current_stream(torch.device("cuda", self.ev.device)).cuda_stream)
         ptr, n = self.swap_table()
         dev = torch.device("cuda", self.ev.device)
         if self._gather_buf is None:
             self._gather_buf = torch.empty(self.world * n, dtype=torch.float64, device=dev)
-        # zero-copy view of the library's table
-        table = _tensor_from_ptr(torch, ptr, n, dev)
+        table = _tensor_from_ptr(torch, ptr, n, dev)   # zero-copy view of the library's table
         for _ in range(n_iter):
             capi.check(self._lib.rfinv_pt_local_step(self.ev.handle))
             dist.all_gather_into_tensor(self._gather_buf, table)
             capi.check(self._lib.rfinv_pt_apply_swap(self.ev.handle, self._gather_buf.data_ptr(), self.world))
         self.ev.synchronize()
+
+    def reduce_outputs(self) -> None:
+        """output_results' mpi_reduce / mpi_gather (src/mcmc_out.f90:52-93): afterwards process 0's hist() / counters() / models()
+        are job-wide.  Collective; call once after the last iteration."""
+        capi.check(self._lib.rfinv_pt_reduce_outputs(self.ev.handle))
 
     # -- results ----------------------------------------------------------------------------------
     def set_logging(self, cap_iters: int) -> None:
@@ -109,7 +140,7 @@ class ParallelTempering:
 
     def models(self):
         """Recorded models of the local non-tempered chains: (vp_model, vs_model) [n_models][nbin_z] (all_models)."""
-        cap = max(1, (self.cfg.niter // max(self.cfg.ncorr, 1)) * self.n_local)
+        cap = max(1, (self.cfg.niter // max(self.cfg.ncorr, 1)) * self.n_local * self.world)   # job-wide after reduce_outputs()
         vp = np.zeros((cap, self.cfg.nbin_z)); vs = np.zeros((cap, self.cfg.nbin_z))
         n = C.c_int64(0)
         capi.check(self._lib.rfinv_pt_get_models(self.ev.handle, cap, _p(vp, capi.dp), _p(vs, capi.dp), C.byref(n)))

@@ -2,7 +2,7 @@
 
 ``--nproc`` is the number of MPI ranks the reference would be started with (``mpirun -np N``): N virtual ranks of
 N_CHAINS chains each, all resident on the GPU(s).  Under torchrun (one process per GPU) the virtual ranks are split
-over the processes and the per-iteration swap exchange is one NCCL all-gather.  Writes the reference's output files
+over the processes and the per-iteration swap exchange is one NCCL all-gather issued by the library itself.  Writes the reference's output files
 into OUT_DIR."""
 from __future__ import annotations
 
@@ -28,7 +28,9 @@ def run(params_path: str, nproc: int, verbose: bool = True, n_iter: int = None):
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torch.distributed only carries the library's communicator id between the processes (gloo: no second NCCL communicator)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
     if rank == 0:
         os.makedirs(cfg.out_dir, exist_ok=True)
         rio.write_side_copies(params_path, cfg.out_dir, os.path.dirname(os.path.abspath(params_path)))
@@ -44,26 +46,11 @@ def run(params_path: str, nproc: int, verbose: bool = True, n_iter: int = None):
         done += step
         if verbose and rank == 0:
             print(f" Iteration #: {done} / {n_tot}", flush=True)
+    if world > 1:                                         # the reference's mpi_reduce / mpi_gather (src/mcmc_out.f90:52-93)
+        pt.reduce_outputs()                               # ncclReduce / ncclSend+Recv inside the library: process 0 is job-wide now
     hist, cnt = pt.hist(), pt.counters()
     vp_model, vs_model = pt.models()
     lh = cnt["likelihood_hist"]
-    if world > 1:                                         # the reference's mpi_reduce / mpi_gather (src/mcmc_out.f90:52-93)
-        dev = torch.device("cuda", local_rank)
-        for key in list(hist.keys()) + ["nprop", "naccept", "lh"]:
-            src = lh if key == "lh" else (cnt[key] if key in cnt else hist[key])
-            t = torch.as_tensor(np.asarray(src), device=dev)
-            dist.all_reduce(t)
-            val = t.cpu().numpy()
-            if key == "lh":
-                lh = val
-            elif key in cnt:
-                cnt[key] = val
-            else:
-                hist[key] = val if val.ndim else int(val)
-        gathered_vp, gathered_vs = [None] * world, [None] * world
-        dist.all_gather_object(gathered_vp, vp_model)
-        dist.all_gather_object(gathered_vs, vs_model)
-        vp_model, vs_model = np.concatenate(gathered_vp), np.concatenate(gathered_vs)
     if rank == 0:
         if verbose:                                       # summary, src/mcmc_out.f90:99-107
             labels = ["Birth proposal", "Death proposal", "Moving interface depth proposal", "Perturbing dVs proposal"]

@@ -335,8 +335,8 @@ np.savez(sys.argv[1], **out)
 
 def test_large_host_batch_with_overlapped_upload_equals_the_device_resident_entry():
     """rfinv_eval_batch uploads the models as the caller holds them (chain slowest; prep_kernel reads that layout), batches
-    of >= 8192 models in pieces of 2048 on a second stream with prep_kernel already running and waiting per model for its
-    piece.  Same arithmetic: logL, validity flags and traces must equal the device-resident (chain fastest, no upload)
+    of >= 8192 models in four pieces on a second stream, prep_kernel launched per piece behind the event that marks the
+    piece's arrival.  Same arithmetic: logL, validity flags and traces must equal the device-resident (chain fastest, no upload)
     evaluation to the last bit; ragged size, invalid models included."""
     import torch
     cfg = helpers.attach_obs_and_rinv(helpers.small_config(sdep=2.0), noise=0.01)
@@ -356,7 +356,7 @@ def test_large_host_batch_with_overlapped_upload_equals_the_device_resident_entr
                                   d["sig"].data_ptr(), logl.data_ptr(), 0, valid.data_ptr())
         torch.cuda.synchronize()
         ll_h2, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])      # again, other stream, warm buffers
-    assert n_launch == 5                            # prep, forward, quadform, sig layout, logL: the pieces of the upload share one launch each
+    assert n_launch == 7                            # prep_kernel per piece of the upload (4), forward, quadform (+ logL), sig layout
     assert np.array_equal(ll_h, logl.cpu().numpy(), equal_nan=True) and np.array_equal(ll_h, ll_h2, equal_nan=True)
     assert np.array_equal(val_h, valid.cpu().numpy().astype(bool)) and not val_h[5000:5040].all()
     sub = np.arange(0, n, 97)
@@ -428,3 +428,48 @@ def test_parity_on_the_joint_p_and_s_workload_is_bounded_by_the_conditioning_of_
     assert np.max(err / cond) < 1e-12
     ok = well.all(axis=1)
     assert helpers.logl_err(cfg, ll_g[ok], ll_o[ok], m["sig"][ok]) < 1e-11
+
+
+def test_async_slots_match_the_synchronous_call():
+    """rfinv_eval_batch_begin / _end (two groups of chains in flight, each on its own stream and workspace) return exactly what
+    rfinv_eval_batch returns for the same models, whatever the order the slots are begun and ended in."""
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(sdep=2.0, ntrc=2), noise=0.01)
+    m = workloads.draw_models(cfg, 600, seed=11, dvs_scale=0.3)
+    with Evaluator(cfg) as ev:
+        ll_ref, _, val_ref = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_valid=True)
+        halves = [slice(0, 350), slice(350, 600)]
+        parts = [{k: np.ascontiguousarray(v[s]) for k, v in m.items()} for s in halves]
+        for order in ((0, 1), (1, 0)):
+            out = [np.full(p["k"].shape[0], np.nan) for p in parts]
+            val = [np.zeros(p["k"].shape[0], dtype=np.uint8) for p in parts]
+            for rep in range(3):          # slots are reusable
+                for s in (0, 1):
+                    p = parts[s]
+                    ev.calc_likelihood_begin(s, p["k"], p["z"], p["dvp"], p["dvs"], p["sig"], out[s], val[s])
+                for s in order:
+                    ev.calc_likelihood_end(s)
+            assert np.array_equal(np.concatenate(out), ll_ref)
+            assert np.array_equal(np.concatenate(val).astype(bool), val_ref)
+        # a slot in flight cannot be begun again
+        p = parts[0]
+        o = np.empty(p["k"].shape[0])
+        ev.calc_likelihood_begin(0, p["k"], p["z"], p["dvp"], p["dvs"], p["sig"], o)
+        with pytest.raises(capi.RfinvError):
+            ev.calc_likelihood_begin(0, p["k"], p["z"], p["dvp"], p["dvs"], p["sig"], o)
+        ev.calc_likelihood_end(0)
+        with pytest.raises(capi.RfinvError):
+            ev.calc_likelihood_begin(2, p["k"], p["z"], p["dvp"], p["dvs"], p["sig"], o)
+
+
+def test_large_host_batch_goes_up_in_pieces_and_matches_small_batches():
+    """>= 8192 models: rfinv_eval_batch uploads in pieces and launches prep_kernel per piece behind the piece's event; the
+    result equals the evaluation of the same models in small batches (one piece, no overlap) bit for bit."""
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(), noise=0.01)
+    m = workloads.draw_models(cfg, 9000, seed=5, dvs_scale=0.3)
+    with Evaluator(cfg) as ev:
+        ll_big, _, val_big = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_valid=True)
+        ll_small = np.concatenate([ev.calc_likelihood(m["k"][s:s + 1500], m["z"][s:s + 1500], m["dvp"][s:s + 1500], m["dvs"][s:s + 1500],
+                                                      m["sig"][s:s + 1500])[0] for s in range(0, 9000, 1500)])
+    assert np.array_equal(ll_big, ll_small)
+    ok = oracle_c.eval_batch(cfg, m["k"][:64], m["z"][:64], m["dvp"][:64], m["dvs"][:64], m["sig"][:64])
+    assert helpers.logl_err(cfg, ll_big[:64], ok[0], m["sig"][:64]) < RTOL and np.array_equal(val_big[:64], ok[2])

@@ -10,7 +10,7 @@ so = os.path.join(ROOT, "rf_inv_b200", "librfinv_b200_prof.so")
 src = [os.path.join(rbuild.CSRC, s) for s in rbuild.SOURCES]
 if "--build" in sys.argv or not os.path.exists(so):
     flags = [f for f in rbuild.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-    subprocess.check_call([rbuild.nvcc_path(), "-ccbin", "/usr/bin/g++"] + flags + ["-DRFINV_PHASE_TIMING", "-shared", "-o", so] + src + ["-lcudart"])
+    subprocess.check_call([rbuild.nvcc_path(), "-ccbin", "/usr/bin/g++"] + flags + ["-DRFINV_PHASE_TIMING", "-shared", "-o", so] + src + ["-lcudart", "-ldl"])
     if "--build" in sys.argv:
         sys.exit(0)
 lib = capi.load(so)
