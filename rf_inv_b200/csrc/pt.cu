@@ -688,6 +688,7 @@ void rfinv_handle::free_pt() {
   cudaFree(d.nk); cudaFree(d.nz); cudaFree(d.nsig); cudaFree(d.namp); cudaFree(d.nvpz); cudaFree(d.nvsz); cudaFree(d.nvpvsz); cudaFree(d.nmod);
   cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count); cudaFree(d.ocean_bin);
   cudaFree(pt->d_lhist); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
+  if (pt->capture_stream) cudaStreamDestroy(pt->capture_stream);
   for (cudaGraphExec_t g : pt->graph) if (g) cudaGraphExecDestroy(g);
   delete pt;
   pt = nullptr;
@@ -973,10 +974,18 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
     if (use_graph) {
       cudaGraphExec_t& g = s->graph[record ? 1 : 0];
       if (!g) {
+        // captured on a stream of its own (the caller's may be the legacy default stream, which cannot capture); replayed on
+        // the handle's stream
         cudaGraph_t graph = nullptr;
-        RFINV_CUDA_CHECK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        if (!s->capture_stream) RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&s->capture_stream, cudaStreamNonBlocking));
+        cudaStream_t user_stream = h->stream;
+        RFINV_CUDA_CHECK(cudaStreamSynchronize(user_stream));
+        h->stream = s->capture_stream;
+        cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { h->stream = user_stream; rfinv_set_error("cudaStreamBeginCapture: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
         st = pt_enqueue_iteration(h, world, record);
-        cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+        e = cudaStreamEndCapture(h->stream, &graph);
+        h->stream = user_stream;
         if (st != RFINV_OK) { if (graph) cudaGraphDestroy(graph); return st; }
         if (e != cudaSuccess) { rfinv_set_error("cudaStreamEndCapture: %s", cudaGetErrorString(e)); return RFINV_ERR_CUDA; }
         e = cudaGraphInstantiate(&g, graph, 0);

@@ -53,6 +53,7 @@ struct PtState {
   // the burn-in); invalidated when something that is baked into the launches changes (logging, capacity)
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   int graph_world = 0;
+  cudaStream_t capture_stream = nullptr;
   double* d_gather = nullptr;  // swap tables of all processes (distributed run)
   int cap_gather = 0;
   int cap_lhist = 0;

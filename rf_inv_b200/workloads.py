@@ -108,9 +108,9 @@ def models_valid(cfg: RFConfig, k, z, dvp, dvs) -> np.ndarray:
     return ok
 
 
-def draw_models(cfg: RFConfig, n: int, seed: int = 1, dvs_scale: float = None) -> Dict[str, np.ndarray]:
-    """n random valid models drawn like init_model (src/model.f90:62-95): k uniform on [k_min, k_max),
-    interfaces uniform on [z_min, z_max], velocity perturbations from the prior, rejection until valid.
+def draw_models(cfg: RFConfig, n: int, seed: int = 1, dvs_scale: float = None, k_fixed: int = None) -> Dict[str, np.ndarray]:
+    """n random valid models drawn like init_model (src/model.f90:62-95): k uniform on [k_min, k_max) -- or k_fixed for
+    every model --, interfaces uniform on [z_min, z_max], velocity perturbations from the prior, rejection until valid.
     (numpy's generator, not the reference's mt19937 stream: these are benchmark / parity inputs.)"""
     rng = np.random.default_rng(seed)
     km, T = cfg.k_max, cfg.ntrc
@@ -120,6 +120,8 @@ def draw_models(cfg: RFConfig, n: int, seed: int = 1, dvs_scale: float = None) -
     while todo.size:
         m = todo.size
         kk = rng.integers(cfg.k_min, cfg.k_max, m).astype(np.int32)
+        if k_fixed is not None:
+            kk[:] = k_fixed
         zz = np.zeros((m, km - 1)); pp = np.zeros((m, km)); ss = np.zeros((m, km))
         for i in range(m):
             zz[i, :kk[i]] = rng.uniform(cfg.z_min, cfg.z_max, kk[i])
