@@ -261,7 +261,11 @@ __global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict_
 // 16 384 models, pieces of 1024 / 2048 / 4096 / 8192 give 9.3 / 9.9 / 10.2 / 9.8 M evals/s end to end (every copy costs a few
 // microseconds of set-up; the first piece is exposed).
 constexpr int UPLOAD_PIECE_MIN = 2048;
-static int upload_piece(int C) { return std::max(UPLOAD_PIECE_MIN, ((C / RFINV_UPLOAD_PIECES + 255) / 256) * 256); }
+static int upload_pieces() {   // RFINV_UPLOAD_PIECES_N=1..4 (tuning)
+  static const int n = getenv("RFINV_UPLOAD_PIECES_N") ? std::min(RFINV_UPLOAD_PIECES, std::max(1, atoi(getenv("RFINV_UPLOAD_PIECES_N")))) : RFINV_UPLOAD_PIECES;
+  return n;
+}
+static int upload_piece(int C) { return std::max(UPLOAD_PIECE_MIN, ((C / upload_pieces() + 255) / 256) * 256); }
 
 }  // namespace
 
@@ -303,7 +307,7 @@ void EvalWorkspace::release() {
 int rfinv_handle::eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs,
                               const double* sig, double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid,
                               const int* active, int n_active, const ModelBatch* layout, EvalWorkspace* w, cudaStream_t s,
-                              bool prep_done) {
+                              bool prep_done, cudaEvent_t before_quadform) {
   if (!w) w = this;
   if (!s) s = stream;
   // misfit scratch is sized by capacity; its [t][c] stride uses the C of this call
@@ -321,6 +325,7 @@ int rfinv_handle::eval_device(int C, const int* k, const double* z, const double
   if ((st = rfinv_launch_forward(dc, mb, out, w->d_scratch, s, &n_fwd, prep_done)) != RFINV_OK) return st;
   launches += n_fwd;
   if (timed) cudaEventRecord(ev[1], s);
+  if (before_quadform) RFINV_CUDA_CHECK(cudaStreamWaitEvent(s, before_quadform, 0));
   // logL leaves the same kernel (its last CTA per block of 64 chains sums the traces): no separate loglik_kernel launch
   if ((st = rfinv_launch_quadform(dc, C, w->d_misfit, w->d_phi, w->d_qpart, w->d_qcnt, active, n_active, nullptr, s, logl ? sig : nullptr, logl)) != RFINV_OK) return st;
   ++launches;
@@ -697,7 +702,7 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
   // transfer is exposed and nothing ever polls (RFINV_UPLOAD_OVERLAP=0: plain copies on the handle's stream).
   static const bool overlap_ok = !(getenv("RFINV_UPLOAD_OVERLAP") && atoi(getenv("RFINV_UPLOAD_OVERLAP")) == 0);
   const int km = h->cfg.k_max, T = h->cfg.ntrc;
-  const bool pieces = overlap_ok && C >= RFINV_UPLOAD_PIECES * UPLOAD_PIECE_MIN;
+  const bool pieces = overlap_ok && upload_pieces() > 1 && C >= upload_pieces() * UPLOAD_PIECE_MIN;
   const int piece = pieces ? upload_piece(C) : C;
   ModelBatch mb;
   mb.chain_major = 1;
@@ -727,19 +732,19 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
       RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[ip], 0));
     }
     if ((st = rfinv_launch_prep(h->dc, mb, is_valid ? h->d_valid : nullptr, h->d_scratch, h->stream, c0, (int)n)) != RFINV_OK) return st;
-    if (ip == 0) {  // sig (only the likelihood reads it) travels behind the first piece: it has landed long before forward_kernel ends
-      const size_t nel = (size_t)C * T;
-      RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * nel, cudaMemcpyHostToDevice, up));
-      to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, up>>>(h->d_stage, h->d_sig, C, 0, C, T);
-      RFINV_CUDA_CHECK(cudaGetLastError());
-      if (pieces) RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[RFINV_UPLOAD_PIECES + 1], up));
-    }
   }
-  if (pieces) RFINV_CUDA_CHECK(cudaStreamWaitEvent(h->stream, h->ev_copy[RFINV_UPLOAD_PIECES + 1], 0));
+  {  // sig: only the likelihood (the tail of quadform_kernel) reads it; it travels last and forward_kernel does not wait for it
+    const size_t nel = (size_t)C * T;
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * nel, cudaMemcpyHostToDevice, up));
+    to_soa_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, up>>>(h->d_stage, h->d_sig, C, 0, C, T);
+    RFINV_CUDA_CHECK(cudaGetLastError());
+    if (pieces) RFINV_CUDA_CHECK(cudaEventRecord(h->ev_copy[RFINV_UPLOAD_PIECES + 1], up));
+  }
   const bool timing_saved = h->timing;
   h->timing = false;   // ev[0] is already on the stream (before the first piece of prep_kernel)
   st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, h->d_logl, nullptr, rft ? h->d_rft_full : nullptr,
-                      is_valid ? h->d_valid : nullptr, nullptr, 0, &mb, nullptr, nullptr, /*prep_done=*/true);
+                      is_valid ? h->d_valid : nullptr, nullptr, 0, &mb, nullptr, nullptr, /*prep_done=*/true,
+                      pieces ? h->ev_copy[RFINV_UPLOAD_PIECES + 1] : nullptr);
   h->timing = timing_saved;
   if (st != RFINV_OK) return st;
   h->launches += ip + 1;   // prep_kernel per piece, sig layout kernel

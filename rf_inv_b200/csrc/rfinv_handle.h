@@ -65,7 +65,8 @@ struct rfinv_handle : EvalWorkspace {
   int eval_device(int C, const int* k, const double* z, const double* dvp, const double* dvs, const double* sig,
                   double* logl, double* rft_smp, double* rft_full, uint8_t* is_valid, const int* active, int n_active,
                   const ModelBatch* layout = nullptr, EvalWorkspace* w = nullptr, cudaStream_t s = nullptr,
-                  bool prep_done = false);   // layout: chain_major field to take over (host path); prep_done: prep_kernel already ran
+                  bool prep_done = false,    // layout: chain_major field to take over (host path); prep_done: prep_kernel already ran
+                  cudaEvent_t before_quadform = nullptr);   // the quadratic form (which reads sig) waits for this event
 };
 
 // comm.cu: all-gather of `count` doubles per process over the handle's communicator, on stream s (capturable)
