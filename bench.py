@@ -464,6 +464,26 @@ def main():
                    "exchange": "none (single process)" if world == 1 else
                                "one ncclAllGather of the (T, logL, next-uniform) tables per iteration, issued by the library inside the iteration's graph"}
         pt.close()
+        if not args.no_configs:
+            # the same loop with chains as deep as the evaluation batch: a dVs prior of 0.3 km/s lets init_model keep models with
+            # many interfaces (the configured prior of 2 km/s rejects them: k stays near 2.5 above)
+            import copy
+            dcfg = copy.copy(cfg)
+            dcfg.dvs_prior = 0.3
+            ptd = ParallelTempering(dcfg, nproc_total, device=local_rank, world=world, rank=rank)
+            ptd.ev.set_stream(leg.stream.cuda_stream)
+            if world > 1:
+                ptd.init_comm(dist, torch)
+            run_d = (lambda n: ptd.run(n)) if world == 1 else (lambda n: ptd.run_distributed(n))
+            run_d(5)
+            barrier()
+            n0 = ptd.counters()["n_eval"]
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(leg.stream); run_d(100); e1.record(leg.stream); e1.synchronize()
+            ms_d = allmax(e0.elapsed_time(e1))
+            pt_info["deep_chains"] = {"iters_per_s": 100 / (ms_d * 1e-3), "forward_evals_per_s": allsum(ptd.counters()["n_eval"] - n0) / (ms_d * 1e-3),
+                                      "k_mean_after": round(float(np.mean(ptd.state()["k"])), 2), "dvs_prior": 0.3, "iters": 100}
+            ptd.close()
         if world > 1:
             # identity of the distributed run on the real NCCL path: 100 iterations, accept flags / proposal types / swaps /
             # final state of N processes == one process holding every virtual rank

@@ -117,6 +117,16 @@ int32_t rfinv_set_stream(rfinv_handle* h, uint64_t cuda_stream);
 int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const double* z, const double* dvp,
                          const double* dvs, const double* sig, double* logl, double* rft, uint8_t* is_valid);
 
+/* calc_likelihood with its per-call fwd_flag (src/likelihood.f90:56-82), batched: fwd_flag[c] != 0 evaluates model c like
+ * rfinv_eval_batch and RETURNS its per-trace quadratic forms phi[c][t] = m^T R^-1 m; fwd_flag[c] == 0 -- a sigma-only
+ * proposal -- skips the forward model: phi[c][:] is READ (the values the host kept from the evaluation that produced the
+ * chain's current RF) and logL follows from them with the proposed sig, which is what the reference computes by taking the
+ * chain's cached rft through the same misfit and quadratic form again.  phi[C][ntrc] in / out; k, z, dvp, dvs of the models
+ * with fwd_flag == 0 are not looked at; their is_valid comes back 1 (format_model is not run for them). */
+int32_t rfinv_eval_batch_flags(rfinv_handle* h, int32_t C, const uint8_t* fwd_flag, const int32_t* k, const double* z,
+                               const double* dvp, const double* dvs, const double* sig, double* phi, double* logl,
+                               uint8_t* is_valid);
+
 /* Asynchronous form of rfinv_eval_batch for hosts that keep two (or more) groups of chains in flight, e.g. the two halves of
  * the chains of one MPI rank of the reference (src/pt_mcmc.f90:77-201 proposes and judges every chain independently):
  * _begin queues upload, evaluation and the read-back of logl (and is_valid, may be NULL) of one batch on the stream and

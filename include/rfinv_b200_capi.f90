@@ -56,6 +56,70 @@ module rfinv_b200_capi
        type(c_ptr), value :: is_valid   ! c_loc(int8 array) or c_null_ptr
      end function rfinv_eval_batch
 
+     ! calc_likelihood with its per-call fwd_flag, batched (src/likelihood.f90:74-82): phi(ntrc, C) is written for the models
+     ! with fwd_flag /= 0 and read (the cached values of the chain's current RF) for sigma-only proposals
+     integer(c_int32_t) function rfinv_eval_batch_flags(handle, c, fwd_flag, k, z, dvp, dvs, sig, phi, logl, is_valid) &
+          & bind(C, name="rfinv_eval_batch_flags")
+       import :: c_int32_t, c_int8_t, c_ptr, c_double
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: c
+       integer(c_int8_t), intent(in) :: fwd_flag(*)
+       integer(c_int32_t), intent(in) :: k(*)
+       real(c_double), intent(in) :: z(*), dvp(*), dvs(*), sig(*)
+       real(c_double), intent(inout) :: phi(*)
+       real(c_double), intent(out) :: logl(*)
+       type(c_ptr), value :: is_valid
+     end function rfinv_eval_batch_flags
+
+     ! asynchronous pair: two groups of chains in flight, slot = 0 or 1 (arrays must stay untouched until _end returns)
+     integer(c_int32_t) function rfinv_eval_batch_begin(handle, slot, c, k, z, dvp, dvs, sig, logl, is_valid) &
+          & bind(C, name="rfinv_eval_batch_begin")
+       import :: c_int32_t, c_ptr, c_double
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: slot, c
+       integer(c_int32_t), intent(in) :: k(*)
+       real(c_double), intent(in) :: z(*), dvp(*), dvs(*), sig(*)
+       real(c_double), intent(out) :: logl(*)
+       type(c_ptr), value :: is_valid
+     end function rfinv_eval_batch_begin
+
+     integer(c_int32_t) function rfinv_eval_batch_end(handle, slot) bind(C, name="rfinv_eval_batch_end")
+       import :: c_int32_t, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: slot
+     end function rfinv_eval_batch_end
+
+     ! communicator of the distributed run: the id is created on one MPI rank and broadcast by the host, e.g.
+     !   if (rank == 0) ierr = rfinv_comm_create_id(id);  call mpi_bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD, ierr)
+     !   ierr = rfinv_comm_init(handle, id, nproc_gpu, rank)
+     integer(c_int32_t) function rfinv_comm_id_bytes() bind(C, name="rfinv_comm_id_bytes")
+       import :: c_int32_t
+     end function rfinv_comm_id_bytes
+
+     integer(c_int32_t) function rfinv_comm_create_id(id) bind(C, name="rfinv_comm_create_id")
+       import :: c_int32_t, c_int8_t
+       integer(c_int8_t), intent(out) :: id(*)
+     end function rfinv_comm_create_id
+
+     integer(c_int32_t) function rfinv_comm_init(handle, id, world, rank) bind(C, name="rfinv_comm_init")
+       import :: c_int32_t, c_int8_t, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int8_t), intent(in) :: id(*)
+       integer(c_int32_t), value :: world, rank
+     end function rfinv_comm_init
+
+     ! pt_control over all processes (in-library ncclAllGather per iteration), then output_results' reduces and gathers
+     integer(c_int32_t) function rfinv_pt_run_distributed(handle, n_iter) bind(C, name="rfinv_pt_run_distributed")
+       import :: c_int32_t, c_ptr
+       type(c_ptr), value :: handle
+       integer(c_int32_t), value :: n_iter
+     end function rfinv_pt_run_distributed
+
+     integer(c_int32_t) function rfinv_pt_reduce_outputs(handle) bind(C, name="rfinv_pt_reduce_outputs")
+       import :: c_int32_t, c_ptr
+       type(c_ptr), value :: handle
+     end function rfinv_pt_reduce_outputs
+
      integer(c_int32_t) function rfinv_pt_init(handle, nproc_total, rank_begin, rank_count) bind(C, name="rfinv_pt_init")
        import :: c_int32_t, c_ptr
        type(c_ptr), value :: handle

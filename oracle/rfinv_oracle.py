@@ -803,8 +803,13 @@ def make_syn(cfg: Config):
     if cfg.is_ray_common:
         noise_sigma[:] = rng.grnd() * (cfg.sig_max[0] - cfg.sig_min[0]) + cfg.sig_min[0]
         white = np.array([gauss(rng) * noise_sigma[0] for _ in range(n)])
+        # make_syn.f90:86-92 as written: the loop loads rx from noise(:,1) and stores the result in noise(:,itrc) -- at
+        # itrc = 1 that overwrites noise(:,1), so the traces from the second on are shaped by flt(:,1) AND flt(:,itrc)
+        src = white
         for t in range(T):
-            noise[t] = c2r(np.fft.rfft(white) * flt[:, t], n)
+            noise[t] = c2r(np.fft.rfft(src) * flt[:, t], n)
+            if t == 0:
+                src = noise[0].copy()
     else:
         for t in range(T):
             noise_sigma[t] = rng.grnd() * (cfg.sig_max[t] - cfg.sig_min[t]) + cfg.sig_min[t]

@@ -32,6 +32,7 @@ SIGNATURES = {
     "rfinv_destroy": (None, [C.c_void_p]),
     "rfinv_set_stream": (C.c_int32, [C.c_void_p, C.c_uint64]),
     "rfinv_eval_batch": (C.c_int32, [C.c_void_p, C.c_int32, i32p, dp, dp, dp, dp, dp, dp, u8p]),
+    "rfinv_eval_batch_flags": (C.c_int32, [C.c_void_p, C.c_int32, u8p, i32p, dp, dp, dp, dp, dp, dp, u8p]),
     "rfinv_eval_batch_begin": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, i32p, dp, dp, dp, dp, dp, u8p]),
     "rfinv_eval_batch_end": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_eval_batch_device": (C.c_int32, [C.c_void_p, C.c_int32] + [C.c_uint64] * 8),

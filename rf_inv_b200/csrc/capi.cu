@@ -257,6 +257,13 @@ __global__ void to_soa_kernel(const double* __restrict__ in, double* __restrict_
   const int c = (int)(idx % n), i = (int)(idx / n);
   out[(size_t)i * C + c0 + c] = in[(size_t)c * len + i];
 }
+// chain-fastest device layout -> chain-major host layout: out[c*len + i] = in[i*C + c]
+__global__ void from_soa_kernel(const double* __restrict__ in, double* __restrict__ out, int C, int len) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)C * len) return;
+  const int i = (int)(idx % len), c = (int)(idx / len);
+  out[idx] = in[(size_t)i * C + c];
+}
 // Large uploads (rfinv_eval_batch) go up in RFINV_UPLOAD_PIECES pieces of at least UPLOAD_PIECE_MIN models: measured at
 // 16 384 models, pieces of 1024 / 2048 / 4096 / 8192 give 9.3 / 9.9 / 10.2 / 9.8 M evals/s end to end (every copy costs a few
 // microseconds of set-up; the first piece is exposed).
@@ -755,6 +762,68 @@ int32_t rfinv_eval_batch(rfinv_handle* h, int32_t C, const int32_t* k, const dou
                                      cudaMemcpyDeviceToHost, h->stream));
   if (is_valid) RFINV_CUDA_CHECK(cudaMemcpyAsync(is_valid, h->d_valid, (size_t)C, cudaMemcpyDeviceToHost, h->stream));
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  return RFINV_OK;
+}
+
+// calc_likelihood with a per-model fwd_flag (src/likelihood.f90:74-82).  The reference's fwd_flag = .false. branch takes the
+// chain's cached rft and evaluates the same misfit and quadratic form again: phi does not change, only sigma does.  The
+// stateless batched form carries the cached quantity through the caller: phi[c][t] is written for the models that were
+// propagated and read for the others.
+int32_t rfinv_eval_batch_flags(rfinv_handle* h, int32_t C, const uint8_t* fwd_flag, const int32_t* k, const double* z,
+                               const double* dvp, const double* dvs, const double* sig, double* phi, double* logl,
+                               uint8_t* is_valid) {
+  int st = RFINV_OK;
+  if (!h || C < 0 || (C > 0 && (!fwd_flag || !k || !z || !dvp || !dvs || !sig || !phi || !logl))) {
+    rfinv_set_error("rfinv_eval_batch_flags: NULL argument");
+    return RFINV_ERR_ARG;
+  }
+  if (C == 0) return RFINV_OK;
+  std::vector<int> active;
+  active.reserve(C);
+  for (int c = 0; c < C; ++c)
+    if (fwd_flag[c]) {
+      if (k[c] < 1 || k[c] > h->cfg.k_max - 1) { rfinv_set_error("rfinv_eval_batch_flags: k[%d]=%d outside [1,k_max-1]", c, k[c]); return RFINV_ERR_ARG; }
+      active.push_back(c);
+    }
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  if ((st = h->ensure_capacity(C)) != RFINV_OK) return st;
+  const int km = h->cfg.k_max, T = h->cfg.ntrc;
+  const size_t n = (size_t)C;
+  cudaStream_t s = h->stream;
+  int* d_active = nullptr;
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_active, sizeof(int) * std::max<size_t>(active.size(), 1)));
+  auto fail = [&](int code) { cudaFree(d_active); return code; };
+#define TRY_CUDA(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { rfinv_set_error("rfinv_eval_batch_flags: %s", cudaGetErrorString(e__)); return fail(RFINV_ERR_CUDA); } } while (0)
+  TRY_CUDA(cudaMemcpyAsync(h->d_k, k, sizeof(int) * n, cudaMemcpyHostToDevice, s));
+  TRY_CUDA(cudaMemcpyAsync(h->d_z, z, sizeof(double) * n * (km - 1), cudaMemcpyHostToDevice, s));
+  TRY_CUDA(cudaMemcpyAsync(h->d_dvs, dvs, sizeof(double) * n * km, cudaMemcpyHostToDevice, s));
+  if (h->cfg.vp_mode == 1) TRY_CUDA(cudaMemcpyAsync(h->d_dvp, dvp, sizeof(double) * n * km, cudaMemcpyHostToDevice, s));
+  TRY_CUDA(cudaMemcpyAsync(h->d_stage, sig, sizeof(double) * n * T, cudaMemcpyHostToDevice, s));
+  to_soa_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, s>>>(h->d_stage, h->d_sig, C, 0, C, T);
+  // the cached quadratic forms of every model, chain fastest; the propagated models overwrite theirs
+  TRY_CUDA(cudaMemcpyAsync(h->d_stage, phi, sizeof(double) * n * T, cudaMemcpyHostToDevice, s));
+  to_soa_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, s>>>(h->d_stage, h->d_phi, C, 0, C, T);
+  TRY_CUDA(cudaGetLastError());
+  if (is_valid) TRY_CUDA(cudaMemsetAsync(h->d_valid, 1, n, s));   // models that are not propagated are not re-validated
+  if (!active.empty()) {
+    TRY_CUDA(cudaMemcpyAsync(d_active, active.data(), sizeof(int) * active.size(), cudaMemcpyHostToDevice, s));
+    ModelBatch layout;
+    layout.chain_major = 1;
+    st = h->eval_device(C, h->d_k, h->d_z, h->d_dvp, h->d_dvs, h->d_sig, nullptr, nullptr, nullptr, is_valid ? h->d_valid : nullptr,
+                        d_active, (int)active.size(), &layout);
+    if (st != RFINV_OK) return fail(st);
+  }
+  if ((st = rfinv_launch_loglik(h->dc, C, h->d_phi, h->d_sig, h->d_logl, s)) != RFINV_OK) return fail(st);
+  h->launches += 3;
+  TRY_CUDA(cudaMemcpyAsync(logl, h->d_logl, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  // phi back, chain slowest like the caller's array (through the staging buffer)
+  from_soa_kernel<<<(unsigned)((n * T + 255) / 256), 256, 0, s>>>(h->d_phi, h->d_stage, C, T);
+  TRY_CUDA(cudaGetLastError());
+  TRY_CUDA(cudaMemcpyAsync(phi, h->d_stage, sizeof(double) * n * T, cudaMemcpyDeviceToHost, s));
+  if (is_valid) TRY_CUDA(cudaMemcpyAsync(is_valid, h->d_valid, n, cudaMemcpyDeviceToHost, s));
+  TRY_CUDA(cudaStreamSynchronize(s));
+#undef TRY_CUDA
+  cudaFree(d_active);
   return RFINV_OK;
 }
 

@@ -245,23 +245,60 @@ __device__ bool model_valid_warp(const DevConfig& cfg, int k, double z0, double 
   return __all_sync(0xffffffffu, ok);
 }
 
+// STAGED: the states of the rank's chains are first brought into shared memory with coalesced loads (the chains of a rank
+// are neighbours in the chain-fastest arrays: one 128-byte line serves 16 of them) and the proposals leave the same way --
+// one memory latency per rank instead of one per chain, a third of the sectors.  Per warp: 2 x nchains x stride doubles
+// (pt_propose_smem_doubles); ranks with too many chains for that use the direct variant.
+__host__ __device__ inline int pt_propose_stride(int km, int T) { return (3 * km + T) | 1; }     // odd: conflict-free transposition
+__host__ __device__ inline size_t pt_propose_smem_doubles(int km, int T, int nchains) { return (size_t)2 * nchains * pt_propose_stride(km, T); }
+template <bool STAGED>
 __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p) {
+  extern __shared__ __align__(16) double pp_smem[];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= p.G) return;
-  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc, nch = p.nchains;
+  const int S = pt_propose_stride(km, T);
+  double* s_in = pp_smem + (size_t)(threadIdx.x >> 5) * pt_propose_smem_doubles(km, T, nch);   // [nchains][S]: z | dvp | dvs | sig of a chain
+  double* s_out = s_in + (size_t)nch * S;
+  const int c0 = r * nch;
+  if (STAGED) {
+    const int rows = 3 * km - 1 + T;            // rows of the chain-fastest state: z (km-1), dvp (km), dvs (km), sig (T)
+    for (int idx = lane; idx < rows * nch; idx += 32) {
+      const int row = idx / nch, ic = idx - row * nch;
+      double v; int col;
+      if (row < km - 1) { v = p.z[(size_t)row * Cl + c0 + ic]; col = row; }
+      else if (row < 2 * km - 1) { v = p.dvp[(size_t)(row - (km - 1)) * Cl + c0 + ic]; col = km + row - (km - 1); }
+      else if (row < 3 * km - 1) { v = p.dvs[(size_t)(row - (2 * km - 1)) * Cl + c0 + ic]; col = 2 * km + row - (2 * km - 1); }
+      else { v = p.sig[(size_t)(row - (3 * km - 1)) * Cl + c0 + ic]; col = 3 * km + row - (3 * km - 1); }
+      s_in[ic * S + col] = v;
+    }
+    for (int ic = lane; ic < nch; ic += 32) s_in[ic * S + km - 1] = 0.0;     // element km-1 of z does not exist
+  }
   Mt g(p.mt, r, p.mti[r], /*warp=*/true);
   __syncwarp();
   const bool has1 = lane + 32 < km;
-  for (int ic = 0; ic < p.nchains; ++ic) {
-    const int c = r * p.nchains + ic;
+  // per-chain scalars of the proposals, kept by lane (ic & 31) until the coalesced store at the end (STAGED)
+  int o_pk = 0, o_itype = 0, o_pflag = 0;
+  double o_logr = 0.0, o_lp12 = 0.0;
+  for (int ic = 0; ic < nch; ++ic) {
+    const int c = c0 + ic;
     int pk = p.k[c];
     // current state, distributed (element km-1 of z does not exist: 0)
-    double z0 = lane < km - 1 ? p.z[(size_t)lane * Cl + c] : 0.0;
-    double z1 = lane + 32 < km - 1 ? p.z[(size_t)(lane + 32) * Cl + c] : 0.0;
-    double dp0 = lane < km ? p.dvp[(size_t)lane * Cl + c] : 0.0, dp1 = has1 ? p.dvp[(size_t)(lane + 32) * Cl + c] : 0.0;
-    double ds0 = lane < km ? p.dvs[(size_t)lane * Cl + c] : 0.0, ds1 = has1 ? p.dvs[(size_t)(lane + 32) * Cl + c] : 0.0;
-    double sg = lane < T ? p.sig[(size_t)lane * Cl + c] : 0.0;
+    double z0, z1, dp0, dp1, ds0, ds1, sg;
+    if (STAGED) {
+      const double* sc = s_in + ic * S;
+      z0 = lane < km - 1 ? sc[lane] : 0.0; z1 = lane + 32 < km - 1 ? sc[lane + 32] : 0.0;
+      dp0 = lane < km ? sc[km + lane] : 0.0; dp1 = has1 ? sc[km + lane + 32] : 0.0;
+      ds0 = lane < km ? sc[2 * km + lane] : 0.0; ds1 = has1 ? sc[2 * km + lane + 32] : 0.0;
+      sg = lane < T ? sc[3 * km + lane] : 0.0;
+    } else {
+      z0 = lane < km - 1 ? p.z[(size_t)lane * Cl + c] : 0.0;
+      z1 = lane + 32 < km - 1 ? p.z[(size_t)(lane + 32) * Cl + c] : 0.0;
+      dp0 = lane < km ? p.dvp[(size_t)lane * Cl + c] : 0.0; dp1 = has1 ? p.dvp[(size_t)(lane + 32) * Cl + c] : 0.0;
+      ds0 = lane < km ? p.dvs[(size_t)lane * Cl + c] : 0.0; ds1 = has1 ? p.dvs[(size_t)(lane + 32) * Cl + c] : 0.0;
+      sg = lane < T ? p.sig[(size_t)lane * Cl + c] : 0.0;
+    }
     const double cz0 = z0, cz1 = z1, cdp0 = dp0, cdp1 = dp1, cds0 = ds0, cds1 = ds1;  // the chain's current values
     double log_prior12 = 0.0;
     bool null_flag = false;
@@ -329,20 +366,46 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
       do { rr = g.grnd(); } while (!(rr >= 2.220446049250313e-16));
       log_r = log(rr);
     }
-    if (lane < km - 1) p.pz[(size_t)lane * Cl + c] = z0;
-    if (lane + 32 < km - 1) p.pz[(size_t)(lane + 32) * Cl + c] = z1;
-    if (lane < km) { p.pdvp[(size_t)lane * Cl + c] = dp0; p.pdvs[(size_t)lane * Cl + c] = ds0; }
-    if (has1) { p.pdvp[(size_t)(lane + 32) * Cl + c] = dp1; p.pdvs[(size_t)(lane + 32) * Cl + c] = ds1; }
-    if (lane < T) p.psig[(size_t)lane * Cl + c] = sg;
-    if (lane == 0) {
-      p.pk[c] = pk;
-      p.itype[c] = (int8_t)itype;
-      p.pflag[c] = (int8_t)(null_flag ? -1 : (itype == p.it_sig ? 2 : 1));  // 1: forward needed, 2: cached RF (fwd_flag false)
-      p.log_r[c] = log_r;
-      p.log_prior12[c] = log_prior12;
+    const int flag = null_flag ? -1 : (itype == p.it_sig ? 2 : 1);  // 1: forward needed, 2: cached RF (fwd_flag false)
+    if (STAGED) {
+      double* so = s_out + ic * S;
+      if (lane < km - 1) so[lane] = z0;
+      if (lane + 32 < km - 1) so[lane + 32] = z1;
+      if (lane < km) { so[km + lane] = dp0; so[2 * km + lane] = ds0; }
+      if (has1) { so[km + lane + 32] = dp1; so[2 * km + lane + 32] = ds1; }
+      if (lane < T) so[3 * km + lane] = sg;
+      if (nch <= 32) {
+        if (lane == ic) { o_pk = pk; o_itype = itype; o_pflag = flag; o_logr = log_r; o_lp12 = log_prior12; }
+      } else if (lane == 0) {
+        p.pk[c] = pk; p.itype[c] = (int8_t)itype; p.pflag[c] = (int8_t)flag; p.log_r[c] = log_r; p.log_prior12[c] = log_prior12;
+      }
+    } else {
+      if (lane < km - 1) p.pz[(size_t)lane * Cl + c] = z0;
+      if (lane + 32 < km - 1) p.pz[(size_t)(lane + 32) * Cl + c] = z1;
+      if (lane < km) { p.pdvp[(size_t)lane * Cl + c] = dp0; p.pdvs[(size_t)lane * Cl + c] = ds0; }
+      if (has1) { p.pdvp[(size_t)(lane + 32) * Cl + c] = dp1; p.pdvs[(size_t)(lane + 32) * Cl + c] = ds1; }
+      if (lane < T) p.psig[(size_t)lane * Cl + c] = sg;
+      if (lane == 0) {
+        p.pk[c] = pk; p.itype[c] = (int8_t)itype; p.pflag[c] = (int8_t)flag; p.log_r[c] = log_r; p.log_prior12[c] = log_prior12;
+      }
     }
   }
   if (lane == 0) p.mti[r] = g.mti;
+  if (STAGED) {
+    __syncwarp();
+    const int rows = 3 * km - 1 + T;
+    for (int idx = lane; idx < rows * nch; idx += 32) {
+      const int row = idx / nch, ic = idx - row * nch;
+      if (row < km - 1) p.pz[(size_t)row * Cl + c0 + ic] = s_out[ic * S + row];
+      else if (row < 2 * km - 1) p.pdvp[(size_t)(row - (km - 1)) * Cl + c0 + ic] = s_out[ic * S + km + row - (km - 1)];
+      else if (row < 3 * km - 1) p.pdvs[(size_t)(row - (2 * km - 1)) * Cl + c0 + ic] = s_out[ic * S + 2 * km + row - (2 * km - 1)];
+      else p.psig[(size_t)(row - (3 * km - 1)) * Cl + c0 + ic] = s_out[ic * S + 3 * km + row - (3 * km - 1)];
+    }
+    if (nch <= 32 && lane < nch) {
+      const int c = c0 + lane;
+      p.pk[c] = o_pk; p.itype[c] = (int8_t)o_itype; p.pflag[c] = (int8_t)o_pflag; p.log_r[c] = o_logr; p.log_prior12[c] = o_lp12;
+    }
+  }
 }
 
 // ordered compaction of the chains that need a forward evaluation (single CTA, deterministic)
@@ -876,7 +939,17 @@ static int pt_enqueue_local(rfinv_handle* h, bool record) {
   PtDev& d = s->dev;
   cudaStream_t q = h->stream;
   int st;
-  pt_propose_kernel<<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d);
+  {
+    // staged variant while a warp's share of shared memory stays below 48 KB; 1, 2 or 4 warps per CTA accordingly
+    const size_t per_warp = sizeof(double) * pt_propose_smem_doubles(h->dc.k_max, h->dc.ntrc, d.nchains);
+    if (per_warp <= 48 * 1024) {
+      const int warps = per_warp <= 12 * 1024 ? 4 : (per_warp <= 24 * 1024 ? 2 : 1);
+      RFINV_CUDA_CHECK(cudaFuncSetAttribute(pt_propose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * warps)));
+      pt_propose_kernel<true><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d);
+    } else {
+      pt_propose_kernel<false><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d);
+    }
+  }
   pt_compact_kernel<<<1, 1024, 0, q>>>(d);
   RFINV_CUDA_CHECK(cudaGetLastError());
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;

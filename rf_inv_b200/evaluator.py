@@ -100,6 +100,24 @@ class Evaluator:
                                               _p(valid, capi.u8p)))
         return logl, rft, (valid.astype(bool) if valid is not None else None)
 
+    def calc_likelihood_flags(self, fwd_flag, k, z, dvp, dvs, sig, phi: np.ndarray, want_valid: bool = False):
+        """calc_likelihood with a per-model fwd_flag (src/likelihood.f90:74-82).  `phi[C][ntrc]` is updated in place: written
+        for the models with fwd_flag, read (the cached value of the chain's current RF) for the others.
+        Returns (log_likelihood[C], is_valid[C] or None)."""
+        n, k, z, dvp, dvs = self._models(k, z, dvp, dvs)
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        flags = np.ascontiguousarray(fwd_flag, dtype=np.uint8)
+        if sig.shape != (n, self.cfg.ntrc) or flags.shape != (n,):
+            raise ValueError("expected sig[C][ntrc], fwd_flag[C]")
+        if phi.dtype != np.float64 or phi.shape != (n, self.cfg.ntrc) or not phi.flags["C_CONTIGUOUS"]:
+            raise ValueError("phi must be a C-contiguous float64 array [C][ntrc] (updated in place)")
+        logl = np.empty(n)
+        valid = np.empty(n, dtype=np.uint8) if want_valid else None
+        capi.check(self._lib.rfinv_eval_batch_flags(self.handle, n, _p(flags, capi.u8p), _p(k, capi.i32p), _p(z, capi.dp),
+                                                    _p(dvp, capi.dp), _p(dvs, capi.dp), _p(sig, capi.dp), _p(phi, capi.dp),
+                                                    _p(logl, capi.dp), _p(valid, capi.u8p)))
+        return logl, (valid.astype(bool) if valid is not None else None)
+
     def calc_likelihood_begin(self, slot: int, k, z, dvp, dvs, sig, logl: np.ndarray, valid: Optional[np.ndarray] = None):
         """Asynchronous calc_likelihood of one group of chains in `slot` (0 or 1): returns at once, `logl` (and `valid`) are
         filled when calc_likelihood_end(slot) returns.  The arrays are used in place (no copies: pass C-contiguous arrays of the

@@ -67,7 +67,7 @@ def synthesize(cfg: RFConfig, device: int = 0) -> Dict[str, np.ndarray]:
             return out
 
         white = np.zeros((T, n)); noise_sigma = np.zeros(T)
-        if c.is_ray_common:                  # one noise series, shaped by every trace's filter (make_syn.f90:81-93)
+        if c.is_ray_common:                  # one noise series for all traces (make_syn.f90:81-93)
             noise_sigma[:] = draw(0, 1)[0] * (c.sig_max[0] - c.sig_min[0]) + c.sig_min[0]
             white[:] = draw(1, n) * noise_sigma[0]
         else:                                # make_syn.f90:95-110
@@ -78,6 +78,14 @@ def synthesize(cfg: RFConfig, device: int = 0) -> Dict[str, np.ndarray]:
         trace_of = np.arange(T, dtype=np.int32)
         capi.check(lib.rfinv_filter_traces(h, T, trace_of.ctypes.data_as(capi.i32p), white.ctypes.data_as(capi.dp),
                                            noise.ctypes.data_as(capi.dp)))
+        if c.is_ray_common and T > 1:
+            # make_syn.f90:86-92 as written: every pass of the loop loads rx from noise(:,1), which the first pass has
+            # already replaced by its filtered version -- traces 2.. are shaped by flt(:,1) and then by their own filter
+            again = np.ascontiguousarray(np.repeat(noise[:1], T - 1, axis=0))
+            out2 = np.empty((T - 1, n))
+            capi.check(lib.rfinv_filter_traces(h, T - 1, trace_of[1:].copy().ctypes.data_as(capi.i32p), again.ctypes.data_as(capi.dp),
+                                               out2.ctypes.data_as(capi.dp)))
+            noise[1:] = out2
     finally:
         pt.close()
     L = int(nlay[0])

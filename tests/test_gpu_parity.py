@@ -146,16 +146,24 @@ def test_post_critical_ray_gives_nan_like_the_reference():
 
 
 def test_internal_r_inv_matches_lapack_route():
-    # r_inv = NULL: the library builds R^-1 itself (Jacobi eigen-solver) instead of LAPACK dgesvd
+    """r_inv = NULL: the library builds R^-1 itself (Householder + QL eigen-solver) instead of the caller's LAPACK dgesvd.
+    The two matrices are two backward-stable evaluations of the same truncated pseudo-inverse and agree to < 1e-9 of the
+    largest entry; logL inherits exactly that input difference, |d phi| <= ||dR^-1||_2 ||m||^2 -- asserted below -- which
+    for entries of R^-1 up to 1/1e-3 amounts to up to ~1e-8 of the logL scale.  (A drop-in host passes the LAPACK matrix
+    and gets 1e-9; this route exists for hosts without LAPACK.)"""
     cfg = helpers.attach_obs_and_rinv(helpers.small_config(a_gus=[4.0, 2.5]), noise=0.01)
     ref = cfg.r_inv.copy()
     m = workloads.draw_models(cfg, 16, seed=8, dvs_scale=0.3)
-    ll_o, _, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    ll_o, rft_o, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
     cfg.r_inv = None
     with Evaluator(cfg) as ev:
         own = ev.r_inv()
         ll_g, _, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
     assert np.max(np.abs(own - ref)) / np.max(np.abs(ref)) < 1e-9
+    # the logL difference is the difference of the two input matrices, not of the arithmetic: bound it by that
+    mis = rft_o[:, :, :cfg.nsmp] - cfg.obs[None, :, :]
+    bound = sum(np.linalg.norm(own[t] - ref[t], 2) * np.sum(mis[:, t, :] ** 2, axis=1) / (2.0 * m["sig"][:, t] ** 2) for t in range(cfg.ntrc))
+    assert (np.abs(ll_g - ll_o) <= bound + 1e-9 * np.abs(ll_o)).all()
     assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < 1e-8
 
 
@@ -473,3 +481,63 @@ def test_large_host_batch_goes_up_in_pieces_and_matches_small_batches():
     assert np.array_equal(ll_big, ll_small)
     ok = oracle_c.eval_batch(cfg, m["k"][:64], m["z"][:64], m["dvp"][:64], m["dvs"][:64], m["sig"][:64])
     assert helpers.logl_err(cfg, ll_big[:64], ok[0], m["sig"][:64]) < RTOL and np.array_equal(val_big[:64], ok[2])
+
+
+def test_per_model_fwd_flag_matches_the_oracles_cached_rf_branch():
+    """rfinv_eval_batch_flags against calc_likelihood(fwd_flag) of the oracle (src/likelihood.f90:74-82): models with fwd_flag
+    are propagated, sigma-only proposals (fwd_flag = .false.) re-use the chain's cached RF -- here through the cached
+    quadratic forms the first call returned."""
+    import rfinv_oracle as pyo
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(ntrc=2, sig_min=[0.005, 0.005], sig_max=[0.05, 0.05]), noise=0.01)
+    n = 48
+    cur = workloads.draw_models(cfg, n, seed=9, dvs_scale=0.3)        # the chains' current states
+    rng = np.random.default_rng(4)
+    phi = np.zeros((n, cfg.ntrc))
+    with Evaluator(cfg) as ev:
+        ll0, _ = ev.calc_likelihood_flags(np.ones(n, dtype=np.uint8), cur["k"], cur["z"], cur["dvp"], cur["dvs"], cur["sig"], phi)
+        ll_ref, rft_ref, _ = ev.calc_likelihood(cur["k"], cur["z"], cur["dvp"], cur["dvs"], cur["sig"], want_rft=True)
+        assert np.array_equal(ll0, ll_ref)
+        # proposals: every other chain proposes a new sigma only (fwd_flag false), the rest a new model
+        flags = (np.arange(n) % 2).astype(np.uint8)
+        prop = workloads.draw_models(cfg, n, seed=10, dvs_scale=0.3)
+        prop["sig"] = rng.uniform(0.005, 0.05, (n, cfg.ntrc))
+        phi_cached = phi.copy()
+        ll1, valid = ev.calc_likelihood_flags(flags, prop["k"], prop["z"], prop["dvp"], prop["dvs"], prop["sig"], phi, want_valid=True)
+        assert np.array_equal(phi[flags == 0], phi_cached[flags == 0]) and not np.array_equal(phi[flags == 1], phi_cached[flags == 1])
+    pc = helpers.py_config(cfg)
+    flt = pyo.init_filter(pc)
+    r_inv = np.ascontiguousarray(np.transpose(cfg.r_inv, (2, 1, 0)))
+    ll_o = np.empty(n)
+    for c in range(n):
+        cached = np.ascontiguousarray(rft_ref[c].T)                   # the chain's rft(nfft, ntrc) as the reference keeps it
+        ll_o[c], _ = pyo.calc_likelihood(pc, flt, r_inv, int(prop["k"][c]), prop["z"][c], prop["dvp"][c], prop["dvs"][c], prop["sig"][c],
+                                         fwd_flag=bool(flags[c]), cached_rft=cached)
+    assert helpers.logl_err(cfg, ll1, ll_o, prop["sig"]) < RTOL
+    assert valid[flags == 0].all()
+
+
+def _arbiter_variants():
+    path = os.path.join(helpers.GOLDEN, "arbiter_vectors.npz")
+    return sorted({k.split("/")[0] for k in np.load(path).files})
+
+
+@pytest.mark.parametrize("name", _arbiter_variants())
+def test_cuda_against_the_extended_precision_arbiter(name):
+    """The CUDA path against the mpmath arbiter (oracle/arbiter_mp.py; fixture tests/golden/arbiter_vectors.npz), next to the C
+    oracle on the same models: the CUDA error is within the north star's 1e-9 wherever the reference's normalisation is well
+    conditioned (cond <= 1e3), and nowhere worse than the dense fp64 restatement of the reference plus 1e-12 of the scale --
+    on the ill-conditioned S traces of the joint P + S workload (cond up to 1e7) BOTH fp64 evaluations sit eps * cond away
+    from the exact value of the reference's formulas."""
+    import test_arbiter as ta
+    cfg, m, mp_ = ta.load_variant(name)
+    ll_o, rft_o, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    with Evaluator(cfg) as ev:
+        ll_g, rft_g, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+    eg_rft, eg_ll = ta.errors_vs_arbiter(cfg, m, mp_, rft_g, ll_g)
+    eo_rft, eo_ll = ta.errors_vs_arbiter(cfg, m, mp_, rft_o, ll_o)
+    c = np.maximum(mp_["cond"], 1.0)
+    cm = c.max(axis=1)
+    assert (eg_rft[c <= 1e3] <= 1e-9).all() and (eg_ll[cm <= 1e3] <= 1e-9).all()
+    assert (eg_rft <= eo_rft + 1e-12 * c).all(), float(np.max((eg_rft - eo_rft) / c))
+    assert (eg_ll <= eo_ll + 1e-11 * cm).all(), float(np.max((eg_ll - eo_ll) / cm))
+    assert (eg_rft <= 1e-12 * c).all() and (eg_ll <= 1e-11 * cm).all()      # and in absolute terms: eps * cond with a small constant

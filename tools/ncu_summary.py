@@ -34,14 +34,28 @@ for r in rows[2:]:
     lines.append("")
     lines.append("warp stall reasons (warps stalled per issue-active cycle): " + ", ".join(f"{n} {v:.2f}" for v, n in sorted(st, reverse=True)[:8]))
     lines.append("")
+# SASS opcode mix, one table per captured launch: the source page lists the launches one after the other, each introduced
+# by a "Kernel Name" row and an "Address" header row (summing over all of them, as the first version of this tool did, gives
+# a total that belongs to no launch)
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
-try:
-    hi = next(i for i, r in enumerate(srows) if r and r[0] == "Address")
-    h = srows[hi]
+sections, cur = [], None
+for r in srows:
+    if r and r[0] == "Kernel Name":
+        cur = {"name": r[1] if len(r) > 1 else "?", "hdr": None, "rows": []}
+        sections.append(cur)
+    elif cur is not None and r and r[0] == "Address":
+        cur["hdr"] = r
+    elif cur is not None and cur["hdr"] is not None:
+        cur["rows"].append(r)
+seen = set()
+for sec in sections:
+    h = sec["hdr"]
+    if h is None:
+        continue
     iS, iX, iSrc = h.index("# Samples"), h.index("Instructions Executed"), h.index("Source")
     ops, smp = collections.Counter(), collections.Counter()
-    for r in srows[hi + 1:]:
+    for r in sec["rows"]:
         try: x, s = int(r[iX]), int(r[iS])
         except (ValueError, IndexError): continue
         toks = r[iSrc].split()
@@ -49,11 +63,13 @@ try:
         op = (toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]).split(".")[0]
         ops[op] += x; smp[op] += s
     tx, ts = sum(ops.values()), max(sum(smp.values()), 1)
-    lines += ["SASS opcode mix of the first captured launch (warp-level instructions executed, stall samples):", "",
+    if (sec["name"], tx) in seen:      # the page repeats a launch (views); one table each
+        continue
+    seen.add((sec["name"], tx))
+    lines += [f"SASS opcode mix of `{sec['name'][:80]}` (warp-level instructions executed: {tx} = smsp__inst_executed.sum of that launch; stall samples):", "",
               "| opcode | executed | share | samples |", "|---|---|---|---|"]
-    for op, x in ops.most_common(14):
-        lines.append(f"| {op} | {x} | {100.0 * x / tx:.1f}% | {100.0 * smp[op] / ts:.1f}% |")
-except StopIteration:
-    pass
+    for op, x in ops.most_common(12):
+        lines.append(f"| {op} | {x} | {100.0 * x / max(tx, 1):.1f}% | {100.0 * smp[op] / ts:.1f}% |")
+    lines.append("")
 open(out, "w").write("\n".join(lines) + "\n")
 print("wrote", out)
