@@ -262,16 +262,39 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
   double* s_in = pp_smem + (size_t)(threadIdx.x >> 5) * pt_propose_smem_doubles(km, T, nch);   // [nchains][S]: z | dvp | dvs | sig of a chain
   double* s_out = s_in + (size_t)nch * S;
   const int c0 = r * nch;
+  // row `row` of the chain-fastest state (z: km-1 rows, dvp: km, dvs: km, sig: T) -> its array and its column in a staged chain
+  auto state_row = [&](int row, const double* z, const double* dvp, const double* dvs, const double* sig, int& col) -> const double* {
+    if (row < km - 1) { col = row; return z + (size_t)row * Cl; }
+    if (row < 2 * km - 1) { col = km + row - (km - 1); return dvp + (size_t)(row - (km - 1)) * Cl; }
+    if (row < 3 * km - 1) { col = 2 * km + row - (2 * km - 1); return dvs + (size_t)(row - (2 * km - 1)) * Cl; }
+    col = 3 * km + row - (3 * km - 1);
+    return sig + (size_t)(row - (3 * km - 1)) * Cl;
+  };
+  const int rows = 3 * km - 1 + T;
+  // lane -> (chain, first row): whole rows of nch chains per warp instruction when nch divides 32, else element by element
+  const bool even = nch <= 32 && 32 % nch == 0;
+  const int st_ic = even ? lane % nch : 0, st_row0 = even ? lane / nch : 0, st_step = even ? 32 / nch : 1;
   if (STAGED) {
-    const int rows = 3 * km - 1 + T;            // rows of the chain-fastest state: z (km-1), dvp (km), dvs (km), sig (T)
-    for (int idx = lane; idx < rows * nch; idx += 32) {
-      const int row = idx / nch, ic = idx - row * nch;
-      double v; int col;
-      if (row < km - 1) { v = p.z[(size_t)row * Cl + c0 + ic]; col = row; }
-      else if (row < 2 * km - 1) { v = p.dvp[(size_t)(row - (km - 1)) * Cl + c0 + ic]; col = km + row - (km - 1); }
-      else if (row < 3 * km - 1) { v = p.dvs[(size_t)(row - (2 * km - 1)) * Cl + c0 + ic]; col = 2 * km + row - (2 * km - 1); }
-      else { v = p.sig[(size_t)(row - (3 * km - 1)) * Cl + c0 + ic]; col = 3 * km + row - (3 * km - 1); }
-      s_in[ic * S + col] = v;
+    if (even) {
+      for (int row = st_row0; row < rows; row += 8 * st_step) {     // eight independent loads in flight per lane
+        double v[8]; int col[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int rr = row + q * st_step;
+          col[q] = 0; v[q] = 0.0;
+          if (rr < rows) v[q] = state_row(rr, p.z, p.dvp, p.dvs, p.sig, col[q])[c0 + st_ic];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (row + q * st_step < rows) s_in[st_ic * S + col[q]] = v[q];
+      }
+    } else {
+      for (int idx = lane; idx < rows * nch; idx += 32) {
+        const int row = idx / nch, ic = idx - row * nch;
+        int col;
+        const double v = state_row(row, p.z, p.dvp, p.dvs, p.sig, col)[c0 + ic];
+        s_in[ic * S + col] = v;
+      }
     }
     for (int ic = lane; ic < nch; ic += 32) s_in[ic * S + km - 1] = 0.0;     // element km-1 of z does not exist
   }
@@ -393,13 +416,19 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
   if (lane == 0) p.mti[r] = g.mti;
   if (STAGED) {
     __syncwarp();
-    const int rows = 3 * km - 1 + T;
-    for (int idx = lane; idx < rows * nch; idx += 32) {
-      const int row = idx / nch, ic = idx - row * nch;
-      if (row < km - 1) p.pz[(size_t)row * Cl + c0 + ic] = s_out[ic * S + row];
-      else if (row < 2 * km - 1) p.pdvp[(size_t)(row - (km - 1)) * Cl + c0 + ic] = s_out[ic * S + km + row - (km - 1)];
-      else if (row < 3 * km - 1) p.pdvs[(size_t)(row - (2 * km - 1)) * Cl + c0 + ic] = s_out[ic * S + 2 * km + row - (2 * km - 1)];
-      else p.psig[(size_t)(row - (3 * km - 1)) * Cl + c0 + ic] = s_out[ic * S + 3 * km + row - (3 * km - 1)];
+    if (even) {
+      for (int row = st_row0; row < rows; row += st_step) {
+        int col;
+        double* dst = const_cast<double*>(state_row(row, p.pz, p.pdvp, p.pdvs, p.psig, col));
+        dst[c0 + st_ic] = s_out[st_ic * S + col];
+      }
+    } else {
+      for (int idx = lane; idx < rows * nch; idx += 32) {
+        const int row = idx / nch, ic = idx - row * nch;
+        int col;
+        double* dst = const_cast<double*>(state_row(row, p.pz, p.pdvp, p.pdvs, p.psig, col));
+        dst[c0 + ic] = s_out[ic * S + col];
+      }
     }
     if (nch <= 32 && lane < nch) {
       const int c = c0 + lane;
@@ -408,38 +437,36 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
   }
 }
 
-// ordered compaction of the chains that need a forward evaluation (single CTA, deterministic)
+// Ordered compaction of the chains that need a forward evaluation: one CTA, ONE round -- thread t owns the q = ceil(Cl / 1024)
+// consecutive chains [t q, (t+1) q), counts their flags, the CTA scans the 1024 counts (warp shuffles + one scan of the warp
+// totals) and every thread writes its chains at its offset.  Deterministic, ascending chain order.
 __global__ void __launch_bounds__(1024) pt_compact_kernel(const PtDev p) {
-  // ordered list of the chains whose proposal needs a forward evaluation: one CTA, per round 1024 chains -- warp
-  // ballots, then a scan of the 32 warp counts by the first warp (two barriers per round)
   __shared__ int s_warp[32];
-  __shared__ int s_base;
-  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_base = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int q = (p.Cl + 1023) / 1024;
+  const int c_begin = tid * q, c_end = min(p.Cl, c_begin + q);
+  int cnt = 0;
+  for (int c = c_begin; c < c_end; ++c) cnt += p.pflag[c] == 1;
+  int incl = cnt;                                   // inclusive scan inside the warp
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
   __syncthreads();
-  for (int start = 0; start < p.Cl; start += nthr) {
-    const int c = start + tid;
-    const bool f = c < p.Cl && p.pflag[c] == 1;
-    const unsigned b = __ballot_sync(0xffffffffu, f);
-    if (lane == 0) s_warp[warp] = __popc(b);
-    __syncthreads();
-    const int base = s_base;
-    if (warp == 0) {
-      int v = lane < (nthr >> 5) ? s_warp[lane] : 0;
-      for (int o = 1; o < 32; o <<= 1) {   // inclusive scan of the warp counts
-        const int u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-      }
-      s_warp[lane] = v;
+  if (warp == 0) {
+    int v = s_warp[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
     }
-    __syncthreads();
-    if (f) p.active[base + (warp ? s_warp[warp - 1] : 0) + __popc(b & ((1u << lane) - 1u))] = c;
-    const int total = s_warp[(nthr >> 5) - 1];
-    __syncthreads();
-    if (tid == 0) s_base = base + total;
+    s_warp[lane] = v;                               // inclusive scan of the warp totals
   }
   __syncthreads();
-  if (tid == 0) { *p.n_active = s_base; *p.n_eval += (unsigned long long)s_base; }
+  int pos = (warp ? s_warp[warp - 1] : 0) + incl - cnt;
+  for (int c = c_begin; c < c_end; ++c)
+    if (p.pflag[c] == 1) p.active[pos++] = c;
+  if (tid == 0) { const int total = s_warp[31]; *p.n_active = total; *p.n_eval += (unsigned long long)total; }
 }
 
 // ---------------- acceptance: src/pt_mcmc.f90:178-201, one thread per chain ----------------
@@ -503,24 +530,34 @@ __global__ void pt_adopt_kernel(const DevConfig cfg, const PtDev p) {
   dst[(size_t)row * Cl + c] = src[(size_t)row * Cl + c];
 }
 
-// likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200); fixed-order tree sum
-__global__ void pt_lhist_kernel(const PtDev p, double* lhist) {   // lhist[iteration]
-  double* out = lhist + *p.it_dev;
+// likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200).  One CTA per 1024 chains (one
+// coalesced load per thread, tree sum); the CTA that arrives last adds the per-CTA sums in CTA order: the same value from run
+// to run whatever the schedule.
+__global__ void __launch_bounds__(1024) pt_lhist_kernel(const PtDev p, double* lhist, double* part, int* arrived) {
   __shared__ double s[1024];
-  const int tid = threadIdx.x;
-  double acc = 0.0;
-  const int per = (p.Cl + blockDim.x - 1) / blockDim.x;
-  for (int i = 0; i < per; ++i) {
-    const int c = tid * per + i;
-    if (c < p.Cl && p.temps[c] <= 1.0 + (double)1.0e-6f) acc += p.logl[c];
-  }
-  s[tid] = acc;
+  __shared__ int s_last;
+  const int tid = threadIdx.x, c = blockIdx.x * 1024 + tid;
+  double v = 0.0;
+  if (c < p.Cl) { const double t = p.temps[c], l = p.logl[c]; v = t <= 1.0 + (double)1.0e-6f ? l : 0.0; }
+  s[tid] = v;
   __syncthreads();
-  for (int o = blockDim.x >> 1; o > 0; o >>= 1) {
+  for (int o = 512; o > 0; o >>= 1) {
     if (tid < o) s[tid] += s[tid + o];
     __syncthreads();
   }
-  if (tid == 0) *out = s[0];
+  if (tid == 0) {
+    part[blockIdx.x] = s[0];
+    __threadfence();
+    s_last = atomicAdd(arrived, 1) == (int)gridDim.x - 1;
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    double acc = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(part + b);
+    lhist[*p.it_dev] = acc;
+    *arrived = 0;
+  }
 }
 
 // Swap table of this process (src/pt_mcmc.f90:501-571 needs (T, logL) of two chains anywhere in the job):
@@ -750,7 +787,7 @@ void rfinv_handle::free_pt() {
   cudaFree(d.log_flags); cudaFree(d.log_itypes); cudaFree(d.log_swaps);
   cudaFree(d.nk); cudaFree(d.nz); cudaFree(d.nsig); cudaFree(d.namp); cudaFree(d.nvpz); cudaFree(d.nvsz); cudaFree(d.nvpvsz); cudaFree(d.nmod);
   cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count); cudaFree(d.ocean_bin);
-  cudaFree(pt->d_lhist); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
+  cudaFree(pt->d_lhist); cudaFree(pt->d_lh_part); cudaFree(pt->d_lh_cnt); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
   if (pt->capture_stream) cudaStreamDestroy(pt->capture_stream);
   for (cudaGraphExec_t g : pt->graph) if (g) cudaGraphExecDestroy(g);
   delete pt;
@@ -849,6 +886,7 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   A(dalloc(&s->d_table, (size_t)s->table_len));
   s->cap_lhist = c.nburn + c.niter > 0 ? c.nburn + c.niter : 1024;
   A(dalloc(&s->d_lhist, (size_t)s->cap_lhist));
+  A(dalloc(&s->d_lh_part, (Cl + 1023) / 1024)); A(dalloc(&s->d_lh_cnt, 1));
   A(h->ensure_capacity(d.Cl));
 #undef A
   pt_init_kernel<<<(d.G + 63) / 64, 64, 0, h->stream>>>(h->dc, d);
@@ -958,7 +996,7 @@ static int pt_enqueue_local(rfinv_handle* h, bool record) {
     const long long n_el = (long long)(3 * h->dc.k_max - 1 + 2 * h->dc.ntrc) * d.Cl;
     pt_adopt_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, q>>>(h->dc, d);
   }
-  pt_lhist_kernel<<<1, 1024, 0, q>>>(d, s->d_lhist);
+  pt_lhist_kernel<<<(d.Cl + 1023) / 1024, 1024, 0, q>>>(d, s->d_lhist, s->d_lh_part, s->d_lh_cnt);
   if (record) {
     pt_coldscan_kernel<<<1, 1024, 0, q>>>(d);
     pt_record_kernel<<<d.Cl, 128, 0, q>>>(h->dc, d);

@@ -58,6 +58,8 @@ struct PtState {
   int cap_gather = 0;
   int cap_lhist = 0;
   double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
+  double* d_lh_part = nullptr; // per-CTA sums of pt_lhist_kernel
+  int* d_lh_cnt = nullptr;     // its arrival counter
   double* d_table = nullptr;   // swap table of this process
   int table_len = 0;
   int log_cap = 0, log_base = 0;
