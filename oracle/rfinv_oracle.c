@@ -344,19 +344,21 @@ static void water_level_decon(const cplx* y, const cplx* x, cplx* z, int n, doub
   }
 }
 
-/* ---- FFTW c2r stand-in: radix-2 inverse FFT of the Hermitian extension ---- */
+/* ---- FFTW c2r stand-in (src/fftw.f90:44): radix-2 inverse FFT of the Hermitian extension for powers of two; any other
+ * length (FFTW takes any) by the defining sum over the half spectrum -- O(n^2), independent of the product's Bluestein path ---- */
 typedef struct {
-  int n;
-  cplx* tw;   /* exp(+2 pi i j / n), j < n/2 */
+  int n, pow2;
+  cplx* tw;   /* exp(+2 pi i j / n), j < n */
   int* rev;
 } fft_plan;
 
 static fft_plan* fft_plan_create(int n) {
   fft_plan* p = (fft_plan*)malloc(sizeof(fft_plan));
   p->n = n;
-  p->tw = (cplx*)malloc(sizeof(cplx) * (size_t)(n / 2 > 0 ? n / 2 : 1));
+  p->pow2 = (n & (n - 1)) == 0;
+  p->tw = (cplx*)malloc(sizeof(cplx) * (size_t)(n > 0 ? n : 1));
   p->rev = (int*)malloc(sizeof(int) * (size_t)n);
-  for (int j = 0; j < n / 2; ++j) p->tw[j] = c_make(cos(2.0 * PI * j / n), sin(2.0 * PI * j / n));
+  for (int j = 0; j < n; ++j) p->tw[j] = c_make(cos(2.0 * PI * j / n), sin(2.0 * PI * j / n));
   int bits = 0;
   while ((1 << bits) < n) ++bits;
   for (int i = 0; i < n; ++i) {
@@ -374,6 +376,23 @@ static void fft_plan_destroy(fft_plan* p) {
 /* x[m] = sum_j X[j] exp(+2 pi i j m / n), X Hermitian from half[0..n/2]; work has n entries */
 static void c2r(const fft_plan* p, const cplx* half, double* out, cplx* work) {
   int n = p->n, nh = n / 2;
+  if (!p->pow2) {
+    /* x[m] = X0 + [n even] (-1)^m X_{n/2} + 2 sum_{0 < j < n/2} Re(X_j e^{+2 pi i j m / n}); imaginary parts of the
+     * DC and Nyquist bins are ignored like FFTW's c2r does */
+    int jtop = (n & 1) ? nh : nh - 1;   /* last bin with a distinct mirror */
+    for (int m = 0; m < n; ++m) {
+      double acc = 0.0;
+      for (int j = jtop; j >= 1; --j) {   /* small terms first: the Gaussian filter decays with j */
+        cplx w = p->tw[(int)(((long long)j * m) % n)];
+        acc += half[j].re * w.re - half[j].im * w.im;
+      }
+      acc = 2.0 * acc + half[0].re;
+      if (!(n & 1)) acc += (m & 1) ? -half[nh].re : half[nh].re;
+      out[m] = acc;
+    }
+    (void)work;
+    return;
+  }
   work[p->rev[0]] = c_make(half[0].re, 0.0);
   work[p->rev[nh]] = c_make(half[nh].re, 0.0);
   for (int j = 1; j < nh; ++j) {

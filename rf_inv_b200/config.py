@@ -143,8 +143,8 @@ class RFConfig:
         for name in ("rayps", "a_gus", "ipha", "sig_min", "sig_max"):
             if len(getattr(self, name)) != self.ntrc:
                 raise ValueError(f"{name} must have ntrc={self.ntrc} entries")
-        if self.nfft & (self.nfft - 1) or not (32 <= self.nfft <= 4096):
-            raise ValueError("nfft must be a power of two in [32, 4096]")
+        if not (64 <= self.nfft <= 4096) or (self.nfft & (self.nfft - 1) and self.nfft > 2048):
+            raise ValueError("nfft must be a power of two in [64, 4096] or any other length in [64, 2048]")
         if not (1 <= self.nsmp <= self.nfft):
             raise ValueError("nsmp must be in [1, nfft]")
         if self.bdep < 0.0:

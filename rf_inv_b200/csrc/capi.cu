@@ -50,7 +50,7 @@ void build_filter(const rfinv_config& c, std::vector<double>& flt) {
 // groups kept for trace t, rounded up to a value the kernel is instantiated for.  Full band when the water-level
 // deconvolution is on (its water level is the maximum over all bins) or RFINV_FULL_BAND=1.
 void band_limits(DevConfig& d, const std::vector<double>& flt) {
-  const int nh = d.nh, jfull = rfinv_forward_bins_per_thread(d.nfft), nthr = (d.nfft / 2) / jfull;
+  const int nh = d.nh, jfull = rfinv_forward_bins_per_thread(d.nfft_p2), nthr = (d.nfft_p2 / 2) / jfull;
   static const bool full_band = getenv("RFINV_FULL_BAND") && atoi(getenv("RFINV_FULL_BAND")) != 0;
   const int allowed[6] = {1, 2, 3, 4, 6, 8};
   d.jb_max = 1;
@@ -86,6 +86,48 @@ void build_twiddles(int n, std::vector<double2>& tw) {
   }
   tw[0] = make_double2(1.0, 0.0);
   if (n % 4 == 0) { tw[n / 4] = make_double2(0.0, 1.0); tw[n / 2] = make_double2(-1.0, 0.0); tw[3 * n / 4] = make_double2(0.0, -1.0); }
+}
+
+// Bluestein tables for a transform length n that is not a power of two (forward.cu, bluestein_inverse): the chirp
+// w[m] = exp(+i pi m^2 / n) -- m^2 reduced mod 2n in integers, so the angle stays in [0, 2 pi) -- and
+// B = FFT_M(b) / M with b[m mod M] = conj(w[m]) for |m| < n, zero elsewhere (M >= 2n - 1 a power of two).  B is computed
+// in long double by a plain radix-2 transform: it multiplies every spectrum, so it should carry no error of its own.
+void build_chirp(int n, int M, std::vector<double2>& chirp, std::vector<double2>& chirp_b) {
+  const long double pi = 3.14159265358979323846264338327950288L;
+  std::vector<long double> wr(n), wi(n);
+  chirp.resize(n);
+  for (long long m = 0; m < n; ++m) {
+    const long long r = (m * m) % (2LL * n);
+    const long double ang = pi * (long double)r / (long double)n;
+    wr[m] = cosl(ang); wi[m] = sinl(ang);
+    chirp[m] = make_double2((double)wr[m], (double)wi[m]);
+  }
+  std::vector<long double> br(M, 0.0L), bi(M, 0.0L);
+  for (int m = 0; m < n; ++m) {
+    br[m] = wr[m]; bi[m] = -wi[m];
+    if (m) { br[M - m] = wr[m]; bi[M - m] = -wi[m]; }
+  }
+  // forward transform (sign -), decimation in time
+  int bits = 0; while ((1 << bits) < M) ++bits;
+  for (int i = 0; i < M; ++i) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) if (i & (1 << b)) r |= 1 << (bits - 1 - b);
+    if (r > i) { std::swap(br[i], br[r]); std::swap(bi[i], bi[r]); }
+  }
+  for (int len = 2; len <= M; len <<= 1) {
+    const int hl = len / 2;
+    for (int j = 0; j < hl; ++j) {
+      const long double ang = -2.0L * pi * (long double)j / (long double)len;
+      const long double c = cosl(ang), s_ = sinl(ang);
+      for (int s0 = 0; s0 < M; s0 += len) {
+        const long double xr = br[s0 + j + hl] * c - bi[s0 + j + hl] * s_, xi = br[s0 + j + hl] * s_ + bi[s0 + j + hl] * c;
+        br[s0 + j + hl] = br[s0 + j] - xr; bi[s0 + j + hl] = bi[s0 + j] - xi;
+        br[s0 + j] += xr; bi[s0 + j] += xi;
+      }
+    }
+  }
+  chirp_b.resize(M);
+  for (int m = 0; m < M; ++m) chirp_b[m] = make_double2((double)(br[m] / M), (double)(bi[m] / M));
 }
 
 // Eigen-decomposition of a symmetric matrix (row-major n x n): A = V diag(w) V^T, v[i*n + e] = component i of
@@ -228,8 +270,10 @@ int upload(const std::vector<T>& h, T** d) {
 int check_config(const rfinv_config* c) {
   if (!c) { rfinv_set_error("config is NULL"); return RFINV_ERR_ARG; }
   if (c->ntrc < 1 || c->ntrc > RFINV_MAX_TRC) { rfinv_set_error("ntrc must be in [1,%d]", RFINV_MAX_TRC); return RFINV_ERR_ARG; }
-  if (c->nfft < 64 || c->nfft > 4096 || (c->nfft & (c->nfft - 1))) {
-    rfinv_set_error("nfft=%d unsupported: the shared-memory FFT needs a power of two in [64,4096]", c->nfft);
+  // powers of two run the shared-memory FFT directly; any other length goes through Bluestein's convolution on twice the
+  // next power of two, which must still fit the shared memory of an SM
+  if (c->nfft < 64 || c->nfft > 4096 || ((c->nfft & (c->nfft - 1)) && c->nfft > 2048)) {
+    rfinv_set_error("nfft=%d unsupported: the shared-memory FFT takes powers of two in [64,4096] and any other length in [64,2048]", c->nfft);
     return RFINV_ERR_ARG;
   }
   if (c->nsmp < 1 || c->nsmp > c->nfft) { rfinv_set_error("nsmp must be in [1,nfft]"); return RFINV_ERR_ARG; }
@@ -389,7 +433,10 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   DevConfig& d = h->dc;
   std::memset(&d, 0, sizeof(d));
   d.ntrc = T; d.nfft = cfg->nfft; d.nh = cfg->nfft / 2 + 1; d.nsmp = S;
-  d.log2n = 0; while ((1 << d.log2n) < cfg->nfft) ++d.log2n;
+  d.nfft_p2 = 64; while (d.nfft_p2 < cfg->nfft) d.nfft_p2 <<= 1;
+  d.fft_general = d.nfft_p2 != cfg->nfft;
+  d.fft_len = d.fft_general ? 2 * d.nfft_p2 : cfg->nfft;
+  d.log2n = 0; while ((1 << d.log2n) < d.fft_len) ++d.log2n;
   d.deconv_mode = cfg->deconv_mode; d.vp_mode = cfg->vp_mode; d.k_min = cfg->k_min; d.k_max = cfg->k_max;
   d.prior_mode = cfg->prior_mode; d.nref = cfg->nref;
   d.ray_common = 1;  // check_ray, src/forward.f90:59-76
@@ -407,7 +454,9 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   build_filter(*cfg, flt);
   band_limits(d, flt);
   std::vector<double2> tw;
-  build_twiddles(cfg->nfft, tw);
+  build_twiddles(d.fft_len, tw);
+  std::vector<double2> chirp, chirp_b;
+  if (d.fft_general) build_chirp(cfg->nfft, d.fft_len, chirp, chirp_b);
   // R^-1: symmetrised (the quadratic form only sees the symmetric part) and zero padded to the tile
   const int Sp = d.nsmp_pad;
   std::vector<double> rpad((size_t)T * Sp * Sp, 0.0);
@@ -566,13 +615,14 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
 #define RFINV_TRY(x) do { st = (x); if (st != RFINV_OK) { rfinv_destroy(h); return st; } } while (0)
   RFINV_TRY(upload(flt, &h->d_flt));
   RFINV_TRY(upload(tw, &h->d_tw));
+  if (d.fft_general) { RFINV_TRY(upload(chirp, &h->d_chirp)); RFINV_TRY(upload(chirp_b, &h->d_chirp_b)); }
   RFINV_TRY(upload(h->h_obs, &h->d_obs));
   RFINV_TRY(upload(h->h_vp_ref, &h->d_vp_ref));
   RFINV_TRY(upload(h->h_vs_ref, &h->d_vs_ref));
   RFINV_TRY(upload(rpad, &h->d_r_inv));
   RFINV_TRY(upload(wfac, &h->d_w_fac));
 #undef RFINV_TRY
-  d.flt = h->d_flt; d.tw = h->d_tw; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv; d.w_fac = h->d_w_fac;
+  d.flt = h->d_flt; d.tw = h->d_tw; d.chirp = h->d_chirp; d.chirp_b = h->d_chirp_b; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv; d.w_fac = h->d_w_fac;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { rfinv_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); rfinv_destroy(h); return RFINV_ERR_CUDA; }
   h->own_stream = true;
@@ -587,7 +637,7 @@ void rfinv_destroy(rfinv_handle* h) {
   h->free_pt();              // first: the captured iteration graphs hold references on the communicator (ncclCommDestroy waits for them)
   rfinv_comm_destroy(h);
   h->free_workspace();
-  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
+  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_chirp); cudaFree(h->d_chirp_b); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_copy) {
     cudaStreamSynchronize(h->stream_copy);

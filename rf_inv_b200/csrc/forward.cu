@@ -25,7 +25,7 @@
 #include <cstdlib>
 #include "rfinv_common.cuh"
 
-#ifdef RFINV_PHASE_TIMING
+#if defined(RFINV_PHASE_TIMING) && !defined(RFINV_FWD_GENERAL_TU)
 // Debug build only (tools/phase_timing.py): per-phase cycle totals of forward_kernel, summed over CTAs.
 __device__ unsigned long long g_phase[16];
 #define PHASE_MARK(i)                                                            \
@@ -411,7 +411,7 @@ __global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatc
   const double p2 = __dmul_rn(p, p);
   const double nyq = (double)(cfg.nfft / 2);
   int nyq_doublings = 0;
-  while ((nthr_fwd << nyq_doublings) < cfg.nfft / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d
+  while ((nthr_fwd << nyq_doublings) < cfg.nfft_p2 / 2) ++nyq_doublings;   // nfft/2 = nthr_fwd * 2^d (nfft a power of two)
   for (int la = lane; la <= ka; la += 32) {
     const PrepShared S = LA[la];
     const double h = S.h, rho = S.rho, beta2 = S.beta2;
@@ -458,9 +458,14 @@ __global__ void __maxnreg__(80) prep_kernel(const DevConfig cfg, const ModelBatc
       // Nyquist = (nfft/2) bins = nyq_doublings doublings of the stride rotation; its bin carries the smallest
       // filter weight of the whole spectrum, so the doubled rounding error is immaterial
       double cn = csx, sn2 = snx, ce = cse, se = sne;
-      for (int d = 0; d < nyq_doublings; ++d) {
-        const double c2 = fma(cn, cn, -sn2 * sn2), s2 = 2.0 * cn * sn2; cn = c2; sn2 = s2;
-        const double c3 = fma(ce, ce, -se * se), s3 = 2.0 * ce * se; ce = c3; se = s3;
+      if (cfg.fft_general) {   // nfft/2 is not the stride times a power of two: straight from the angle
+        sincos(nyq * thx, &sn2, &cn);
+        sincos(nyq * the, &se, &ce);
+      } else {
+        for (int d = 0; d < nyq_doublings; ++d) {
+          const double c2 = fma(cn, cn, -sn2 * sn2), s2 = 2.0 * cn * sn2; cn = c2; sn2 = s2;
+          const double c3 = fma(ce, ce, -se * se), s3 = 2.0 * ce * se; ce = c3; se = s3;
+        }
       }
       Z.tr[4] = cn; Z.tr[5] = sn2; Z.tr[6] = ce; Z.tr[7] = se;
     } else {   // half space: its ray-dependent quantities go to the ray constants through shared memory
@@ -852,6 +857,58 @@ __device__ __forceinline__ double fft_inverse_dif(double2* buf, int n, const dou
   }
 }
 
+// ---- transform lengths that are not a power of two (FFTW accepts any, src/fftw.f90:43-45): Bluestein's chirp-z form ----
+// x[t] = sum_f Z[f] exp(+2 pi i f t / n) with f t = (f^2 + t^2 - (t - f)^2) / 2 is a convolution,
+//   x[t] = w[t] * sum_f (Z[f] w[f]) conj(w[t - f]),   w[m] = exp(+i pi m^2 / n),
+// evaluated as a circular convolution of length M = cfg.fft_len (a power of two >= 2n) by the power-of-two transform above:
+// the caller has stored conj(Z[f] w[f]) at logical position f < n and zeros in [n, M); the forward transform is the
+// conjugate of the inverse one; cfg.chirp_b = FFT_M(conj(w) wrapped around M) / M comes from the host.  The transforms
+// leave element m at bit-reversed position, so the two element-wise passes in between are pair swaps (p, brev p): each
+// thread reads both members and writes both, no second buffer.  On return x[t] sits at logical position t (natural
+// order) for t < n.  Returns the maximum imaginary part over t < n like fft_inverse_dif.
+template <int LOG2M, class Sync>
+__device__ __forceinline__ double bluestein_inverse_m(double2* buf, int n, const double2* __restrict__ chirp,
+                                                      const double2* __restrict__ chirp_b, const double2* twq, double* s_red,
+                                                      int tid, int nthr, Sync sync) {
+  constexpr unsigned M = 1u << LOG2M;
+  constexpr int PSH = LOG2M >= 9 ? LOG2M - 3 : 31;
+  fft_inverse_dif_n<LOG2M, Sync>(buf, twq, s_red, tid, nthr, sync);       // conj(A[m]) at position brev(m)
+  for (unsigned p = tid; p < M; p += nthr) {
+    const unsigned q = __brev(p) >> (32 - LOG2M);
+    if (p > q) continue;
+    const double2 u = buf[fpad(p, PSH)], v = buf[fpad(q, PSH)];           // u = conj(A[q]), v = conj(A[p])
+    const double2 bq = chirp_b[q], bp = chirp_b[p];
+    buf[fpad(q, PSH)] = cmul(make_double2(u.x, -u.y), bq);                // natural order: position m <- A[m] B[m]
+    if (p != q) buf[fpad(p, PSH)] = cmul(make_double2(v.x, -v.y), bp);
+  }
+  sync();
+  fft_inverse_dif_n<LOG2M, Sync>(buf, twq, s_red, tid, nthr, sync);       // c[t] (the 1/M is in chirp_b) at position brev(t)
+  double vmax = -INFINITY;
+  for (unsigned p = tid; p < M; p += nthr) {
+    const unsigned q = __brev(p) >> (32 - LOG2M);
+    if (p > q) continue;
+    const double2 u = buf[fpad(p, PSH)], v = buf[fpad(q, PSH)];           // u = c[q], v = c[p]
+    if (q < (unsigned)n) { const double2 x = cmul(u, chirp[q]); buf[fpad(q, PSH)] = x; vmax = fmax(vmax, x.y); }
+    if (p != q && p < (unsigned)n) { const double2 x = cmul(v, chirp[p]); buf[fpad(p, PSH)] = x; vmax = fmax(vmax, x.y); }
+  }
+  publish_max(vmax, s_red + 32, tid);   // (second half of s_red: the first one may still be read by a slower warp)
+  sync();
+  const int nw = (nthr + 31) >> 5;
+  double r = s_red[32];
+  for (int i = 1; i < nw; ++i) r = fmax(r, s_red[32 + i]);
+  return r;
+}
+template <int LO, int HI, class Sync>
+__device__ __forceinline__ double bluestein_inverse(double2* buf, const DevConfig& cfg, const double2* twq, double* s_red, int tid,
+                                                    int nthr, Sync sync) {
+  if constexpr (LO == HI) {
+    return bluestein_inverse_m<LO, Sync>(buf, cfg.nfft, cfg.chirp, cfg.chirp_b, twq, s_red, tid, nthr, sync);
+  } else {
+    if (cfg.log2n == LO) return bluestein_inverse_m<LO, Sync>(buf, cfg.nfft, cfg.chirp, cfg.chirp_b, twq, s_red, tid, nthr, sync);
+    return bluestein_inverse<LO + 1, HI, Sync>(buf, cfg, twq, s_red, tid, nthr, sync);
+  }
+}
+
 template <class Sync>
 __device__ __forceinline__ double block_max(double v, double* scratch, int tid, int nthr, Sync sync) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -1028,10 +1085,16 @@ __device__ __forceinline__ void propagate_groups(int jm, const RayConst* s_rc, c
 // Surface response of the thread's first J bin groups (the groups above them are zero filled).  STAGE = false: straight into the packed, filtered spectrum
 // Z = X_r + i X_v with Hermitian extension (src/forward.f90:168, 199) in the padded FFT buffer; STAGE = true: the
 // unfiltered spectra go to s_fr / s_fv (common rays, water-level deconvolution).  Thread 0 adds the two edge bins.
-template <int J, bool STAGE>
+// GEN (nfft not a power of two, Bluestein): bins from jtop on do not exist (the thread grid is laid out for the next power of
+// two); position f of the buffer takes conj(Z[f] w[f]) with the chirp w, w[n - f] = (-1)^n w[f]; zeros in [n, fft_len).
+template <int J, bool STAGE, bool GEN>
 __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha,
                                                  int n, int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                                 double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh) {
+                                                 double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh,
+                                                 const double2* __restrict__ chirp = nullptr, int fft_len = 0) {
+  const bool odd = GEN && (n & 1);
+  const int jtop = odd ? nh : nh - 1;     // regular bins: [1, jtop); an even length has its Nyquist bin at nh - 1 (prep_kernel)
+  const double wsgn = odd ? -1.0 : 1.0;
   double h14[4], h23[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { h14[i] = s_rc->h14[i]; h23[i] = s_rc->h23[i]; }
@@ -1042,11 +1105,22 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
   for (int m = 0; m < J; ++m) {
     const int j = tid + m * nthr;
     double2 fr, fv;
-    if (STAGE && buried) surface_response_buried(h14, h23, wa[m], wb[m], ipha, s_fr[j], s_fv[j], fr, fv);   // station pass left them there
-    else surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv, STAGE ? 1.0 : flt[j]);   // filtered on the way out
+    const bool live = !GEN || j < jtop;
+    if (STAGE && buried) { if (live) surface_response_buried(h14, h23, wa[m], wb[m], ipha, s_fr[j], s_fv[j], fr, fv); }   // station pass left them there
+    else surface_response(h14, h23, wa[m], wb[m], cw, ipha, fr, fv, STAGE ? 1.0 : (live ? flt[j] : 0.0));   // filtered on the way out
     rot(cw, sw, cbw, sbw);
     if (STAGE) {
-      if (j > 0) { s_fr[j] = fr; s_fv[j] = fv; }
+      if (j > 0 && live) { s_fr[j] = fr; s_fv[j] = fv; }
+    } else if (GEN) {
+      if (j > 0 && live) {
+        const double2 xv = fv;
+        const double2 xr = ipha == 1 ? fr : xv;
+        const double2 w = chirp[j];
+        const double2 a = cmul(make_double2(xr.x - xv.y, xr.y + xv.x), w);
+        const double2 b = cmul(make_double2(xr.x + xv.y, xv.x - xr.y), w);
+        s_buf[fpad(j, psh)] = make_double2(a.x, -a.y);
+        s_buf[fpad(n - j, psh)] = make_double2(wsgn * b.x, -wsgn * b.y);
+      }
     } else if (j > 0) {
       const double2 xv = fv;
       const double2 xr = ipha == 1 ? fr : xv;
@@ -1056,10 +1130,12 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
   }
   for (int m = J; m < jfull; ++m) {    // bins above the band limit of this trace (band_limits(), capi.cu)
     const int j = tid + m * nthr;
+    if (GEN && j >= jtop) continue;
     if (STAGE) { s_fr[j] = make_double2(0.0, 0.0); s_fv[j] = make_double2(0.0, 0.0); }
     else { s_buf[fpad(j, psh)] = make_double2(0.0, 0.0); s_buf[fpad(n - j, psh)] = make_double2(0.0, 0.0); }
   }
-  if (!STAGE && tid == 0 && 2 * jfull * nthr < n) {
+  if (GEN && !STAGE) for (int f = n + tid; f < fft_len; f += nthr) s_buf[fpad(f, psh)] = make_double2(0.0, 0.0);
+  if (!GEN && !STAGE && tid == 0 && 2 * jfull * nthr < n) {
     // pruned first FFT stage (jfull = the kernel variant's bin groups): the butterfly with offset 0 still reads its leg
     // n - jfull*nthr, the mirror of the first bin above the band limit
     s_buf[fpad(jfull * nthr, psh)] = make_double2(0.0, 0.0);
@@ -1068,12 +1144,20 @@ __device__ __forceinline__ void surface_and_pack(const RayConst* s_rc, const Wav
   if (tid == 0) {  // the two bins off the regular grid
     if (STAGE) {
       s_fr[0] = s_rc->edge[0]; s_fv[0] = s_rc->edge[1];
-      s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3];
+      if (!odd) { s_fr[nh - 1] = s_rc->edge[2]; s_fv[nh - 1] = s_rc->edge[3]; }
     } else {       // c2r ignores the imaginary parts of DC and Nyquist
       const double f0 = flt[0], f1 = flt[nh - 1];
       const double2 r0 = ipha == 1 ? s_rc->edge[0] : s_rc->edge[1], r1 = ipha == 1 ? s_rc->edge[2] : s_rc->edge[3];
-      s_buf[fpad(0, psh)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
-      s_buf[fpad(nh - 1, psh)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
+      if (GEN) {
+        s_buf[fpad(0, psh)] = make_double2(r0.x * f0, -s_rc->edge[1].x * f0);     // w[0] = 1
+        if (!odd) {
+          const double2 a = cmul(make_double2(r1.x * f1, s_rc->edge[3].x * f1), chirp[nh - 1]);
+          s_buf[fpad(nh - 1, psh)] = make_double2(a.x, -a.y);
+        }
+      } else {
+        s_buf[fpad(0, psh)] = make_double2(r0.x * f0, s_rc->edge[1].x * f0);
+        s_buf[fpad(nh - 1, psh)] = make_double2(r1.x * f1, s_rc->edge[3].x * f1);
+      }
     }
   }
 }
@@ -1091,6 +1175,7 @@ __device__ __forceinline__ int obs_pre_index(int S, int q, int tid, int nthr) {
   const int pr = tid + (q >> 1) * nthr;
   return pr < (S >> 1) ? ((q & 1) ? S - 1 - pr : pr) : S;   // S = nothing to fetch
 }
+template <bool GEN>
 __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOutputs& out, const double2* s_buf, int C, int c,
                                               int t, int ipha, int npre, double scale, const double* obs_pre, int tid, int nthr) {
   const int n = cfg.nfft, S = cfg.nsmp, Sp = cfg.nsmp_pad, nmask = n - 1, brev_shift = 32 - cfg.log2n, psh = fft_pad_shift(cfg.log2n);
@@ -1100,6 +1185,12 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
   double* __restrict__ smp = smp_base ? smp_base + ((size_t)t * C + c) * S : nullptr;
   const double* __restrict__ obs = cfg.obs + (size_t)t * S;
   auto sample = [&](int i) {
+    if constexpr (GEN) {   // Bluestein leaves the trace in natural order; the circular shift is a true modulo
+      int f = (ipha == 1 ? i - npre : npre - i - 1) % n;
+      if (f < 0) f += n;
+      const double v = s_buf[fpad(f, psh)].x * scale;
+      return ipha == 1 ? v : -v;
+    }
     const int f = ipha == 1 ? ((i - npre) & nmask)            // src/forward.f90:178-184
                             : ((npre - i - 1) & nmask);       // src/forward.f90:187-193
     const double v = s_buf[fpad((int)(__brev((unsigned)f) >> brev_shift), psh)].x * scale;
@@ -1138,11 +1229,12 @@ __device__ __forceinline__ void write_outputs(const DevConfig& cfg, const EvalOu
   }
 }
 
-template <int JB, bool STAGE, bool MIXED>
+template <int JB, bool STAGE, bool MIXED, bool GEN>
 __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, const Wave* wa, const Wave* wb, int jfull, int ipha, int n,
                                                int nh, int tid, int nthr, const double* __restrict__ flt, double2* s_buf,
-                                               double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh) {
-#define SURF(JM) surface_and_pack<JM, STAGE>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried, s_tabw, psh)
+                                               double2* s_fr, double2* s_fv, bool buried, const double2* s_tabw, int psh,
+                                               const double2* __restrict__ chirp, int fft_len) {
+#define SURF(JM) surface_and_pack<JM, STAGE, GEN>(s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, flt, s_buf, s_fr, s_fv, buried, s_tabw, psh, chirp, fft_len)
   if (!MIXED || jm >= JB) { SURF(JB); return; }
   if constexpr (MIXED) {
   if constexpr (JB > 6) if (jm == 6) { SURF(6); return; }
@@ -1164,7 +1256,7 @@ __device__ __forceinline__ void surface_groups(int jm, const RayConst* s_rc, con
 // in-place FFT buffer; the unfiltered spectra only when they must outlive one FFT (common rays) or feed the
 // water-level deconvolution; two sets of layer / ray constants; quarter-wave twiddles.
 // ------------------------------------------------------------------------------------------------
-template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
+template <int J, int BMAX, int MINB, bool MIXED, bool BURIED, bool GEN = false>
 __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg, const ModelBatch mb, const EvalOutputs out,
                                                              const double* __restrict__ lc_in,
                                                              const double* __restrict__ rc_in, int* __restrict__ counter,
@@ -1180,15 +1272,16 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || buried;   // spectra staged in shared memory
 
   constexpr int n_hi = nthr >> 4;                     // table split: tid = 16*hi + lo
+  const int nf = GEN ? cfg.fft_len : n;             // points of the shared-memory transform
   const size_t tab_entries = trig_table_entries(km, nthr);
-  const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
+  const size_t region0 = tab_entries > fft_buf_elems(nf) ? tab_entries : fft_buf_elems(nf);
   double2* s_buf = reinterpret_cast<double2*>(smem_raw);
   double2* s_tab = s_buf;                             // dead before the FFT buffer is first written
   double2* s_fr = s_buf + region0;                    // [nh+1] unfiltered radial spectrum (or deconvolved RF spectrum)
   double2* s_fv = s_fr + (nh + 1);                    // [nh+1] unfiltered vertical spectrum
   double2* s_twq = s_fr + (general ? 2 * (nh + 1) : 0);   // per-stage FFT twiddle tables
-  double* s_red = reinterpret_cast<double*>(s_twq + fft_twiddle_entries(n));   // [32]
-  RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 32);     // [2]
+  double* s_red = reinterpret_cast<double*>(s_twq + fft_twiddle_entries(nf));   // [64]
+  RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 64);     // [2]
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
   double2* s_tabw = reinterpret_cast<double2*>(s_lc2 + 2 * (size_t)km);   // [16 + n_hi] water-layer phase table (not aliased)
 
@@ -1211,7 +1304,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   // iteration, so nobody waits for the round trip).
   int item = blockIdx.x, slot = 0;
   pdl_trigger();                               // quadform_kernel may queue up behind this grid
-  fill_fft_twiddles(s_twq, cfg.tw, n, tid, nthr);   // (nothing of prep_kernel is touched before pdl_wait)
+  fill_fft_twiddles(s_twq, cfg.tw, nf, tid, nthr);   // (nothing of prep_kernel is touched before pdl_wait)
   pdl_wait();                                  // prep_kernel (and everything before it on the stream) is complete
   const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   if (item >= n_items) return;
@@ -1252,7 +1345,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 #pragma unroll
         for (int m = 0; m < J; ++m) {
           const int j = tid + m * nthr;
-          if (m < jm) {
+          if (m < jm && (!GEN || j < nh)) {
             s_fr[j] = make_double2(fma(c0, wa[m].a1, c1 * wa[m].b1), fma(c2, wa[m].a2, c3 * wa[m].b2));
             s_fv[j] = make_double2(fma(c0, wb[m].a1, c1 * wb[m].b1), fma(c2, wb[m].a2, c3 * wb[m].b2));
           }
@@ -1263,14 +1356,14 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
     __syncthreads();   // the trigonometric tables are dead: their region becomes the FFT buffer
 
     // ---- surface response per bin; straight into the packed, filtered spectrum when no staging is needed ----
-    const int jfull = (n >> 1) / nthr;
+    const int jfull = (cfg.nfft_p2 >> 1) / nthr;
 #ifdef RFINV_NO_FFT_PRUNE
     constexpr bool kPruned = false;
 #else
-    constexpr bool kPruned = true;   // the first FFT stage skips the bin groups from J on: nobody has to zero them
+    constexpr bool kPruned = !GEN;   // the first FFT stage skips the bin groups from J on: nobody has to zero them
 #endif
-    if (general) surface_groups<J, true, MIXED>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw, psh);
-    else surface_groups<J, false, MIXED>(jm, s_rc, wa, wb, kPruned ? J : jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw, psh);
+    if (general) surface_groups<J, true, MIXED, GEN>(jm, s_rc, wa, wb, jfull, ipha, n, nh, tid, nthr, nullptr, s_buf, s_fr, s_fv, buried, s_tabw, psh, cfg.chirp, nf);
+    else surface_groups<J, false, MIXED, GEN>(jm, s_rc, wa, wb, kPruned ? J : jfull, ipha, n, nh, tid, nthr, cfg.flt + (size_t)t0 * nh, s_buf, s_fr, s_fv, false, s_tabw, psh, cfg.chirp, nf);
     __syncthreads();
     PHASE_MARK(3);
 
@@ -1313,13 +1406,26 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
           const double2 xr = make_double2(src_r[j].x * f, src_r[j].y * f);
           double2 xv = make_double2(0.0, 0.0);
           if (cfg.deconv_mode == 0) xv = make_double2(s_fv[j].x * f, s_fv[j].y * f);
-          if (j == 0 || j == nh - 1) {
+          const bool edge_bin = j == 0 || (j == nh - 1 && !(GEN && (n & 1)));   // DC, Nyquist of an even length: real
+          if constexpr (GEN) {   // Bluestein: conj(Z[f] w[f]), w[n - f] = (-1)^n w[f]
+            const double2 w = cfg.chirp[j];
+            if (edge_bin) {
+              const double2 a = cmul(make_double2(xr.x, xv.x), w);
+              s_buf[fpad(j, psh)] = make_double2(a.x, -a.y);
+            } else {
+              const double sg = (n & 1) ? -1.0 : 1.0;
+              const double2 a = cmul(make_double2(xr.x - xv.y, xr.y + xv.x), w), b = cmul(make_double2(xr.x + xv.y, xv.x - xr.y), w);
+              s_buf[fpad(j, psh)] = make_double2(a.x, -a.y);
+              s_buf[fpad(n - j, psh)] = make_double2(sg * b.x, -sg * b.y);
+            }
+          } else if (edge_bin) {
             s_buf[fpad(j, psh)] = make_double2(xr.x, xv.x);
           } else {
             s_buf[fpad(j, psh)] = make_double2(xr.x - xv.y, xr.y + xv.x);
             s_buf[fpad(n - j, psh)] = make_double2(xr.x + xv.y, xv.x - xr.y);
           }
         }
+        if constexpr (GEN) for (int f = n + tid; f < nf; f += nthr) s_buf[fpad(f, psh)] = make_double2(0.0, 0.0);
         __syncthreads();
       }
       PHASE_MARK(4);
@@ -1333,10 +1439,12 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
       // threads per CTA fix the transform length: 32 -> 64/128, 64 -> 256/512, 128 -> 1024, 256 -> 2048/4096
       constexpr int FLO = BMAX <= 32 ? 6 : (BMAX <= 64 ? 8 : (BMAX <= 128 ? 10 : 11));
       constexpr int FHI = BMAX <= 32 ? 7 : (BMAX <= 64 ? 9 : (BMAX <= 128 ? 10 : 12));
-      const double mx = fft_inverse_dif<FLO, FHI, CtaSync, J, nthr>(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
+      double mx;
+      if constexpr (GEN) mx = bluestein_inverse<FLO + 1, (FHI + 1 > 12 ? 12 : FHI + 1), CtaSync>(s_buf, cfg, s_twq, s_red, tid, nthr, CtaSync());
+      else mx = fft_inverse_dif<FLO, FHI, CtaSync, J, nthr>(s_buf, n, s_twq, s_red, tid, nthr, CtaSync());
       PHASE_MARK(5);
       const double scale = cfg.deconv_mode == 0 ? 1.0 / mx : 1.0;   // src/forward.f90:197-203
-      write_outputs(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
+      write_outputs<GEN>(cfg, out, s_buf, C, c, t, ipha, s_rc->npre, scale, obs_pre, tid, nthr);
       if (tid == 0 && t + 1 == t_end) s_next = (int)gridDim.x + next2;
       asm volatile("cp.async.wait_all;\n" ::);   // the next item's constants, in flight since the top of this iteration
       __syncthreads();   // the buffer is rewritten by the next trace / the next item's tables; constants and s_next published
@@ -1352,17 +1460,50 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
 // shaping of make_syn (src/make_syn.f90:96-100; plans src/fftw.f90:44-45).  One CTA per series.  For real x the
 // forward transform is the conjugate of the inverse one, so both directions run through fft_inverse_dif.
 // ------------------------------------------------------------------------------------------------
+template <bool GEN>
 __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg, const double* __restrict__ in,
                                                            const int* __restrict__ trace_of, double* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, nthr = blockDim.x, n = cfg.nfft, nh = cfg.nh, brev_shift = 32 - cfg.log2n, psh = fft_pad_shift(cfg.log2n);
+  const int nf = cfg.fft_len;
   double2* b0 = reinterpret_cast<double2*>(smem_raw);
-  double2* b1 = b0 + fft_buf_elems(n);
-  double2* s_tw = b1 + fft_buf_elems(n);
-  double* s_red = reinterpret_cast<double*>(s_tw + fft_twiddle_entries(n));
+  double2* b1 = b0 + fft_buf_elems(nf);
+  double2* s_tw = b1 + fft_buf_elems(nf);
+  double* s_red = reinterpret_cast<double*>(s_tw + fft_twiddle_entries(nf));   // [64]
   const double* x = in + (size_t)blockIdx.x * n;
   const double* __restrict__ flt = cfg.flt + (size_t)trace_of[blockIdx.x] * nh;
-  fill_fft_twiddles(s_tw, cfg.tw, n, tid, nthr);
+  fill_fft_twiddles(s_tw, cfg.tw, nf, tid, nthr);
+  if constexpr (GEN) {
+    // any length (Bluestein): both transforms leave their result in natural order
+    const bool odd = n & 1;
+    for (int i = tid; i < nf; i += nthr) {
+      double2 v = make_double2(0.0, 0.0);
+      if (i < n) { const double2 w = cfg.chirp[i]; const double xi = x[i]; v = make_double2(xi * w.x, -xi * w.y); }   // conj(x w)
+      b0[fpad(i, psh)] = v;
+      if (i >= n) b1[fpad(i, psh)] = v;
+    }
+    __syncthreads();
+    bluestein_inverse<7, 12>(b0, cfg, s_tw, s_red, tid, nthr, CtaSync());
+    for (int f = tid; f < nh; f += nthr) {
+      const double2 v = b0[fpad(f, psh)];
+      const double g = flt[f];
+      const double2 w = cfg.chirp[f];
+      const bool edge_bin = f == 0 || (f == nh - 1 && !odd);
+      double2 y = make_double2(v.x * g, -v.y * g);                // r2c bin f (conjugate), filtered
+      if (edge_bin) y.y = 0.0;                                    // c2r ignores these imaginary parts
+      const double2 a = cmul(y, w);
+      b1[fpad(f, psh)] = make_double2(a.x, -a.y);
+      if (!edge_bin) {
+        const double sg = odd ? -1.0 : 1.0;
+        const double2 b = cmul(make_double2(y.x, -y.y), w);
+        b1[fpad(n - f, psh)] = make_double2(sg * b.x, -sg * b.y);
+      }
+    }
+    __syncthreads();
+    bluestein_inverse<7, 12>(b1, cfg, s_tw, s_red, tid, nthr, CtaSync());
+    for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad(i, psh)].x;
+    return;
+  }
   for (int i = tid; i < n; i += nthr) b0[fpad(i, psh)] = make_double2(x[i], 0.0);
   __syncthreads();
   fft_inverse_dif<6, 12>(b0, n, s_tw, s_red, tid, nthr, CtaSync());
@@ -1422,39 +1563,47 @@ __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, in
 }
 
 size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
-  const size_t n = cfg.nfft, nh = cfg.nh, km = cfg.k_max;
+  const size_t n = cfg.fft_len, nh = cfg.nh, km = cfg.k_max;
   const size_t tab_entries = trig_table_entries(km, nthr);
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || cfg.bdep > 0.0;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
-  return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 32 + 2 * sizeof(RayConst) +
+  return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 64 + 2 * sizeof(RayConst) +
          2 * sizeof(LayerConst) * km + sizeof(double2) * (16 + (nthr >> 4));
 }
 
-template <int J, int BMAX, int MINB, bool MIXED, bool BURIED>
+template <int J, int BMAX, int MINB, bool MIXED, bool BURIED, bool GEN = false>
 int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
                      const double* rc, int* counter, int nthr, cudaStream_t stream, const TraceSel& sel) {
   static const size_t extra = getenv("RFINV_FWD_EXTRA_SMEM") ? (size_t)atoi(getenv("RFINV_FWD_EXTRA_SMEM")) : 0;  // occupancy experiments
   const size_t smem = forward_smem_bytes(cfg, nthr) + extra;
   if (nthr != BMAX) { rfinv_set_error("forward_kernel<%d,%d>: launched with %d threads", J, BMAX, nthr); return RFINV_ERR_ARG; }
-  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  RFINV_CUDA_CHECK(cudaFuncSetAttribute(forward_kernel<J, BMAX, MINB, MIXED, BURIED, GEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, n_sm = 0, per_sm = 0;
   RFINV_CUDA_CHECK(cudaGetDevice(&dev));
   RFINV_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED, BURIED>, nthr, smem));
+  RFINV_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, forward_kernel<J, BMAX, MINB, MIXED, BURIED, GEN>, nthr, smem));
   if (per_sm < 1) { rfinv_set_error("forward_kernel does not fit on an SM (%zu bytes of shared memory)", smem); return RFINV_ERR_CUDA; }
   const int n_models = mb.active ? mb.n_active : mb.C;
   const long long items = (long long)n_models * sel.n;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  RFINV_CUDA_CHECK(rfinv_launch_pdl(forward_kernel<J, BMAX, MINB, MIXED, BURIED>, dim3(grid), dim3(nthr), smem, stream, cfg, mb, out, lc, rc, counter, sel));
+  RFINV_CUDA_CHECK(rfinv_launch_pdl(forward_kernel<J, BMAX, MINB, MIXED, BURIED, GEN>, dim3(grid), dim3(nthr), smem, stream, cfg, mb, out, lc, rc, counter, sel));
   return RFINV_OK;
 }
 
 // kernel variant for a group of traces that keep JB bin groups: <bin groups per thread that are propagated (band limit),
 // upper bound of threads per CTA, CTAs per SM, MIXED = the variant is wider than the group>
+#ifndef RFINV_FWD_GENERAL_TU
+}  // namespace
+// the variants for transform lengths that are not powers of two are compiled in forward_general.cu
+int rfinv_launch_forward_group_general(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
+                                       const double* rc, int* counter, int nthr, cudaStream_t stream, int sel_n,
+                                       unsigned long long sel_packed);
+namespace {
 int launch_forward_group(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc, const double* rc,
                          int* counter, int nthr, cudaStream_t stream, const TraceSel& sel, int JB) {
+  if (cfg.fft_general) return rfinv_launch_forward_group_general(cfg, mb, out, lc, rc, counter, nthr, stream, sel.n, sel.packed);
 #define FWD(JJ, BB, MM)                                                                                   \
   do {                                                                                                    \
     if (cfg.bdep > 0.0) return launch_forward_t<JJ, BB, MM, true, true>(cfg, mb, out, lc, rc, counter, nthr, stream, sel); \
@@ -1475,8 +1624,30 @@ int launch_forward_group(const DevConfig& cfg, const ModelBatch& mb, const EvalO
   FWD(8, 256, 1);
 #undef FWD
 }
+#endif   // !RFINV_FWD_GENERAL_TU
 
 }  // namespace
+
+#ifdef RFINV_FWD_GENERAL_TU
+// Any transform length (Bluestein): one variant per thread count, the widest bin-group count of that thread count with the
+// band limit of the trace read at run time (MIXED).
+int rfinv_launch_forward_group_general(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, const double* lc,
+                                       const double* rc, int* counter, int nthr, cudaStream_t stream, int sel_n,
+                                       unsigned long long sel_packed) {
+  TraceSel sel;
+  sel.n = sel_n; sel.packed = sel_packed;
+#define FWDG(JJ, BB, MM)                                                                                                \
+  do {                                                                                                                  \
+    if (cfg.bdep > 0.0) return launch_forward_t<JJ, BB, MM, true, true, true>(cfg, mb, out, lc, rc, counter, nthr, stream, sel); \
+    return launch_forward_t<JJ, BB, MM, true, false, true>(cfg, mb, out, lc, rc, counter, nthr, stream, sel);           \
+  } while (0)
+  if (nthr <= 32) FWDG(2, 32, 8);
+  if (nthr <= 64) FWDG(4, 64, 6);
+  if (nthr <= 128) FWDG(4, 128, 4);
+  FWDG(4, 256, 2);
+#undef FWDG
+}
+#else
 
 int rfinv_forward_bins_per_thread(int nfft) {
   if (nfft <= 64) return 1;
@@ -1493,8 +1664,7 @@ size_t rfinv_forward_scratch_doubles(const DevConfig& cfg, long long n_models) {
 // prep_kernel for the models [m_begin, m_begin + m_count) of the batch; scratch as in rfinv_launch_forward
 int rfinv_launch_prep(const DevConfig& cfg, const ModelBatch& mb, uint8_t* is_valid, double* scratch, cudaStream_t stream,
                       int m_begin, int m_count) {
-  const int J = rfinv_forward_bins_per_thread(cfg.nfft);
-  const int nthr = (cfg.nfft / 2) / J;
+  const int nthr = rfinv_forward_threads(cfg);
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long n_items = (long long)n_models * ntr_eff;
@@ -1525,8 +1695,7 @@ int rfinv_launch_prep(const DevConfig& cfg, const ModelBatch& mb, uint8_t* is_va
 // scratch: rfinv_forward_scratch_doubles(cfg, n_models) doubles of device memory
 int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalOutputs& out, double* scratch,
                          cudaStream_t stream, int* n_kernels, bool prep_done) {
-  const int J = rfinv_forward_bins_per_thread(cfg.nfft);
-  const int nthr = (cfg.nfft / 2) / J;
+  const int nthr = rfinv_forward_threads(cfg);
   const int n_models = mb.active ? mb.n_active : mb.C;
   const int ntr_eff = cfg.ray_common ? 1 : cfg.ntrc;
   const long long n_items = (long long)n_models * ntr_eff;
@@ -1560,10 +1729,15 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
 int rfinv_launch_filter_traces(const DevConfig& cfg, int n_series, const double* in, const int* trace_of, double* out,
                                cudaStream_t stream) {
   if (n_series == 0) return RFINV_OK;
-  const size_t smem = sizeof(double2) * (2 * fft_buf_elems(cfg.nfft) + fft_twiddle_entries(cfg.nfft)) + sizeof(double) * 32;
-  RFINV_CUDA_CHECK(cudaFuncSetAttribute(filter_traces_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int nthr = cfg.nfft / 8 < 32 ? 32 : (cfg.nfft / 8 > 128 ? 128 : cfg.nfft / 8);
-  filter_traces_kernel<<<n_series, nthr, smem, stream>>>(cfg, in, trace_of, out);
+  const size_t smem = sizeof(double2) * (2 * fft_buf_elems(cfg.fft_len) + fft_twiddle_entries(cfg.fft_len)) + sizeof(double) * 64;
+  const int nthr = cfg.fft_len / 8 < 32 ? 32 : (cfg.fft_len / 8 > 128 ? 128 : cfg.fft_len / 8);
+  if (cfg.fft_general) {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(filter_traces_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    filter_traces_kernel<true><<<n_series, nthr, smem, stream>>>(cfg, in, trace_of, out);
+  } else {
+    RFINV_CUDA_CHECK(cudaFuncSetAttribute(filter_traces_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    filter_traces_kernel<false><<<n_series, nthr, smem, stream>>>(cfg, in, trace_of, out);
+  }
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -1575,3 +1749,4 @@ int rfinv_launch_format_model(const DevConfig& cfg, const ModelBatch& mb, int* n
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
+#endif   // !RFINV_FWD_GENERAL_TU

@@ -14,7 +14,13 @@
 
 // Immutable per-handle constants, passed to kernels by value (the reference's module globals).
 struct DevConfig {
-  int ntrc, nfft, nh, nsmp, log2n;
+  int ntrc, nfft, nh, nsmp;
+  int log2n;                    // log2 of fft_len
+  // Transform lengths.  nfft a power of two: the shared-memory FFT runs on nfft points directly (fft_general = 0,
+  // nfft_p2 = fft_len = nfft).  Any other length (FFTW accepts any, src/fftw.f90:43-45): threads and bin groups are laid
+  // out for nfft_p2 = the next power of two (bins beyond nfft/2 are masked) and the transform is Bluestein's chirp-z
+  // convolution on fft_len = 2 nfft_p2 points (forward.cu, bluestein_inverse).
+  int fft_general, nfft_p2, fft_len;
   int deconv_mode, vp_mode, k_min, k_max, prior_mode, nref, ray_common;
   int nsmp_pad;                 // nsmp rounded up to the likelihood tile (64)
   double bdep;                  // receiver depth below the surface / sea floor (0 = at the surface)
@@ -26,7 +32,9 @@ struct DevConfig {
   int jbins[RFINV_MAX_TRC];     // frequency-bin groups (of blockDim bins each) of forward_kernel that carry signal for the trace
   int jb_max;                   // largest jbins[]: picks the kernel variant
   const double* flt;            // [ntrc][nh]   Gaussian filter, src/forward.f90:95-119
-  const double2* tw;            // [nfft]       exp(+2 pi i m / nfft)
+  const double2* tw;            // [fft_len]    exp(+2 pi i m / fft_len)
+  const double2* chirp;         // [nfft]       fft_general: exp(+i pi m^2 / nfft)
+  const double2* chirp_b;       // [fft_len]    fft_general: FFT_fft_len(conj(chirp) wrapped around fft_len) / fft_len
   const double* obs;            // [ntrc][nsmp]
   const double* vp_ref;         // [nref]
   const double* vs_ref;         // [nref]
@@ -138,8 +146,9 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
 // host path launches it piece by piece behind the pieces of the upload
 int rfinv_launch_prep(const DevConfig& cfg, const ModelBatch& mb, uint8_t* is_valid, double* scratch, cudaStream_t stream,
                       int m_begin, int m_count);
-// bins per thread of forward_kernel for the full band (threads per CTA = nfft/2 / this)
-int rfinv_forward_bins_per_thread(int nfft);
+// bins per thread of forward_kernel for the full band (threads per CTA = nfft_p2/2 / this); nfft_p2 = DevConfig::nfft_p2
+int rfinv_forward_bins_per_thread(int nfft_p2);
+inline int rfinv_forward_threads(const DevConfig& cfg) { return (cfg.nfft_p2 / 2) / rfinv_forward_bins_per_thread(cfg.nfft_p2); }
 // phi[ntrc][C] = m^T R^-1 m per trace and model.  partial / counters: scratch sized by the two functions below, the
 // counters zeroed at allocation
 size_t rfinv_quadform_partial_doubles(const DevConfig& cfg, int C);

@@ -75,10 +75,13 @@ def test_create_rejects_bad_configs_before_touching_cuda(lib):
     cfg = helpers.small_config()
     cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp))
     c = cfg.to_c()
-    c.nfft = 300                                   # FFTW accepts it, the shared-memory FFT does not
+    c.nfft = 3000                                  # lengths that are not powers of two go through Bluestein up to 2048
     h = C.c_void_p()
     assert lib.rfinv_create(C.byref(c), 0, C.byref(h)) == capi.RFINV_ERR_ARG
-    assert b"power of two" in lib.rfinv_last_error()
+    assert b"any other length in [64,2048]" in lib.rfinv_last_error()
+    c = cfg.to_c()
+    c.nfft = 8192
+    assert lib.rfinv_create(C.byref(c), 0, C.byref(h)) == capi.RFINV_ERR_ARG
     c = cfg.to_c()
     c.deconv_mode = 2                              # src/params.f90:195-199
     assert lib.rfinv_create(C.byref(c), 0, C.byref(h)) == capi.RFINV_ERR_ARG
@@ -100,7 +103,8 @@ def test_config_validation_and_modes():
     assert helpers.small_config(rayps=[0.06, 0.06]).is_ray_common
     assert not helpers.small_config(rayps=[0.06, 0.06], ipha=[1, -1]).is_ray_common
     with pytest.raises(ValueError):
-        helpers.small_config(nfft=300).to_c()
+        helpers.small_config(nfft=3000).to_c()
+    helpers.small_config(nfft=300).to_c()          # FFTW accepts any length (src/fftw.f90:43-45); so does the library up to 2048
     with pytest.raises(ValueError):
         helpers.small_config(rayps=[0.06]).to_c()
     # sig_mode threshold is the float32 literal 1.0e-5 (src/params.f90:262)

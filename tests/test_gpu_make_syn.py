@@ -31,13 +31,15 @@ def _compare(cfg):
     return got, ref
 
 
-@pytest.mark.parametrize("variant", ["distinct_rays_sigma_range", "common_ray", "sea_laplace_n1024"])
+@pytest.mark.parametrize("variant", ["distinct_rays_sigma_range", "common_ray", "sea_laplace_n1024", "n1000_any_length", "n375_odd_length"])
 def test_synthesize_matches_restatement(variant):
     kw = {
         "distinct_rays_sigma_range": dict(sig_min=[0.005, 0.01], sig_max=[0.05, 0.01], nchains=3, iseed=4242),
         "common_ray": dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0], sig_min=[0.01, 0.01], sig_max=[0.03, 0.03], nchains=2),
         "sea_laplace_n1024": dict(nfft=1024, nsmp=400, sdep=1.5, prior_mode=1, k_max=14, z_max=30.0, nchains=2,
                                   sig_min=[0.01, 0.02], sig_max=[0.02, 0.04], iseed=99),
+        "n1000_any_length": dict(nfft=1000, nsmp=400, nchains=2, sig_min=[0.01, 0.02], sig_max=[0.02, 0.04], iseed=7),
+        "n375_odd_length": dict(nfft=375, nsmp=150, rayps=[0.06, 0.06], nchains=2, sig_min=[0.01, 0.01], sig_max=[0.03, 0.03], iseed=8),
     }[variant]
     cfg = helpers.attach_obs_and_rinv(helpers.small_config(**kw))
     got, _ = _compare(cfg)

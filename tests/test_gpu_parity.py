@@ -32,6 +32,14 @@ VARIANTS = {
     "n2048_k30": dict(nfft=2048, nsmp=1000, k_max=30, z_max=40.0),
     "n4096": dict(nfft=4096, nsmp=300, k_max=12),
     "nsmp_eq_nfft": dict(nfft=128, nsmp=128),
+    # transform lengths that are not powers of two (FFTW takes any, src/fftw.f90:43-45): Bluestein path
+    "n2000_k30": dict(nfft=2000, nsmp=1000, k_max=30, z_max=40.0), "n1000_sea": dict(nfft=1000, nsmp=400, sdep=2.0, k_max=16),
+    "n600_S_deconv": dict(nfft=600, nsmp=250, sdep=1.0, ipha=[-1, -1], deconv_mode=1),
+    "n250_common": dict(nfft=250, nsmp=101, rayps=[0.06, 0.06], a_gus=[2.0, 4.0]),
+    "n100_tstart": dict(nfft=100, nsmp=100, t_start=-1.0), "n375_odd": dict(nfft=375, nsmp=150, ipha=[1, -1], rayps=[0.06, 0.11]),
+    "n1501_odd_deconv": dict(nfft=1501, nsmp=500, deconv_mode=1), "n1536_mixed_widths": dict(nfft=1536, nsmp=512, ntrc=3,
+        rayps=[0.05, 0.06, 0.07], a_gus=[2.0, 4.0, 8.0], ipha=[1, 1, 1], sig_min=[0.01] * 3, sig_max=[0.01] * 3),
+    "buried_n360": dict(bdep=2.5, sdep=1.0, nfft=360, nsmp=150),
     # buried station (BOREHOLE_DEP; commented out in the reference, src/forward.f90:289-338, 493-516)
     "buried_land": dict(bdep=1.0), "buried_sea": dict(bdep=1.0, sdep=2.0),
     "buried_S": dict(bdep=7.3, ipha=[-1, -1], rayps=[0.10, 0.12]), "buried_half_space": dict(bdep=25.0),
@@ -58,6 +66,25 @@ def test_eval_batch_matches_oracle(name):
     assert np.array_equal(val_g, val_o)
     assert helpers.rel_err_rft(rft_g, rft_o) < RTOL
     assert helpers.logl_err(cfg, ll_g, ll_o, m["sig"]) < RTOL
+
+
+@pytest.mark.parametrize("nfft", [96, 250, 375, 1000, 2000])
+def test_lengths_that_are_not_powers_of_two_against_numpy_irfft(nfft):
+    """The complete RF (prop_rft(nfft, ntrc)) of the Bluestein path against the numpy restatement, whose c2r is
+    numpy.fft.irfft(x, n) * n for any n (the C restatement sums the defining series instead): three independent
+    evaluations of the same transform."""
+    import rfinv_oracle as pyo
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(nfft=nfft, nsmp=min(101, nfft), sdep=1.0, ipha=[1, -1], rayps=[0.06, 0.10]), noise=0.01)
+    m = workloads.draw_models(cfg, 6, seed=11, dvs_scale=0.3)
+    with Evaluator(cfg) as ev:
+        ll, rft, _ = ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_rft=True)
+    pc = helpers.py_config(cfg)
+    flt = pyo.init_filter(pc)
+    rinv = np.transpose(cfg.r_inv, (2, 1, 0))
+    for i in range(6):
+        ll_n, rft_n = pyo.calc_likelihood(pc, flt, rinv, int(m["k"][i]), m["z"][i], m["dvp"][i], m["dvs"][i], m["sig"][i])
+        assert helpers.rel_err_rft(rft[i][None], rft_n.T[None]) < RTOL
+        assert helpers.logl_err(cfg, ll[i:i + 1], np.array([ll_n]), m["sig"][i:i + 1]) < RTOL
 
 
 def test_golden_traces_from_reference_fixture():

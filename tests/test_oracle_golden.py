@@ -125,6 +125,22 @@ def test_numpy_oracle_reproduces_committed_vectors(name):
         assert helpers.logl_err(cfg, np.array([ll]), V[name + "/logl"][i:i + 1], V[name + "/sig"][i:i + 1]) < 1e-11
 
 
+@pytest.mark.parametrize("nfft", [96, 250, 375, 1000])
+def test_c_oracle_matches_numpy_oracle_for_lengths_that_are_not_powers_of_two(nfft):
+    """FFTW takes any length (src/fftw.f90:43-45).  numpy restatement: numpy.fft.irfft(x, n) * n; C restatement: the
+    defining sum over the half spectrum -- independent of each other and of the product's Bluestein path."""
+    cfg = helpers.attach_obs_and_rinv(helpers.small_config(nfft=nfft, nsmp=min(101, nfft), sdep=1.0, ipha=[1, -1], rayps=[0.06, 0.10]), noise=0.01)
+    m = workloads.draw_models(cfg, 4, seed=11, dvs_scale=0.3)
+    ll, rft, _ = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
+    pc = helpers.py_config(cfg)
+    flt = pyo.init_filter(pc)
+    rinv = np.transpose(cfg.r_inv, (2, 1, 0))
+    for i in range(4):
+        ll_n, rft_n = pyo.calc_likelihood(pc, flt, rinv, int(m["k"][i]), m["z"][i], m["dvp"][i], m["dvs"][i], m["sig"][i])
+        assert helpers.rel_err_rft(rft[i][None], rft_n.T[None]) < 1e-12
+        assert helpers.logl_err(cfg, ll[i:i + 1], np.array([ll_n]), m["sig"][i:i + 1]) < 1e-10
+
+
 def test_format_model_c_vs_numpy_bit_exact():
     cfg = helpers.small_config(sdep=2.0, vp_mode=1)
     pc = helpers.py_config(cfg)
