@@ -447,6 +447,7 @@ def main():
                 pt.run_distributed(n)
 
         pt_iters(5)
+        pt_exchange = pt.exchange_mode
         barrier()
         n_eval0 = pt.counters()["n_eval"]
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -461,8 +462,11 @@ def main():
                    "forward_evals_per_s": n_eval / (pt_ms * 1e-3), "iters": args.pt_iters, "chains_total": world * pt.n_local,
                    "virtual_ranks": nproc_total, "chains_per_rank": nch, "k_mean_after": round(k_pt, 2),
                    "launch": "one CUDA graph launch per iteration (rfinv_pt_run / rfinv_pt_run_distributed)",
-                   "exchange": "none (single process)" if world == 1 else
-                               "one ncclAllGather of the (T, logL, next-uniform) tables per iteration, issued by the library inside the iteration's graph"}
+                   "exchange": "none (single process)" if world == 1 else (
+                       "peer memory: pt_table_kernel stores the (T, logL, next-uniform) table into every process's gather buffer (CUDA IPC "
+                       "over NVLink) and raises a flag, pt_swap_kernel waits for the flags -- no collective call in the iteration"
+                       if pt_exchange == "peer memory" else
+                       "one ncclAllGather of the (T, logL, next-uniform) tables per iteration, issued by the library inside the iteration's graph")}
         pt.close()
         if not args.no_configs:
             # the same loop with chains as deep as the evaluation batch: a dVs prior of 0.3 km/s lets init_model keep models with

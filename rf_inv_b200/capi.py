@@ -55,6 +55,7 @@ SIGNATURES = {
     "rfinv_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "rfinv_comm_destroy": (C.c_int32, [C.c_void_p]),
     "rfinv_comm_info": (C.c_int32, [C.c_void_p, i32p, i32p, i32p]),
+    "rfinv_pt_exchange_mode": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_run_distributed": (C.c_int32, [C.c_void_p, C.c_int32]),
     "rfinv_pt_reduce_outputs": (C.c_int32, [C.c_void_p]),
     "rfinv_pt_local_step": (C.c_int32, [C.c_void_p]),

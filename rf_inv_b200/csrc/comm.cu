@@ -20,7 +20,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclUint64 = 5, ncclFloat64 = 8 };
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclUint64 = 5, ncclFloat64 = 8 };
 enum { ncclSum = 0 };
 
 struct NcclApi {
@@ -72,6 +72,95 @@ int rfinv_comm_allgather(rfinv_handle* h, const double* send, double* recv, size
   if (!api || !h->comm) { rfinv_set_error("no communicator: call rfinv_comm_init first"); return RFINV_ERR_STATE; }
   RFINV_NCCL_CHECK(api, api->AllGather(send, recv, count, ncclFloat64, (ncclComm_t)h->comm, s));
   return RFINV_OK;
+}
+
+// ---- swap exchange over peer memory (rfinv_pt.h: PtPeers) ---------------------------------------------------------
+// Collective over the handle's communicator, outside any capture: every process allocates its gather buffer and flag
+// words (one allocation), exports it through CUDA IPC, the 64-byte handles travel by ncclAllGather, every process maps its peers'
+// buffers (cudaIpcMemLazyEnablePeerAccess: NVLink peer access) and the outcome is agreed on by a second all-gather -- one
+// process that cannot map a peer (no peer access, another node, IPC forbidden by the container) keeps the NCCL all-gather
+// for everybody.  RFINV_PT_EXCHANGE=nccl forces that.  The all-gathers double as the barrier between "my flags are zero"
+// and "a peer raises one".
+int rfinv_comm_peer_setup(rfinv_handle* h) {
+  PtState* s = h->pt;
+  NcclApi* api = nccl_api();
+  if (!s || !api || !h->comm) { rfinv_set_error("rfinv_comm_peer_setup: no communicator"); return RFINV_ERR_STATE; }
+  const int world = h->comm_world, me = h->comm_rank;
+  ncclComm_t comm = (ncclComm_t)h->comm;
+  cudaStream_t q = h->stream;
+  s->peer_state = -1;
+  const char* mode = getenv("RFINV_PT_EXCHANGE");
+  int want = !(mode && std::strcmp(mode, "nccl") == 0) && world <= RFINV_MAX_PEERS;
+  RFINV_CUDA_CHECK(cudaSetDevice(h->device));
+  struct Blob { cudaIpcMemHandle_t mem; int ok; int pad[3]; };
+  Blob mine;
+  std::memset(&mine, 0, sizeof(mine));
+  const size_t n_gather = (size_t)2 * world * s->table_len;
+  if (want) {
+    // one allocation (one IPC handle): [2][world][table_len] doubles, then world + 1 flag words
+    if (cudaMalloc((void**)&s->d_peer_gather, sizeof(double) * n_gather + sizeof(unsigned long long) * (world + 1)) != cudaSuccess ||
+        cudaMalloc((void**)&s->peers.done, sizeof(int)) != cudaSuccess) want = 0;
+  }
+  if (want) {
+    s->d_peer_flags = reinterpret_cast<unsigned long long*>(s->d_peer_gather + n_gather);
+    cudaMemset(s->d_peer_gather, 0, sizeof(double) * n_gather + sizeof(unsigned long long) * (world + 1));
+    cudaMemset(s->peers.done, 0, sizeof(int));
+    if (cudaIpcGetMemHandle(&mine.mem, s->d_peer_gather) != cudaSuccess) want = 0;
+    cudaDeviceSynchronize();
+  }
+  cudaGetLastError();
+  mine.ok = want;
+  // exchange the blobs
+  std::vector<Blob> all(world);
+  char* d_blobs = nullptr;
+  RFINV_CUDA_CHECK(cudaMalloc((void**)&d_blobs, sizeof(Blob) * (world + 1)));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(d_blobs + sizeof(Blob) * world, &mine, sizeof(Blob), cudaMemcpyHostToDevice, q));
+  RFINV_NCCL_CHECK(api, api->AllGather(d_blobs + sizeof(Blob) * world, d_blobs, sizeof(Blob), ncclInt8, comm, q));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_blobs, sizeof(Blob) * world, cudaMemcpyDeviceToHost, q));
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(q));
+  int ok = 1;
+  for (int r = 0; r < world; ++r) ok &= all[r].ok;
+  PtPeers& px = s->peers;
+  px.world = world; px.me = me; px.table_len = s->table_len;
+  if (ok) {
+    for (int r = 0; r < world && ok; ++r) {
+      if (r == me) { px.gather[r] = s->d_peer_gather; px.flag[r] = s->d_peer_flags; continue; }
+      void* g = nullptr;
+      if (cudaIpcOpenMemHandle(&g, all[r].mem, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; g = nullptr; }
+      px.gather[r] = (double*)g;
+      px.flag[r] = g ? reinterpret_cast<unsigned long long*>((double*)g + n_gather) : nullptr;
+    }
+    cudaGetLastError();
+  }
+  // agree on the outcome
+  int* d_ok = reinterpret_cast<int*>(d_blobs);
+  std::vector<int> oks(world, 0);
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(d_ok + world, &ok, sizeof(int), cudaMemcpyHostToDevice, q));
+  RFINV_NCCL_CHECK(api, api->AllGather(d_ok + world, d_ok, 1, ncclInt32, comm, q));
+  RFINV_CUDA_CHECK(cudaMemcpyAsync(oks.data(), d_ok, sizeof(int) * world, cudaMemcpyDeviceToHost, q));
+  RFINV_CUDA_CHECK(cudaStreamSynchronize(q));
+  cudaFree(d_blobs);
+  int all_ok = 1;
+  for (int r = 0; r < world; ++r) all_ok &= oks[r];
+  if (all_ok) { s->peer_state = 1; return RFINV_OK; }
+  rfinv_comm_peer_release(h);
+  s->peer_state = -1;
+  return RFINV_OK;
+}
+
+void rfinv_comm_peer_release(rfinv_handle* h) {
+  PtState* s = h->pt;
+  if (!s) return;
+  PtPeers& px = s->peers;
+  for (int r = 0; r < px.world && r < RFINV_MAX_PEERS; ++r) {
+    if (r == px.me) continue;
+    if (px.gather[r]) cudaIpcCloseMemHandle(px.gather[r]);
+  }
+  cudaFree(s->d_peer_gather); cudaFree(px.done);   // (the flag words live in the gather allocation)
+  s->d_peer_gather = nullptr; s->d_peer_flags = nullptr;
+  std::memset(&px, 0, sizeof(px));
+  s->peer_state = 0;
+  cudaGetLastError();
 }
 
 extern "C" {

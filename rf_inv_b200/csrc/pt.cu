@@ -564,33 +564,83 @@ __global__ void __launch_bounds__(1024) pt_lhist_kernel(const PtDev p, double* l
 //   [0,Cl) temps | [Cl,2Cl) logL | [2Cl,2Cl+G) next uniform of every local stream | +0,+1: itarget1, itarget2 (-1 if
 //   this process does not own virtual rank 0).  The owner of rank 0 draws the pair first (consuming its stream).
 // One warp per virtual rank (cooperative mt19937 reload), plus a grid-stride copy of temps / logL.
-__global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* table) {
+// PEER: every entry also goes straight into slot `me` of every process's gather buffer (peer memory over NVLink), and the
+// last CTA to finish raises this process's flag on every process (rfinv_pt.h, PtPeers) -- the all-gather of the swap
+// exchange (src/pt_mcmc.f90:518-571) fused into the kernel that builds the table.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+template <bool PEER>
+__global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* table, const PtPeers px) {
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int r = gtid >> 5, lane = threadIdx.x & 31;
-  for (int c = gtid; c < p.Cl; c += gridDim.x * blockDim.x) {
-    table[c] = p.temps[c];
-    table[p.Cl + c] = p.logl[c];
-  }
-  if (r >= p.G) return;
-  Mt g(p.mt, r, p.mti[r], /*warp=*/true);
-  __syncwarp();
-  if (r == 0) {
-    double t1 = -1.0, t2 = -1.0;
-    if (p.rank_begin == 0 && p.nchains >= 2) {
-      const int n_all = p.nproc_total * p.nchains;
-      const int i1 = (int)(g.grnd() * (double)n_all);
-      int i2;
-      do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
-      t1 = i1; t2 = i2;
+  const int it = PEER ? *p.it_dev : 0;
+  const size_t slot = PEER ? ((size_t)(it & 1) * px.world + px.me) * px.table_len : 0;
+  auto put = [&](int idx, double v) {
+    table[idx] = v;
+    if (PEER) {
+#pragma unroll 1
+      for (int q = 0; q < px.world; ++q) px.gather[q][slot + idx] = v;
     }
-    if (lane == 0) { table[2 * p.Cl + p.G] = t1; table[2 * p.Cl + p.G + 1] = t2; }
+  };
+  for (int c = gtid; c < p.Cl; c += gridDim.x * blockDim.x) {
+    put(c, p.temps[c]);
+    put(p.Cl + c, p.logl[c]);
   }
-  const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
-  if (lane == 0) { table[2 * p.Cl + r] = u; p.mti[r] = g.mti; }
+  if (r < p.G) {
+    Mt g(p.mt, r, p.mti[r], /*warp=*/true);
+    __syncwarp();
+    if (r == 0) {
+      double t1 = -1.0, t2 = -1.0;
+      if (p.rank_begin == 0 && p.nchains >= 2) {
+        const int n_all = p.nproc_total * p.nchains;
+        const int i1 = (int)(g.grnd() * (double)n_all);
+        int i2;
+        do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
+        t1 = i1; t2 = i2;
+      }
+      if (lane == 0) { put(2 * p.Cl + p.G, t1); put(2 * p.Cl + p.G + 1, t2); }
+    }
+    const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
+    if (lane == 0) { put(2 * p.Cl + r, u); p.mti[r] = g.mti; }
+  }
+  if (PEER) {
+    __threadfence_system();     // this thread's stores into peer memory are ordered before the arrival below
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int arrived = atomicAdd(px.done, 1);
+      if (arrived == (int)gridDim.x - 1) {       // every CTA's stores precede its arrival: the table is complete everywhere
+        *px.done = 0;
+        __threadfence_system();
+        for (int q = 0; q < px.world; ++q) st_release_sys(px.flag[q] + px.me, (unsigned long long)it + 1ULL);
+      }
+    }
+  }
 }
 
 // judge_pt (src/pt_mcmc.f90:580-595) evaluated identically by every process from the gathered tables.
-__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len) {
+// PEER: `gathered` is this process's own gather buffer; lane q first waits until process q has raised its flag for this
+// iteration (bounded: a peer that never arrives -- it stopped on an error -- sets the error word instead of hanging the GPU).
+template <bool PEER>
+__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len, const PtPeers px) {
+  if (PEER) {
+    const int it = *p.it_dev;
+    if ((int)threadIdx.x < world) {
+      const unsigned long long* f = px.flag[px.me] + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) < (unsigned long long)it + 1ULL) {
+        if (clock64() - t0 > 40000000000LL) { px.flag[px.me][world] = 1ULL; break; }   // ~20 s
+        __nanosleep(200);
+      }
+    }
+    __syncwarp();
+    gathered += (size_t)(it & 1) * world * table_len;
+  }
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   const int log_slot = pt_log_slot(p);
   *p.it_dev += 1;                    // the iteration is complete: the last kernel of its launch sequence
@@ -790,6 +840,7 @@ void rfinv_handle::free_pt() {
   cudaFree(pt->d_lhist); cudaFree(pt->d_lh_part); cudaFree(pt->d_lh_cnt); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
   if (pt->capture_stream) cudaStreamDestroy(pt->capture_stream);
   for (cudaGraphExec_t g : pt->graph) if (g) cudaGraphExecDestroy(g);
+  rfinv_comm_peer_release(this);
   delete pt;
   pt = nullptr;
 }
@@ -972,7 +1023,7 @@ static int pt_reserve_lhist(rfinv_handle* h, int upto) {
 
 // The launches of one iteration except the swap decision: proposal pass, batched evaluation, acceptance, likelihood
 // history, (posterior bookkeeping,) and this process's swap table.  Nothing here depends on the host's iteration counter.
-static int pt_enqueue_local(rfinv_handle* h, bool record) {
+static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = false) {
   PtState* s = h->pt;
   PtDev& d = s->dev;
   cudaStream_t q = h->stream;
@@ -1004,7 +1055,8 @@ static int pt_enqueue_local(rfinv_handle* h, bool record) {
   }
   {
     const int nb_rank = (d.G * 32 + 127) / 128, nb_copy = (d.Cl + 127) / 128;
-    pt_table_kernel<<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table);
+    if (s->peer_state == 1 && peer_exchange) pt_table_kernel<true><<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table, s->peers);
+    else pt_table_kernel<false><<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table, s->peers);
   }
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
@@ -1041,7 +1093,7 @@ int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t 
     rfinv_set_error("rfinv_pt_apply_swap: world=%d inconsistent with nproc_total=%d, rank_count=%d", world, s->dev.nproc_total, s->dev.G);
     return RFINV_ERR_ARG;
   }
-  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len);
+  pt_swap_kernel<false><<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len, s->peers);
   RFINV_CUDA_CHECK(cudaGetLastError());
   s->it_done++;
   return RFINV_OK;
@@ -1052,13 +1104,19 @@ int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t 
 static int pt_enqueue_iteration(rfinv_handle* h, int world, bool record) {
   PtState* s = h->pt;
   int st;
-  if ((st = pt_enqueue_local(h, record)) != RFINV_OK) return st;
+  const bool peer = world > 1 && s->peer_state == 1;
+  if ((st = pt_enqueue_local(h, record, peer)) != RFINV_OK) return st;
+  if (peer) {   // the table went into every process's gather buffer while it was built; the swap kernel waits for the flags
+    pt_swap_kernel<true><<<1, 32, 0, h->stream>>>(s->dev, s->d_peer_gather, world, s->table_len, s->peers);
+    RFINV_CUDA_CHECK(cudaGetLastError());
+    return RFINV_OK;
+  }
   const double* gathered = s->d_table;
   if (world > 1) {
     if ((st = rfinv_comm_allgather(h, s->d_table, s->d_gather, (size_t)s->table_len, h->stream)) != RFINV_OK) return st;
     gathered = s->d_gather;
   }
-  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, gathered, world, s->table_len);
+  pt_swap_kernel<false><<<1, 32, 0, h->stream>>>(s->dev, gathered, world, s->table_len, s->peers);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -1072,7 +1130,11 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
   int st;
   RFINV_CUDA_CHECK(cudaSetDevice(h->device));
   if ((st = pt_reserve_lhist(h, s->it_done + n_iter)) != RFINV_OK) return st;
-  if (world > 1 && s->cap_gather < world * s->table_len) {
+  if (world > 1 && s->peer_state == 0) {   // first distributed run since rfinv_pt_init: try the peer-memory exchange (collective)
+    if ((st = rfinv_comm_peer_setup(h)) != RFINV_OK) return st;
+    pt_drop_graphs(s);
+  }
+  if (world > 1 && s->peer_state != 1 && s->cap_gather < world * s->table_len) {
     cudaFree(s->d_gather); s->d_gather = nullptr; s->cap_gather = 0;
     if ((st = dalloc(&s->d_gather, (size_t)world * s->table_len)) != RFINV_OK) return st;
     s->cap_gather = world * s->table_len;
@@ -1110,6 +1172,11 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
     s->it_done++;
   }
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (world > 1 && s->peer_state == 1) {
+    unsigned long long err = 0ULL;
+    RFINV_CUDA_CHECK(cudaMemcpy(&err, s->d_peer_flags + world, sizeof(err), cudaMemcpyDeviceToHost));
+    if (err) { rfinv_set_error("rfinv_pt_run_distributed: a process never delivered its swap table (peer-memory exchange timed out)"); return RFINV_ERR_STATE; }
+  }
   return RFINV_OK;
 }
 
@@ -1126,7 +1193,12 @@ int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter) {
   return pt_iterate(h, n_iter, 1);
 }
 
-// one process per GPU: the handle's communicator (rfinv_comm_init) carries the per-iteration all-gather
+int32_t rfinv_pt_exchange_mode(rfinv_handle* h) {
+  if (!h || !h->pt || !h->comm || h->comm_world < 2) return 0;
+  return h->pt->peer_state == 1 ? 1 : (h->pt->peer_state == -1 ? 2 : 0);
+}
+
+// one process per GPU: the handle's communicator (rfinv_comm_init) carries the per-iteration exchange
 int32_t rfinv_pt_run_distributed(rfinv_handle* h, int32_t n_iter) {
   int st = pt_require(h, "rfinv_pt_run_distributed");
   if (st != RFINV_OK) return st;

@@ -73,5 +73,9 @@ struct rfinv_handle : EvalWorkspace {
 // comm.cu: all-gather of `count` doubles per process over the handle's communicator, on stream s (capturable)
 int rfinv_comm_allgather(rfinv_handle* h, const double* send, double* recv, size_t count, cudaStream_t s);
 extern "C" int32_t rfinv_comm_destroy(rfinv_handle* h);
+// comm.cu: peer-memory swap exchange (CUDA IPC over NVLink); collective over the handle's communicator.  Leaves
+// h->pt->peer_state = 1 (on) or -1 (some process cannot map its peers: the NCCL all-gather stays)
+int rfinv_comm_peer_setup(rfinv_handle* h);
+void rfinv_comm_peer_release(rfinv_handle* h);
 // pt.cu: after the job-wide sum, the bins whose means the reference assigns go back to the assigned value
 int rfinv_pt_fix_assigned_bins(rfinv_handle* h);

@@ -46,6 +46,21 @@ struct PtDev {
 
 struct ncclComm;   // NCCL communicator (comm.cu)
 
+// Swap exchange over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every process owns a gather buffer
+// [2][world][table_len] and a flag word per source process, both opened by every other process through CUDA IPC.
+// pt_table_kernel stores this process's swap table straight into slot `me` of EVERY process's gather buffer (parity =
+// iteration & 1) while it builds it, and the last of its CTAs then raises flag[me] = iteration + 1 on every process;
+// pt_swap_kernel waits for the `world` flags of its own process and reads its own buffer.  No collective call, no extra
+// launch: the exchange rides on the two kernels the iteration runs anyway.  (Double buffering: a process can only be one
+// iteration ahead of the slowest one, because its pt_swap_kernel needs every flag of the iteration before.)
+#define RFINV_MAX_PEERS 16
+struct PtPeers {
+  int world, me, table_len;
+  double* gather[RFINV_MAX_PEERS];               // gather buffer of process q (own: local memory, others: IPC mappings)
+  unsigned long long* flag[RFINV_MAX_PEERS];     // flag words of process q: [world] epochs + [world] the error word
+  int* done;                                     // arrival counter of pt_table_kernel's CTAs (local)
+};
+
 struct PtState {
   PtDev dev;
   int it_done = 0;
@@ -54,8 +69,13 @@ struct PtState {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   int graph_world = 0;
   cudaStream_t capture_stream = nullptr;
-  double* d_gather = nullptr;  // swap tables of all processes (distributed run)
+  double* d_gather = nullptr;  // swap tables of all processes (distributed run, NCCL all-gather)
   int cap_gather = 0;
+  // peer-memory exchange (comm.cu: rfinv_comm_peer_setup); peer_state 0 = not tried, 1 = on, -1 = unavailable (NCCL all-gather)
+  PtPeers peers = {};
+  int peer_state = 0;
+  double* d_peer_gather = nullptr;
+  unsigned long long* d_peer_flags = nullptr;
   int cap_lhist = 0;
   double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
   double* d_lh_part = nullptr; // per-CTA sums of pt_lhist_kernel

@@ -79,6 +79,12 @@ class ParallelTempering:
         self.init_comm(dist, torch)
         capi.check(self._lib.rfinv_pt_run_distributed(self.ev.handle, int(n_iter)))
 
+    @property
+    def exchange_mode(self) -> str:
+        """How run_distributed moves the swap tables: "peer memory" (stores into IPC-mapped peer buffers from the kernel that
+        builds the table), "nccl all-gather", or "none" (single process / not run yet)."""
+        return {0: "none", 1: "peer memory", 2: "nccl all-gather"}[int(self._lib.rfinv_pt_exchange_mode(self.ev.handle))]
+
     def run_distributed_torch(self, n_iter: int, dist, torch) -> None:
         """The same loop with the exchange done by torch.distributed (kept for comparison with the in-library collective).
         The handle must share torch's current stream (set_stream), or the all-gather races with the library's kernels."""

@@ -27,7 +27,8 @@ def identity_check(cfg, nproc_total, n_iter, world, rank, local_rank, dist, torc
     pt.init_comm(dist, torch)
     say("communicator up")
     pt.run_distributed(n_iter, dist, torch)
-    say("distributed run done")
+    exchange = pt.exchange_mode
+    say("distributed run done (exchange: %s)" % exchange)
     flags, itypes, swaps = pt.log(n_iter)
     st = pt.state()
     pt.reduce_outputs()
@@ -73,7 +74,7 @@ def identity_check(cfg, nproc_total, n_iter, world, rank, local_rank, dist, torc
                 parts["hist_" + k] = bool(np.allclose(hist[k], rhist[k], rtol=1e-12))
         detail = dict(flags_sha1=hashlib.sha1(r["flags"].tobytes()).hexdigest()[:16], accepted=int((r["flags"] == 1).sum()),
                       swaps_accepted=int(r["swaps"][:, 2].sum()), nmod=None if hist is None else int(hist["nmod"]),
-                      failed=[k for k, v in parts.items() if not v])
+                      failed=[k for k, v in parts.items() if not v], exchange=exchange)
     ok = all(parts.values())
     if not ok:
         say("FAILED: " + ", ".join(k for k, v in parts.items() if not v))
