@@ -750,7 +750,11 @@ __device__ __forceinline__ void publish_max(double v, double* s_red, int tid) {
 // PLO..PHI (first stage only; empty when PLO > PHI): legs of every butterfly that hold zeros because their bins lie above the
 // band limit of the trace (bins [J NT, n - J NT] except Nyquist): not loaded, not added.  The one exception is the
 // butterfly with offset 0 (thread 0), whose leg 4 is the Nyquist bin: its contribution (+-X on the 8 outputs) is added back.
-template <int LOG2N, int N, class Sync, int PLO = 8, int PHI = -1>
+// WL (warp-local later stages): with exactly one butterfly per thread and stage (n = 8 nthr) the butterflies of a warp cover,
+// from the second stage on, the same 256 consecutive elements in every stage -- after the first stage the warps no longer
+// exchange data until the transform is complete, so those stages are separated by __syncwarp instead of a CTA barrier (no
+// warp waits for the slowest one four times per transform).
+template <int LOG2N, int N, class Sync, int PLO = 8, int PHI = -1, bool WL = false>
 __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restrict__ stw, double& vmax, double* s_red, int tid,
                                            int nthr, Sync sync) {
   constexpr unsigned n = 1u << LOG2N, stride = N >> 3;
@@ -797,8 +801,9 @@ __device__ __forceinline__ void fft_stage8(double2* buf, const double2* __restri
     buf[pos[1]] = v[4]; buf[pos[5]] = v[5]; buf[pos[3]] = v[6]; buf[pos[7]] = v[7];
   }
   if (last) publish_max(vmax, s_red, tid);   // N == 8: no stage follows
-  sync();
-  if constexpr (N >= 64) fft_stage8<LOG2N, (N >> 3), Sync>(buf, stw + 7 * stride, vmax, s_red, tid, nthr, sync);
+  if constexpr (WL && N < (1 << LOG2N) && !(last && LOG2N % 3 == 0)) __syncwarp();   // (the barrier that ends the transform stays)
+  else sync();
+  if constexpr (N >= 64) fft_stage8<LOG2N, (N >> 3), Sync, 8, -1, WL>(buf, stw + 7 * stride, vmax, s_red, tid, nthr, sync);
 }
 
 // JP, NT (optional): the spectrum is zero in bins [JP NT, n - JP NT] except Nyquist (band limit of forward_kernel)
@@ -813,10 +818,17 @@ __device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2*
 #endif
   constexpr int PSH = LOG2N >= 9 ? LOG2N - 3 : 31;
   constexpr int REM = LOG2N % 3;          // what is left after the radix-8 stages: 1 (N = 1), 2 or 4
+#ifdef RFINV_NO_FFT_WARPLOCAL
+  constexpr bool WL = false;
+#else
+  constexpr bool WL = NT >= 32 && (NT << 3) == (1 << LOG2N) && LOG2N >= 9;   // one butterfly per thread and stage, whole warps
+#endif
   double vmax = -INFINITY;
-  fft_stage8<LOG2N, (1 << LOG2N), Sync, PLO, PHI>(buf, twq, vmax, s_red, tid, nthr, sync);
+  fft_stage8<LOG2N, (1 << LOG2N), Sync, PLO, PHI, WL>(buf, twq, vmax, s_red, tid, nthr, sync);
   if (REM == 2) {
-    for (unsigned j = tid; j < (n >> 2); j += nthr) {
+    // WL: the 64 quads of the warp's own 256 elements (two per lane) instead of quads tid, tid + nthr
+    for (unsigned jj = tid; jj < (n >> 2); jj += nthr) {
+      const unsigned j = WL ? (((unsigned)tid >> 5) << 6) + ((unsigned)tid & 31u) + ((jj >= (unsigned)nthr) ? 32u : 0u) : jj;
       const unsigned p0 = fpad(j << 2, PSH);     // the four elements share a pad group
       const double2 v0 = buf[p0], v1 = buf[p0 + 1], v2 = buf[p0 + 2], v3 = buf[p0 + 3];
       const double2 a0 = make_double2(v0.x + v2.x, v0.y + v2.y), a1 = make_double2(v0.x - v2.x, v0.y - v2.y);
@@ -829,7 +841,9 @@ __device__ __forceinline__ double fft_inverse_dif_n(double2* buf, const double2*
     publish_max(vmax, s_red, tid);
     sync();
   } else if (REM == 1) {
-    for (unsigned j = tid; j < (n >> 1); j += nthr) {
+    // WL: the 128 pairs of the warp's own 256 elements (four per lane) instead of pairs tid + i nthr
+    for (unsigned jj = tid, i = 0; jj < (n >> 1); jj += nthr, ++i) {
+      const unsigned j = WL ? (((unsigned)tid >> 5) << 7) + ((unsigned)tid & 31u) + 32u * i : jj;
       const unsigned p0 = fpad(j << 1, PSH);     // both elements share a pad group
       const double2 a = buf[p0], b = buf[p0 + 1];
       const double2 r0 = make_double2(a.x + b.x, a.y + b.y), r1 = make_double2(a.x - b.x, a.y - b.y);
