@@ -12,11 +12,14 @@
 
 static thread_local char g_err[1024] = "";
 
-bool rfinv_pdl_enabled() {
-  // measured on B200 (target shape, 16 384 chains, interleaved A/B): 1.3087 ms per step with programmatic launches against
-  // 1.2954 ms without -- the early forward_kernel CTAs get in the way of prep_kernel's last wave.  Off unless RFINV_PDL=1.
-  static const bool on = getenv("RFINV_PDL") && atoi(getenv("RFINV_PDL")) != 0;
-  return on;
+int rfinv_pdl_mode() {
+  // Programmatic dependent launch per kernel boundary, measured on B200 (target shape, 16 384 chains, 30 interleaved rounds):
+  //   none 1.2933 / 1.2953 ms per step;  prep -> forward only 1.3076 (forward_kernel's early CTAs cost prep_kernel's last wave
+  //   more than the hidden launch gains);  forward -> quadform only 1.2913 / 1.2933 (quadform_kernel's CTAs take the slots
+  //   forward_kernel's CTAs free one by one);  both 1.3056.  Default: the forward -> quadform edge.
+  // RFINV_PDL: bit 0 = the prep_kernel -> forward_kernel edge, bit 1 = the forward_kernel -> quadform_kernel edge.
+  static const int mode = getenv("RFINV_PDL") ? atoi(getenv("RFINV_PDL")) : 2;
+  return mode;
 }
 
 void rfinv_set_error(const char* fmt, ...) {

@@ -1602,7 +1602,7 @@ int launch_forward_t(const DevConfig& cfg, const ModelBatch& mb, const EvalOutpu
   const long long items = (long long)n_models * sel.n;
   const long long resident = (long long)n_sm * per_sm;   // persistent CTAs: one wave, items handed out dynamically
   const unsigned grid = (unsigned)(items < resident ? items : resident);
-  RFINV_CUDA_CHECK(rfinv_launch_pdl(forward_kernel<J, BMAX, MINB, MIXED, BURIED, GEN>, dim3(grid), dim3(nthr), smem, stream, cfg, mb, out, lc, rc, counter, sel));
+  RFINV_CUDA_CHECK(rfinv_launch_pdl(1, forward_kernel<J, BMAX, MINB, MIXED, BURIED, GEN>, dim3(grid), dim3(nthr), smem, stream, cfg, mb, out, lc, rc, counter, sel));
   return RFINV_OK;
 }
 

@@ -291,7 +291,7 @@ int rfinv_launch_quadform(const DevConfig& cfg, int C, const double* misfit, dou
     if (dev >= 0 && dev < 64) resident_of_device[dev] = (int)resident;
   }
   const long long items = (long long)ntile * cfg.ntrc * ((n_rows + TM - 1) / TM);
-  RFINV_CUDA_CHECK(rfinv_launch_pdl(quadform_kernel, dim3((unsigned)(items < resident ? items : resident)), dim3(QF_THREADS), 0, stream, cfg, C,
+  RFINV_CUDA_CHECK(rfinv_launch_pdl(2, quadform_kernel, dim3((unsigned)(items < resident ? items : resident)), dim3(QF_THREADS), 0, stream, cfg, C,
                                     misfit, phi, partial, arrivals, work, active, n_active, n_active_dev, sig, logl));
   return RFINV_OK;
 }

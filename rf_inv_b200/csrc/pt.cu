@@ -29,7 +29,23 @@ struct Mt {
   uint32_t* mt;
   int mti;
   bool warp;   // true: called by all 32 lanes of a warp in lock step
+  // warp mode: a window of the next 32 state words, one per lane (word win_base + lane), refilled with ONE coalesced load
+  // every 32 draws -- a draw is a shuffle, not a dependent trip to the L2 (the chains of a rank draw ~90 numbers per iteration
+  // one after the other)
+  uint32_t win = 0;
+  int win_base = -1024;
   __device__ Mt(uint32_t* base, int r, int mti_, bool warp_ = false) : mt(base + (size_t)r * 624), mti(mti_), warp(warp_) {}
+  __device__ void refill() {
+    win_base = mti;
+    const int i = mti + (int)(threadIdx.x & 31);
+    win = i < 624 ? mt[i] : 0u;
+  }
+  __device__ uint32_t word() {   // state word mti (after any reload), without consuming it
+    if (mti >= 624) { reload(); if (warp) refill(); }
+    if (!warp) return mt[mti];
+    if (mti - win_base >= 32 || mti < win_base) refill();
+    return __shfl_sync(0xffffffffu, win, mti - win_base);
+  }
   __device__ uint32_t& w(int i) { return mt[i]; }
   __device__ static uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far) {
     const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
@@ -68,12 +84,12 @@ struct Mt {
     return (double)y * 2.3283064365386963e-10;  // y / 2^32 (src/mt19937.f90:125-129: [0,1)); a power of two: the product is the exact quotient
   }
   __device__ double grnd() {
-    if (mti >= 624) reload();
-    return temper(w(mti++));
+    const uint32_t y = word();
+    ++mti;
+    return temper(y);
   }
   __device__ double peek() {  // next output without consuming it
-    if (mti >= 624) reload();
-    return temper(w(mti));
+    return temper(word());
   }
 };
 

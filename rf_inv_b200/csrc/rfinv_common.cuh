@@ -115,15 +115,15 @@ void rfinv_set_error(const char* fmt, ...);
 // (a kernel that never does releases its dependents when it exits).  Opt-in (RFINV_PDL=1): measured slower, see capi.cu.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool rfinv_pdl_enabled();
+int rfinv_pdl_mode();   // bit 0: prep_kernel -> forward_kernel edge, bit 1: forward_kernel -> quadform_kernel edge
 template <typename... KArgs, typename... Args>
-cudaError_t rfinv_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+cudaError_t rfinv_launch_pdl(int edge_bit, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = rfinv_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = (rfinv_pdl_mode() & edge_bit) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -11,8 +11,13 @@ from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 
 out = {"tolerance": 1e-9, "configs": {}}
-for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192), ("c3_deconv", 8192), ("c3_common", 8192), ("c4", 8192), ("c4_laplace", 4096), ("c5", 4096), ("target", 8192)]:
-    cfg = helpers.attach_obs_and_rinv(workloads.make_config(name), noise=0.01)
+# "<workload>@<nfft>": the workload with its transform length changed to one that is not a power of two (Bluestein path)
+for name, n in [("sample", 8192), ("c2", 8192), ("c3", 8192), ("c3_buried", 8192), ("c3_deconv", 8192), ("c3_common", 8192), ("c4", 8192), ("c4_laplace", 4096), ("c5", 4096), ("target", 8192),
+                ("target@1000", 2048), ("c3@600", 2048), ("c5@2000", 1024), ("sample@375", 4096)]:
+    base = workloads.make_config(name.split("@")[0])
+    if "@" in name:
+        base.nfft = int(name.split("@")[1]); base.nsmp = min(base.nsmp, base.nfft // 2)
+    cfg = helpers.attach_obs_and_rinv(base, noise=0.01)
     m = workloads.draw_models(cfg, n, seed=2024, dvs_scale=0.5)
     t0 = time.time()
     ll_o, rft_o, val_o, cond = oracle_c.eval_batch(cfg, m["k"], m["z"], m["dvp"], m["dvs"], m["sig"], want_cond=True)

@@ -10,7 +10,9 @@ from rf_inv_b200.evaluator import Evaluator
 from rf_inv_b200.pt import ParallelTempering
 for kw in (dict(sdep=2.0, ntrc=2), dict(nfft=1024, nsmp=300, k_max=12, ntrc=2, rayps=[0.05, 0.07], a_gus=[2.0, 4.0], sig_min=[0.01, 0.01], sig_max=[0.02, 0.01]),
            dict(rayps=[0.06, 0.06], a_gus=[2.0, 4.0]), dict(deconv_mode=1), dict(bdep=1.0, sdep=2.0), dict(bdep=25.0),
-           dict(bdep=6.0, rayps=[0.06, 0.06], nsmp=100)):
+           dict(bdep=6.0, rayps=[0.06, 0.06], nsmp=100),
+           dict(nfft=250, nsmp=101, sdep=1.0), dict(nfft=375, nsmp=150, ipha=[1, -1], rayps=[0.06, 0.11]),     # Bluestein path, even / odd
+           dict(nfft=600, nsmp=200, deconv_mode=1), dict(nfft=1000, nsmp=300, bdep=2.0, k_max=12)):
     cfg = helpers.attach_obs_and_rinv(helpers.small_config(**kw), noise=0.01)
     m = workloads.draw_models(cfg, 40, seed=3, dvs_scale=0.3)
     with Evaluator(cfg) as ev:
