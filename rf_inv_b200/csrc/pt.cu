@@ -29,23 +29,9 @@ struct Mt {
   uint32_t* mt;
   int mti;
   bool warp;   // true: called by all 32 lanes of a warp in lock step
-  // warp mode: a window of the next 32 state words, one per lane (word win_base + lane), refilled with ONE coalesced load
-  // every 32 draws -- a draw is a shuffle, not a dependent trip to the L2 (the chains of a rank draw ~90 numbers per iteration
-  // one after the other)
-  uint32_t win = 0;
-  int win_base = -1024;
   __device__ Mt(uint32_t* base, int r, int mti_, bool warp_ = false) : mt(base + (size_t)r * 624), mti(mti_), warp(warp_) {}
-  __device__ void refill() {
-    win_base = mti;
-    const int i = mti + (int)(threadIdx.x & 31);
-    win = i < 624 ? mt[i] : 0u;
-  }
-  __device__ uint32_t word() {   // state word mti (after any reload), without consuming it
-    if (mti >= 624) { reload(); if (warp) refill(); }
-    if (!warp) return mt[mti];
-    if (mti - win_base >= 32 || mti < win_base) refill();
-    return __shfl_sync(0xffffffffu, win, mti - win_base);
-  }
+  // (measured: serving the draws of a warp from a register window of the next 32 state words -- one coalesced load per 32
+  // draws, a shuffle per draw -- is slower than reading the word, which hits the L1: 867 vs 860 us per PT iteration)
   __device__ uint32_t& w(int i) { return mt[i]; }
   __device__ static uint32_t twist(uint32_t cur, uint32_t nxt, uint32_t far) {
     const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7fffffffu);
@@ -84,12 +70,12 @@ struct Mt {
     return (double)y * 2.3283064365386963e-10;  // y / 2^32 (src/mt19937.f90:125-129: [0,1)); a power of two: the product is the exact quotient
   }
   __device__ double grnd() {
-    const uint32_t y = word();
-    ++mti;
-    return temper(y);
+    if (mti >= 624) reload();
+    return temper(w(mti++));
   }
   __device__ double peek() {  // next output without consuming it
-    return temper(word());
+    if (mti >= 624) reload();
+    return temper(w(mti));
   }
 };
 
@@ -268,7 +254,7 @@ __device__ bool model_valid_warp(const DevConfig& cfg, int k, double z0, double 
 __host__ __device__ inline int pt_propose_stride(int km, int T) { return (3 * km + T) | 1; }     // odd: conflict-free transposition
 __host__ __device__ inline size_t pt_propose_smem_doubles(int km, int T, int nchains) { return (size_t)2 * nchains * pt_propose_stride(km, T); }
 template <bool STAGED>
-__global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p) {
+__global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p, double* __restrict__ table) {
   extern __shared__ __align__(16) double pp_smem[];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -429,7 +415,24 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
       }
     }
   }
-  if (lane == 0) p.mti[r] = g.mti;
+  // The rank's part of the swap table (src/pt_mcmc.f90:501-516), here because it is the rank's last use of its stream in the
+  // iteration: the owner of virtual rank 0 draws the pair (consuming its stream), then every rank leaves the NEXT uniform of
+  // its stream -- what judge_pt would draw if the rank turns out to be rank1 -- without consuming it (pt_swap_kernel does).
+  if (r == 0) {
+    double t1 = -1.0, t2 = -1.0;
+    if (p.rank_begin == 0 && p.nchains >= 2) {
+      const int n_all = p.nproc_total * p.nchains;
+      const int i1 = (int)(g.grnd() * (double)n_all);
+      int i2;
+      do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
+      t1 = i1; t2 = i2;
+    }
+    if (lane == 0) { table[2 * Cl + p.G] = t1; table[2 * Cl + p.G + 1] = t2; }
+  }
+  {
+    const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
+    if (lane == 0) { table[2 * Cl + r] = u; p.mti[r] = g.mti; }
+  }
   if (STAGED) {
     __syncwarp();
     if (even) {
@@ -451,39 +454,24 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
       p.pk[c] = o_pk; p.itype[c] = (int8_t)o_itype; p.pflag[c] = (int8_t)o_pflag; p.log_r[c] = o_logr; p.log_prior12[c] = o_lp12;
     }
   }
+  // List of the chains that need a forward evaluation (pflag == 1), built here: one atomicAdd per rank reserves the rank's
+  // slots, its chains go in ascending order.  The order of the ranks in the list follows their arrival -- it only decides
+  // which CTA evaluates which chain; every chain's result is computed on its own (no sum runs across rows of a block), so the
+  // results do not depend on it.  *p.n_active was left at zero by the previous iteration's pt_swap_kernel.
+  __syncwarp();
+  for (int base = 0; base < nch; base += 32) {
+    const int ic = base + lane;
+    int f;
+    if (STAGED && nch <= 32) f = lane < nch && o_pflag == 1;
+    else f = ic < nch && __ldcg(reinterpret_cast<const signed char*>(p.pflag) + c0 + ic) == 1;   // written by lane 0 above
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    int pos = 0;
+    if (lane == 0 && m) { pos = atomicAdd(p.n_active, __popc(m)); atomicAdd(p.n_eval, (unsigned long long)__popc(m)); }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (f) p.active[pos + __popc(m & ((1u << lane) - 1u))] = c0 + ic;
+  }
 }
 
-// Ordered compaction of the chains that need a forward evaluation: one CTA, ONE round -- thread t owns the q = ceil(Cl / 1024)
-// consecutive chains [t q, (t+1) q), counts their flags, the CTA scans the 1024 counts (warp shuffles + one scan of the warp
-// totals) and every thread writes its chains at its offset.  Deterministic, ascending chain order.
-__global__ void __launch_bounds__(1024) pt_compact_kernel(const PtDev p) {
-  __shared__ int s_warp[32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = (p.Cl + 1023) / 1024;
-  const int c_begin = tid * q, c_end = min(p.Cl, c_begin + q);
-  int cnt = 0;
-  for (int c = c_begin; c < c_end; ++c) cnt += p.pflag[c] == 1;
-  int incl = cnt;                                   // inclusive scan inside the warp
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += u;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    int v = s_warp[lane];
-    for (int o = 1; o < 32; o <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += u;
-    }
-    s_warp[lane] = v;                               // inclusive scan of the warp totals
-  }
-  __syncthreads();
-  int pos = (warp ? s_warp[warp - 1] : 0) + incl - cnt;
-  for (int c = c_begin; c < c_end; ++c)
-    if (p.pflag[c] == 1) p.active[pos++] = c;
-  if (tid == 0) { const int total = s_warp[31]; *p.n_active = total; *p.n_eval += (unsigned long long)total; }
-}
 
 // ---------------- acceptance: src/pt_mcmc.f90:178-201, one thread per chain ----------------
 // slot of the current iteration in the optional logs, or -1
@@ -493,96 +481,6 @@ __device__ __forceinline__ int pt_log_slot(const PtDev& p) {
   return (s >= 0 && s < p.log_cap) ? s : -1;
 }
 
-__global__ void pt_accept_kernel(const DevConfig cfg, const PtDev p) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= p.Cl) return;
-  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
-  const int flag = p.pflag[c];
-  const double temp = p.temps[c];
-  int yn = 0;
-  if (flag != -1) {
-    double ll = 0.0;
-    for (int t = 0; t < T; ++t) {  // src/likelihood.f90:94-96; sigma-only proposals reuse the cached phi (same rft, same obs)
-      const double ph = flag == 1 ? p.pphi[(size_t)t * Cl + c] : p.phi[(size_t)t * Cl + c];
-      const double s = p.psig[(size_t)t * Cl + c];
-      ll = __dsub_rn(__dsub_rn(ll, __ddiv_rn(__dmul_rn(0.5, ph), __dmul_rn(s, s))), __dmul_rn((double)cfg.nsmp, log(s)));
-    }
-    const double del_s = __dadd_rn(__ddiv_rn(__dsub_rn(ll, p.logl[c]), temp), p.log_prior12[c]);  // src/pt_mcmc.f90:608
-    yn = p.log_r[c] <= del_s;
-    if (yn) {   // the model arrays follow in pt_adopt_kernel (one thread per array element instead of a loop per chain)
-      p.logl[c] = ll;
-      p.k[c] = p.pk[c];
-      if (flag == 1) p.slot[c] ^= 1;  // the proposal's RF samples were written to the other slot
-    }
-  }
-  p.pflag[c] = (int8_t)(yn ? (flag == 1 ? 3 : 4) : 0);   // for pt_adopt_kernel: 3 = adopt model and phi, 4 = model only
-  if (temp <= 1.0 + (double)1.0e-6f) {  // src/pt_mcmc.f90:196-201
-    atomicAdd(&p.nprop[p.itype[c] - 1], 1ULL);
-    if (yn) atomicAdd(&p.naccept[p.itype[c] - 1], 1ULL);
-  }
-  const int log_slot = pt_log_slot(p);
-  if (log_slot >= 0) {
-    p.log_flags[(size_t)log_slot * Cl + c] = (int8_t)(flag == -1 ? -1 : yn);
-    p.log_itypes[(size_t)log_slot * Cl + c] = p.itype[c];
-  }
-}
-
-// accepted proposals become the current state (src/pt_mcmc.f90:186-194): rows z | dvp | dvs | sig | phi, chain fastest
-__global__ void pt_adopt_kernel(const DevConfig cfg, const PtDev p) {
-  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
-  const int rows = 3 * km - 1 + 2 * T;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)rows * Cl) return;
-  int row = (int)(idx / Cl);
-  const int c = (int)(idx - (long long)row * Cl);
-  const int code = p.pflag[c];
-  if (code < 3) return;
-  const double* src; double* dst;
-  if (row < km - 1) { src = p.pz; dst = p.z; }
-  else if ((row -= km - 1) < km) { src = p.pdvp; dst = p.dvp; }
-  else if ((row -= km) < km) { src = p.pdvs; dst = p.dvs; }
-  else if ((row -= km) < T) { src = p.psig; dst = p.sig; }
-  else { if (code != 3) return; row -= T; src = p.pphi; dst = p.phi; }
-  dst[(size_t)row * Cl + c] = src[(size_t)row * Cl + c];
-}
-
-// likelihood_hist(it) = sum of logL over non-tempered chains (src/pt_mcmc.f90:199-200).  One CTA per 1024 chains (one
-// coalesced load per thread, tree sum); the CTA that arrives last adds the per-CTA sums in CTA order: the same value from run
-// to run whatever the schedule.
-__global__ void __launch_bounds__(1024) pt_lhist_kernel(const PtDev p, double* lhist, double* part, int* arrived) {
-  __shared__ double s[1024];
-  __shared__ int s_last;
-  const int tid = threadIdx.x, c = blockIdx.x * 1024 + tid;
-  double v = 0.0;
-  if (c < p.Cl) { const double t = p.temps[c], l = p.logl[c]; v = t <= 1.0 + (double)1.0e-6f ? l : 0.0; }
-  s[tid] = v;
-  __syncthreads();
-  for (int o = 512; o > 0; o >>= 1) {
-    if (tid < o) s[tid] += s[tid + o];
-    __syncthreads();
-  }
-  if (tid == 0) {
-    part[blockIdx.x] = s[0];
-    __threadfence();
-    s_last = atomicAdd(arrived, 1) == (int)gridDim.x - 1;
-  }
-  __syncthreads();
-  if (s_last && tid == 0) {
-    __threadfence();
-    double acc = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) acc += __ldcg(part + b);
-    lhist[*p.it_dev] = acc;
-    *arrived = 0;
-  }
-}
-
-// Swap table of this process (src/pt_mcmc.f90:501-571 needs (T, logL) of two chains anywhere in the job):
-//   [0,Cl) temps | [Cl,2Cl) logL | [2Cl,2Cl+G) next uniform of every local stream | +0,+1: itarget1, itarget2 (-1 if
-//   this process does not own virtual rank 0).  The owner of rank 0 draws the pair first (consuming its stream).
-// One warp per virtual rank (cooperative mt19937 reload), plus a grid-stride copy of temps / logL.
-// PEER: every entry also goes straight into slot `me` of every process's gather buffer (peer memory over NVLink), and the
-// last CTA to finish raises this process's flag on every process (rfinv_pt.h, PtPeers) -- the all-gather of the swap
-// exchange (src/pt_mcmc.f90:518-571) fused into the kernel that builds the table.
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -591,11 +489,63 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-template <bool PEER>
-__global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* table, const PtPeers px) {
-  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int r = gtid >> 5, lane = threadIdx.x & 31;
-  const int it = PEER ? *p.it_dev : 0;
+
+// judge_pt (src/pt_mcmc.f90:580-595) on the gathered swap tables (`world` tables of table_len doubles, process order; a
+// single process: its own table); called by ONE thread.  Ends the iteration: advances the device-side iteration counter and
+// empties the list of chains to evaluate.
+__device__ void pt_swap_decide(const PtDev& p, const double* gathered, int world, int table_len) {
+  const int log_slot = pt_log_slot(p);
+  *p.it_dev += 1;                    // the iteration is complete
+  *p.n_active = 0;                   // pt_propose_kernel of the next iteration appends to an empty list
+  if (p.nchains < 2) return;
+  const int G = p.G, Cl = p.Cl;
+  const double* t0 = gathered;  // process 0 owns virtual rank 0
+  const int i1 = (int)__ldcg(t0 + 2 * Cl + G), i2 = (int)__ldcg(t0 + 2 * Cl + G + 1);
+  const int own1 = i1 / Cl, own2 = i2 / Cl, l1 = i1 - own1 * Cl, l2 = i2 - own2 * Cl;
+  const double* ta = gathered + (size_t)own1 * table_len;
+  const double* tb = gathered + (size_t)own2 * table_len;
+  const double temp1 = __ldcg(ta + l1), temp2 = __ldcg(tb + l2), e1 = __ldcg(ta + Cl + l1), e2 = __ldcg(tb + Cl + l2);
+  const int rank1_local = l1 / p.nchains;
+  const double u = __ldcg(ta + 2 * Cl + rank1_local);
+  const double del_s = __dmul_rn(__dsub_rn(e2, e1), __dsub_rn(__ddiv_rn(1.0, temp1), __ddiv_rn(1.0, temp2)));
+  const int yn = log(u) <= del_s;
+  const int me = p.rank_begin / G;
+  if (me == own1) {
+    p.mti[rank1_local] += 1;  // the stream of rank1 consumed the judge_pt uniform
+    if (yn) p.temps[l1] = temp2;
+  }
+  if (me == own2 && yn) p.temps[l2] = temp1;
+  if (log_slot >= 0) {
+    p.log_swaps[3 * log_slot] = i1; p.log_swaps[3 * log_slot + 1] = i2; p.log_swaps[3 * log_slot + 2] = yn;
+  }
+}
+
+// ---------------- the tail of an iteration in ONE kernel, one thread per chain ----------------
+//   acceptance            src/pt_mcmc.f90:178-201 (judge_mcmc :600-621)
+//   adoption              src/pt_mcmc.f90:186-194: the accepted proposal becomes the state (rows z | dvp | dvs | sig | phi)
+//   likelihood_hist(it)   src/pt_mcmc.f90:199-200: tree sum per CTA; the CTA that arrives last adds the per-CTA sums in CTA order
+//                         (the same value from run to run whatever the schedule)
+//   swap table            [0,Cl) temps | [Cl,2Cl) logL | [2Cl,2Cl+G) next uniform of every local stream | itarget1, itarget2
+//                         (the last G + 2 entries were left by pt_propose_kernel)
+// PEER: every entry of the table also goes straight into slot `me` of every process's gather buffer (peer memory over
+// NVLink) and the last CTA raises this process's flag on every process (rfinv_pt.h, PtPeers) -- the all-gather of the swap
+// exchange (src/pt_mcmc.f90:518-571) fused into the kernel that produces its payload.
+// SWAP (single process, no bookkeeping kernels in between): the last CTA also takes the swap decision.
+// (Four kernels -- accept, adopt, likelihood history, table -- and a fifth for the swap until round 2: every boundary
+// between two small dependent kernels costs more than the kernels themselves.)
+constexpr int PT_FIN_THREADS = 128;   // 32 chains per CTA: warp 0 decides, the four warps share the rows of the adoption
+constexpr int PT_FIN_CHAINS = 32;
+template <bool PEER, bool SWAP>
+__global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConfig cfg, const PtDev p, double* __restrict__ table,
+                                                                   const PtPeers px, double* __restrict__ lhist,
+                                                                   double* __restrict__ part, int* __restrict__ arrived) {
+  __shared__ double s_sum[PT_FIN_THREADS / 32];
+  __shared__ int s_code[PT_FIN_CHAINS];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x * PT_FIN_CHAINS + lane;
+  const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
+  const int it = *p.it_dev;
   const size_t slot = PEER ? ((size_t)(it & 1) * px.world + px.me) * px.table_len : 0;
   auto put = [&](int idx, double v) {
     table[idx] = v;
@@ -604,38 +554,110 @@ __global__ void __launch_bounds__(128) pt_table_kernel(const PtDev p, double* ta
       for (int q = 0; q < px.world; ++q) px.gather[q][slot + idx] = v;
     }
   };
-  for (int c = gtid; c < p.Cl; c += gridDim.x * blockDim.x) {
-    put(c, p.temps[c]);
-    put(p.Cl + c, p.logl[c]);
-  }
-  if (r < p.G) {
-    Mt g(p.mt, r, p.mti[r], /*warp=*/true);
-    __syncwarp();
-    if (r == 0) {
-      double t1 = -1.0, t2 = -1.0;
-      if (p.rank_begin == 0 && p.nchains >= 2) {
-        const int n_all = p.nproc_total * p.nchains;
-        const int i1 = (int)(g.grnd() * (double)n_all);
-        int i2;
-        do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
-        t1 = i1; t2 = i2;
+  double cold_logl = 0.0;
+  if (warp == 0) {
+    int code = 0;   // 3: adopt model and phi, 4: model only (sigma-only proposal), 0: nothing
+    if (c < Cl) {
+      const int flag = p.pflag[c];
+      const double temp = p.temps[c];
+      double logl = p.logl[c];
+      int yn = 0;
+      if (flag != -1) {
+        double ll = 0.0;
+        for (int t = 0; t < T; ++t) {  // src/likelihood.f90:94-96; sigma-only proposals reuse the cached phi (same rft, same obs)
+          const double ph = flag == 1 ? p.pphi[(size_t)t * Cl + c] : p.phi[(size_t)t * Cl + c];
+          const double sg = p.psig[(size_t)t * Cl + c];
+          ll = __dsub_rn(__dsub_rn(ll, __ddiv_rn(__dmul_rn(0.5, ph), __dmul_rn(sg, sg))), __dmul_rn((double)cfg.nsmp, log(sg)));
+        }
+        const double del_s = __dadd_rn(__ddiv_rn(__dsub_rn(ll, logl), temp), p.log_prior12[c]);  // src/pt_mcmc.f90:608
+        yn = p.log_r[c] <= del_s;
+        if (yn) {
+          logl = ll;
+          p.logl[c] = ll;
+          p.k[c] = p.pk[c];
+          if (flag == 1) p.slot[c] ^= 1;  // the proposal's RF samples were written to the other slot
+          code = flag == 1 ? 3 : 4;
+        }
       }
-      if (lane == 0) { put(2 * p.Cl + p.G, t1); put(2 * p.Cl + p.G + 1, t2); }
+      const bool cold = temp <= 1.0 + (double)1.0e-6f;
+      if (cold) {  // src/pt_mcmc.f90:196-201
+        atomicAdd(&p.nprop[p.itype[c] - 1], 1ULL);
+        if (yn) atomicAdd(&p.naccept[p.itype[c] - 1], 1ULL);
+        cold_logl = logl;
+      }
+      const int log_slot = pt_log_slot(p);
+      if (log_slot >= 0) {
+        p.log_flags[(size_t)log_slot * Cl + c] = (int8_t)(flag == -1 ? -1 : yn);
+        p.log_itypes[(size_t)log_slot * Cl + c] = p.itype[c];
+      }
+      put(c, temp);
+      put(Cl + c, logl);
     }
-    const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
-    if (lane == 0) { put(2 * p.Cl + r, u); p.mti[r] = g.mti; }
+    s_code[lane] = code;
+    // likelihood history: fixed tree over the CTA's chains
+    for (int o = 16; o > 0; o >>= 1) cold_logl += __shfl_down_sync(0xffffffffu, cold_logl, o);
+    if (lane == 0) part[blockIdx.x] = cold_logl;
   }
-  if (PEER) {
-    __threadfence_system();     // this thread's stores into peer memory are ordered before the arrival below
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int arrived = atomicAdd(px.done, 1);
-      if (arrived == (int)gridDim.x - 1) {       // every CTA's stores precede its arrival: the table is complete everywhere
-        *px.done = 0;
-        __threadfence_system();
-        for (int q = 0; q < px.world; ++q) st_release_sys(px.flag[q] + px.me, (unsigned long long)it + 1ULL);
+  __syncthreads();
+  {
+    // the accepted proposals become the state (src/pt_mcmc.f90:186-194): rows z | dvp | dvs | sig | phi of the chain-fastest
+    // arrays; lane <-> chain (coalesced), the four warps take every fourth row, eight independent copies in flight
+    const int code = s_code[lane];
+    if (code >= 3) {
+      const int rows = 3 * km - 1 + T + (code == 3 ? T : 0);   // phi only when the forward model ran
+      auto row_ptrs = [&](int row, const double*& src, double*& dst) {
+        if (row < km - 1) { src = p.pz; dst = p.z; }
+        else if ((row -= km - 1) < km) { src = p.pdvp; dst = p.dvp; }
+        else if ((row -= km) < km) { src = p.pdvs; dst = p.dvs; }
+        else if ((row -= km) < T) { src = p.psig; dst = p.sig; }
+        else { row -= T; src = p.pphi; dst = p.phi; }
+        src += (size_t)row * Cl + c; dst += (size_t)row * Cl + c;
+      };
+      for (int row0 = warp; row0 < rows; row0 += 8 * (PT_FIN_THREADS / 32)) {
+        double v[8]; double* d[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int row = row0 + q * (PT_FIN_THREADS / 32);
+          d[q] = nullptr;
+          if (row < rows) { const double* sp; row_ptrs(row, sp, d[q]); v[q] = *sp; }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) if (d[q]) *d[q] = v[q];
       }
     }
+  }
+  if (PEER) {   // the rank entries and the pair, left in the local table by pt_propose_kernel
+    for (int i = blockIdx.x * PT_FIN_THREADS + tid; i < p.G + 2; i += (int)gridDim.x * PT_FIN_THREADS) {
+      const double v = __ldcg(table + 2 * Cl + i);
+#pragma unroll 1
+      for (int q = 0; q < px.world; ++q) px.gather[q][slot + 2 * Cl + i] = v;
+    }
+  }
+  if (PEER) __threadfence_system();     // this thread's stores into peer memory are ordered before the arrival below
+  else __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(arrived, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  // the last CTA (every CTA's stores precede its arrival): the per-CTA sums in a fixed order -- thread t adds the sums of the
+  // CTAs t, t + 128, ..., then the same tree as above -- with all loads in flight at once
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned b = tid; b < gridDim.x; b += PT_FIN_THREADS) tot += __ldcg(part + b);
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_down_sync(0xffffffffu, tot, o);
+  __syncthreads();              // (s_sum is being reused)
+  if ((tid & 31) == 0) s_sum[tid >> 5] = tot;
+  __syncthreads();
+  if (tid == 0) {
+    double acc = 0.0;
+    for (int w = 0; w < PT_FIN_THREADS / 32; ++w) acc += s_sum[w];
+    lhist[it] = acc;
+    *arrived = 0;
+    if (PEER) {
+      __threadfence_system();
+      for (int q = 0; q < px.world; ++q) st_release_sys(px.flag[q] + px.me, (unsigned long long)it + 1ULL);
+    }
+    if (SWAP) pt_swap_decide(p, table, 1, px.table_len);
   }
 }
 
@@ -658,29 +680,7 @@ __global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world,
     gathered += (size_t)(it & 1) * world * table_len;
   }
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  const int log_slot = pt_log_slot(p);
-  *p.it_dev += 1;                    // the iteration is complete: the last kernel of its launch sequence
-  if (p.nchains < 2) return;
-  const int G = p.G, Cl = p.Cl;
-  const double* t0 = gathered;  // process 0 owns virtual rank 0
-  const int i1 = (int)t0[2 * Cl + G], i2 = (int)t0[2 * Cl + G + 1];
-  const int own1 = i1 / Cl, own2 = i2 / Cl, l1 = i1 - own1 * Cl, l2 = i2 - own2 * Cl;
-  const double* ta = gathered + (size_t)own1 * table_len;
-  const double* tb = gathered + (size_t)own2 * table_len;
-  const double temp1 = ta[l1], temp2 = tb[l2], e1 = ta[Cl + l1], e2 = tb[Cl + l2];
-  const int rank1_local = l1 / p.nchains;
-  const double u = ta[2 * Cl + rank1_local];
-  const double del_s = __dmul_rn(__dsub_rn(e2, e1), __dsub_rn(__ddiv_rn(1.0, temp1), __ddiv_rn(1.0, temp2)));
-  const int yn = log(u) <= del_s;
-  const int me = p.rank_begin / G;
-  if (me == own1) {
-    p.mti[rank1_local] += 1;  // the stream of rank1 consumed the judge_pt uniform
-    if (yn) p.temps[l1] = temp2;
-  }
-  if (me == own2 && yn) p.temps[l2] = temp1;
-  if (log_slot >= 0) {
-    p.log_swaps[3 * log_slot] = i1; p.log_swaps[3 * log_slot + 1] = i2; p.log_swaps[3 * log_slot + 2] = yn;
-  }
+  pt_swap_decide(p, gathered, world, table_len);
 }
 
 // ordered numbering of the non-tempered chains (deterministic slot of each recorded model in all_models)
@@ -953,7 +953,7 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
   A(dalloc(&s->d_table, (size_t)s->table_len));
   s->cap_lhist = c.nburn + c.niter > 0 ? c.nburn + c.niter : 1024;
   A(dalloc(&s->d_lhist, (size_t)s->cap_lhist));
-  A(dalloc(&s->d_lh_part, (Cl + 1023) / 1024)); A(dalloc(&s->d_lh_cnt, 1));
+  A(dalloc(&s->d_lh_part, (Cl + PT_FIN_CHAINS - 1) / PT_FIN_CHAINS)); A(dalloc(&s->d_lh_cnt, 1));
   A(h->ensure_capacity(d.Cl));
 #undef A
   pt_init_kernel<<<(d.G + 63) / 64, 64, 0, h->stream>>>(h->dc, d);
@@ -1039,7 +1039,9 @@ static int pt_reserve_lhist(rfinv_handle* h, int upto) {
 
 // The launches of one iteration except the swap decision: proposal pass, batched evaluation, acceptance, likelihood
 // history, (posterior bookkeeping,) and this process's swap table.  Nothing here depends on the host's iteration counter.
-static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = false) {
+// fuse_swap: a single process -- the swap decision is taken by the last CTA of pt_finish_kernel (unless bookkeeping kernels
+// have to run in between)
+static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = false, bool fuse_swap = false) {
   PtState* s = h->pt;
   PtDev& d = s->dev;
   cudaStream_t q = h->stream;
@@ -1050,29 +1052,24 @@ static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = f
     if (per_warp <= 48 * 1024) {
       const int warps = per_warp <= 12 * 1024 ? 4 : (per_warp <= 24 * 1024 ? 2 : 1);
       RFINV_CUDA_CHECK(cudaFuncSetAttribute(pt_propose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * warps)));
-      pt_propose_kernel<true><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d);
+      pt_propose_kernel<true><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d, s->d_table);
     } else {
-      pt_propose_kernel<false><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d);
+      pt_propose_kernel<false><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d, s->d_table);
     }
   }
-  pt_compact_kernel<<<1, 1024, 0, q>>>(d);
   RFINV_CUDA_CHECK(cudaGetLastError());
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
-  pt_accept_kernel<<<(d.Cl + 127) / 128, 128, 0, q>>>(h->dc, d);
   {
-    const long long n_el = (long long)(3 * h->dc.k_max - 1 + 2 * h->dc.ntrc) * d.Cl;
-    pt_adopt_kernel<<<(unsigned)((n_el + 255) / 256), 256, 0, q>>>(h->dc, d);
+    const unsigned nb = (unsigned)((d.Cl + PT_FIN_CHAINS - 1) / PT_FIN_CHAINS);
+    const bool peer = s->peer_state == 1 && peer_exchange;
+    if (peer) pt_finish_kernel<true, false><<<nb, PT_FIN_THREADS, 0, q>>>(h->dc, d, s->d_table, s->peers, s->d_lhist, s->d_lh_part, s->d_lh_cnt);
+    else if (fuse_swap && !record) pt_finish_kernel<false, true><<<nb, PT_FIN_THREADS, 0, q>>>(h->dc, d, s->d_table, s->peers, s->d_lhist, s->d_lh_part, s->d_lh_cnt);
+    else pt_finish_kernel<false, false><<<nb, PT_FIN_THREADS, 0, q>>>(h->dc, d, s->d_table, s->peers, s->d_lhist, s->d_lh_part, s->d_lh_cnt);
   }
-  pt_lhist_kernel<<<(d.Cl + 1023) / 1024, 1024, 0, q>>>(d, s->d_lhist, s->d_lh_part, s->d_lh_cnt);
-  if (record) {
+  if (record) {   // posterior bookkeeping of the state after acceptance, before the swap (src/pt_mcmc.f90:204-286)
     pt_coldscan_kernel<<<1, 1024, 0, q>>>(d);
     pt_record_kernel<<<d.Cl, 128, 0, q>>>(h->dc, d);
     pt_record_finish_kernel<<<1, 1, 0, q>>>(d);
-  }
-  {
-    const int nb_rank = (d.G * 32 + 127) / 128, nb_copy = (d.Cl + 127) / 128;
-    if (s->peer_state == 1 && peer_exchange) pt_table_kernel<true><<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table, s->peers);
-    else pt_table_kernel<false><<<nb_rank > nb_copy ? nb_rank : nb_copy, 128, 0, q>>>(d, s->d_table, s->peers);
   }
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
@@ -1121,7 +1118,8 @@ static int pt_enqueue_iteration(rfinv_handle* h, int world, bool record) {
   PtState* s = h->pt;
   int st;
   const bool peer = world > 1 && s->peer_state == 1;
-  if ((st = pt_enqueue_local(h, record, peer)) != RFINV_OK) return st;
+  if ((st = pt_enqueue_local(h, record, peer, world == 1)) != RFINV_OK) return st;
+  if (world == 1 && !record) return RFINV_OK;   // pt_finish_kernel took the swap decision
   if (peer) {   // the table went into every process's gather buffer while it was built; the swap kernel waits for the flags
     pt_swap_kernel<true><<<1, 32, 0, h->stream>>>(s->dev, s->d_peer_gather, world, s->table_len, s->peers);
     RFINV_CUDA_CHECK(cudaGetLastError());

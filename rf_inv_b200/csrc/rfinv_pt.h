@@ -48,7 +48,7 @@ struct ncclComm;   // NCCL communicator (comm.cu)
 
 // Swap exchange over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every process owns a gather buffer
 // [2][world][table_len] and a flag word per source process, both opened by every other process through CUDA IPC.
-// pt_table_kernel stores this process's swap table straight into slot `me` of EVERY process's gather buffer (parity =
+// pt_finish_kernel stores this process's swap table straight into slot `me` of EVERY process's gather buffer (parity =
 // iteration & 1) while it builds it, and the last of its CTAs then raises flag[me] = iteration + 1 on every process;
 // pt_swap_kernel waits for the `world` flags of its own process and reads its own buffer.  No collective call, no extra
 // launch: the exchange rides on the two kernels the iteration runs anyway.  (Double buffering: a process can only be one
@@ -58,7 +58,7 @@ struct PtPeers {
   int world, me, table_len;
   double* gather[RFINV_MAX_PEERS];               // gather buffer of process q (own: local memory, others: IPC mappings)
   unsigned long long* flag[RFINV_MAX_PEERS];     // flag words of process q: [world] epochs + [world] the error word
-  int* done;                                     // arrival counter of pt_table_kernel's CTAs (local)
+  int* done;                                     // (spare counter, local)
 };
 
 struct PtState {
@@ -78,7 +78,7 @@ struct PtState {
   unsigned long long* d_peer_flags = nullptr;
   int cap_lhist = 0;
   double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
-  double* d_lh_part = nullptr; // per-CTA sums of pt_lhist_kernel
+  double* d_lh_part = nullptr; // per-CTA sums of the likelihood history (pt_finish_kernel)
   int* d_lh_cnt = nullptr;     // its arrival counter
   double* d_table = nullptr;   // swap table of this process
   int table_len = 0;

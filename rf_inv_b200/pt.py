@@ -163,7 +163,7 @@ class ParallelTempering:
 
 
 def build_table(temps, logl, peeks, pair=(-1, -1)) -> np.ndarray:
-    """Host-side layout of one process's swap table (what pt_table_kernel / pt_peek_kernel write)."""
+    """Host-side layout of one process's swap table (what pt_finish_kernel / pt_propose_kernel write)."""
     return np.concatenate([np.asarray(temps, dtype=np.float64), np.asarray(logl, dtype=np.float64),
                            np.asarray(peeks, dtype=np.float64), np.asarray(pair, dtype=np.float64)])
 

@@ -2,7 +2,7 @@
 # per-kernel device times of the PT iteration (ncu, serialised): tools/pt_launches.sh tag
 tag=${1:-r02}
 mkdir -p gpurun_out
-RFINV_PT_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 260 --csv --log-file gpurun_out/launches_pt_$tag.csv python tools/pt_time.py 40 > gpurun_out/pt_under_ncu_$tag.log 2>&1
+RFINV_PT_GRAPH=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 150 -c 120 --csv --log-file gpurun_out/launches_pt_$tag.csv python tools/pt_time.py 40 > gpurun_out/pt_under_ncu_$tag.log 2>&1
 python - <<PY
 import csv, collections
 rows = list(csv.reader(open("gpurun_out/launches_pt_$tag.csv")))
