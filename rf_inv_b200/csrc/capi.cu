@@ -459,7 +459,15 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
   std::vector<double2> tw;
   build_twiddles(d.fft_len, tw);
   std::vector<double2> chirp, chirp_b;
-  if (d.fft_general) build_chirp(cfg->nfft, d.fft_len, chirp, chirp_b);
+  std::vector<double2> twq;
+  if (d.fft_general) {
+    build_chirp(cfg->nfft, d.fft_len, chirp, chirp_b);
+    // per-stage twiddle tables of the radix-8 stages, [q - 1][offset] per stage (what fill_fft_twiddles builds in shared memory)
+    for (int N = d.fft_len; N > 8; N >>= 3) {
+      const int stride = N >> 3, tmul = d.fft_len / N;
+      for (int i = 0; i < 7 * stride; ++i) { const int q = i / stride + 1, o = i - (q - 1) * stride; twq.push_back(tw[(size_t)q * o * tmul]); }
+    }
+  }
   // R^-1: symmetrised (the quadratic form only sees the symmetric part) and zero padded to the tile
   const int Sp = d.nsmp_pad;
   std::vector<double> rpad((size_t)T * Sp * Sp, 0.0);
@@ -618,14 +626,14 @@ int32_t rfinv_create(const rfinv_config* cfg, int32_t device, rfinv_handle** out
 #define RFINV_TRY(x) do { st = (x); if (st != RFINV_OK) { rfinv_destroy(h); return st; } } while (0)
   RFINV_TRY(upload(flt, &h->d_flt));
   RFINV_TRY(upload(tw, &h->d_tw));
-  if (d.fft_general) { RFINV_TRY(upload(chirp, &h->d_chirp)); RFINV_TRY(upload(chirp_b, &h->d_chirp_b)); }
+  if (d.fft_general) { RFINV_TRY(upload(chirp, &h->d_chirp)); RFINV_TRY(upload(chirp_b, &h->d_chirp_b)); RFINV_TRY(upload(twq, &h->d_twq)); }
   RFINV_TRY(upload(h->h_obs, &h->d_obs));
   RFINV_TRY(upload(h->h_vp_ref, &h->d_vp_ref));
   RFINV_TRY(upload(h->h_vs_ref, &h->d_vs_ref));
   RFINV_TRY(upload(rpad, &h->d_r_inv));
   RFINV_TRY(upload(wfac, &h->d_w_fac));
 #undef RFINV_TRY
-  d.flt = h->d_flt; d.tw = h->d_tw; d.chirp = h->d_chirp; d.chirp_b = h->d_chirp_b; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv; d.w_fac = h->d_w_fac;
+  d.flt = h->d_flt; d.tw = h->d_tw; d.chirp = h->d_chirp; d.chirp_b = h->d_chirp_b; d.twq = h->d_twq; d.obs = h->d_obs; d.vp_ref = h->d_vp_ref; d.vs_ref = h->d_vs_ref; d.r_inv = h->d_r_inv; d.w_fac = h->d_w_fac;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { rfinv_set_error("cudaStreamCreate: %s", cudaGetErrorString(e)); rfinv_destroy(h); return RFINV_ERR_CUDA; }
   h->own_stream = true;
@@ -640,7 +648,7 @@ void rfinv_destroy(rfinv_handle* h) {
   h->free_pt();              // first: the captured iteration graphs hold references on the communicator (ncclCommDestroy waits for them)
   rfinv_comm_destroy(h);
   h->free_workspace();
-  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_chirp); cudaFree(h->d_chirp_b); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
+  cudaFree(h->d_flt); cudaFree(h->d_tw); cudaFree(h->d_chirp); cudaFree(h->d_chirp_b); cudaFree(h->d_twq); cudaFree(h->d_obs); cudaFree(h->d_vp_ref); cudaFree(h->d_vs_ref); cudaFree(h->d_r_inv); cudaFree(h->d_w_fac);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   if (h->stream_copy) {
     cudaStreamSynchronize(h->stream_copy);

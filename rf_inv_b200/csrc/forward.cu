@@ -1293,8 +1293,9 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   double2* s_tab = s_buf;                             // dead before the FFT buffer is first written
   double2* s_fr = s_buf + region0;                    // [nh+1] unfiltered radial spectrum (or deconvolved RF spectrum)
   double2* s_fv = s_fr + (nh + 1);                    // [nh+1] unfiltered vertical spectrum
-  double2* s_twq = s_fr + (general ? 2 * (nh + 1) : 0);   // per-stage FFT twiddle tables
-  double* s_red = reinterpret_cast<double*>(s_twq + fft_twiddle_entries(nf));   // [64]
+  double2* s_twq_sm = s_fr + (general ? 2 * (nh + 1) : 0);   // per-stage FFT twiddle tables (GEN: read from global memory instead --
+  const double2* s_twq = GEN ? cfg.twq : s_twq_sm;           //  the two transforms of twice the length need the room for their buffer)
+  double* s_red = reinterpret_cast<double*>(s_twq_sm + (GEN ? 0 : fft_twiddle_entries(nf)));   // [64]
   RayConst* s_rc2 = reinterpret_cast<RayConst*>(s_red + 64);     // [2]
   LayerConst* s_lc2 = reinterpret_cast<LayerConst*>(s_rc2 + 2);  // [2][km]
   double2* s_tabw = reinterpret_cast<double2*>(s_lc2 + 2 * (size_t)km);   // [16 + n_hi] water-layer phase table (not aliased)
@@ -1318,7 +1319,7 @@ __global__ void __launch_bounds__(BMAX, MINB) forward_kernel(const DevConfig cfg
   // iteration, so nobody waits for the round trip).
   int item = blockIdx.x, slot = 0;
   pdl_trigger();                               // quadform_kernel may queue up behind this grid
-  fill_fft_twiddles(s_twq, cfg.tw, nf, tid, nthr);   // (nothing of prep_kernel is touched before pdl_wait)
+  if (!GEN) fill_fft_twiddles(s_twq_sm, cfg.tw, nf, tid, nthr);   // (nothing of prep_kernel is touched before pdl_wait)
   pdl_wait();                                  // prep_kernel (and everything before it on the stream) is complete
   const int n_items = (mb.n_active_dev ? *mb.n_active_dev : (mb.active ? mb.n_active : C)) * sel.n;
   if (item >= n_items) return;
@@ -1482,11 +1483,12 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
   const int nf = cfg.fft_len;
   double2* b0 = reinterpret_cast<double2*>(smem_raw);
   double2* b1 = b0 + fft_buf_elems(nf);
-  double2* s_tw = b1 + fft_buf_elems(nf);
-  double* s_red = reinterpret_cast<double*>(s_tw + fft_twiddle_entries(nf));   // [64]
+  double2* s_tw_sm = b1 + fft_buf_elems(nf);
+  const double2* s_tw = GEN ? cfg.twq : s_tw_sm;      // GEN: twiddle tables from global memory
+  double* s_red = reinterpret_cast<double*>(s_tw_sm + (GEN ? 0 : fft_twiddle_entries(nf)));   // [64]
   const double* x = in + (size_t)blockIdx.x * n;
   const double* __restrict__ flt = cfg.flt + (size_t)trace_of[blockIdx.x] * nh;
-  fill_fft_twiddles(s_tw, cfg.tw, nf, tid, nthr);
+  if (!GEN) fill_fft_twiddles(s_tw_sm, cfg.tw, nf, tid, nthr);
   if constexpr (GEN) {
     // any length (Bluestein): both transforms leave their result in natural order
     const bool odd = n & 1;
@@ -1582,7 +1584,7 @@ size_t forward_smem_bytes(const DevConfig& cfg, int nthr) {
   const size_t region0 = tab_entries > fft_buf_elems(n) ? tab_entries : fft_buf_elems(n);
   const bool general = cfg.ray_common || cfg.deconv_mode == 1 || cfg.bdep > 0.0;
   const size_t spectra = general ? 2 * (nh + 1) : 0;
-  return sizeof(double2) * (region0 + spectra + fft_twiddle_entries(n)) + sizeof(double) * 64 + 2 * sizeof(RayConst) +
+  return sizeof(double2) * (region0 + spectra + (cfg.fft_general ? 0 : fft_twiddle_entries(n))) + sizeof(double) * 64 + 2 * sizeof(RayConst) +
          2 * sizeof(LayerConst) * km + sizeof(double2) * (16 + (nthr >> 4));
 }
 
@@ -1743,7 +1745,7 @@ int rfinv_launch_forward(const DevConfig& cfg, const ModelBatch& mb, const EvalO
 int rfinv_launch_filter_traces(const DevConfig& cfg, int n_series, const double* in, const int* trace_of, double* out,
                                cudaStream_t stream) {
   if (n_series == 0) return RFINV_OK;
-  const size_t smem = sizeof(double2) * (2 * fft_buf_elems(cfg.fft_len) + fft_twiddle_entries(cfg.fft_len)) + sizeof(double) * 64;
+  const size_t smem = sizeof(double2) * (2 * fft_buf_elems(cfg.fft_len) + (cfg.fft_general ? 0 : fft_twiddle_entries(cfg.fft_len))) + sizeof(double) * 64;
   const int nthr = cfg.fft_len / 8 < 32 ? 32 : (cfg.fft_len / 8 > 128 ? 128 : cfg.fft_len / 8);
   if (cfg.fft_general) {
     RFINV_CUDA_CHECK(cudaFuncSetAttribute(filter_traces_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

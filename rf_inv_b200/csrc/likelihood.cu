@@ -129,6 +129,11 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
       cp_async_commit();
       for (int ks = 0; ks < nk; ++ks) {
         const int cur = ks & 1;
+        // ONE barrier per k-slab: it publishes the slab that has just landed and, at the same time, tells every thread that
+        // the other buffer (read during the previous slab) is free -- so the next slab is requested right behind it and has
+        // the whole of this slab's MMAs to arrive
+        cp_async_wait<0>();
+        __syncthreads();
         if (ks + 1 < nk) {
           const int k0 = (ks + 1) * TK;
 #pragma unroll
@@ -137,11 +142,7 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
             cp_async16(&sB[cur ^ 1][cp_off[q]], b_base + (size_t)cp_row[q] * Sp + k0 + (cp_off[q] - cp_row[q] * LDS_STRIDE));
           }
           cp_async_commit();
-          cp_async_wait<1>();
-        } else {
-          cp_async_wait<0>();
         }
-        __syncthreads();
         if (rank == 0 && ks == jt * (TN / TK) && jt > 0) {   // entering the diagonal tile: what came before counts twice
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -172,7 +173,6 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
               }
           }
         }
-        __syncthreads();
       }
       // row-dot with M[:, jt]: lane holds Y[row = 8i + fr][col = 8j + 2*fk + {0,1}] of its warp sub-tile
 #pragma unroll

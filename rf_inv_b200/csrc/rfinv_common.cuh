@@ -33,6 +33,8 @@ struct DevConfig {
   int jb_max;                   // largest jbins[]: picks the kernel variant
   const double* flt;            // [ntrc][nh]   Gaussian filter, src/forward.f90:95-119
   const double2* tw;            // [fft_len]    exp(+2 pi i m / fft_len)
+  const double2* twq;           // fft_general: the per-stage twiddle tables of the radix-8 stages for fft_len points (layout of
+                                // fill_fft_twiddles, forward.cu), read from global memory / L1 instead of a shared-memory copy
   const double2* chirp;         // [nfft]       fft_general: exp(+i pi m^2 / nfft)
   const double2* chirp_b;       // [fft_len]    fft_general: FFT_fft_len(conj(chirp) wrapped around fft_len) / fft_len
   const double* obs;            // [ntrc][nsmp]

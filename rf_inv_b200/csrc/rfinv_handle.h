@@ -34,7 +34,7 @@ struct rfinv_handle : EvalWorkspace {
   // constants in HBM
   double* d_flt = nullptr;
   double2* d_tw = nullptr;
-  double2 *d_chirp = nullptr, *d_chirp_b = nullptr;   // Bluestein tables (nfft not a power of two)
+  double2 *d_chirp = nullptr, *d_chirp_b = nullptr, *d_twq = nullptr;   // Bluestein tables (nfft not a power of two)
   double* d_obs = nullptr;
   double* d_vp_ref = nullptr;
   double* d_vs_ref = nullptr;
