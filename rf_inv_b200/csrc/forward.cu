@@ -1518,8 +1518,7 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
     __syncthreads();
     bluestein_inverse<7, 12>(b1, cfg, s_tw, s_red, tid, nthr, CtaSync());
     for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad(i, psh)].x;
-    return;
-  }
+  } else {
   for (int i = tid; i < n; i += nthr) b0[fpad(i, psh)] = make_double2(x[i], 0.0);
   __syncthreads();
   fft_inverse_dif<6, 12>(b0, n, s_tw, s_red, tid, nthr, CtaSync());
@@ -1537,6 +1536,7 @@ __global__ void __launch_bounds__(128) filter_traces_kernel(const DevConfig cfg,
   __syncthreads();
   fft_inverse_dif<6, 12>(b1, n, s_tw, s_red, tid, nthr, CtaSync());
   for (int i = tid; i < n; i += nthr) out[(size_t)blockIdx.x * n + i] = b1[fpad((int)(__brev((unsigned)i) >> brev_shift), psh)].x;
+  }
 }
 
 __global__ void format_model_kernel(const DevConfig cfg, const ModelBatch mb, int* nlay_out, double* alpha,

@@ -158,7 +158,6 @@ __global__ void __launch_bounds__(QF_THREADS, 4) quadform_kernel(const DevConfig
           for (int i = 0; i < 4; ++i) a[i] = A[i * 8 * LDS_STRIDE + kk];
 #pragma unroll
           for (int j = 0; j < 4; ++j) b[j] = B[j * 16 * LDS_STRIDE + kk];
-#pragma unroll
           if (jw == 4) {                            // the hot path stays one straight run of 16 DMMA
 #pragma unroll
             for (int i = 0; i < 4; ++i)

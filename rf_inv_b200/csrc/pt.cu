@@ -716,7 +716,7 @@ __global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
   if (ord < 0) return;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc, S = cfg.nsmp;
-  __shared__ double s_alpha[RFINV_MAX_LAY], s_beta[RFINV_MAX_LAY], s_top[RFINV_MAX_LAY + 1];
+  __shared__ double s_alpha[RFINV_MAX_LAY], s_beta[RFINV_MAX_LAY];
   __shared__ int s_iz1[RFINV_MAX_LAY + 1], s_nlay;
   const double dbin_amp = (p.amp_max - p.amp_min) / p.nbin_amp, dbin_vp = (cfg.vp_max - cfg.vp_min) / p.nbin_vp;
   const double dbin_vs = (cfg.vs_max - cfg.vs_min) / p.nbin_vs, dbin_z = (cfg.z_max - 0.0) / p.nbin_z;
@@ -747,7 +747,7 @@ __global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
     int n = 0;
     double tmpz = 0.0;
     if (cfg.sdep > 0.0) {
-      s_alpha[n] = 1.5; s_beta[n] = -999.0; s_top[n] = tmpz; s_iz1[n] = (int)(tmpz / dbin_z) + 1;
+      s_alpha[n] = 1.5; s_beta[n] = -999.0; s_iz1[n] = (int)(tmpz / dbin_z) + 1;
       tmpz = __dadd_rn(tmpz, cfg.sdep); ++n;
     }
     for (int l = 0; l <= k; ++l) {
@@ -758,7 +758,7 @@ __global__ void pt_record_kernel(const DevConfig cfg, const PtDev p) {
              dvs_l = p.dvs[(size_t)(km - 1) * Cl + c]; dvp_l = p.dvp[(size_t)(km - 1) * Cl + c]; }
       double a, b;
       layer_velocity(cfg, zc, dvs_l, dvp_l, a, b);
-      s_alpha[n] = a; s_beta[n] = b; s_top[n] = tmpz;
+      s_alpha[n] = a; s_beta[n] = b;
       s_iz1[n] = (int)(__ddiv_rn(tmpz, dbin_z)) + 1;
       tmpz = __dadd_rn(tmpz, h);
       ++n;
