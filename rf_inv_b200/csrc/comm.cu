@@ -97,14 +97,15 @@ int rfinv_comm_peer_setup(rfinv_handle* h) {
   std::memset(&mine, 0, sizeof(mine));
   const size_t n_gather = (size_t)2 * world * s->table_len;
   if (want) {
-    // one allocation (one IPC handle): [2][world][table_len] doubles, then world + 1 flag words
-    if (cudaMalloc((void**)&s->d_peer_gather, sizeof(double) * n_gather + sizeof(unsigned long long) * (world + 1)) != cudaSuccess ||
-        cudaMalloc((void**)&s->peers.done, sizeof(int)) != cudaSuccess) want = 0;
+    // one allocation (one IPC handle): [2][world][table_len] doubles, then the flag words and pair slots (rfinv_pt.h)
+    if (cudaMalloc((void**)&s->d_peer_gather, sizeof(double) * (n_gather + pt_peer_tail_words(world))) != cudaSuccess ||
+        cudaMalloc((void**)&s->peers.done, 2 * sizeof(int)) != cudaSuccess) want = 0;
   }
   if (want) {
     s->d_peer_flags = reinterpret_cast<unsigned long long*>(s->d_peer_gather + n_gather);
-    cudaMemset(s->d_peer_gather, 0, sizeof(double) * n_gather + sizeof(unsigned long long) * (world + 1));
-    cudaMemset(s->peers.done, 0, sizeof(int));
+    cudaMemset(s->d_peer_gather, 0, sizeof(double) * (n_gather + pt_peer_tail_words(world)));
+    const int applied[2] = {s->it_done, s->it_done};   // every swap of the iterations run so far has been applied in full
+    cudaMemcpy(s->peers.done, applied, sizeof(applied), cudaMemcpyHostToDevice);
     if (cudaIpcGetMemHandle(&mine.mem, s->d_peer_gather) != cudaSuccess) want = 0;
     cudaDeviceSynchronize();
   }

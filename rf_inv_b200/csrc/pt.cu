@@ -247,14 +247,50 @@ __device__ bool model_valid_warp(const DevConfig& cfg, int k, double z0, double 
   return __all_sync(0xffffffffu, ok);
 }
 
+// ---- peer-memory exchange (rfinv_pt.h, PtPeers) ----
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long* pt_pair_flag(const PtPeers& px, int q) { return px.flag[q] + px.world + 1; }
+__device__ __forceinline__ double* pt_pair_slot(const PtPeers& px, int q, int it) {   // slot of iteration `it`
+  return reinterpret_cast<double*>(px.flag[q] + px.world + 2) + 2 * (it & 3);
+}
+// waits until *f >= want (a flag a peer raises); bounded: a peer that never arrives -- it stopped on an error -- sets this
+// process's error word instead of hanging the GPU (the host checks the word after the run)
+__device__ __forceinline__ void pt_peer_wait(const PtPeers& px, const unsigned long long* f, unsigned long long want) {
+  const long long t0 = clock64();
+  while (ld_acquire_sys(f) < want) {
+    if (clock64() - t0 > 40000000000LL) { px.flag[px.me][px.world] = 1ULL; break; }   // ~20 s
+    __nanosleep(100);
+  }
+}
+// the swap proposal of an iteration, from the pair drawn by virtual rank 0 (global chain indices)
+struct SwapPlan { int i1, i2, own1, own2, l1, l2, rank1_local; };
+__device__ __forceinline__ SwapPlan pt_swap_plan(const PtDev& p, double t1, double t2) {
+  SwapPlan s;
+  s.i1 = (int)t1; s.i2 = (int)t2;
+  s.own1 = s.i1 / p.Cl; s.own2 = s.i2 / p.Cl;
+  s.l1 = s.i1 - s.own1 * p.Cl; s.l2 = s.i2 - s.own2 * p.Cl;
+  s.rank1_local = s.l1 / p.nchains;
+  return s;
+}
+
 // STAGED: the states of the rank's chains are first brought into shared memory with coalesced loads (the chains of a rank
 // are neighbours in the chain-fastest arrays: one 128-byte line serves 16 of them) and the proposals leave the same way --
 // one memory latency per rank instead of one per chain, a third of the sectors.  Per warp: 2 x nchains x stride doubles
 // (pt_propose_smem_doubles); ranks with too many chains for that use the direct variant.
 __host__ __device__ inline int pt_propose_stride(int km, int T) { return (3 * km + T) | 1; }     // odd: conflict-free transposition
 __host__ __device__ inline size_t pt_propose_smem_doubles(int km, int T, int nchains) { return (size_t)2 * nchains * pt_propose_stride(km, T); }
-template <bool STAGED>
-__global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p, double* __restrict__ table) {
+// PEER (several processes, peer-memory exchange): the warp first applies the stream shift of the previous iteration's swap --
+// judge_pt's draw from the stream of rank1, known from the pair alone -- and the owner of virtual rank 0 publishes the pair it
+// draws at the end to every process.
+template <bool STAGED, bool PEER>
+__global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, const PtDev p, double* __restrict__ table, const PtPeers px) {
   extern __shared__ __align__(16) double pp_smem[];
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -300,7 +336,16 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
     }
     for (int ic = lane; ic < nch; ic += 32) s_in[ic * S + km - 1] = 0.0;     // element km-1 of z does not exist
   }
-  Mt g(p.mt, r, p.mti[r], /*warp=*/true);
+  int shift = 0;
+  const int it_now = PEER ? *p.it_dev : 0;
+  if (PEER && p.nchains >= 2 && px.done[0] < it_now) {     // swap it_now - 1: its pair was published an iteration ago
+    if (lane == 0) pt_peer_wait(px, pt_pair_flag(px, px.me), (unsigned long long)it_now);
+    __syncwarp();
+    const double* pr = pt_pair_slot(px, px.me, it_now - 1);
+    const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
+    if (sp.own1 == px.me && sp.rank1_local == r) shift = 1;   // the stream of rank1 consumed the judge_pt uniform
+  }
+  Mt g(p.mt, r, p.mti[r] + shift, /*warp=*/true);
   __syncwarp();
   const bool has1 = lane + 32 < km;
   // per-chain scalars of the proposals, kept by lane (ic & 31) until the coalesced store at the end (STAGED)
@@ -427,7 +472,14 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
       do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
       t1 = i1; t2 = i2;
     }
-    if (lane == 0) { table[2 * Cl + p.G] = t1; table[2 * Cl + p.G + 1] = t2; }
+    if (lane == 0) {
+      table[2 * Cl + p.G] = t1; table[2 * Cl + p.G + 1] = t2;
+      if (PEER && p.rank_begin == 0) {   // the pair goes to every process now: it is all the next proposal pass needs
+        for (int q = 0; q < px.world; ++q) { double* ps = pt_pair_slot(px, q, it_now); ps[0] = t1; ps[1] = t2; }
+        __threadfence_system();
+        for (int q = 0; q < px.world; ++q) st_release_sys(pt_pair_flag(px, q), (unsigned long long)it_now + 1ULL);
+      }
+    }
   }
   {
     const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
@@ -479,15 +531,6 @@ __device__ __forceinline__ int pt_log_slot(const PtDev& p) {
   if (!p.log_flags) return -1;
   const int s = *p.it_dev - p.log_base;
   return (s >= 0 && s < p.log_cap) ? s : -1;
-}
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
 }
 
 // judge_pt (src/pt_mcmc.f90:580-595) on the gathered swap tables (`world` tables of table_len doubles, process order; a
@@ -556,10 +599,39 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
   };
   double cold_logl = 0.0;
   if (warp == 0) {
+    // PEER: the previous iteration's swap exchanges its two temperatures here, in front of their first reader (every CTA takes
+    // the decision for itself from the tables that arrived during this iteration; the owners' threads adopt the new values)
+    int sw_l1 = -1, sw_l2 = -1;
+    double sw_t1 = 0.0, sw_t2 = 0.0;
+    if (PEER && p.nchains >= 2 && px.done[1] < it) {
+      if (lane < px.world) pt_peer_wait(px, px.flag[px.me] + lane, (unsigned long long)it);
+      __syncwarp();
+      const double* pr = pt_pair_slot(px, px.me, it - 1);
+      const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
+      const double* gathered = px.gather[px.me] + (size_t)((it - 1) & 1) * px.world * px.table_len;
+      const double* ta = gathered + (size_t)sp.own1 * px.table_len;
+      const double* tb = gathered + (size_t)sp.own2 * px.table_len;
+      const double temp1 = __ldcg(ta + sp.l1), temp2 = __ldcg(tb + sp.l2), e1 = __ldcg(ta + Cl + sp.l1), e2 = __ldcg(tb + Cl + sp.l2);
+      const double u = __ldcg(ta + 2 * Cl + sp.rank1_local);
+      const double del_s = __dmul_rn(__dsub_rn(e2, e1), __dsub_rn(__ddiv_rn(1.0, temp1), __ddiv_rn(1.0, temp2)));
+      const int yn = log(u) <= del_s;
+      if (yn) {
+        if (sp.own1 == px.me) { sw_l1 = sp.l1; sw_t1 = temp2; }
+        if (sp.own2 == px.me) { sw_l2 = sp.l2; sw_t2 = temp1; }
+      }
+      if (blockIdx.x == 0 && lane == 0 && p.log_flags) {
+        const int ls = it - 1 - p.log_base;
+        if (ls >= 0 && ls < p.log_cap) { p.log_swaps[3 * ls] = sp.i1; p.log_swaps[3 * ls + 1] = sp.i2; p.log_swaps[3 * ls + 2] = yn; }
+      }
+    }
     int code = 0;   // 3: adopt model and phi, 4: model only (sigma-only proposal), 0: nothing
     if (c < Cl) {
       const int flag = p.pflag[c];
-      const double temp = p.temps[c];
+      double temp = p.temps[c];
+      if (PEER) {
+        if (c == sw_l1) { temp = sw_t1; p.temps[c] = temp; }
+        else if (c == sw_l2) { temp = sw_t2; p.temps[c] = temp; }
+      }
       double logl = p.logl[c];
       int yn = 0;
       if (flag != -1) {
@@ -633,8 +705,10 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
       for (int q = 0; q < px.world; ++q) px.gather[q][slot + 2 * Cl + i] = v;
     }
   }
-  if (PEER) __threadfence_system();     // this thread's stores into peer memory are ordered before the arrival below
-  else __threadfence();
+  // the table entries (warp 0; PEER: also the rank entries pushed above) are ordered before the arrival below; the adopted
+  // rows are only read by later kernels and need no fence
+  if (PEER) { if (warp == 0 || blockIdx.x * PT_FIN_THREADS + tid < p.G + 2) __threadfence_system(); }
+  else if (warp == 0) __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(arrived, 1) == (int)gridDim.x - 1;
   __syncthreads();
@@ -656,31 +730,50 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
     if (PEER) {
       __threadfence_system();
       for (int q = 0; q < px.world; ++q) st_release_sys(px.flag[q] + px.me, (unsigned long long)it + 1ULL);
+      px.done[0] = it; px.done[1] = it;   // the swaps of the iterations before this one are applied; this one's follows in the next
+      *p.it_dev = it + 1;                 // the iteration is complete
+      *p.n_active = 0;
     }
     if (SWAP) pt_swap_decide(p, table, 1, px.table_len);
   }
 }
 
 // judge_pt (src/pt_mcmc.f90:580-595) evaluated identically by every process from the gathered tables.
-// PEER: `gathered` is this process's own gather buffer; lane q first waits until process q has raised its flag for this
-// iteration (bounded: a peer that never arrives -- it stopped on an error -- sets the error word instead of hanging the GPU).
-template <bool PEER>
-__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len, const PtPeers px) {
-  if (PEER) {
-    const int it = *p.it_dev;
-    if ((int)threadIdx.x < world) {
-      const unsigned long long* f = px.flag[px.me] + threadIdx.x;
-      const long long t0 = clock64();
-      while (ld_acquire_sys(f) < (unsigned long long)it + 1ULL) {
-        if (clock64() - t0 > 40000000000LL) { px.flag[px.me][world] = 1ULL; break; }   // ~20 s
-        __nanosleep(200);
-      }
-    }
-    __syncwarp();
-    gathered += (size_t)(it & 1) * world * table_len;
-  }
+__global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world, int table_len) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   pt_swap_decide(p, gathered, world, table_len);
+}
+
+// Peer-memory exchange: the swap of the LAST iteration of a run, in full (stream shift, temperatures, log) -- inside the
+// run every swap is applied one iteration later by pt_propose_kernel / pt_finish_kernel.  One warp.
+__global__ void pt_drain_kernel(const PtDev p, const PtPeers px) {
+  const int lane = threadIdx.x & 31;
+  const int it = *p.it_dev;                   // iterations completed; the pending swap is that of iteration it - 1
+  if (p.nchains < 2 || it < 1 || px.done[1] >= it) return;
+  if (lane < px.world) pt_peer_wait(px, px.flag[px.me] + lane, (unsigned long long)it);
+  if (lane == 0) pt_peer_wait(px, pt_pair_flag(px, px.me), (unsigned long long)it);
+  __syncwarp();
+  if (lane != 0) return;
+  const int Cl = p.Cl;
+  const double* pr = pt_pair_slot(px, px.me, it - 1);
+  const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
+  const double* gathered = px.gather[px.me] + (size_t)((it - 1) & 1) * px.world * px.table_len;
+  const double* ta = gathered + (size_t)sp.own1 * px.table_len;
+  const double* tb = gathered + (size_t)sp.own2 * px.table_len;
+  const double temp1 = __ldcg(ta + sp.l1), temp2 = __ldcg(tb + sp.l2), e1 = __ldcg(ta + Cl + sp.l1), e2 = __ldcg(tb + Cl + sp.l2);
+  const double u = __ldcg(ta + 2 * Cl + sp.rank1_local);
+  const double del_s = __dmul_rn(__dsub_rn(e2, e1), __dsub_rn(__ddiv_rn(1.0, temp1), __ddiv_rn(1.0, temp2)));
+  const int yn = log(u) <= del_s;
+  if (sp.own1 == px.me) {
+    if (px.done[0] < it) p.mti[sp.rank1_local] += 1;
+    if (yn) p.temps[sp.l1] = temp2;
+  }
+  if (sp.own2 == px.me && yn) p.temps[sp.l2] = temp1;
+  if (p.log_flags) {
+    const int ls = it - 1 - p.log_base;
+    if (ls >= 0 && ls < p.log_cap) { p.log_swaps[3 * ls] = sp.i1; p.log_swaps[3 * ls + 1] = sp.i2; p.log_swaps[3 * ls + 2] = yn; }
+  }
+  px.done[0] = it; px.done[1] = it;
 }
 
 // ordered numbering of the non-tempered chains (deterministic slot of each recorded model in all_models)
@@ -1051,10 +1144,14 @@ static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = f
     const size_t per_warp = sizeof(double) * pt_propose_smem_doubles(h->dc.k_max, h->dc.ntrc, d.nchains);
     if (per_warp <= 48 * 1024) {
       const int warps = per_warp <= 12 * 1024 ? 4 : (per_warp <= 24 * 1024 ? 2 : 1);
-      RFINV_CUDA_CHECK(cudaFuncSetAttribute(pt_propose_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * warps)));
-      pt_propose_kernel<true><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d, s->d_table);
+      RFINV_CUDA_CHECK(cudaFuncSetAttribute(pt_propose_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * warps)));
+      const bool peer = s->peer_state == 1 && peer_exchange;
+      RFINV_CUDA_CHECK(cudaFuncSetAttribute(pt_propose_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * warps)));
+      if (peer) pt_propose_kernel<true, true><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d, s->d_table, s->peers);
+      else pt_propose_kernel<true, false><<<(d.G + warps - 1) / warps, 32 * warps, per_warp * warps, q>>>(h->dc, d, s->d_table, s->peers);
     } else {
-      pt_propose_kernel<false><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d, s->d_table);
+      if (s->peer_state == 1 && peer_exchange) pt_propose_kernel<false, true><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d, s->d_table, s->peers);
+      else pt_propose_kernel<false, false><<<(d.G * 32 + 127) / 128, 128, 0, q>>>(h->dc, d, s->d_table, s->peers);
     }
   }
   RFINV_CUDA_CHECK(cudaGetLastError());
@@ -1106,7 +1203,7 @@ int32_t rfinv_pt_apply_swap(rfinv_handle* h, uint64_t gathered_dev_ptr, int32_t 
     rfinv_set_error("rfinv_pt_apply_swap: world=%d inconsistent with nproc_total=%d, rank_count=%d", world, s->dev.nproc_total, s->dev.G);
     return RFINV_ERR_ARG;
   }
-  pt_swap_kernel<false><<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len, s->peers);
+  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, reinterpret_cast<const double*>(gathered_dev_ptr), world, s->table_len);
   RFINV_CUDA_CHECK(cudaGetLastError());
   s->it_done++;
   return RFINV_OK;
@@ -1120,17 +1217,13 @@ static int pt_enqueue_iteration(rfinv_handle* h, int world, bool record) {
   const bool peer = world > 1 && s->peer_state == 1;
   if ((st = pt_enqueue_local(h, record, peer, world == 1)) != RFINV_OK) return st;
   if (world == 1 && !record) return RFINV_OK;   // pt_finish_kernel took the swap decision
-  if (peer) {   // the table went into every process's gather buffer while it was built; the swap kernel waits for the flags
-    pt_swap_kernel<true><<<1, 32, 0, h->stream>>>(s->dev, s->d_peer_gather, world, s->table_len, s->peers);
-    RFINV_CUDA_CHECK(cudaGetLastError());
-    return RFINV_OK;
-  }
+  if (peer) return RFINV_OK;   // pair and table went to every process from inside the kernels; the swap is applied an iteration later
   const double* gathered = s->d_table;
   if (world > 1) {
     if ((st = rfinv_comm_allgather(h, s->d_table, s->d_gather, (size_t)s->table_len, h->stream)) != RFINV_OK) return st;
     gathered = s->d_gather;
   }
-  pt_swap_kernel<false><<<1, 32, 0, h->stream>>>(s->dev, gathered, world, s->table_len, s->peers);
+  pt_swap_kernel<<<1, 32, 0, h->stream>>>(s->dev, gathered, world, s->table_len);
   RFINV_CUDA_CHECK(cudaGetLastError());
   return RFINV_OK;
 }
@@ -1184,6 +1277,10 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
       return st;
     }
     s->it_done++;
+  }
+  if (world > 1 && s->peer_state == 1) {   // the last swap of this run (inside the run every swap is applied an iteration later)
+    pt_drain_kernel<<<1, 32, 0, h->stream>>>(s->dev, s->peers);
+    RFINV_CUDA_CHECK(cudaGetLastError());
   }
   RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (world > 1 && s->peer_state == 1) {

@@ -46,20 +46,31 @@ struct PtDev {
 
 struct ncclComm;   // NCCL communicator (comm.cu)
 
-// Swap exchange over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every process owns a gather buffer
-// [2][world][table_len] and a flag word per source process, both opened by every other process through CUDA IPC.
-// pt_finish_kernel stores this process's swap table straight into slot `me` of EVERY process's gather buffer (parity =
-// iteration & 1) while it builds it, and the last of its CTAs then raises flag[me] = iteration + 1 on every process;
-// pt_swap_kernel waits for the `world` flags of its own process and reads its own buffer.  No collective call, no extra
-// launch: the exchange rides on the two kernels the iteration runs anyway.  (Double buffering: a process can only be one
-// iteration ahead of the slowest one, because its pt_swap_kernel needs every flag of the iteration before.)
+// Swap exchange over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every process owns ONE buffer, opened
+// by every other process through CUDA IPC:
+//   gather [2][world][table_len] doubles | table flags [world] | error word | pair flag | pair [4][2] doubles
+// * pt_propose_kernel of the process that owns virtual rank 0 draws the pair of iteration i and stores it straight into the
+//   pair slot i & 3 of EVERY process, then raises pair flag = i + 1 everywhere (four slots: the owner of rank 0 may draw the
+//   pair of iteration i while the slowest process still reads that of iteration i - 2);
+// * pt_finish_kernel stores this process's swap table into slot `me` of EVERY process's gather buffer (parity i & 1) while it
+//   builds it, and the last of its CTAs raises table flag[me] = i + 1 everywhere.
+// No collective call, no extra launch: the exchange rides on the kernels the iteration runs anyway.  And nobody waits for it
+// at the end of the iteration: swap i is APPLIED one iteration later, where its parts are needed -- the stream shift of rank1
+// (judge_pt's draw, src/pt_mcmc.f90:590) at the top of pt_propose_kernel of iteration i + 1, which only needs the pair; the
+// exchange of the two temperatures at the top of pt_finish_kernel of iteration i + 1 (the acceptance test is the first reader of
+// a temperature), which needs the tables.  By then both arrived most of an iteration ago, so the processes drift by up to an
+// iteration instead of meeting at every swap.  pt_drain_kernel applies the last swap of a run.  (Double buffering suffices: a
+// process needs every table flag of iteration i - 1 to finish iteration i, so it is never two iterations ahead of anyone.)
 #define RFINV_MAX_PEERS 16
 struct PtPeers {
   int world, me, table_len;
-  double* gather[RFINV_MAX_PEERS];               // gather buffer of process q (own: local memory, others: IPC mappings)
-  unsigned long long* flag[RFINV_MAX_PEERS];     // flag words of process q: [world] epochs + [world] the error word
-  int* done;                                     // (spare counter, local)
+  double* gather[RFINV_MAX_PEERS];               // buffer of process q (own: local memory, others: IPC mappings)
+  unsigned long long* flag[RFINV_MAX_PEERS];     // its flag words: [world] table epochs, [world] error, [world + 1] pair epoch;
+                                                 // the pair slots follow as doubles (pt_pair_slot)
+  int* done;                                     // local: [0] swaps whose stream shift is applied, [1] swaps whose temperatures are
 };
+// words of 8 bytes behind the gather buffer
+inline size_t pt_peer_tail_words(int world) { return (size_t)world + 2 + 8; }
 
 struct PtState {
   PtDev dev;

@@ -28,6 +28,8 @@ for rep in range(3):
     torch.cuda.synchronize()
     t0 = time.perf_counter(); run(n_it); dt = time.perf_counter() - t0
     best = max(best, n_it / dt)
+st = pt.state()
+print(f"[process {rank}] forward evaluations {pt.counters()['n_eval']}, mean k {st['k'].mean():.3f}, sum of (k + 1) over chains {int((st['k'] + 1).sum())}", flush=True)
 if rank == 0:
     print(f"world {world} exchange {pt.exchange_mode}: {best:.1f} iterations/s ({16384 * world} chains)", flush=True)
 pt.close()
