@@ -99,12 +99,12 @@ int rfinv_comm_peer_setup(rfinv_handle* h) {
   if (want) {
     // one allocation (one IPC handle): [2][world][table_len] doubles, then the flag words and pair slots (rfinv_pt.h)
     if (cudaMalloc((void**)&s->d_peer_gather, sizeof(double) * (n_gather + pt_peer_tail_words(world))) != cudaSuccess ||
-        cudaMalloc((void**)&s->peers.done, 2 * sizeof(int)) != cudaSuccess) want = 0;
+        cudaMalloc((void**)&s->peers.done, 4 * sizeof(int)) != cudaSuccess) want = 0;
   }
   if (want) {
     s->d_peer_flags = reinterpret_cast<unsigned long long*>(s->d_peer_gather + n_gather);
     cudaMemset(s->d_peer_gather, 0, sizeof(double) * (n_gather + pt_peer_tail_words(world)));
-    const int applied[2] = {s->it_done, s->it_done};   // every swap of the iterations run so far has been applied in full
+    const int applied[4] = {s->it_done, s->it_done, s->it_done, 0};   // every swap of the iterations run so far has been applied in full
     cudaMemcpy(s->peers.done, applied, sizeof(applied), cudaMemcpyHostToDevice);
     if (cudaIpcGetMemHandle(&mine.mem, s->d_peer_gather) != cudaSuccess) want = 0;
     cudaDeviceSynchronize();
@@ -125,7 +125,7 @@ int rfinv_comm_peer_setup(rfinv_handle* h) {
   px.world = world; px.me = me; px.table_len = s->table_len;
   if (ok) {
     for (int r = 0; r < world && ok; ++r) {
-      if (r == me) { px.gather[r] = s->d_peer_gather; px.flag[r] = s->d_peer_flags; continue; }
+      if (r == me) { px.gather[r] = s->d_peer_gather; px.flag[r] = s->d_peer_flags; px.own_gather = s->d_peer_gather; px.own_flag = s->d_peer_flags; continue; }
       void* g = nullptr;
       if (cudaIpcOpenMemHandle(&g, all[r].mem, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; g = nullptr; }
       px.gather[r] = (double*)g;

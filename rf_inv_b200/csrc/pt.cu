@@ -256,16 +256,18 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned long long* pt_pair_flag(const PtPeers& px, int q) { return px.flag[q] + px.world + 1; }
-__device__ __forceinline__ double* pt_pair_slot(const PtPeers& px, int q, int it) {   // slot of iteration `it`
-  return reinterpret_cast<double*>(px.flag[q] + px.world + 2) + 2 * (it & 3);
+// (the arrays of PtPeers are only indexed by compile-time constants -- unrolled loops over RFINV_MAX_PEERS with a predicate -- or
+// through own_gather / own_flag: a run-time index would make every thread copy the parameter block to local memory)
+__device__ __forceinline__ unsigned long long* pt_pair_flag(unsigned long long* flag_base, int world) { return flag_base + world + 1; }
+__device__ __forceinline__ double* pt_pair_slot(unsigned long long* flag_base, int world, int it) {   // slot of iteration `it`
+  return reinterpret_cast<double*>(flag_base + world + 2) + 2 * (it & 3);
 }
 // waits until *f >= want (a flag a peer raises); bounded: a peer that never arrives -- it stopped on an error -- sets this
 // process's error word instead of hanging the GPU (the host checks the word after the run)
 __device__ __forceinline__ void pt_peer_wait(const PtPeers& px, const unsigned long long* f, unsigned long long want) {
   const long long t0 = clock64();
   while (ld_acquire_sys(f) < want) {
-    if (clock64() - t0 > 40000000000LL) { px.flag[px.me][px.world] = 1ULL; break; }   // ~20 s
+    if (clock64() - t0 > 40000000000LL) { px.own_flag[px.world] = 1ULL; break; }   // ~20 s
     __nanosleep(100);
   }
 }
@@ -339,12 +341,13 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
   int shift = 0;
   const int it_now = PEER ? *p.it_dev : 0;
   if (PEER && p.nchains >= 2 && px.done[0] < it_now) {     // swap it_now - 1: its pair was published an iteration ago
-    if (lane == 0) pt_peer_wait(px, pt_pair_flag(px, px.me), (unsigned long long)it_now);
+    if (lane == 0) pt_peer_wait(px, pt_pair_flag(px.own_flag, px.world), (unsigned long long)it_now);
     __syncwarp();
-    const double* pr = pt_pair_slot(px, px.me, it_now - 1);
+    const double* pr = pt_pair_slot(px.own_flag, px.world, it_now - 1);
     const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
     if (sp.own1 == px.me && sp.rank1_local == r) shift = 1;   // the stream of rank1 consumed the judge_pt uniform
   }
+  if (PEER) table += (size_t)(it_now & 1) * (2 * Cl + p.G + 2);   // the local table alternates: the previous one is being pushed
   Mt g(p.mt, r, p.mti[r] + shift, /*warp=*/true);
   __syncwarp();
   const bool has1 = lane + 32 < km;
@@ -472,14 +475,7 @@ __global__ void __launch_bounds__(128) pt_propose_kernel(const DevConfig cfg, co
       do { i2 = (int)(g.grnd() * (double)n_all); } while (i2 == i1);
       t1 = i1; t2 = i2;
     }
-    if (lane == 0) {
-      table[2 * Cl + p.G] = t1; table[2 * Cl + p.G + 1] = t2;
-      if (PEER && p.rank_begin == 0) {   // the pair goes to every process now: it is all the next proposal pass needs
-        for (int q = 0; q < px.world; ++q) { double* ps = pt_pair_slot(px, q, it_now); ps[0] = t1; ps[1] = t2; }
-        __threadfence_system();
-        for (int q = 0; q < px.world; ++q) st_release_sys(pt_pair_flag(px, q), (unsigned long long)it_now + 1ULL);
-      }
-    }
+    if (lane == 0) { table[2 * Cl + p.G] = t1; table[2 * Cl + p.G + 1] = t2; }   // (PEER: pt_pairpush_kernel takes it to the other processes)
   }
   {
     const double u = g.peek();   // may reload the state (mti 624 -> 0); nothing is consumed
@@ -589,14 +585,8 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
   const int c = blockIdx.x * PT_FIN_CHAINS + lane;
   const int km = cfg.k_max, Cl = p.Cl, T = cfg.ntrc;
   const int it = *p.it_dev;
-  const size_t slot = PEER ? ((size_t)(it & 1) * px.world + px.me) * px.table_len : 0;
-  auto put = [&](int idx, double v) {
-    table[idx] = v;
-    if (PEER) {
-#pragma unroll 1
-      for (int q = 0; q < px.world; ++q) px.gather[q][slot + idx] = v;
-    }
-  };
+  if (PEER) table += (size_t)(it & 1) * (2 * Cl + p.G + 2);   // pt_push_kernel takes it to the other processes during the next iteration
+  auto put = [&](int idx, double v) { table[idx] = v; };
   double cold_logl = 0.0;
   if (warp == 0) {
     // PEER: the previous iteration's swap exchanges its two temperatures here, in front of their first reader (every CTA takes
@@ -604,11 +594,11 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
     int sw_l1 = -1, sw_l2 = -1;
     double sw_t1 = 0.0, sw_t2 = 0.0;
     if (PEER && p.nchains >= 2 && px.done[1] < it) {
-      if (lane < px.world) pt_peer_wait(px, px.flag[px.me] + lane, (unsigned long long)it);
+      if (lane < px.world) pt_peer_wait(px, px.own_flag + lane, (unsigned long long)it);
       __syncwarp();
-      const double* pr = pt_pair_slot(px, px.me, it - 1);
+      const double* pr = pt_pair_slot(px.own_flag, px.world, it - 1);
       const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
-      const double* gathered = px.gather[px.me] + (size_t)((it - 1) & 1) * px.world * px.table_len;
+      const double* gathered = px.own_gather + (size_t)((it - 1) & 1) * px.world * px.table_len;
       const double* ta = gathered + (size_t)sp.own1 * px.table_len;
       const double* tb = gathered + (size_t)sp.own2 * px.table_len;
       const double temp1 = __ldcg(ta + sp.l1), temp2 = __ldcg(tb + sp.l2), e1 = __ldcg(ta + Cl + sp.l1), e2 = __ldcg(tb + Cl + sp.l2);
@@ -698,17 +688,9 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
       }
     }
   }
-  if (PEER) {   // the rank entries and the pair, left in the local table by pt_propose_kernel
-    for (int i = blockIdx.x * PT_FIN_THREADS + tid; i < p.G + 2; i += (int)gridDim.x * PT_FIN_THREADS) {
-      const double v = __ldcg(table + 2 * Cl + i);
-#pragma unroll 1
-      for (int q = 0; q < px.world; ++q) px.gather[q][slot + 2 * Cl + i] = v;
-    }
-  }
-  // the table entries (warp 0; PEER: also the rank entries pushed above) are ordered before the arrival below; the adopted
-  // rows are only read by later kernels and need no fence
-  if (PEER) { if (warp == 0 || blockIdx.x * PT_FIN_THREADS + tid < p.G + 2) __threadfence_system(); }
-  else if (warp == 0) __threadfence();
+  // the table entries (warp 0) are ordered before the arrival below; the adopted rows are only read by later kernels and
+  // need no fence
+  if (warp == 0) __threadfence();
   __syncthreads();
   if (tid == 0) s_last = atomicAdd(arrived, 1) == (int)gridDim.x - 1;
   __syncthreads();
@@ -728,8 +710,6 @@ __global__ void __launch_bounds__(PT_FIN_THREADS) pt_finish_kernel(const DevConf
     lhist[it] = acc;
     *arrived = 0;
     if (PEER) {
-      __threadfence_system();
-      for (int q = 0; q < px.world; ++q) st_release_sys(px.flag[q] + px.me, (unsigned long long)it + 1ULL);
       px.done[0] = it; px.done[1] = it;   // the swaps of the iterations before this one are applied; this one's follows in the next
       *p.it_dev = it + 1;                 // the iteration is complete
       *p.n_active = 0;
@@ -744,20 +724,65 @@ __global__ void pt_swap_kernel(const PtDev p, const double* gathered, int world,
   pt_swap_decide(p, gathered, world, table_len);
 }
 
+// Peer-memory exchange, side branch of the iteration (rfinv_pt.h).  pt_pairpush_kernel: one warp; the owner of virtual rank 0
+// takes the pair pt_propose_kernel has just drawn (local table, parity it & 1) to every process.
+__global__ void pt_pairpush_kernel(const PtDev p, const double* __restrict__ table, const PtPeers px) {
+  if (p.rank_begin != 0 || p.nchains < 2 || threadIdx.x != 0) return;
+  const int it = *p.it_dev;
+  const double* tab = table + (size_t)(it & 1) * px.table_len + 2 * p.Cl + p.G;
+  const double t1 = __ldcg(tab), t2 = __ldcg(tab + 1);
+#pragma unroll
+  for (int q = 0; q < RFINV_MAX_PEERS; ++q)
+    if (q < px.world) { double* ps = pt_pair_slot(px.flag[q], px.world, it); ps[0] = t1; ps[1] = t2; }
+  __threadfence_system();
+#pragma unroll
+  for (int q = 0; q < RFINV_MAX_PEERS; ++q)
+    if (q < px.world) st_release_sys(pt_pair_flag(px.flag[q], px.world), (unsigned long long)it + 1ULL);
+}
+
+// pt_push_kernel: the swap table of the iteration before (local table, parity (it - 1) & 1) goes into slot `me` of every
+// process's gather buffer; the last CTA raises this process's table flag everywhere.  Runs beside pt_propose_kernel of iteration
+// `it` (and once more in front of pt_drain_kernel); a table is pushed once (done[2]).
+constexpr int PT_PUSH_THREADS = 256;
+__global__ void __launch_bounds__(PT_PUSH_THREADS) pt_push_kernel(const PtDev p, const double* __restrict__ table, const PtPeers px) {
+  __shared__ int s_last;
+  const int it = *p.it_dev;
+  if (it < 1 || px.done[2] >= it) return;          // nothing to push (uniform over the grid: done[2] only changes at the very end)
+  const int prev = it - 1;
+  const double* tab = table + (size_t)(prev & 1) * px.table_len;
+  const size_t slot = ((size_t)(prev & 1) * px.world + px.me) * px.table_len;
+  for (int i = blockIdx.x * PT_PUSH_THREADS + threadIdx.x; i < px.table_len; i += gridDim.x * PT_PUSH_THREADS) {
+    const double v = __ldcg(tab + i);
+#pragma unroll
+    for (int q = 0; q < RFINV_MAX_PEERS; ++q) if (q < px.world) px.gather[q][slot + i] = v;
+  }
+  __threadfence_system();     // this thread's stores into peer memory are ordered before the arrival below
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(px.done + 3, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {   // every CTA's stores precede its arrival: the table is complete everywhere
+    __threadfence_system();
+#pragma unroll
+    for (int q = 0; q < RFINV_MAX_PEERS; ++q) if (q < px.world) st_release_sys(px.flag[q] + px.me, (unsigned long long)it);
+    px.done[3] = 0;
+    px.done[2] = it;
+  }
+}
+
 // Peer-memory exchange: the swap of the LAST iteration of a run, in full (stream shift, temperatures, log) -- inside the
 // run every swap is applied one iteration later by pt_propose_kernel / pt_finish_kernel.  One warp.
 __global__ void pt_drain_kernel(const PtDev p, const PtPeers px) {
   const int lane = threadIdx.x & 31;
   const int it = *p.it_dev;                   // iterations completed; the pending swap is that of iteration it - 1
   if (p.nchains < 2 || it < 1 || px.done[1] >= it) return;
-  if (lane < px.world) pt_peer_wait(px, px.flag[px.me] + lane, (unsigned long long)it);
-  if (lane == 0) pt_peer_wait(px, pt_pair_flag(px, px.me), (unsigned long long)it);
+  if (lane < px.world) pt_peer_wait(px, px.own_flag + lane, (unsigned long long)it);
+  if (lane == 0) pt_peer_wait(px, pt_pair_flag(px.own_flag, px.world), (unsigned long long)it);
   __syncwarp();
   if (lane != 0) return;
   const int Cl = p.Cl;
-  const double* pr = pt_pair_slot(px, px.me, it - 1);
+  const double* pr = pt_pair_slot(px.own_flag, px.world, it - 1);
   const SwapPlan sp = pt_swap_plan(p, __ldcg(pr), __ldcg(pr + 1));
-  const double* gathered = px.gather[px.me] + (size_t)((it - 1) & 1) * px.world * px.table_len;
+  const double* gathered = px.own_gather + (size_t)((it - 1) & 1) * px.world * px.table_len;
   const double* ta = gathered + (size_t)sp.own1 * px.table_len;
   const double* tb = gathered + (size_t)sp.own2 * px.table_len;
   const double temp1 = __ldcg(ta + sp.l1), temp2 = __ldcg(tb + sp.l2), e1 = __ldcg(ta + Cl + sp.l1), e2 = __ldcg(tb + Cl + sp.l2);
@@ -948,6 +973,8 @@ void rfinv_handle::free_pt() {
   cudaFree(d.vp_mean); cudaFree(d.vs_mean); cudaFree(d.vpvs_mean); cudaFree(d.vp_model); cudaFree(d.vs_model); cudaFree(d.cold_ordinal); cudaFree(d.cold_count); cudaFree(d.ocean_bin);
   cudaFree(pt->d_lhist); cudaFree(pt->d_lh_part); cudaFree(pt->d_lh_cnt); cudaFree(pt->d_table); cudaFree(pt->d_gather); cudaFree(d.it_dev);
   if (pt->capture_stream) cudaStreamDestroy(pt->capture_stream);
+  if (pt->side_stream) cudaStreamDestroy(pt->side_stream);
+  for (cudaEvent_t e : pt->ev_side) if (e) cudaEventDestroy(e);
   for (cudaGraphExec_t g : pt->graph) if (g) cudaGraphExecDestroy(g);
   rfinv_comm_peer_release(this);
   delete pt;
@@ -1043,7 +1070,7 @@ int32_t rfinv_pt_init(rfinv_handle* h, int32_t nproc_total, int32_t rank_begin, 
     }
   }
   s->table_len = (int)(2 * Cl + G + 2);
-  A(dalloc(&s->d_table, (size_t)s->table_len));
+  A(dalloc(&s->d_table, (size_t)2 * s->table_len));
   s->cap_lhist = c.nburn + c.niter > 0 ? c.nburn + c.niter : 1024;
   A(dalloc(&s->d_lhist, (size_t)s->cap_lhist));
   A(dalloc(&s->d_lh_part, (Cl + PT_FIN_CHAINS - 1) / PT_FIN_CHAINS)); A(dalloc(&s->d_lh_cnt, 1));
@@ -1139,6 +1166,13 @@ static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = f
   PtDev& d = s->dev;
   cudaStream_t q = h->stream;
   int st;
+  const bool peer_side = s->peer_state == 1 && peer_exchange;
+  if (peer_side) {   // side branch of the iteration: the previous iteration's table goes to the other processes beside the proposal pass
+    RFINV_CUDA_CHECK(cudaEventRecord(s->ev_side[0], q));
+    RFINV_CUDA_CHECK(cudaStreamWaitEvent(s->side_stream, s->ev_side[0], 0));
+    const int nbp = (s->table_len + PT_PUSH_THREADS - 1) / PT_PUSH_THREADS;
+    pt_push_kernel<<<nbp < 64 ? nbp : 64, PT_PUSH_THREADS, 0, s->side_stream>>>(d, s->d_table, s->peers);
+  }
   {
     // staged variant while a warp's share of shared memory stays below 48 KB; 1, 2 or 4 warps per CTA accordingly
     const size_t per_warp = sizeof(double) * pt_propose_smem_doubles(h->dc.k_max, h->dc.ntrc, d.nchains);
@@ -1155,7 +1189,14 @@ static int pt_enqueue_local(rfinv_handle* h, bool record, bool peer_exchange = f
     }
   }
   RFINV_CUDA_CHECK(cudaGetLastError());
+  if (peer_side) {   // the pair just drawn goes to the other processes beside the evaluation
+    RFINV_CUDA_CHECK(cudaEventRecord(s->ev_side[1], q));
+    RFINV_CUDA_CHECK(cudaStreamWaitEvent(s->side_stream, s->ev_side[1], 0));
+    pt_pairpush_kernel<<<1, 32, 0, s->side_stream>>>(d, s->d_table, s->peers);
+    RFINV_CUDA_CHECK(cudaEventRecord(s->ev_side[2], s->side_stream));
+  }
   if ((st = pt_eval(h, /*proposal=*/true, /*all=*/false)) != RFINV_OK) return st;
+  if (peer_side) RFINV_CUDA_CHECK(cudaStreamWaitEvent(q, s->ev_side[2], 0));   // the side branch joins in front of pt_finish_kernel
   {
     const unsigned nb = (unsigned)((d.Cl + PT_FIN_CHAINS - 1) / PT_FIN_CHAINS);
     const bool peer = s->peer_state == 1 && peer_exchange;
@@ -1247,6 +1288,10 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
     s->cap_gather = world * s->table_len;
     pt_drop_graphs(s);
   }
+  if (world > 1 && s->peer_state == 1 && !s->side_stream) {   // (created outside any capture)
+    RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : s->ev_side) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   static const bool use_graph = !(getenv("RFINV_PT_GRAPH") && atoi(getenv("RFINV_PT_GRAPH")) == 0);
   if (s->graph_world != world) { pt_drop_graphs(s); s->graph_world = world; }
   for (int it = 0; it < n_iter; ++it) {
@@ -1278,7 +1323,9 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
     }
     s->it_done++;
   }
-  if (world > 1 && s->peer_state == 1) {   // the last swap of this run (inside the run every swap is applied an iteration later)
+  if (world > 1 && s->peer_state == 1) {   // the last table and the last swap of this run (inside the run every swap is applied an iteration later)
+    const int nbp = (s->table_len + PT_PUSH_THREADS - 1) / PT_PUSH_THREADS;
+    pt_push_kernel<<<nbp < 64 ? nbp : 64, PT_PUSH_THREADS, 0, h->stream>>>(s->dev, s->d_table, s->peers);
     pt_drain_kernel<<<1, 32, 0, h->stream>>>(s->dev, s->peers);
     RFINV_CUDA_CHECK(cudaGetLastError());
   }

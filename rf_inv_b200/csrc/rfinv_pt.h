@@ -49,25 +49,31 @@ struct ncclComm;   // NCCL communicator (comm.cu)
 // Swap exchange over peer memory (one process per GPU on one NVLink / NVSwitch box).  Every process owns ONE buffer, opened
 // by every other process through CUDA IPC:
 //   gather [2][world][table_len] doubles | table flags [world] | error word | pair flag | pair [4][2] doubles
-// * pt_propose_kernel of the process that owns virtual rank 0 draws the pair of iteration i and stores it straight into the
-//   pair slot i & 3 of EVERY process, then raises pair flag = i + 1 everywhere (four slots: the owner of rank 0 may draw the
-//   pair of iteration i while the slowest process still reads that of iteration i - 2);
-// * pt_finish_kernel stores this process's swap table into slot `me` of EVERY process's gather buffer (parity i & 1) while it
-//   builds it, and the last of its CTAs raises table flag[me] = i + 1 everywhere.
-// No collective call, no extra launch: the exchange rides on the kernels the iteration runs anyway.  And nobody waits for it
-// at the end of the iteration: swap i is APPLIED one iteration later, where its parts are needed -- the stream shift of rank1
-// (judge_pt's draw, src/pt_mcmc.f90:590) at the top of pt_propose_kernel of iteration i + 1, which only needs the pair; the
-// exchange of the two temperatures at the top of pt_finish_kernel of iteration i + 1 (the acceptance test is the first reader of
-// a temperature), which needs the tables.  By then both arrived most of an iteration ago, so the processes drift by up to an
-// iteration instead of meeting at every swap.  pt_drain_kernel applies the last swap of a run.  (Double buffering suffices: a
-// process needs every table flag of iteration i - 1 to finish iteration i, so it is never two iterations ahead of anyone.)
+// Stores into peer memory, system-scope fences and release stores cost microseconds each, so none of them sits on the
+// iteration's critical path: two small kernels on a SIDE BRANCH of the iteration's graph do them while the main branch computes.
+// * pt_pairpush_kernel (behind pt_propose_kernel, beside prep / forward / quadform): the process that owns virtual rank 0
+//   stores the pair of iteration i into pair slot i & 3 of EVERY process and raises pair flag = i + 1 everywhere (four slots:
+//   the pair of iteration i may be drawn while the slowest process still reads that of iteration i - 2);
+// * pt_push_kernel (at the top of iteration i + 1, beside pt_propose_kernel): stores the swap table of iteration i -- which
+//   pt_finish_kernel left in the local table, parity i & 1 -- into slot `me` of EVERY process's gather buffer and raises table
+//   flag[me] = i + 1 everywhere.
+// And nobody waits for the exchange at the end of the iteration: swap i is APPLIED one iteration later, where its parts are
+// needed -- the stream shift of rank1 (judge_pt's draw, src/pt_mcmc.f90:590) at the top of pt_propose_kernel of iteration i + 1,
+// which only needs the pair; the exchange of the two temperatures at the top of pt_finish_kernel of iteration i + 1 (the
+// acceptance test is the first reader of a temperature), which needs the tables.  By then both arrived most of an iteration
+// ago, so the processes drift by up to an iteration instead of meeting at every swap.  pt_drain_kernel applies the last swap of
+// a run.  (Double buffering suffices: a process needs every table flag of iteration i - 1 to finish iteration i, so it is
+// never two iterations ahead of anyone.)
 #define RFINV_MAX_PEERS 16
 struct PtPeers {
   int world, me, table_len;
   double* gather[RFINV_MAX_PEERS];               // buffer of process q (own: local memory, others: IPC mappings)
   unsigned long long* flag[RFINV_MAX_PEERS];     // its flag words: [world] table epochs, [world] error, [world + 1] pair epoch;
                                                  // the pair slots follow as doubles (pt_pair_slot)
-  int* done;                                     // local: [0] swaps whose stream shift is applied, [1] swaps whose temperatures are
+  double* own_gather;                            // = gather[me], flag[me]: kept apart so that no kernel indexes the arrays above with
+  unsigned long long* own_flag;                  // a run-time value (the parameter block would be copied to local memory per thread)
+  int* done;                                     // local: [0] swaps whose stream shift is applied, [1] swaps whose temperatures are,
+                                                 // [2] tables pushed, [3] arrival counter of pt_push_kernel
 };
 // words of 8 bytes behind the gather buffer
 inline size_t pt_peer_tail_words(int world) { return (size_t)world + 2 + 8; }
@@ -80,6 +86,8 @@ struct PtState {
   cudaGraphExec_t graph[2] = {nullptr, nullptr};
   int graph_world = 0;
   cudaStream_t capture_stream = nullptr;
+  cudaStream_t side_stream = nullptr;      // side branch of the iteration (peer-memory exchange)
+  cudaEvent_t ev_side[3] = {nullptr, nullptr, nullptr};
   double* d_gather = nullptr;  // swap tables of all processes (distributed run, NCCL all-gather)
   int cap_gather = 0;
   // peer-memory exchange (comm.cu: rfinv_comm_peer_setup); peer_state 0 = not tried, 1 = on, -1 = unavailable (NCCL all-gather)
@@ -91,7 +99,7 @@ struct PtState {
   double* d_lhist = nullptr;   // likelihood_hist(it), src/pt_mcmc.f90:199-200
   double* d_lh_part = nullptr; // per-CTA sums of the likelihood history (pt_finish_kernel)
   int* d_lh_cnt = nullptr;     // its arrival counter
-  double* d_table = nullptr;   // swap table of this process
+  double* d_table = nullptr;   // swap table of this process, [2][table_len] (the peer-memory exchange alternates, the others use [0])
   int table_len = 0;
   int log_cap = 0, log_base = 0;
   long long n_eval = 0;

@@ -7,7 +7,9 @@ sys.path.insert(0, ROOT)
 import numpy as np
 import torch
 import torch.distributed as dist
-from rf_inv_b200 import workloads
+from rf_inv_b200 import workloads, capi
+if os.environ.get("RFINV_LIB"):
+    capi._lib = capi.load(os.environ["RFINV_LIB"])
 from rf_inv_b200.pt import ParallelTempering
 
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
