@@ -463,8 +463,8 @@ def main():
                    "virtual_ranks": nproc_total, "chains_per_rank": nch, "k_mean_after": round(k_pt, 2),
                    "launch": "one CUDA graph launch per iteration (rfinv_pt_run / rfinv_pt_run_distributed)",
                    "exchange": "none (single process)" if world == 1 else (
-                       "peer memory: pt_table_kernel stores the (T, logL, next-uniform) table into every process's gather buffer (CUDA IPC "
-                       "over NVLink) and raises a flag, pt_swap_kernel waits for the flags -- no collective call in the iteration"
+                       "peer memory: the pair and the (T, logL, next-uniform) table go into every process's buffers (CUDA IPC over NVLink) from "
+                       "a side branch of the iteration's graph; the swap is applied one iteration later -- no collective call, no waiting"
                        if pt_exchange == "peer memory" else
                        "one ncclAllGather of the (T, logL, next-uniform) tables per iteration, issued by the library inside the iteration's graph")}
         pt.close()

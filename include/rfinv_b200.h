@@ -198,7 +198,8 @@ int32_t rfinv_pt_run(rfinv_handle* h, int32_t n_iter);
  * Replaces the reference's MPI traffic on this path: pt_control's swap exchange (src/pt_mcmc.f90:518-571: mpi_bcast of the
  * pair, mpi_send / mpi_recv of temperature and likelihood) becomes ONE ncclAllGather of the swap tables per iteration on the
  * handle's stream -- or, when every GPU can map its peers' memory (one NVLink / NVSwitch box), no collective call at all: the
- * tables are stored into peer memory by the kernel that builds them (rfinv_pt_exchange_mode); output_results' 14 mpi_reduce and 2 mpi_gather (src/mcmc_out.f90:52-93) become rfinv_pt_reduce_outputs.
+ * pair and the tables are stored into peer memory by two small kernels on a side branch of the iteration's graph and the swap
+ * is applied one iteration later (rfinv_pt_exchange_mode); output_results' 14 mpi_reduce and 2 mpi_gather (src/mcmc_out.f90:52-93) become rfinv_pt_reduce_outputs.
  * NCCL is bound at run time (libnccl.so.2, or the file named by RFINV_NCCL_LIB).  The host only carries the communicator id
  * from one process to the others (MPI_Bcast of rfinv_comm_id_bytes() bytes in the Fortran host).                          */
 int32_t rfinv_comm_id_bytes(void);
@@ -210,8 +211,9 @@ int32_t rfinv_comm_destroy(rfinv_handle* h);
 /* world / rank of the handle's communicator (1 / 0 without one) and the version of the NCCL library bound (0: none). */
 int32_t rfinv_comm_info(rfinv_handle* h, int32_t* world, int32_t* rank, int32_t* nccl_version);
 /* How rfinv_pt_run_distributed exchanges the swap tables: 0 = not decided yet (no distributed run since rfinv_pt_init) or a
- * single process; 1 = peer memory -- every process stores its table straight into the gather buffers of all processes
- * (CUDA IPC mappings over NVLink) from the kernel that builds it and raises a flag, no collective call in the iteration;
+ * single process; 1 = peer memory -- every process stores the pair and its table straight into the buffers of all processes
+ * (CUDA IPC mappings over NVLink) from a side branch of the iteration's graph and raises a flag; no collective call, and no
+ * process waits for another at the end of an iteration (the swap is applied one iteration later, where its parts are needed);
  * 2 = one ncclAllGather per iteration (some process could not map its peers, or RFINV_PT_EXCHANGE=nccl). */
 int32_t rfinv_pt_exchange_mode(rfinv_handle* h);
 /* pt_control (src/pt_mcmc.f90:468-576) for n_iter iterations over the processes of the communicator; process q must have

@@ -120,7 +120,7 @@ module rfinv_b200_capi
        type(c_ptr), value :: handle
      end function rfinv_pt_reduce_outputs
 
-     ! 1: swap tables stored straight into peer memory (NVLink) by the kernel that builds them; 2: one ncclAllGather per iteration
+     ! 1: pair and swap tables stored straight into peer memory (NVLink) from a side branch of the iteration; 2: one ncclAllGather per iteration
      integer(c_int32_t) function rfinv_pt_exchange_mode(handle) bind(C, name="rfinv_pt_exchange_mode")
        import :: c_int32_t, c_ptr
        type(c_ptr), value :: handle

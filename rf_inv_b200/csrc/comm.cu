@@ -2,7 +2,8 @@
 //
 // Replaces the reference's MPI traffic on this path (paths relative to the reference checkout):
 //   pt_control's swap exchange      src/pt_mcmc.f90:518-571  (mpi_bcast of the pair, mpi_send / mpi_recv of temperature and
-//                                   likelihood between the two ranks)   ->  ONE ncclAllGather of the swap tables per iteration
+//                                   likelihood between the two ranks)   ->  stores into peer memory (rfinv_pt.h: PtPeers), or
+//                                                                           ONE ncclAllGather of the swap tables per iteration
 //   output_results' 14 reduces      src/mcmc_out.f90:52-79   ->  ncclReduce of the device-resident bookkeeping arrays to process 0
 //   output_results' 2 gathers       src/mcmc_out.f90:86-93   ->  ncclSend / ncclRecv of the recorded models to process 0
 // NCCL is bound at run time (dlopen of libnccl.so.2: the copy the host process already loaded, e.g. torch's, or the system
