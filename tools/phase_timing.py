@@ -19,7 +19,9 @@ from rf_inv_b200.evaluator import Evaluator
 wl = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "target"
 cfg = workloads.make_config(wl)
 cfg.obs = np.zeros((cfg.ntrc, cfg.nsmp)); cfg.r_inv = np.zeros((cfg.ntrc, cfg.nsmp, cfg.nsmp))
-m = workloads.draw_models(cfg, 4096, seed=100, dvs_scale=0.3)
+# --k N: every model with N interfaces (e.g. --k 3: the layer counts of the chains inside the PT loop, k_mean 2.5 - 3)
+k_fixed = int(sys.argv[sys.argv.index("--k") + 1]) if "--k" in sys.argv else None
+m = workloads.draw_models(cfg, 4096, seed=100, dvs_scale=0.3, k_fixed=k_fixed)
 names = ["stage consts", "trig tables", "layer loop", "epilogue(surface)", "deconv+Z build", "fft", "max/shift/output"]
 with Evaluator(cfg) as ev:
     ev.calc_likelihood(m["k"], m["z"], m["dvp"], m["dvs"], m["sig"])
