@@ -1288,6 +1288,13 @@ static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
     s->cap_gather = world * s->table_len;
     pt_drop_graphs(s);
   }
+  if (world > 1 && s->peer_state == 1) {
+    // every run ends with pt_drain_kernel, so at this point every swap of the iterations done so far is applied -- also when
+    // some of them were driven through rfinv_pt_local_step / rfinv_pt_apply_swap in between
+    const int applied[3] = {s->it_done, s->it_done, s->it_done};
+    RFINV_CUDA_CHECK(cudaMemcpyAsync(s->peers.done, applied, sizeof(applied), cudaMemcpyHostToDevice, h->stream));
+    RFINV_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
   if (world > 1 && s->peer_state == 1 && !s->side_stream) {   // (created outside any capture)
     RFINV_CUDA_CHECK(cudaStreamCreateWithFlags(&s->side_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : s->ev_side) RFINV_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
