@@ -16,6 +16,7 @@ def run_both(cfg, nproc, n_iter):
     pt.set_logging(n_iter)
     st0 = pt.state()
     pt.run(n_iter)
+    assert pt.exchange_mode == "none"        # a single process exchanges nothing
     flags, itypes, swaps = pt.log(n_iter)
     st, cnt = pt.state(), pt.counters()
     pt.close()
@@ -60,7 +61,8 @@ def test_sample_syn_config_200_iterations():
     assert g["swaps"][:, 2].sum() > 0
 
 
-@pytest.mark.parametrize("variant", ["sigma_solved_vp_solved", "laplace_prior_joint_PS", "single_chain_per_rank"])
+@pytest.mark.parametrize("variant", ["sigma_solved_vp_solved", "laplace_prior_joint_PS", "single_chain_per_rank", "transform_length_250",
+                                     "transform_length_375_odd"])
 def test_proposal_variants(variant):
     if variant == "sigma_solved_vp_solved":           # 6 proposal types, sea layer, common rays
         cfg = helpers.small_config(sdep=2.0, vp_mode=1, rayps=[0.06, 0.06], a_gus=[2.5, 4.0], nfft=128, nsmp=64,
@@ -70,6 +72,10 @@ def test_proposal_variants(variant):
         cfg = helpers.small_config(prior_mode=1, dvs_prior=0.3, dvp_prior=0.1, vp_mode=1, ipha=[1, -1], rayps=[0.06, 0.10],
                                    nfft=128, nsmp=64, nchains=3, ncool=1, t_high=5.0, iseed=4242)
         nproc, n_iter = 5, 120
+    elif variant.startswith("transform_length"):       # N_FFT that is not a power of two: the Bluestein kernels inside the PT loop
+        n = 250 if variant.endswith("250") else 375
+        cfg = helpers.small_config(sdep=1.0, nfft=n, nsmp=101, nchains=4, ncool=1, t_high=8.0, iseed=31337)
+        nproc, n_iter = 5, 80
     else:                                               # nchains < 2: the swap step is skipped entirely (pt_mcmc.f90:498)
         cfg = helpers.small_config(nfft=64, nsmp=40, nchains=1, ncool=1, iseed=99)
         nproc, n_iter = 8, 60
