@@ -33,7 +33,12 @@ from rf_inv_b200 import workloads  # noqa: E402
 
 METRIC = "forward+likelihood evals/sec"
 UNIT = "evals/s"
-DEFAULT_CHAINS = {"target": 16384, "c2": 4096, "c3": 8192, "c3_buried": 8192, "c4": 16384, "c5": 65536, "sample": 4096}
+# models per GPU and step.  Target shape: 32 768 -- the three kernels of a step are persistent, dynamically scheduled grids whose ramp and
+# tail are paid once per launch (measured on one B200: 4096 models 10.25, 8192 11.73, 16 384 12.53, 32 768 12.90, 65 536 13.15 M evals/s;
+# DESIGN.md section 6); round 1 and the first half of round 2 quoted 16 384.
+DEFAULT_CHAINS = {"target": 32768, "c2": 4096, "c3": 8192, "c3_buried": 8192, "c4": 16384, "c5": 65536, "sample": 4096}
+# chains per GPU of the PT-MCMC leg of the primary workload (iterations/s depend on the chain count: kept at round 1's figure)
+PT_CHAINS = {"target": 16384}
 # totals that BASELINE.json fixes for the whole job (strong scaling: chains per GPU = total / N); the others are per GPU
 FIXED_TOTAL = {"c4": 16384, "c5": 65536}
 SIDE_CONFIGS = ["sample", "c2", "c3", "c3_buried", "c4", "c5"]
@@ -434,7 +439,8 @@ def main():
     if args.pt_iters > 0:
         from rf_inv_b200.pt import ParallelTempering
         nch = cfg.nchains
-        nproc_total = world * max(1, chains // nch)
+        pt_chains = min(chains, PT_CHAINS.get(args.workload, chains)) if not args.chains else chains
+        nproc_total = world * max(1, pt_chains // nch)
         pt = ParallelTempering(cfg, nproc_total, device=local_rank, world=world, rank=rank)
         pt.ev.set_stream(leg.stream.cuda_stream)
         if world > 1:
