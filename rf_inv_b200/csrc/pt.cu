@@ -1270,9 +1270,9 @@ static int pt_enqueue_iteration(rfinv_handle* h, int world, bool record) {
 }
 
 // pt_control's loop (src/pt_mcmc.f90:488-572) for n_iter iterations over `world` processes.  The launch sequence of an
-// iteration -- a dozen kernels and, with several processes, one ncclAllGather -- is captured once per variant (with /
-// without the bookkeeping kernels) in a CUDA graph and replayed: one launch per iteration instead of twelve
-// (RFINV_PT_GRAPH=0: plain launches).
+// iteration -- five kernels; with several processes also the two kernels of the peer-memory exchange on a side branch, or one
+// ncclAllGather and the swap kernel -- is captured once per variant (with / without the bookkeeping kernels) in a CUDA graph and
+// replayed: one launch per iteration (RFINV_PT_GRAPH=0: plain launches).
 static int pt_iterate(rfinv_handle* h, int n_iter, int world) {
   PtState* s = h->pt;
   int st;
